@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Headline benchmark: posterior evaluations / second for the batched bandpower lnL.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ...]
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on): Planck-lite-sized TT/TE/EE
+bandpower likelihood, 613 bins, dense FP64 covariance, 9 sampled parameters, stretch-move ensemble.
+One "step" = one full stretch-move step (both half-ensemble updates, each = proposal + priors +
+foreground build + DMMA binning + DMMA triangular solve + accept) over all walkers = one posterior
+evaluation per walker.  Scaling is weak: --walkers walkers PER GPU (default 65536), sharded row-wise;
+the complementary half is all-gathered over NCCL before each half-update.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import multiprocessing
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "posterior evals/sec (whole box) for batched bandpower lnL"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="planck_lite", choices=["planck_lite", "spt_multifreq"])
+    ap.add_argument("--walkers", type=int, default=65536, help="walkers per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_problem(name):
+    from cosmoslik_b200 import synthetic
+    return synthetic.planck_lite_problem(0) if name == "planck_lite" else synthetic.spt_multifreq_problem(0)
+
+
+def config_of(args, prob, nwalkers_total):
+    win = ("top-hat plik-lite bins (block-sparse window matrix; all-zero DMMA blocks skipped)"
+           if args.workload == "planck_lite" else "Gaussian bumps + 1e-10 tails (numerically dense windows)")
+    return {"workload": "BASELINE configs[3] planck_lite TT/TE/EE 613 bins" if args.workload == "planck_lite"
+            else "BASELINE configs[2] spt_multifreq 6 spectra x 50 bins",
+            "n_data": int(prob["n"]), "ndim": len(prob["truth"]), "sampler": "stretch move a=2",
+            "walkers_total": int(nwalkers_total), "walkers_per_gpu": int(args.walkers),
+            "windows": win, "l2": "working set (R matrix %d MB per half-step) exceeds L2; no explicit flush"
+            % (prob["n"] * args.walkers // 2 * 8 // 2 ** 20), "parallelism": "walker-sharded x%d" % args.gpus}
+
+
+# ------------------------------------------------------------------------------------- oracle arm
+def _oracle_slik(workload):
+    from cosmoslik_b200 import synthetic
+    from oracle import likes as olikes, runtime as ort
+    ns = types.SimpleNamespace(SlikPlugin=ort.Plugin, param=ort.Param, mspec_lnl=olikes.MspecLike, egfs=olikes.Egfs)
+    prob = make_problem(workload)
+    return prob, ort.Slik(synthetic.build_script(ns, prob)())
+
+
+_worker_state = {}
+
+
+def _limit_blas_threads():
+    """one BLAS thread per process, as BASELINE.md's plan prescribes (OMP_NUM_THREADS=1)"""
+    try:
+        from threadpoolctl import threadpool_limits
+        _worker_state["blas_limit"] = threadpool_limits(1)
+    except Exception:
+        pass
+
+
+def _worker_init(workload):
+    _limit_blas_threads()
+    _worker_state["prob"], _worker_state["slik"] = _oracle_slik(workload)
+
+
+def _worker_eval(X):
+    slik = _worker_state["slik"]
+    return [slik.evaluate(*x)[0] for x in X]
+
+
+def _sample_points(prob, n, seed=1):
+    names = sorted(prob["truth"])
+    x0 = np.array([prob["truth"][k] for k in names])
+    sc = np.array([prob["scales"][k] for k in names])
+    return x0 + sc * np.random.RandomState(seed).standard_normal((n, len(names)))
+
+
+def cpu_baseline_single(workload, budget_s):
+    """the oracle port (numpy/scipy, scalar per-walker calls like the reference) on ONE host core"""
+    _limit_blas_threads()
+    prob, slik = _oracle_slik(workload)
+    X = _sample_points(prob, 4096)
+    slik.evaluate(*X[0])
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s and n < len(X):
+        slik.evaluate(*X[n]); n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d oracle Slik.evaluate calls of the same script in %.1f s (1 core, OMP_NUM_THREADS=1)" % (n, dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port: the reference is pure Python and
+    cannot travel to the GPU box) on all host cores, a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    prob = make_problem(args.workload)
+    per_core = 24
+    X = _sample_points(prob, per_core * cores)
+    chunks = np.array_split(X, cores)
+    ctx = multiprocessing.get_context("fork")
+    with ctx.Pool(cores, initializer=_worker_init, initargs=(args.workload,)) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_worker_eval, chunks)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_worker_eval, chunks)
+        dt = time.perf_counter() - t0
+    value = len(X) * args.steps / dt
+    sample = "%d evaluations per step (%d per core) through the oracle's Slik.evaluate, Pool(%d)" % (len(X), per_core, cores)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": config_of(args, prob, args.walkers * args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], False
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.thread.start(); return self
+
+    def __exit__(self, *a):
+        self.stop = True; self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------- B200 arm
+def fp64_peak():
+    """FP64 tensor roofline denominator: measured cuBLAS DGEMM on this pool's B200 (tools/measure_peaks.py,
+    committed under profiles/); MEASURED_PEAKS.json has no FP64 figure."""
+    path = os.path.join(ROOT, "profiles", "measured_fp64_peak.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d["fp64_tflops_sustained"], "measured cuBLAS DGEMM sustained (profiles/measured_fp64_peak.json)"
+    return 37.0, "fallback: B200 datasheet FP64 37 TFLOP/s (no measurement yet)"
+
+
+def run_b200(args):
+    import torch
+    import cosmoslik_b200 as cb
+    from cosmoslik_b200 import dist, synthetic
+    rank, size = dist.init_from_env()
+    if size == 1:
+        torch.cuda.set_device(0)
+    dev = torch.cuda.current_device()
+    prob = make_problem(args.workload)
+    ns = types.SimpleNamespace(SlikPlugin=cb.SlikPlugin, param=cb.param, mspec_lnl=cb.likelihoods.mspec_lnl,
+                               egfs=cb.models.egfs)
+    k_total = args.walkers * size
+    sampler = lambda s: cb.samplers.emcee(s, num_samples=k_total, nwalkers=k_total, seed=1234)
+    slik = cb.Slik(synthetic.build_script(ns, prob, sampler=sampler)())
+    prog = slik.program()
+    smp = slik.sampler
+    names = list(slik.get_sampled())
+    # tight initial ball around the truth (a burnt-in ensemble), identical on every rank
+    x0 = np.array([prob["truth"][k] for k in names]); sc = np.array([prob["scales"][k] for k in names])
+    smp.init_pos = x0 + sc * np.random.RandomState(99).standard_normal((k_total, len(names)))
+
+    # ---- device-resident timing: K full stretch steps, CUDA events, max over ranks
+    smp.run(prog, nsteps=max(args.warmup, 3))
+    smp.init_pos = np.zeros((k_total, len(names)))   # placeholder; replaced below by the warmed-up state
+    full = dist.all_gather_rows(smp.stats["pos"][:args.walkers // 2], k_total // 2)
+    full2 = dist.all_gather_rows(smp.stats["pos"][args.walkers // 2:], k_total - k_total // 2)
+    smp.init_pos = torch.cat([full, full2], 0).cpu().numpy()
+    timers = {}
+    smp.timers = timers
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev) as clk:
+        e0.record()
+        smp.run(prog, nsteps=args.steps)
+        e1.record()
+        torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    # smp.run() includes the initial lnl of the start positions (one extra evaluation sweep, as
+    # emcee does); it is inside the timed region and NOT counted as evaluations.
+    if size > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms = float(ms.item())
+    value = k_total * args.steps / (ms * 1e-3)
+    acc_frac = smp.stats["accepted"] / float(smp.stats["evals"])
+    del smp["timers"]
+
+    # ---- per-kernel durations from the event pairs recorded inside the timed region
+    stage_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in timers.items()}
+    stage_n = {k: len(v) for k, v in timers.items()}
+    half = args.walkers // 2
+    fl = prog.flops
+    peak, peak_src = fp64_peak()
+    chi2_flops = fl["trsm"] * half          # executed: n_pad^2 + 64 n_pad per walker (diag-block solves included)
+    chi2_alg = fl["trsm_alg"] * half        # algorithmic: n^2 per walker
+    bin_flops = fl["bin_exec"] * half
+    dom = "chi2" if stage_ms.get("chi2", 0) >= stage_ms.get("bin_residual", 0) else "bin_residual"
+    dom_alg = chi2_alg if dom == "chi2" else fl["bin_dense"] * half
+    dom_exec = chi2_flops if dom == "chi2" else bin_flops
+    achieved = dom_alg / (stage_ms[dom] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": {"chi2": "k_trsm_chi2", "bin_residual": "k_bin_residual"}[dom],
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "ms_per_launch": stage_ms[dom],
+                "executed_tflops": dom_exec / (stage_ms[dom] * 1e-3) / 1e12,
+                "stages_ms_per_launch": stage_ms, "launches_per_stage": stage_n}
+
+    # ---- end to end through the plugin API with HOST buffers (Slik.evaluate_batch -> csl_lnl_host)
+    Xh = torch.from_numpy(smp.init_pos[rank * args.walkers:(rank + 1) * args.walkers].copy()).pin_memory()
+    Oh = torch.empty(args.walkers, dtype=torch.float64).pin_memory()
+    xh, oh = Xh.numpy(), Oh.numpy()
+    for _ in range(3):
+        prog.lnl_host(xh, oh)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        prog.lnl_host(xh, oh)
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if size > 1:
+        torch.distributed.all_reduce(t_e2e, op=torch.distributed.ReduceOp.MAX)
+    e2e = {"value": k_total * args.steps / float(t_e2e.item()), "unit": UNIT,
+           "h2d_bytes_per_step": int(xh.nbytes), "d2h_bytes_per_step": int(oh.nbytes),
+           "api": "Slik.evaluate_batch(numpy [W, ndim]) -> numpy [W] (csl_lnl_host, pinned host buffers)"}
+
+    if rank != 0:
+        return
+    cpu = None
+    if size == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_single(args.workload, args.cpu_seconds)
+    # my kernels per stretch step: per half-update propose, prepare, zero_pad, bin, chi2, combine, accept; + rows
+    launches_per_step = 2 * 7 + 1
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": size, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(args, prob, k_total), "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps + 4,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
+            "acceptance": acc_frac,
+            "flops_per_eval": {"trsm_algorithmic": fl["trsm_alg"], "trsm_executed": fl["trsm"],
+                               "binning_dense": fl["bin_dense"], "binning_executed": fl["bin_exec"]}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""ctypes binding of the C ABI declared in include/cosmoslik_b200.h.
+
+There is no CPU fallback: if the shared library is missing or a CUDA device is
+needed and absent, this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcosmoslik_b200.so")
+
+# geometry constants (keep in sync with the header; checked in tests/test_abi.py)
+BM, BN, KC = 64, 128, 16
+MAX_DIM, MAX_TERMS, MAX_PLAW = 64, 8, 4
+SPEC_STRIDE, TILE_STRIDE, STACK = 64, 32, 16
+OP = dict(PUSHP=0, PUSHC=1, ADD=2, SUB=3, MUL=4, DIV=5, NEG=6, EXP=7, LOG=8, POW=9, SQRT=10, STORE=11, SQR=12)
+S_NLPAD, S_NTERM, S_NPLAW, S_CAL = 0, 1, 2, 3
+S_TERM_COEF, S_TERM_OFF, S_PLAW_AMP, S_PLAW_IDX, S_PLAW_LOGB, S_PLAW_MUL = 8, 16, 24, 28, 32, 36
+T_ROW0, T_NROWS, T_SPEC, T_LBEGIN, T_LEND, T_WINOFF_LO, T_WINOFF_HI, T_WINLD, T_GLO, T_GHI = 0, 1, 2, 3, 4, 5, 6, 7, 8, 16
+
+_i32p, _f64p, _vp = C.c_void_p, C.c_void_p, C.c_void_p
+
+
+class Program(C.Structure):
+    """csl_program_t"""
+    _fields_ = ([(n, C.c_int32) for n in
+                 ("ndim", "ncoef", "ncode", "nbox", "ngauss", "nscalar", "nspec", "ntile",
+                  "n", "n_pad", "resid_mode", "reserved0")] +
+                [(n, C.c_void_p) for n in
+                 ("code_op", "code_arg", "code_val", "box_idx", "box_lo", "box_hi",
+                  "gauss_idx", "gauss_c", "gauss_w", "scalar_coef", "spec_tab", "tile_tab",
+                  "templates", "windows", "data", "direct_coef", "Lmat", "Linv_diag")])
+
+
+_P = C.POINTER(Program)
+_int, _u64, _u32, _dbl = C.c_int, C.c_uint64, C.c_uint32, C.c_double
+
+# name -> (restype, argtypes); every symbol include/cosmoslik_b200.h declares
+SIGNATURES = {
+    "csl_abi_version": (_int, []),
+    "csl_last_error": (C.c_char_p, []),
+    "csl_sizeof_program": (_int, []),
+    "csl_device_info": (_int, [_int, _vp]),
+    "csl_eval_prepare": (_int, [_P, _int, _vp, _vp, _int, _vp, _vp]),
+    "csl_bin_residual": (_int, [_P, _int, _vp, _int, _vp, _int, _vp]),
+    "csl_direct_residual": (_int, [_P, _int, _vp, _int, _vp, _int, _vp]),
+    "csl_chi2": (_int, [_P, _int, _vp, _int, _vp, _vp]),
+    "csl_combine": (_int, [_P, _int, _vp, _int, _vp, _vp, _vp, _vp]),
+    "csl_lnl": (_int, [_P, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "csl_lnl_host": (_int, [_P, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "csl_mh_propose": (_int, [_int, _int, _vp, _vp, _int, _vp, _vp, _u64, _u32, _u32, _vp]),
+    "csl_mh_accept": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _dbl, _dbl,
+                             _vp, _vp, _int, _vp, _vp, _vp]),
+    "csl_mh_gauss_run": (_int, [_P, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp,
+                                _u64, _u32, _u32, _dbl, _dbl, _vp, _vp, _int, _vp]),
+    "csl_mh_moments": (_int, [_int, _int, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
+    "csl_stretch_propose": (_int, [_int, _int, _int, _vp, _vp, _dbl, _vp, _vp, _u64, _u32, _u32, _u32,
+                                   _vp, _vp, _vp]),
+    "csl_stretch_accept": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _u32,
+                                  _vp, _vp]),
+    "csl_emcee_rows": (_int, [_int, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _vp]),
+    "csl_chain_moments": (_int, [_int, _int, _vp, _vp, _int, _int, _vp, _vp]),
+    "csl_philox_mh": (_int, [_int, _int, _u64, _u32, _u32, _vp, _vp, _vp]),
+    "csl_philox_stretch": (_int, [_int, _int, _u64, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
+    "csl_dgemm_dmma": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class CslError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded shared library (built by ``__graft_entry__.build()`` /
+    ``cosmoslik_b200/csrc/build.sh``).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "cosmoslik_b200: %s not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or cosmoslik_b200/csrc/build.sh -- there is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        if L.csl_sizeof_program() != C.sizeof(Program):
+            raise ImportError("cosmoslik_b200: csl_program_t layout mismatch between header and binding")
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().csl_last_error()
+        raise CslError("%s failed (code %d): %s" % (what or "csl call", rc, msg.decode() if msg else ""))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise CslError("cosmoslik_b200 needs a CUDA device (B200, sm_100a); none is visible and there is no CPU fallback")
+    return torch
+
+
+def ptr(t):
+    """device/host pointer of a torch tensor (None -> NULL)"""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

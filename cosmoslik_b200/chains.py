@@ -1,0 +1,311 @@
+"""Chain containers and the chain-file format.
+
+Mirrors the result side of the reference (cosmoslik/chains.py): ``Chain`` is a
+dict name -> 1-D array with the special keys 'lnl' and 'weight'
+(chains.py:33-63); ``Chains`` is a list of them (:345-372); a chain FILE is a
+pickle stream -- a header of column names followed by ``(chain_id, rows)``
+records, ``rows`` a structured array with fields f0..fN (lnl, weight, params)
+(metropolis_hastings.py:181-186,211,221,237; emcee.py:40-46,82), which
+``load_chain`` regroups by chain id (chains.py:930-962).  Files written by this
+package load with the reference's ``load_chain`` and vice versa
+(tests/test_chains_io.py).  Plotting and the CosmoMC text loaders are out of
+scope.
+"""
+import pickle
+import re
+from itertools import chain as _iterchain
+
+import numpy as np
+
+__all__ = ["Chain", "Chains", "get_covariance", "get_correlation", "combine_covs", "load_chain",
+           "ChainWriter", "gelman_rubin"]
+
+
+def _is_listlike(v):
+    return not isinstance(v, str) and hasattr(v, "__iter__")
+
+
+class Chain(dict):
+    """One MCMC chain: parameter name -> array of values, plus 'lnl' and 'weight'."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        for k in list(self):
+            self[k] = np.atleast_1d(self[k])
+        if self and "weight" not in self:
+            self["weight"] = np.ones(len(next(iter(self.values()))))
+
+    def copy(self):
+        return Chain({k: v.copy() for k, v in self.items()})
+
+    def params(self, non_numeric=False, fixed=False):
+        out = set()
+        for k, v in self.items():
+            if k.startswith("_") or k in ("lnl", "weight"):
+                continue
+            numeric = v.ndim == 1 and np.issubdtype(v.dtype, np.number)
+            if not (non_numeric or numeric):
+                continue
+            if not fixed and np.all(v == v[0]):
+                continue
+            out.add(k)
+        return out
+
+    def sample(self, s, keys=None):
+        return Chain((k, self[k][s]) for k in (keys if keys else list(self.keys())))
+
+    def iterrows(self):
+        for i in range(self.length()):
+            yield {k: v[i] for k, v in self.items()}
+
+    def matrix(self, params=None):
+        if params is None:
+            params = self.params()
+        if _is_listlike(params):
+            return np.vstack([self[p] for p in params]).T
+        return self[params]
+
+    # weighted statistics (chains.py:78-96)
+    def cov(self, params=None):
+        return get_covariance(self.matrix(params), self["weight"])
+
+    def corr(self, params=None):
+        return get_correlation(self.matrix(params), self["weight"])
+
+    def mean(self, params=None):
+        return np.average(self.matrix(params), axis=0, weights=self["weight"])
+
+    def std(self, params=None):
+        d = self.matrix(params) - self.mean(params)
+        return np.sqrt(np.average(d ** 2, axis=0, weights=self["weight"]))
+
+    def skew(self, params=None):
+        d = self.matrix(params) - self.mean(params)
+        return np.average(d ** 3, axis=0, weights=self["weight"]) / self.std(params) ** 3
+
+    def acceptance(self):
+        return 1.0 / np.mean(self["weight"])
+
+    def length(self, unique=True):
+        return len(self["weight"]) if unique else np.sum(self["weight"])
+
+    def burnin(self, n):
+        """Drop the leading rows whose cumulative weight stays below n."""
+        first = int(np.searchsorted(np.cumsum(self["weight"]), n, side="left"))
+        return self.sample(slice(first, None))
+
+    def thin(self, delta):
+        """Keep one row per `delta` units of weight (chains.py:235-243)."""
+        c = np.ceil(np.cumsum(np.append(0, self["weight"])) / float(delta))
+        ids = np.where(c[1:] > c[:-1])[0]
+        w = np.diff(c[[0] + list(ids + 1)])
+        t = self.sample(ids)
+        t["weight"] = w
+        return t
+
+    def thinto(self, num):
+        return self.thin(self.length(unique=False) // num)
+
+    def add_gauss_prior(self, params, mean, covstd):
+        c = self.copy()
+        dx = self.matrix(params) - mean
+        if _is_listlike(params):
+            dlnl = np.sum(np.dot(dx, np.linalg.inv(covstd)) * dx, axis=1) / 2
+        else:
+            dlnl = dx ** 2 / 2 / covstd ** 2
+        c["weight"] = c["weight"] * np.exp(-dlnl)
+        c["lnl"] = c["lnl"] + dlnl
+        return c
+
+    def best_fit(self):
+        i = int(np.argmin(self["lnl"]))
+        return {k: v[i] for k, v in self.items()}
+
+    def savecov(self, file, params=None):
+        params = list(params) if params else sorted(self.params())
+        with open(file, "wb") as f:
+            f.write(("# " + " ".join(params) + "\n").encode())
+            np.savetxt(f, self.cov(params))
+
+    def savechain(self, file, params=None):
+        keys = ["lnl", "weight"] + list(params if params else sorted(self.params()))
+        with open(file, "w") as f:
+            f.write("# " + " ".join(keys) + "\n")
+            np.savetxt(f, self.matrix(keys))
+
+    def join(self):
+        return self
+
+    def __repr__(self):
+        return chain_stats(self)
+
+    __str__ = __repr__
+
+
+class Chains(list):
+    """Several chains, e.g. the rows of one batched sampler run."""
+
+    def burnin(self, n):
+        return Chains(c.burnin(n) for c in self)
+
+    def join(self):
+        return Chain((k, np.concatenate([c[k] for c in self])) for k in self[0].keys())
+
+    def params(self, **kw):
+        return self[0].params(**kw)
+
+    def gelman_rubin(self, params=None):
+        params = sorted(self.params()) if params is None else list(params)
+        return dict(zip(params, gelman_rubin(self, params)))
+
+    def __repr__(self):
+        return chain_stats(self)
+
+    __str__ = __repr__
+
+
+def chain_stats(c):
+    lines = [object.__repr__(c)]
+    params = c.params(fixed=True)
+    width = max([12] + [len(p) for p in params]) + 4
+    fmt = "{:>%d}:  {}" % width
+    if isinstance(c, Chains):
+        lines.append(fmt.format("# of chains", len(c)))
+        c = c.join()
+    lines.append(fmt.format("# of steps", c.length()))
+    lines.append(fmt.format("total weight", "%.2f" % c["weight"].sum()))
+    lines.append(fmt.format("acceptance", "%.3g" % c.acceptance()))
+    for p in sorted(params):
+        lines.append(fmt.format(p, "%10.4g ± %.4g" % (c.mean(p), c.std(p))))
+    return "\n".join(lines)
+
+
+def get_covariance(data, weights=None):
+    """Weighted covariance with denominator sum(w) - 1 (chains.py:507-512)."""
+    data = np.asarray(data)
+    if weights is None:
+        return np.cov(data.T)
+    weights = np.asarray(weights)
+    mu = np.sum(data.T * weights, axis=1) / np.sum(weights)
+    z = data - mu
+    return np.dot(z.T * weights, z) / (np.sum(weights) - 1)
+
+
+def get_correlation(data, weights=None):
+    cv = get_covariance(data, weights)
+    sd = np.sqrt(np.diag(cv))
+    return cv / np.outer(sd, sd)
+
+
+def combine_covs(*covs):
+    """Merge covariances given as (names, array), a file ('# names' header then
+    the matrix), a Chain, or {name: std}; later entries override the rows and
+    columns of the names they repeat (chains.py:891-927)."""
+    parsed = []
+    for c in covs:
+        if isinstance(c, tuple):
+            parsed.append((list(c[0]), np.asarray(c[1], dtype=float)))
+        elif isinstance(c, str):
+            with open(c) as f:
+                names = re.sub("#", "", f.readline()).split()
+                parsed.append((names, np.atleast_2d(np.loadtxt(f))))
+        elif isinstance(c, Chain):
+            names = sorted(c.params())
+            parsed.append((names, c.cov(names)))
+        elif isinstance(c, dict):
+            parsed.append((list(c), np.diag([v ** 2 for v in c.values()])))
+        else:
+            raise ValueError("Unrecognized covariance data type.")
+    allnames = list(_iterchain(*[n for n, _ in parsed]))
+    out = np.zeros((len(allnames), len(allnames)))
+    for names, cov in parsed:
+        idx = [allnames.index(n) for n in names]
+        for i in idx:
+            out[i, :] = 0
+            out[:, i] = 0
+        out[np.ix_(idx, idx)] = cov
+    return allnames, out
+
+
+def gelman_rubin(chains, params):
+    """Potential scale reduction per parameter from several chains (Gelman &
+    Rubin 1992) with weighted per-chain means / variances (denominator
+    sum(w) - 1).  Host statement of what ``csl_chain_moments`` + one all-reduce
+    compute on the device."""
+    n, mu, var = [], [], []
+    for c in chains:
+        w = c["weight"]
+        x = c.matrix(params)
+        sw = w.sum()
+        m = (x * w[:, None]).sum(0) / sw
+        n.append(sw); mu.append(m); var.append((w[:, None] * (x - m) ** 2).sum(0) / (sw - 1))
+    return rhat_from_moments(np.array(n), np.array(mu), np.array(var))
+
+
+def rhat_from_moments(n, mu, var):
+    m = mu.shape[0]
+    nbar = n.mean()
+    W = var.mean(0)
+    B_over_n = ((mu - mu.mean(0)) ** 2).sum(0) / (m - 1)
+    return np.sqrt(((nbar - 1) / nbar * W + B_over_n) / W)
+
+
+# --------------------------------------------------------------------------
+# chain files
+# --------------------------------------------------------------------------
+
+class ChainWriter(object):
+    """Append-only pickle-stream writer, flushed per block so a running chain can
+    be read (doc/quickstart.md:53).
+
+    header_kind 'ndarray' writes the numpy array of names the MH sampler writes
+    (metropolis_hastings.py:183-186), 'list' the plain list emcee writes
+    (emcee.py:40-44)."""
+
+    def __init__(self, path, names, header_kind="ndarray"):
+        self.f = open(path, "wb")
+        self.ncol = len(names)
+        self.dtype = np.dtype(",".join(["f8"] * self.ncol))
+        header = np.hstack([names]) if header_kind == "ndarray" else list(names)
+        pickle.dump(header, self.f, protocol=pickle.HIGHEST_PROTOCOL)
+
+    def write(self, chain_id, rows):
+        """rows: float array [m, ncol] (lnl, weight, params...)"""
+        rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, self.ncol)
+        rec = rows.view(self.dtype).reshape(-1)
+        pickle.dump((chain_id, rec), self.f, protocol=pickle.HIGHEST_PROTOCOL)
+
+    def flush(self):
+        self.f.flush()
+
+    def close(self):
+        if not self.f.closed:
+            self.f.close()
+
+
+def load_chain(filename):
+    """Load a chain file written by this package or by the reference's samplers;
+    also accepts a file holding one pickled Chain / Chains."""
+    with open(filename, "rb") as f:
+        head = pickle.load(f)
+        if isinstance(head, (Chain, Chains)):
+            return head
+        names = [n.decode() if isinstance(n, bytes) else str(n) for n in head]
+        records = []
+        while True:
+            try:
+                records.append(pickle.load(f, encoding="latin1"))
+            except Exception:
+                break
+    ids = []
+    for i, _ in records:
+        if i not in ids:
+            ids.append(i)
+    out = Chains()
+    for i in sorted(ids):
+        blocks = [d for j, d in records if j == i]
+        if blocks[0].dtype.kind == "V":
+            out.append(Chain({n: np.concatenate([b["f%d" % k] for b in blocks]) for k, n in enumerate(names)}))
+        else:
+            out.append(Chain(dict(zip(names, np.vstack(blocks).T))))
+    return out

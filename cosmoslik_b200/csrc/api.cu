@@ -1,0 +1,72 @@
+// C-ABI glue: error reporting, device info and the composed posterior evaluation.
+#include <string.h>
+#include "common.cuh"
+
+thread_local char csl_err_buf[256] = "";
+
+int csl_fail(int code, const char* msg) {
+  snprintf(csl_err_buf, sizeof(csl_err_buf), "%s", msg ? msg : "unknown error");
+  return code;
+}
+
+int csl_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(csl_err_buf, sizeof(csl_err_buf), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+extern "C" int csl_abi_version(void) { return CSL_ABI_VERSION; }
+extern "C" const char* csl_last_error(void) { return csl_err_buf; }
+extern "C" int csl_sizeof_program(void) { return (int)sizeof(csl_program_t); }
+
+extern "C" int csl_device_info(int device, int32_t* out) {
+  CSL_REQUIRE(out, "csl_device_info: null output");
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return csl_fail(CSL_E_NODEVICE, cudaGetErrorString(e));
+  out[0] = prop.multiProcessorCount;
+  out[1] = prop.major;
+  out[2] = prop.minor;
+  out[3] = (int32_t)prop.sharedMemPerBlockOptin;
+  return 0;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+extern "C" int csl_lnl(const csl_program_t* p, int W, const double* x, double* lnl, double* ws_coef,
+                       double* ws_prior, double* ws_R, double* ws_chi2, void* stream) {
+  CSL_REQUIRE(p && x && lnl && ws_prior && W > 0, "csl_lnl: null argument");
+  const int Wp = round_up(W, CSL_BN);
+  int rc = csl_eval_prepare(p, W, x, ws_coef, Wp, ws_prior, stream);
+  if (rc) return rc;
+  const double* chi2 = nullptr;
+  if (p->resid_mode != 0) {
+    CSL_REQUIRE(ws_R && ws_chi2 && ws_coef, "csl_lnl: workspace missing for the quadratic form");
+    if (p->resid_mode == 1) rc = csl_bin_residual(p, Wp, ws_coef, Wp, ws_R, Wp, stream);
+    else rc = csl_direct_residual(p, W, ws_coef, Wp, ws_R, Wp, stream);
+    if (rc) return rc;
+    rc = csl_chi2(p, Wp, ws_R, Wp, ws_chi2, stream);
+    if (rc) return rc;
+    chi2 = ws_chi2;
+  }
+  return csl_combine(p, W, ws_coef, Wp, ws_prior, chi2, lnl, stream);
+}
+
+extern "C" int csl_lnl_host(const csl_program_t* p, int W, const double* x_host, double* lnl_host, double* x_dev,
+                            double* lnl_dev, double* ws_coef, double* ws_prior, double* ws_R, double* ws_chi2,
+                            void* stream) {
+  CSL_REQUIRE(p && x_host && lnl_host && x_dev && lnl_dev && W > 0, "csl_lnl_host: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(x_dev, x_host, (size_t)W * p->ndim * sizeof(double), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+  int rc = csl_lnl(p, W, x_dev, lnl_dev, ws_coef, ws_prior, ws_R, ws_chi2, stream);
+  if (rc) return rc;
+  e = cudaMemcpyAsync(lnl_host, lnl_dev, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+  return 0;
+}

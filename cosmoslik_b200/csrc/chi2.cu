@@ -1,0 +1,149 @@
+// chi2[w] = || L^-1 r_w ||^2 for a tile of 128 walkers per CTA: blocked forward substitution with
+// 64-row blocks.  Off-diagonal updates  T_i = R_i - sum_{j<i} L_ij Y_j  and the diagonal solves
+// Y_i = inv(L_ii) T_i  (diagonal blocks inverted once on the host) all run as FP64 DMMA tile products;
+// column sums of squares are reduced with warp shuffles in a fixed order (bitwise reproducible).
+//   reference: spt_lowl.py:98,133 and mspec_lnl.py:31,73  (cho_factor once; cho_solve + dot per call)
+// The factor streams from L2/HBM once per walker tile (cp.async, two stages); Y_j is re-read from
+// global memory (L2 resident) so any n works, including factors far larger than shared memory.
+#include "common.cuh"
+
+#define CHI2_SMEM_DOUBLES (2 * CSL_ASZ + 2 * CSL_BSZ + CSL_BM * CSL_LDB + 2 * CSL_BN)
+
+__global__ void __launch_bounds__(CSL_THREADS, 1)
+k_trsm_chi2(csl_program_t p, double* R, int ldr, double* __restrict__ chi2) {
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = As + 2 * CSL_ASZ;
+  double* Ts = Bs + 2 * CSL_BSZ;            // [64][CSL_LDB]: T_i as the B operand of the diagonal solve
+  double* red = Ts + CSL_BM * CSL_LDB;      // [2][128]
+  const int c0 = blockIdx.x * CSL_BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 32;
+  const int g = lane >> 2, t = lane & 3;
+  const int npad = p.n_pad, nblk = npad / CSL_BM;
+
+  double colsq[4][2];
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni) colsq[ni][0] = colsq[ni][1] = 0.0;
+
+  for (int i = 0; i < nblk; ++i) {
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    // acc = sum_{j<i} L_ij Y_j
+    gemm_stream_AB(acc, p.Lmat + (long long)i * CSL_BM * npad, npad, R + c0, ldr, i * (CSL_BM / CSL_KC), As, Bs,
+                   tid, wm0, wn0, lane);
+
+    // T_i = R_i - acc  -> shared memory, laid out as a [64 x 128] B operand
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int rl = wm0 + mi * 8 + g;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int cl = wn0 + ni * 8 + 2 * t;
+        double2 r = *reinterpret_cast<const double2*>(R + (long long)(i * CSL_BM + rl) * ldr + c0 + cl);
+        Ts[rl * CSL_LDB + cl] = r.x - acc[mi][ni][0];
+        Ts[rl * CSL_LDB + cl + 1] = r.y - acc[mi][ni][1];
+        acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      }
+    }
+    __syncthreads();
+
+    // Y_i = inv(L_ii) T_i
+    gemm_stream_A(acc, p.Linv_diag + (long long)i * CSL_BM * CSL_BM, CSL_BM, Ts, CSL_BM / CSL_KC, As, tid, wm0,
+                  wn0, lane);
+
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int rl = wm0 + mi * 8 + g;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int cl = wn0 + ni * 8 + 2 * t;
+        double2 y;
+        y.x = acc[mi][ni][0];
+        y.y = acc[mi][ni][1];
+        *reinterpret_cast<double2*>(R + (long long)(i * CSL_BM + rl) * ldr + c0 + cl) = y;
+        colsq[ni][0] = fma(y.x, y.x, colsq[ni][0]);
+        colsq[ni][1] = fma(y.y, y.y, colsq[ni][1]);
+      }
+    }
+    // Y_i must be visible to the cp.async reads of the next block rows (same CTA)
+    __threadfence();
+    __syncthreads();
+  }
+
+  // reduce over the 8 row groups of the warp (lane bits 2..4), then over the two warp rows
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double v = colsq[ni][e];
+      v += shfl_xor_d(v, 4);
+      v += shfl_xor_d(v, 8);
+      v += shfl_xor_d(v, 16);
+      if (g == 0) red[(warp >> 2) * CSL_BN + wn0 + ni * 8 + 2 * t + e] = v;
+    }
+  __syncthreads();
+  if (tid < CSL_BN) chi2[c0 + tid] = red[tid] + red[CSL_BN + tid];
+}
+
+extern "C" int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, double* chi2, void* stream) {
+  CSL_REQUIRE(p && R && chi2, "csl_chi2: null argument");
+  CSL_REQUIRE(p->n_pad > 0 && p->n_pad % CSL_BM == 0 && p->Lmat && p->Linv_diag, "csl_chi2: program has no factor");
+  CSL_REQUIRE(W > 0 && W % CSL_BN == 0 && ldr >= W && (ldr % 2) == 0, "csl_chi2: W must be a positive multiple of 128");
+  static bool attr_set = false;
+  const size_t smem = (size_t)CHI2_SMEM_DOUBLES * sizeof(double);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_trsm_chi2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  k_trsm_chi2<<<W / CSL_BN, CSL_THREADS, smem, (cudaStream_t)stream>>>(*p, R, ldr, chi2);
+  return csl_check_launch("k_trsm_chi2");
+}
+
+// ---- plain FP64 DMMA GEMM on the same tile core (peak / unit tests) ----------------------------------
+__global__ void __launch_bounds__(CSL_THREADS, 2)
+k_dgemm(int M, int N, int K, const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C) {
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = As + 2 * CSL_ASZ;
+  const int m0 = blockIdx.x * CSL_BM, c0 = blockIdx.y * CSL_BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 32;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  gemm_stream_AB(acc, A + (long long)m0 * K, K, B + c0, N, K / CSL_KC, As, Bs, tid, wm0, wn0, lane);
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      double2 y;
+      y.x = acc[mi][ni][0];
+      y.y = acc[mi][ni][1];
+      *reinterpret_cast<double2*>(C + (long long)(m0 + wm0 + mi * 8 + g) * N + c0 + wn0 + ni * 8 + 2 * t) = y;
+    }
+}
+
+extern "C" int csl_dgemm_dmma(int M, int N, int K, const double* A, const double* B, double* C, void* stream) {
+  CSL_REQUIRE(A && B && C, "csl_dgemm_dmma: null argument");
+  CSL_REQUIRE(M > 0 && N > 0 && K > 0 && M % CSL_BM == 0 && N % CSL_BN == 0 && K % CSL_KC == 0,
+              "csl_dgemm_dmma: M%64, N%128, K%16 must be 0");
+  static bool attr_set = false;
+  const size_t smem = (size_t)(2 * CSL_ASZ + 2 * CSL_BSZ) * sizeof(double);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_dgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid(M / CSL_BM, N / CSL_BN);
+  k_dgemm<<<grid, CSL_THREADS, smem, (cudaStream_t)stream>>>(M, N, K, A, B, C);
+  return csl_check_launch("k_dgemm");
+}

@@ -1,0 +1,132 @@
+// Shared device helpers for the cosmoslik_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/cosmoslik_b200.h"
+
+#define CSL_THREADS 256
+#define CSL_LDA (CSL_KC + 4)   // 20 doubles: A-fragment loads hit 16 distinct bank pairs
+#define CSL_LDB (CSL_BN + 4)   // 132 doubles: same for B fragments
+
+extern thread_local char csl_err_buf[256];
+int csl_fail(int code, const char* msg);
+int csl_check_launch(const char* what);
+
+#define CSL_REQUIRE(cond, msg) do { if (!(cond)) return csl_fail(CSL_E_BADARG, msg); } while (0)
+
+// D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor pipe (SASS: DMMA.8x8x4).
+//   a: A[row = lane>>2][k = lane&3]    b: B[k = lane&3][col = lane>>2]
+//   c0,c1: C[row = lane>>2][col = 2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+
+// One k-chunk (CSL_KC columns) of the CTA tile product on a warp tile of 32 x 32:
+// acc[mi][ni][2] += A[wm0 + 8 mi .., :] * B[:, wn0 + 8 ni ..]
+// As: [CSL_BM][CSL_LDA], Bs: [CSL_KC][CSL_LDB].  mmask bit mi = 0 skips an all-zero 8-row group.
+__device__ __forceinline__ void warp_mma_chunk(double (&acc)[4][4][2], const double* __restrict__ As,
+                                               const double* __restrict__ Bs, int wm0, int wn0, int lane,
+                                               unsigned mmask = 0xFu) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < CSL_KC / 4; ++ks) {
+    double a[4], b[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) a[mi] = As[(wm0 + mi * 8 + g) * CSL_LDA + ks * 4 + t];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(ks * 4 + t) * CSL_LDB + wn0 + ni * 8 + g];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      if (mmask & (1u << mi)) {
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
+    }
+  }
+}
+
+// cp.async a [CSL_BM x CSL_KC] tile of a row-major matrix (row stride ld doubles) into As.
+__device__ __forceinline__ void load_A_tile_async(double* As, const double* __restrict__ A, long long ld,
+                                                  int tid) {
+  // 64 rows x 8 chunks of 16 bytes = 512 chunks, 2 per thread
+#pragma unroll
+  for (int it = 0; it < (CSL_BM * CSL_KC / 2) / CSL_THREADS; ++it) {
+    int c = tid + it * CSL_THREADS;
+    int r = c >> 3, q = c & 7;
+    cp_async16(As + r * CSL_LDA + q * 2, A + (long long)r * ld + q * 2);
+  }
+}
+
+// cp.async a [CSL_KC x CSL_BN] tile (row stride ld doubles) into Bs.
+__device__ __forceinline__ void load_B_tile_async(double* Bs, const double* __restrict__ B, long long ld,
+                                                  int tid) {
+  // 16 rows x 64 chunks = 1024 chunks, 4 per thread
+#pragma unroll
+  for (int it = 0; it < (CSL_KC * CSL_BN / 2) / CSL_THREADS; ++it) {
+    int c = tid + it * CSL_THREADS;
+    int r = c >> 6, q = c & 63;
+    cp_async16(Bs + r * CSL_LDB + q * 2, B + (long long)r * ld + q * 2);
+  }
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+#define CSL_ASZ (CSL_BM * CSL_LDA)   // doubles per A stage
+#define CSL_BSZ (CSL_KC * CSL_LDB)   // doubles per B stage
+
+// acc += A[64, 16*nchunk] * B[16*nchunk, 128], both operands streamed from global memory through a
+// two-stage cp.async pipeline.  All threads of the CTA call this; on return the stages are free.
+__device__ __forceinline__ void gemm_stream_AB(double (&acc)[4][4][2], const double* __restrict__ A,
+                                               long long lda, const double* __restrict__ B, long long ldb,
+                                               int nchunk, double* As, double* Bs, int tid, int wm0, int wn0,
+                                               int lane) {
+  if (nchunk <= 0) return;
+  load_A_tile_async(As, A, lda, tid);
+  load_B_tile_async(Bs, B, ldb, tid);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  for (int c = 0; c < nchunk; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < nchunk) {
+      load_A_tile_async(As + (cur ^ 1) * CSL_ASZ, A + (long long)(c + 1) * CSL_KC, lda, tid);
+      load_B_tile_async(Bs + (cur ^ 1) * CSL_BSZ, B + (long long)(c + 1) * CSL_KC * ldb, ldb, tid);
+      cp_async_commit();
+    }
+    warp_mma_chunk(acc, As + cur * CSL_ASZ, Bs + cur * CSL_BSZ, wm0, wn0, lane);
+    cp_async_wait<0>();
+    __syncthreads();
+  }
+}
+
+// Same with the B operand already resident in shared memory as [16*nchunk][CSL_LDB].
+__device__ __forceinline__ void gemm_stream_A(double (&acc)[4][4][2], const double* __restrict__ A,
+                                              long long lda, const double* Bsm, int nchunk, double* As,
+                                              int tid, int wm0, int wn0, int lane) {
+  load_A_tile_async(As, A, lda, tid);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  for (int c = 0; c < nchunk; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < nchunk) {
+      load_A_tile_async(As + (cur ^ 1) * CSL_ASZ, A + (long long)(c + 1) * CSL_KC, lda, tid);
+      cp_async_commit();
+    }
+    warp_mma_chunk(acc, As + cur * CSL_ASZ, Bsm + c * CSL_BSZ, wm0, wn0, lane);
+    cp_async_wait<0>();
+    __syncthreads();
+  }
+}

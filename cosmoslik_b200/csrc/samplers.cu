@@ -1,0 +1,466 @@
+// Sampler kernels: batched Metropolis-Hastings and the affine-invariant stretch move.
+//   reference: cosmoslik_plugins/samplers/metropolis_hastings.py:141-164, 249-253
+//              cosmoslik_plugins/samplers/emcee.py:66-88 (+ third-party emcee 2.x _propose_stretch)
+// One warp per walker: lane i owns parameter i (and i+32), so every global access to a walker's
+// row is one coalesced 8*ndim-byte segment.  These kernels are HBM-bound: ~(24 ndim + 32) B per
+// walker per step.
+#include "common.cuh"
+#include "philox.cuh"
+
+#define SAMP_THREADS 256
+#define SAMP_WARPS (SAMP_THREADS / 32)
+
+__device__ __forceinline__ int warp_global() { return (blockIdx.x * SAMP_THREADS + threadIdx.x) >> 5; }
+
+// ---------------------------------------------------------------------------------------------
+// draw_x  (metropolis_hastings.py:141-142)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SAMP_THREADS)
+k_mh_propose(int W, int nd, const double* __restrict__ cur_x, double* __restrict__ test_x, int mode,
+             const double* __restrict__ inj, const double* __restrict__ F, uint64_t seed, uint32_t step,
+             uint32_t chain0) {
+  extern __shared__ double sF[];
+  if (mode != 0)
+    for (int i = threadIdx.x; i < nd * nd; i += SAMP_THREADS) sF[i] = F[i];
+  __syncthreads();
+  const int w = warp_global(), lane = threadIdx.x & 31;
+  if (w >= W) return;
+  const long long base = (long long)w * nd;
+  const int i0 = lane, i1 = lane + 32;
+  double x0 = (i0 < nd) ? cur_x[base + i0] : 0.0, x1 = (i1 < nd) ? cur_x[base + i1] : 0.0;
+  double d0 = 0.0, d1 = 0.0;
+  if (mode == 0) {
+    if (i0 < nd) d0 = inj[base + i0];
+    if (i1 < nd) d1 = inj[base + i1];
+  } else {
+    double za = 0.0, zb = 0.0;  // mode 1: z[lane], z[lane+32]; mode 2: pair (z[2 lane], z[2 lane + 1])
+    if (mode == 1) {
+      if (i0 < nd) za = inj[base + i0];
+      if (i1 < nd) zb = inj[base + i1];
+    } else if (2 * lane < nd) {
+      philox_normal_pair(seed, chain0 + (uint32_t)w, (uint32_t)lane, step, za, zb);
+    }
+    for (int k = 0; k < nd; ++k) {
+      double zk = (mode == 1) ? shfl_d(k < 32 ? za : zb, k & 31) : shfl_d((k & 1) ? zb : za, k >> 1);
+      if (i0 < nd) d0 = fma(zk, sF[k * nd + i0], d0);
+      if (i1 < nd) d1 = fma(zk, sF[k * nd + i1], d1);
+    }
+  }
+  if (i0 < nd) test_x[base + i0] = __dadd_rn(x0, d0);
+  if (i1 < nd) test_x[base + i1] = __dadd_rn(x1, d1);
+}
+
+// row emission shared by the MH and ensemble kernels: (lnl, weight, x...) at slot nrows[w]
+__device__ __forceinline__ void emit_row(double* rows, int32_t* nrows, int cap, int w, int nd, int lane,
+                                         double lnl, double weight, double x0, double x1) {
+  int slot = nrows[w];
+  __syncwarp();
+  if (slot < cap) {
+    double* r = rows + ((long long)w * cap + slot) * (2 + nd);
+    if (lane == 0) { r[0] = lnl; r[1] = weight; }
+    if (lane < nd) r[2 + lane] = x0;
+    if (lane + 32 < nd) r[2 + lane + 32] = x1;
+  }
+  if (lane == 0) nrows[w] = slot + 1;   // counts past cap signal overflow to the host
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// accept / reject + weight bookkeeping  (metropolis_hastings.py:154-164)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SAMP_THREADS)
+k_mh_accept(int W, int nd, double* __restrict__ cur_x, double* __restrict__ cur_lnl,
+            double* __restrict__ cur_weight, const double* __restrict__ test_x,
+            const double* __restrict__ test_lnl, const double* __restrict__ u, uint64_t seed, uint32_t step,
+            uint32_t chain0, double temp, double max_weight, double* __restrict__ rows,
+            int32_t* __restrict__ nrows, int cap, uint8_t* __restrict__ accepted, double* __restrict__ margin) {
+  const int w = warp_global(), lane = threadIdx.x & 31;
+  if (w >= W) return;
+  const long long base = (long long)w * nd;
+  const double cl = cur_lnl[w], tl = test_lnl[w];
+  double cw = cur_weight[w];
+  const double uu = u ? u[w] : philox_mh_uniform(seed, chain0 + (uint32_t)w, step);
+  const double lhs = log(uu), rhs = __dmul_rn(temp, __dsub_rn(cl, tl));
+  const bool acc = lhs < rhs;   // inf - inf = nan -> false (reject), as in the reference
+  double x0 = (lane < nd) ? cur_x[base + lane] : 0.0, x1 = (lane + 32 < nd) ? cur_x[base + lane + 32] : 0.0;
+  if (acc) {
+    if (cl != CUDART_INF) emit_row(rows, nrows, cap, w, nd, lane, cl, cw, x0, x1);
+    if (lane < nd) cur_x[base + lane] = test_x[base + lane];
+    if (lane + 32 < nd) cur_x[base + lane + 32] = test_x[base + lane + 32];
+    if (lane == 0) { cur_lnl[w] = tl; cur_weight[w] = 1.0; }
+  } else {
+    cw += 1.0;
+    if (cw >= max_weight) {
+      emit_row(rows, nrows, cap, w, nd, lane, cl, cw, x0, x1);
+      cw = 0.0;
+    }
+    if (lane == 0) cur_weight[w] = cw;
+  }
+  if (lane == 0) {
+    if (accepted) accepted[w] = acc ? 1 : 0;
+    if (margin) margin[w] = lhs - rhs;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// whole MH run for a dense Gaussian posterior: nsteps steps in one launch, one warp per chain
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SAMP_THREADS)
+k_mh_gauss_run(csl_program_t p, int W, int nsteps, const double* __restrict__ Lfac,
+               const double* __restrict__ mean, const int32_t* __restrict__ perm, double* __restrict__ cur_x,
+               double* __restrict__ cur_lnl, double* __restrict__ cur_weight, const double* __restrict__ zin,
+               int z_is_delta, const double* __restrict__ uin, const double* __restrict__ F, uint64_t seed,
+               uint32_t step0, uint32_t chain0, double temp, double max_weight, double* __restrict__ rows,
+               int32_t* __restrict__ nrows, int cap) {
+  extern __shared__ double sm[];
+  const int nd = p.ndim, n = p.n;
+  double* sF = sm;                 // [nd*nd]
+  double* sL = sF + nd * nd;       // [n*n]   lower Cholesky factor of the target covariance
+  double* sInv = sL + n * n;       // [n]     1 / L_kk
+  for (int i = threadIdx.x; i < nd * nd; i += SAMP_THREADS) sF[i] = F ? F[i] : 0.0;
+  for (int i = threadIdx.x; i < n * n; i += SAMP_THREADS) sL[i] = Lfac[i];
+  for (int i = threadIdx.x; i < n; i += SAMP_THREADS) sInv[i] = 1.0 / Lfac[i * n + i];
+  __syncthreads();
+  const int w = warp_global(), lane = threadIdx.x & 31;
+  if (w >= W) return;
+  const long long base = (long long)w * nd;
+  double x = (lane < nd) ? cur_x[base + lane] : 0.0;
+  double cl = cur_lnl[w], cw = cur_weight[w];
+  const int myperm = (lane < n) ? perm[lane] : 0;
+  const double mymean = (lane < n) ? mean[lane] : 0.0;
+
+  for (int s = 0; s < nsteps; ++s) {
+    const uint32_t step = step0 + (uint32_t)s;
+    // ---- draw_x
+    double d = 0.0;
+    if (zin && z_is_delta) {
+      if (lane < nd) d = zin[((long long)s * W + w) * nd + lane];
+    } else {
+      double za = 0.0, zb = 0.0;
+      if (zin) { if (lane < nd) za = zin[((long long)s * W + w) * nd + lane]; }
+      else if (2 * lane < nd) philox_normal_pair(seed, chain0 + (uint32_t)w, (uint32_t)lane, step, za, zb);
+      for (int k = 0; k < nd; ++k) {
+        double zk = zin ? shfl_d(za, k) : shfl_d((k & 1) ? zb : za, k >> 1);
+        if (lane < nd) d = fma(zk, sF[k * nd + lane], d);
+      }
+    }
+    const double tx = __dadd_rn(x, d);
+    // ---- priors (likelihoods/priors.py:24-30), evaluated redundantly by every lane
+    bool out = false;
+    for (int b = 0; b < p.nbox; ++b) {
+      double v = shfl_d(tx, p.box_idx[b]);
+      if (!(p.box_lo[b] <= v && v <= p.box_hi[b])) out = true;
+    }
+    double pr = 0.0;
+    for (int k = 0; k < p.ngauss; ++k) {
+      double dv = __dsub_rn(shfl_d(tx, p.gauss_idx[k]), p.gauss_c[k]);
+      double wv = p.gauss_w[k];
+      pr = __dadd_rn(pr, __ddiv_rn(__ddiv_rn(__dmul_rn(dv, dv), 2.0), __dmul_rn(wv, wv)));
+    }
+    // ---- (x-mu)^T C^-1 (x-mu) = || L^-1 (x-mu) ||^2 : column-oriented forward substitution
+    double r = shfl_d(tx, myperm) - mymean;
+    double ss = 0.0;
+    for (int k = 0; k < n; ++k) {
+      double yk = shfl_d(r, k) * sInv[k];
+      if (lane > k && lane < n) r = fma(-sL[lane * n + k], yk, r);
+      ss = fma(yk, yk, ss);
+    }
+    const double tl = out ? CUDART_INF : __dadd_rn(0.5 * ss, pr);
+    // ---- accept (metropolis_hastings.py:154-164)
+    const double uu = uin ? uin[(long long)s * W + w] : philox_mh_uniform(seed, chain0 + (uint32_t)w, step);
+    const bool acc = log(uu) < __dmul_rn(temp, __dsub_rn(cl, tl));
+    if (acc) {
+      if (cl != CUDART_INF) emit_row(rows, nrows, cap, w, nd, lane, cl, cw, x, 0.0);
+      x = tx; cl = tl; cw = 1.0;
+    } else {
+      cw += 1.0;
+      if (cw >= max_weight) {
+        emit_row(rows, nrows, cap, w, nd, lane, cl, cw, x, 0.0);
+        cw = 0.0;
+      }
+    }
+  }
+  if (lane < nd) cur_x[base + lane] = x;
+  if (lane == 0) { cur_lnl[w] = cl; cur_weight[w] = cw; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// get_new_cov sufficient statistics (metropolis_hastings.py:249-253, chains.py:507-512)
+// ---------------------------------------------------------------------------------------------
+#define MOM_BLOCKS 128
+// pass 1 (mean == nullptr): partial[b][0] = sum w, [1..nd] = sum w x.
+// pass 2: partial[b][1+nd + i*nd + k] = sum w (x_i - mean_i)(x_k - mean_k).
+__global__ void __launch_bounds__(SAMP_THREADS)
+k_mh_moments(int W, int nd, const double* __restrict__ rows, const int32_t* __restrict__ nrows, int cap,
+             const double* __restrict__ mean, double* __restrict__ partial) {
+  __shared__ double sx[CSL_MAX_DIM + 2];
+  const int m = 1 + nd + nd * nd;
+  double acc[(CSL_MAX_DIM * CSL_MAX_DIM + SAMP_THREADS - 1) / SAMP_THREADS];
+#pragma unroll
+  for (int q = 0; q < (int)(sizeof(acc) / sizeof(double)); ++q) acc[q] = 0.0;
+  double a1 = 0.0;  // pass 1: thread i < 1+nd accumulates element i
+  const int rl = 2 + nd;
+  for (int w = blockIdx.x; w < W; w += MOM_BLOCKS) {
+    int nr = min(nrows[w], cap);
+    for (int r = nr / 2; r < nr; ++r) {
+      const double* row = rows + ((long long)w * cap + r) * rl;
+      __syncthreads();
+      if (threadIdx.x < rl) sx[threadIdx.x] = row[threadIdx.x];
+      __syncthreads();
+      const double wt = sx[1];
+      if (mean == nullptr) {
+        if (threadIdx.x == 0) a1 += wt;
+        else if (threadIdx.x <= nd) a1 = fma(wt, sx[1 + threadIdx.x], a1);
+      } else {
+        int q = 0;
+        for (int e = threadIdx.x; e < nd * nd; e += SAMP_THREADS, ++q) {
+          int i = e / nd, k = e - i * nd;
+          acc[q] = fma(wt * (sx[2 + i] - mean[i]), sx[2 + k] - mean[k], acc[q]);
+        }
+      }
+    }
+  }
+  double* out = partial + (long long)blockIdx.x * m;
+  if (mean == nullptr) {
+    if (threadIdx.x <= nd) out[threadIdx.x] = a1;
+  } else {
+    int q = 0;
+    for (int e = threadIdx.x; e < nd * nd; e += SAMP_THREADS, ++q) out[1 + nd + e] = acc[q];
+  }
+}
+
+__global__ void k_reduce_partials(int m, int lo, int hi, const double* __restrict__ partial,
+                                  double* __restrict__ out) {
+  int e = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= hi) return;
+  double s = 0.0;
+  for (int b = 0; b < MOM_BLOCKS; ++b) s += partial[(long long)b * m + e];
+  out[e] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stretch move (emcee 2.x _propose_stretch; Goodman & Weare 2010)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SAMP_THREADS)
+k_stretch_propose(int Ns, int Nc, int nd, const double* __restrict__ s, const double* __restrict__ comp, double a,
+                  const double* __restrict__ u_z, const int64_t* __restrict__ jin, uint64_t seed, uint32_t step,
+                  uint32_t half, uint32_t walker0, double* __restrict__ q, double* __restrict__ zz) {
+  const int k = warp_global(), lane = threadIdx.x & 31;
+  if (k >= Ns) return;
+  double uz, ua;
+  int64_t j;
+  if (u_z) { uz = u_z[k]; j = jin[k]; }
+  else philox_stretch(seed, walker0 + (uint32_t)k, half, step, (uint32_t)Nc, uz, j, ua);
+  // zz = ((a - 1.) * u + 1) ** 2. / a
+  double tq = __dadd_rn(__dmul_rn(a - 1.0, uz), 1.0);
+  const double z = __ddiv_rn(__dmul_rn(tq, tq), a);
+  const long long sb = (long long)k * nd, cb = (long long)j * nd;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h;
+    if (i < nd) {
+      double c = comp[cb + i];
+      // q = c - zz * (c - s)
+      q[sb + i] = __dsub_rn(c, __dmul_rn(z, __dsub_rn(c, s[sb + i])));
+    }
+  }
+  if (lane == 0) zz[k] = z;
+}
+
+__global__ void __launch_bounds__(SAMP_THREADS)
+k_stretch_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ lnl_s, const double* __restrict__ q,
+                 const double* __restrict__ lnl_q, const double* __restrict__ zz, const double* __restrict__ u_acc,
+                 uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0, uint32_t Nc,
+                 uint8_t* __restrict__ accepted) {
+  const int k = warp_global(), lane = threadIdx.x & 31;
+  if (k >= Ns) return;
+  double ua;
+  if (u_acc) ua = u_acc[k];
+  else { double uz; int64_t j; philox_stretch(seed, walker0 + (uint32_t)k, half, step, Nc, uz, j, ua); }
+  // lnpdiff = (dim - 1.) * log(zz) + newlnprob - lnprob0 ; accept = lnpdiff > log(u)
+  const double newlnp = -lnl_q[k], lnp0 = -lnl_s[k];
+  const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)nd - 1.0, log(zz[k])), newlnp), lnp0);
+  const bool acc = lnpdiff > log(ua);
+  if (acc) {
+    const long long b = (long long)k * nd;
+    if (lane < nd) s[b + lane] = q[b + lane];
+    if (lane + 32 < nd) s[b + lane + 32] = q[b + lane + 32];
+    if (lane == 0) lnl_s[k] = lnl_q[k];
+  }
+  if (lane == 0 && accepted) accepted[k] = acc ? 1 : 0;
+}
+
+// wrapper bookkeeping, samplers/emcee.py:70-88
+__global__ void __launch_bounds__(SAMP_THREADS)
+k_emcee_rows(int W, int nd, const double* __restrict__ pos_old, const double* __restrict__ pos_new,
+             const double* __restrict__ lnl_new, double* __restrict__ weight, int last_step,
+             double* __restrict__ rows, int32_t* __restrict__ nrows, int cap) {
+  const int w = warp_global(), lane = threadIdx.x & 31;
+  if (w >= W) return;
+  const long long b = (long long)w * nd;
+  double o0 = (lane < nd) ? pos_old[b + lane] : 0.0, o1 = (lane + 32 < nd) ? pos_old[b + lane + 32] : 0.0;
+  double n0 = (lane < nd) ? pos_new[b + lane] : 0.0, n1 = (lane + 32 < nd) ? pos_new[b + lane + 32] : 0.0;
+  const bool same = __all_sync(0xffffffffu, o0 == n0 && o1 == n1);
+  double wt = weight[w];
+  if (same && !last_step) {
+    if (lane == 0) weight[w] = wt + 1.0;
+  } else {
+    emit_row(rows, nrows, cap, w, nd, lane, lnl_new[w], wt, o0, o1);
+    if (lane == 0) weight[w] = 1.0;
+  }
+}
+
+// per-chain weighted count / mean / variance (denominator sum w - 1) over rows [burn, nrows)
+__global__ void __launch_bounds__(SAMP_THREADS)
+k_chain_moments(int W, int nd, const double* __restrict__ rows, const int32_t* __restrict__ nrows, int cap,
+                int burn, double* __restrict__ stats) {
+  const int w = warp_global(), lane = threadIdx.x & 31;
+  if (w >= W) return;
+  const int rl = 2 + nd, nr = min(nrows[w], cap);
+  const double* base = rows + (long long)w * cap * rl;
+  double sw = 0.0, m0 = 0.0, m1 = 0.0;
+  for (int r = burn; r < nr; ++r) {
+    const double wt = base[(long long)r * rl + 1];
+    sw += wt;
+    if (lane < nd) m0 = fma(wt, base[(long long)r * rl + 2 + lane], m0);
+    if (lane + 32 < nd) m1 = fma(wt, base[(long long)r * rl + 2 + lane + 32], m1);
+  }
+  m0 /= sw; m1 /= sw;
+  double v0 = 0.0, v1 = 0.0;
+  for (int r = burn; r < nr; ++r) {
+    const double wt = base[(long long)r * rl + 1];
+    if (lane < nd) { double d = base[(long long)r * rl + 2 + lane] - m0; v0 = fma(wt * d, d, v0); }
+    if (lane + 32 < nd) { double d = base[(long long)r * rl + 2 + lane + 32] - m1; v1 = fma(wt * d, d, v1); }
+  }
+  double* o = stats + (long long)w * (1 + 2 * nd);
+  if (lane == 0) o[0] = sw;
+  if (lane < nd) { o[1 + lane] = m0; o[1 + nd + lane] = v0 / (sw - 1.0); }
+  if (lane + 32 < nd) { o[1 + lane + 32] = m1; o[1 + nd + lane + 32] = v1 / (sw - 1.0); }
+}
+
+// test hooks: the device streams, to be compared with oracle/philox.py
+__global__ void k_philox_mh(int W, int nd, uint64_t seed, uint32_t step, uint32_t chain0, double* z, double* u) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  for (int pr = 0; 2 * pr < nd; ++pr) {
+    double z0, z1;
+    philox_normal_pair(seed, chain0 + (uint32_t)w, (uint32_t)pr, step, z0, z1);
+    z[(long long)w * nd + 2 * pr] = z0;
+    if (2 * pr + 1 < nd) z[(long long)w * nd + 2 * pr + 1] = z1;
+  }
+  u[w] = philox_mh_uniform(seed, chain0 + (uint32_t)w, step);
+}
+__global__ void k_philox_stretch(int Ns, int Nc, uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0,
+                                 double* u_z, int64_t* j, double* u_acc) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Ns) return;
+  philox_stretch(seed, walker0 + (uint32_t)k, half, step, (uint32_t)Nc, u_z[k], j[k], u_acc[k]);
+}
+
+// =============================================================================================
+static inline int warp_grid(int nwarps) { return (nwarps + SAMP_WARPS - 1) / SAMP_WARPS; }
+
+extern "C" int csl_mh_propose(int W, int ndim, const double* cur_x, double* test_x, int mode, const double* inj,
+                              const double* F, uint64_t seed, uint32_t step, uint32_t chain0, void* stream) {
+  CSL_REQUIRE(W > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && cur_x && test_x, "csl_mh_propose: bad argument");
+  CSL_REQUIRE(mode >= 0 && mode <= 2, "csl_mh_propose: mode must be 0, 1 or 2");
+  CSL_REQUIRE(mode == 2 || inj, "csl_mh_propose: injected stream missing");
+  CSL_REQUIRE(mode == 0 || F, "csl_mh_propose: proposal factor missing");
+  size_t smem = mode ? (size_t)ndim * ndim * sizeof(double) : 0;
+  k_mh_propose<<<warp_grid(W), SAMP_THREADS, smem, (cudaStream_t)stream>>>(W, ndim, cur_x, test_x, mode, inj, F,
+                                                                           seed, step, chain0);
+  return csl_check_launch("k_mh_propose");
+}
+
+extern "C" int csl_mh_accept(int W, int ndim, double* cur_x, double* cur_lnl, double* cur_weight,
+                             const double* test_x, const double* test_lnl, const double* u, uint64_t seed,
+                             uint32_t step, uint32_t chain0, double temp, double max_weight, double* rows,
+                             int32_t* nrows, int cap, uint8_t* accepted, double* margin, void* stream) {
+  CSL_REQUIRE(W > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM, "csl_mh_accept: bad W / ndim");
+  CSL_REQUIRE(cur_x && cur_lnl && cur_weight && test_x && test_lnl && rows && nrows && cap > 0,
+              "csl_mh_accept: null argument");
+  k_mh_accept<<<warp_grid(W), SAMP_THREADS, 0, (cudaStream_t)stream>>>(W, ndim, cur_x, cur_lnl, cur_weight, test_x,
+                                                                       test_lnl, u, seed, step, chain0, temp,
+                                                                       max_weight, rows, nrows, cap, accepted, margin);
+  return csl_check_launch("k_mh_accept");
+}
+
+extern "C" int csl_mh_gauss_run(const csl_program_t* p, int W, int nsteps, const double* Lfac, const double* mean,
+                                const int32_t* perm, double* cur_x, double* cur_lnl, double* cur_weight,
+                                const double* z, int z_is_delta, const double* u, const double* F, uint64_t seed,
+                                uint32_t step0, uint32_t chain0, double temp, double max_weight, double* rows,
+                                int32_t* nrows, int cap, void* stream) {
+  CSL_REQUIRE(p && W > 0 && nsteps > 0 && Lfac && mean && perm && cur_x && cur_lnl && cur_weight && rows && nrows,
+              "csl_mh_gauss_run: null argument");
+  CSL_REQUIRE(p->ndim >= 1 && p->ndim <= 32 && p->n >= 1 && p->n <= 32, "csl_mh_gauss_run: ndim and n must be <= 32");
+  CSL_REQUIRE((z && z_is_delta) || F, "csl_mh_gauss_run: proposal factor missing");
+  size_t smem = (size_t)(p->ndim * p->ndim + p->n * p->n + p->n) * sizeof(double);
+  k_mh_gauss_run<<<warp_grid(W), SAMP_THREADS, smem, (cudaStream_t)stream>>>(
+      *p, W, nsteps, Lfac, mean, perm, cur_x, cur_lnl, cur_weight, z, z_is_delta, u, F, seed, step0, chain0, temp,
+      max_weight, rows, nrows, cap);
+  return csl_check_launch("k_mh_gauss_run");
+}
+
+extern "C" int csl_mh_moments(int W, int ndim, const double* rows, const int32_t* nrows, int cap,
+                              const double* mean, double* partial, double* out, void* stream) {
+  CSL_REQUIRE(W > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && rows && nrows && partial && out, "csl_mh_moments: bad argument");
+  const int m = 1 + ndim + ndim * ndim;
+  cudaStream_t s = (cudaStream_t)stream;
+  k_mh_moments<<<MOM_BLOCKS, SAMP_THREADS, 0, s>>>(W, ndim, rows, nrows, cap, mean, partial);
+  int lo = mean ? 1 + ndim : 0, hi = mean ? m : 1 + ndim;
+  k_reduce_partials<<<(hi - lo + 127) / 128, 128, 0, s>>>(m, lo, hi, partial, out);
+  return csl_check_launch("k_mh_moments");
+}
+
+extern "C" int csl_stretch_propose(int Ns, int Nc, int ndim, const double* s, const double* comp, double a,
+                                   const double* u_z, const int64_t* j, uint64_t seed, uint32_t step, uint32_t half,
+                                   uint32_t walker0, double* q, double* zz, void* stream) {
+  CSL_REQUIRE(Ns > 0 && Nc > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && s && comp && q && zz,
+              "csl_stretch_propose: bad argument");
+  CSL_REQUIRE((u_z == nullptr) == (j == nullptr), "csl_stretch_propose: u_z and j must be injected together");
+  k_stretch_propose<<<warp_grid(Ns), SAMP_THREADS, 0, (cudaStream_t)stream>>>(Ns, Nc, ndim, s, comp, a, u_z, j, seed,
+                                                                             step, half, walker0, q, zz);
+  return csl_check_launch("k_stretch_propose");
+}
+
+extern "C" int csl_stretch_accept(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q,
+                                  const double* lnl_q, const double* zz, const double* u_acc, uint64_t seed,
+                                  uint32_t step, uint32_t half, uint32_t walker0, uint8_t* accepted, void* stream) {
+  CSL_REQUIRE(Ns > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && s && lnl_s && q && lnl_q && zz,
+              "csl_stretch_accept: bad argument");
+  k_stretch_accept<<<warp_grid(Ns), SAMP_THREADS, 0, (cudaStream_t)stream>>>(Ns, ndim, s, lnl_s, q, lnl_q, zz, u_acc,
+                                                                            seed, step, half, walker0, (uint32_t)Nc,
+                                                                            accepted);
+  return csl_check_launch("k_stretch_accept");
+}
+
+extern "C" int csl_emcee_rows(int W, int ndim, const double* pos_old, const double* pos_new, const double* lnl_new,
+                              double* weight, int last_step, double* rows, int32_t* nrows, int cap, void* stream) {
+  CSL_REQUIRE(W > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && pos_old && pos_new && lnl_new && weight && rows && nrows,
+              "csl_emcee_rows: bad argument");
+  k_emcee_rows<<<warp_grid(W), SAMP_THREADS, 0, (cudaStream_t)stream>>>(W, ndim, pos_old, pos_new, lnl_new, weight,
+                                                                       last_step, rows, nrows, cap);
+  return csl_check_launch("k_emcee_rows");
+}
+
+extern "C" int csl_chain_moments(int W, int ndim, const double* rows, const int32_t* nrows, int cap, int burn_rows,
+                                 double* stats, void* stream) {
+  CSL_REQUIRE(W > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && rows && nrows && stats, "csl_chain_moments: bad argument");
+  k_chain_moments<<<warp_grid(W), SAMP_THREADS, 0, (cudaStream_t)stream>>>(W, ndim, rows, nrows, cap, burn_rows, stats);
+  return csl_check_launch("k_chain_moments");
+}
+
+extern "C" int csl_philox_mh(int W, int ndim, uint64_t seed, uint32_t step, uint32_t chain0, double* z, double* u,
+                             void* stream) {
+  CSL_REQUIRE(W > 0 && ndim >= 1 && z && u, "csl_philox_mh: bad argument");
+  k_philox_mh<<<(W + 127) / 128, 128, 0, (cudaStream_t)stream>>>(W, ndim, seed, step, chain0, z, u);
+  return csl_check_launch("k_philox_mh");
+}
+
+extern "C" int csl_philox_stretch(int Ns, int Nc, uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0,
+                                  double* u_z, int64_t* j, double* u_acc, void* stream) {
+  CSL_REQUIRE(Ns > 0 && Nc > 0 && u_z && j && u_acc, "csl_philox_stretch: bad argument");
+  k_philox_stretch<<<(Ns + 127) / 128, 128, 0, (cudaStream_t)stream>>>(Ns, Nc, seed, step, half, walker0, u_z, j,
+                                                                      u_acc);
+  return csl_check_launch("k_philox_stretch");
+}

@@ -1,0 +1,94 @@
+"""Walker sharding across the GPUs of one box.
+
+Replaces the reference's MPI layer (cosmoslik/mpi/mpi.py:7-72 and the
+master/worker protocol of metropolis_hastings.py:188-241): one process per GPU
+(``torchrun``), ``torch.distributed`` with the NCCL backend over NVLink for
+device tensors (gloo for the CPU tests), walkers / chains row-sharded.
+
+  proposal adaptation   all_reduce(sum) of [sum w, sum w x, sum w xx^T]   (was M3-M5)
+  stretch move          all_gather of the complementary half's positions  (was mpi_map, M2)
+  Gelman-Rubin          all_gather of per-chain (n, mean, var)
+"""
+import os
+
+
+def _dist():
+    import torch.distributed as d
+    return d if (d.is_available() and d.is_initialized()) else None
+
+
+def get_rank():
+    d = _dist()
+    return d.get_rank() if d else 0
+
+
+def get_size():
+    d = _dist()
+    return d.get_world_size() if d else 1
+
+
+def is_master():
+    return get_rank() == 0
+
+
+def init_from_env(backend=None):
+    """Initialise the process group from torchrun's environment (RANK, WORLD_SIZE,
+    LOCAL_RANK, MASTER_ADDR/PORT) and bind this process to its GPU.  No-op when
+    WORLD_SIZE is 1 or unset."""
+    import torch
+    import torch.distributed as d
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1 or d.is_initialized():
+        return get_rank(), get_size()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+        d.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        d.init_process_group(backend)
+    return d.get_rank(), d.get_world_size()
+
+
+def shard_bounds(n, rank=None, size=None):
+    """[lo, hi) of the contiguous slice of n items owned by `rank` (equal shares; the first
+    n % size ranks take one more)."""
+    rank = get_rank() if rank is None else rank
+    size = get_size() if size is None else size
+    base, extra = divmod(n, size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_reduce_sum(t):
+    d = _dist()
+    if d:
+        d.all_reduce(t, op=d.ReduceOp.SUM)
+    return t
+
+
+def all_gather_rows(local, total_rows):
+    """Concatenate the ranks' row blocks [n_r, ...] in rank order into [total_rows, ...].
+    Uses all_gather_into_tensor when every rank holds the same number of rows."""
+    d = _dist()
+    if not d:
+        return local
+    import torch
+    size = d.get_world_size()
+    if total_rows % size == 0 and local.shape[0] * size == total_rows:
+        out = torch.empty((total_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        d.all_gather_into_tensor(out, local.contiguous())
+        return out
+    parts = []
+    for r in range(size):
+        lo, hi = shard_bounds(total_rows, r, size)
+        parts.append(torch.empty((hi - lo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device))
+    d.all_gather(parts, local.contiguous())
+    return torch.cat(parts, 0)
+
+
+def barrier():
+    d = _dist()
+    if d:
+        d.barrier()

@@ -1,0 +1,353 @@
+"""Compile a traced posterior into the device tables of ``csl_program_t``
+(include/cosmoslik_b200.h) and run it through the C ABI.
+
+Host-side, one-time work only: Cholesky of the covariance (the reference's
+``cho_factor``, spt_lowl.py:98 / ``cholesky``, mspec_lnl.py:31), padding of the
+window matrices to the kernels' tile geometry, and the support analysis that
+lets the binning kernel skip all-zero window blocks.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.linalg as sla
+
+from . import _lib as L
+from .symbolic import (BandpowerTerm, Bin, Const, Expr, GaussTerm, LnlSum, LnlTerm, Par, Un)
+
+
+def _rup(v, m):
+    return (v + m - 1) // m * m
+
+
+class _Code(object):
+    """bytecode emitter for scalar expressions (ops: include/cosmoslik_b200.h CSL_OP_*)"""
+
+    def __init__(self):
+        self.op, self.arg, self.val = [], [], []
+        self.ncoef = 0
+        self._cache = {}
+
+    def _emit(self, op, arg=0, val=0.0):
+        self.op.append(L.OP[op]); self.arg.append(int(arg)); self.val.append(float(val))
+
+    def _walk(self, e):
+        """emit e; return the stack depth it needs"""
+        if isinstance(e, Const):
+            self._emit("PUSHC", val=e.v); return 1
+        if isinstance(e, Par):
+            self._emit("PUSHP", arg=e.index); return 1
+        if isinstance(e, Un):
+            d = self._walk(e.a)
+            self._emit({"neg": "NEG", "sqr": "SQR", "exp": "EXP", "log": "LOG", "sqrt": "SQRT"}[e.op]); return d
+        if isinstance(e, Bin):
+            da = self._walk(e.a); db = self._walk(e.b)
+            self._emit({"add": "ADD", "sub": "SUB", "mul": "MUL", "div": "DIV", "pow": "POW"}[e.op])
+            return max(da, db + 1)
+        raise TypeError("not an expression: %r" % (e,))
+
+    def coef(self, e):
+        """row index of the coefficient holding expression e"""
+        e = Expr.wrap(e)
+        key = repr(e)
+        if key in self._cache:
+            return self._cache[key]
+        depth = self._walk(e)
+        if depth > L.STACK:
+            raise ValueError("parameter expression too deep for the device stack (%d > %d)" % (depth, L.STACK))
+        k = self.ncoef
+        self._emit("STORE", arg=k)
+        self.ncoef += 1
+        self._cache[key] = k
+        return k
+
+
+def _support(rows):
+    """[first, last+1) of the non-zero columns of a block of window rows"""
+    nz = np.flatnonzero(np.any(rows != 0.0, axis=0))
+    if nz.size == 0:
+        return 0, 0
+    return int(nz[0]), int(nz[-1]) + 1
+
+
+class CompiledProgram(object):
+    """Host-side result of compiling a traced posterior: the tables of csl_program_t as
+    numpy arrays (``tables``) plus its integer fields (``meta``).  No CUDA needed."""
+
+    _PTR_FIELDS = ("code_op", "code_arg", "code_val", "box_idx", "box_lo", "box_hi", "gauss_idx", "gauss_c",
+                   "gauss_w", "scalar_coef", "spec_tab", "tile_tab", "templates", "windows", "data",
+                   "direct_coef", "Lmat", "Linv_diag")
+
+    def __init__(self, names, priors, lnl_expr):
+        self.names = list(names)
+        self.ndim = len(self.names)
+        if not (1 <= self.ndim <= L.MAX_DIM):
+            raise ValueError("number of sampled parameters must be in 1..%d" % L.MAX_DIM)
+        self.tables = {}
+        self.meta = dict(ndim=self.ndim, ncoef=0, ncode=0, nbox=0, ngauss=0, nscalar=0, nspec=0, ntile=0,
+                         n=0, n_pad=0, resid_mode=0)
+        self.host = {}
+        self.flops = {}
+        self._build(priors, lnl_expr)
+
+    def _dev(self, name, arr, dtype):
+        a = np.ascontiguousarray(arr, dtype=dtype)
+        if a.size == 0:
+            a = np.zeros(1, dtype=dtype)
+        self.tables[name] = a
+        return a
+
+    def _build(self, priors, lnl_expr):
+        code = _Code()
+        parts = lnl_expr.parts if isinstance(lnl_expr, LnlSum) else [lnl_expr]
+        scalars, quad = [], []
+        for part in parts:
+            if isinstance(part, (BandpowerTerm, GaussTerm)):
+                quad.append(part)
+            elif isinstance(part, LnlTerm):
+                raise TypeError("unsupported likelihood term %r" % (part,))
+            else:
+                scalars.append(code.coef(Expr.wrap(part)))
+        if len(quad) > 1:
+            raise NotImplementedError("one quadratic-form likelihood per script in this version "
+                                      "(sum them into one covariance, as mspec_lnl does)")
+        P = self.meta
+        # ---- priors (likelihoods/priors.py:6-30)
+        idx = {n: i for i, n in enumerate(self.names)}
+        box = [(idx[n], lo, hi) for n, lo, hi in priors.uniform_priors if n in idx]
+        gau = [(idx[n], c, w) for n, c, w in priors.gaussian_priors if n in idx]
+        P['nbox'], P['ngauss'] = len(box), len(gau)
+        self._dev('box_idx', [b[0] for b in box], np.int32)
+        self._dev('box_lo', [b[1] for b in box], np.float64)
+        self._dev('box_hi', [b[2] for b in box], np.float64)
+        self._dev('gauss_idx', [g[0] for g in gau], np.int32)
+        self._dev('gauss_c', [g[1] for g in gau], np.float64)
+        self._dev('gauss_w', [g[2] for g in gau], np.float64)
+        self.host["box"], self.host["gauss"] = box, gau
+
+        self.n = self.n_pad = 0
+        self.gauss_direct = None
+        if quad:
+            q = quad[0]
+            if isinstance(q, BandpowerTerm):
+                self._build_bandpower(P, code, q)
+            else:
+                self._build_gauss(P, code, q)
+        P['n'], P['n_pad'] = self.n, self.n_pad
+        P['nscalar'] = len(scalars)
+        self._dev('scalar_coef', scalars, np.int32)
+        P['ncoef'], P['ncode'] = code.ncoef, len(code.op)
+        self._dev('code_op', code.op, np.int32)
+        self._dev('code_arg', code.arg, np.int32)
+        self._dev('code_val', code.val, np.float64)
+        self.host["code"] = (list(code.op), list(code.arg), list(code.val))
+        self.ncoef = code.ncoef
+
+    def _factor(self, P, cov):
+        """lower Cholesky factor, identity-padded to the 64-row block size, and
+        the inverses of its diagonal blocks"""
+        n = cov.shape[0]
+        npad = _rup(n, L.BM)
+        Lf = np.eye(npad)
+        Lf[:n, :n] = sla.cholesky(cov, lower=True)
+        nblk = npad // L.BM
+        inv = np.empty((nblk, L.BM, L.BM))
+        eye = np.eye(L.BM)
+        for b in range(nblk):
+            s = slice(b * L.BM, (b + 1) * L.BM)
+            inv[b] = sla.solve_triangular(Lf[s, s], eye, lower=True)
+        self.n, self.n_pad = n, npad
+        self.host["L"] = Lf[:n, :n]
+        self._dev('Lmat', Lf, np.float64)
+        self._dev('Linv_diag', inv, np.float64)
+
+    def _build_gauss(self, P, code, q):
+        n = len(q.values)
+        if q.cov.shape != (n, n) or q.mean.shape != (n,):
+            raise ValueError("gaussian likelihood: mean/cov shape mismatch")
+        rows = [code.coef(v) for v in q.values]
+        self._factor(P, q.cov)
+        d = np.zeros(self.n_pad); d[:n] = q.mean
+        P['resid_mode'] = 2
+        self._dev('direct_coef', rows, np.int32)
+        self._dev('data', d, np.float64)
+        if all(isinstance(v, Par) for v in q.values) and n <= 32 and self.ndim <= 32:
+            # whole-run fused kernel is available (csl_mh_gauss_run)
+            self.gauss_direct = dict(perm=np.array([v.index for v in q.values], np.int32),
+                                     L=np.ascontiguousarray(self.host["L"]), mean=np.ascontiguousarray(q.mean))
+
+    def _build_bandpower(self, P, code, q):
+        nspec = len(q.blocks)
+        spec_tab = np.zeros((nspec, L.SPEC_STRIDE), np.int32)
+        tiles, templ, wins, data = [], [], [], []
+        toff = 0      # running offset into the template buffer (doubles)
+        woff = 0      # running offset into the window buffer
+        row0 = 0
+        flops_dense = flops_exec = 0
+        for s, blk in enumerate(q.blocks):
+            nb, nl = blk.windows.shape
+            if blk.data.shape != (nb,):
+                raise ValueError("bandpower likelihood: data/windows shape mismatch in spectrum %d" % s)
+            nlp = _rup(nl, L.KC)
+            m = blk.model
+            if m.size < nl:
+                raise ValueError("bandpower likelihood: model spectrum shorter than the window range")
+            terms = []
+            if m.const is not None and np.any(m.const[:nl] != 0.0):
+                terms.append((Const(1.0), m.const[:nl]))
+            terms += [(c, t[:nl]) for c, t in m.terms]
+            if len(terms) > L.MAX_TERMS or len(m.plaws) > L.MAX_PLAW:
+                raise ValueError("spectrum %d: at most %d template and %d power-law terms" % (s, L.MAX_TERMS, L.MAX_PLAW))
+            rec = spec_tab[s]
+            rec[L.S_NLPAD], rec[L.S_NTERM], rec[L.S_NPLAW] = nlp, len(terms), len(m.plaws)
+            for t, (c, arr) in enumerate(terms):
+                buf = np.zeros(nlp); buf[:nl] = arr
+                rec[L.S_TERM_COEF + t] = code.coef(c); rec[L.S_TERM_OFF + t] = toff
+                templ.append(buf); toff += nlp
+            for k, (amp, idx_e, base, mul) in enumerate(m.plaws):
+                lb = np.zeros(nlp); mu = np.zeros(nlp)
+                with np.errstate(divide="ignore"):
+                    lg = np.log(base[:nl])
+                lb[:nl] = np.where(np.isneginf(lg), -1e300, lg)   # 0**n: 0 for n>0, 1 for n==0, inf for n<0
+                mu[:nl] = mul[:nl]
+                rec[L.S_PLAW_AMP + k] = code.coef(amp); rec[L.S_PLAW_IDX + k] = code.coef(idx_e)
+                rec[L.S_PLAW_LOGB + k] = toff; templ.append(lb); toff += nlp
+                rec[L.S_PLAW_MUL + k] = toff; templ.append(mu); toff += nlp
+            cal = blk.cal
+            if isinstance(cal, Expr) and not (isinstance(cal, Const) and cal.v == 1.0):
+                rec[L.S_CAL] = code.coef(cal)
+            elif not isinstance(cal, Expr) and float(cal) != 1.0:
+                rec[L.S_CAL] = code.coef(Const(float(cal)))
+            else:
+                rec[L.S_CAL] = -1
+            nbp = _rup(nb, L.BM)
+            wp = np.zeros((nbp, nlp)); wp[:nb, :nl] = blk.windows
+            for t0 in range(0, nb, L.BM):
+                nr = min(L.BM, nb - t0)
+                lo, hi = _support(wp[t0:t0 + nr])
+                lo, hi = lo // L.KC * L.KC, _rup(hi, L.KC)
+                rec_t = np.zeros(L.TILE_STRIDE, np.int32)
+                rec_t[L.T_ROW0], rec_t[L.T_NROWS], rec_t[L.T_SPEC] = row0 + t0, nr, s
+                rec_t[L.T_LBEGIN], rec_t[L.T_LEND] = lo, hi
+                off = woff + t0 * nlp
+                lo32 = off & 0xFFFFFFFF
+                rec_t[L.T_WINOFF_LO] = lo32 - (1 << 32) if lo32 >= (1 << 31) else lo32
+                rec_t[L.T_WINOFF_HI] = off >> 32
+                rec_t[L.T_WINLD] = nlp
+                for g8 in range(L.BM // 8):
+                    glo, ghi = _support(wp[t0 + 8 * g8: t0 + 8 * g8 + 8])
+                    rec_t[L.T_GLO + g8], rec_t[L.T_GHI + g8] = glo, ghi
+                    nch = len([c for c in range(lo, hi, L.KC) if c + L.KC > glo and c < ghi])
+                    flops_exec += 2 * 8 * L.KC * nch
+                tiles.append(rec_t)
+            flops_dense += 2 * nb * nl
+            wins.append(wp.ravel()); woff += wp.size
+            data.append(blk.data)
+            row0 += nb
+        n = row0
+        if q.cov.shape != (n, n):
+            raise ValueError("bandpower likelihood: covariance is %s, data vector has %d rows" % (q.cov.shape, n))
+        self._factor(P, q.cov)
+        d = np.zeros(self.n_pad); d[:n] = np.concatenate(data)
+        P['resid_mode'] = 1
+        P['nspec'], P['ntile'] = nspec, len(tiles)
+        self._dev('spec_tab', spec_tab, np.int32)
+        self._dev('tile_tab', np.array(tiles), np.int32)
+        self._dev('templates', np.concatenate(templ) if templ else np.zeros(1), np.float64)
+        self._dev('windows', np.concatenate(wins), np.float64)
+        self._dev('data', d, np.float64)
+        self.host["spec_tab"], self.host["tile_tab"] = spec_tab, np.array(tiles)
+        # algorithmic work per evaluation: dense windows, executed DMMA blocks, TRSM
+        self.flops = dict(bin_dense=flops_dense, bin_exec=flops_exec, trsm=self.n_pad * self.n_pad + self.n_pad * L.BM,
+                          trsm_alg=n * n)
+
+
+
+class DeviceProgram(CompiledProgram):
+    """A compiled posterior resident on one CUDA device."""
+
+    def __init__(self, names, priors, lnl_expr, device=None):
+        torch = L.require_cuda()
+        self.lib = L.lib()
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        super().__init__(names, priors, lnl_expr)
+        self._ws = {}
+        self.dev = {k: torch.from_numpy(v).to(self.device) for k, v in self.tables.items()}
+        P = L.Program()
+        for k, v in self.meta.items():
+            setattr(P, k, int(v))
+        for k in self._PTR_FIELDS:
+            setattr(P, k, self.dev[k].data_ptr() if k in self.dev else None)
+        self.struct = P
+        if self.gauss_direct is not None:
+            self.gauss_direct = {k: torch.from_numpy(v).to(self.device) for k, v in self.gauss_direct.items()}
+
+    # ------------------------------------------------------------------ run
+    def workspace(self, W):
+        Wp = _rup(W, L.BN)
+        ws = self._ws.get(Wp)
+        if ws is None:
+            t = self.torch
+            kw = dict(dtype=t.float64, device=self.device)
+            ws = dict(coef=t.empty((max(self.ncoef, 1), Wp), **kw), prior=t.empty(Wp, **kw),
+                      R=t.empty((max(self.n_pad, 1), Wp), **kw) if self.n_pad else None,
+                      chi2=t.empty(Wp, **kw) if self.n_pad else None,
+                      x=t.empty((Wp, self.ndim), **kw), lnl=t.empty(Wp, **kw))
+            self._ws[Wp] = ws
+        return ws
+
+    def lnl(self, x, out=None, timers=None):
+        """-ln posterior of every row of the device tensor x [W, ndim] -> tensor [W]
+        (batched Slik.evaluate, cosmoslik.py:109-141).  With ``timers`` (a dict) the four stages
+        are launched one by one between CUDA events appended to timers[stage]."""
+        t = self.torch
+        if not (isinstance(x, t.Tensor) and x.is_cuda and x.dtype == t.float64 and x.dim() == 2
+                and x.shape[1] == self.ndim and x.is_contiguous()):
+            raise ValueError("x must be a contiguous float64 CUDA tensor [W, %d]" % self.ndim)
+        W = x.shape[0]
+        ws = self.workspace(W)
+        if out is None:
+            out = t.empty(W, dtype=t.float64, device=self.device)
+        st = L.stream_ptr()
+        if timers is None:
+            L.check(self.lib.csl_lnl(C.byref(self.struct), W, x.data_ptr(), out.data_ptr(), ws["coef"].data_ptr(),
+                                     ws["prior"].data_ptr(), L.ptr(ws["R"]), L.ptr(ws["chi2"]), st), "csl_lnl")
+            return out
+        Wp = _rup(W, L.BN)
+        P = C.byref(self.struct)
+
+        def stage(name, fn):
+            a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            a.record()
+            L.check(fn(), name)
+            b.record()
+            timers.setdefault(name, []).append((a, b))
+
+        stage("prepare", lambda: self.lib.csl_eval_prepare(P, W, x.data_ptr(), ws["coef"].data_ptr(), Wp,
+                                                           ws["prior"].data_ptr(), st))
+        chi2 = None
+        if self.meta["resid_mode"] == 1:
+            stage("bin_residual", lambda: self.lib.csl_bin_residual(P, Wp, ws["coef"].data_ptr(), Wp,
+                                                                    ws["R"].data_ptr(), Wp, st))
+        elif self.meta["resid_mode"] == 2:
+            stage("direct_residual", lambda: self.lib.csl_direct_residual(P, W, ws["coef"].data_ptr(), Wp,
+                                                                          ws["R"].data_ptr(), Wp, st))
+        if self.meta["resid_mode"]:
+            stage("chi2", lambda: self.lib.csl_chi2(P, Wp, ws["R"].data_ptr(), Wp, ws["chi2"].data_ptr(), st))
+            chi2 = ws["chi2"].data_ptr()
+        stage("combine", lambda: self.lib.csl_combine(P, W, ws["coef"].data_ptr(), Wp, ws["prior"].data_ptr(), chi2,
+                                                      out.data_ptr(), st))
+        return out
+
+    def lnl_host(self, x_host, out_host=None):
+        """End-to-end evaluation with HOST numpy buffers through csl_lnl_host (H2D, kernels, D2H)."""
+        x_host = np.ascontiguousarray(x_host, dtype=np.float64)
+        W = x_host.shape[0]
+        ws = self.workspace(W)
+        if out_host is None:
+            out_host = np.empty(W)
+        L.check(self.lib.csl_lnl_host(C.byref(self.struct), W, x_host.ctypes.data, out_host.ctypes.data,
+                                      ws["x"].data_ptr(), ws["lnl"].data_ptr(), ws["coef"].data_ptr(),
+                                      ws["prior"].data_ptr(), L.ptr(ws["R"]), L.ptr(ws["chi2"]), L.stream_ptr()),
+                "csl_lnl_host")
+        return out_host

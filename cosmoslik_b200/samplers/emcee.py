@@ -1,0 +1,169 @@
+"""Affine-invariant ensemble sampler (stretch move), batched on the device.
+
+Constructor keywords and ``sample(lnl)`` follow the reference wrapper
+(samplers/emcee.py:13-88).  The reference delegates the move itself to the
+third-party package ``emcee`` (2.x API); here it is implemented directly
+(Goodman & Weare 2010; emcee 2.x ``_propose_stretch``): the ensemble is split
+in two halves, each half is updated against the other,
+    z = ((a-1) u + 1)^2 / a,   q = c_j - z (c_j - s),
+    accept iff (ndim-1) ln z + lnp(q) - lnp(s) > ln u',
+with ``csl_stretch_propose`` / ``DeviceProgram.lnl`` / ``csl_stretch_accept``.
+The wrapper's bookkeeping -- weights of walkers that did not move, rows
+``(lnl_next, weight, x_old)``, per-walker file records of ``output_freq`` rows
+-- is samplers/emcee.py:66-88 (``csl_emcee_rows``).
+
+With several GPUs the walkers of BOTH halves are row-sharded; before each
+half-update the complementary half's positions are all-gathered over NCCL
+(this replaces the reference's ``mpi_map`` pool, mpi.py:40-64).  Partner
+indices and uniforms are keyed by GLOBAL walker id, so the chain is identical
+for any number of GPUs.
+
+Extra keywords: ``a`` (stretch scale, emcee default 2), ``seed``, ``streams``
+(callable ``step -> (u_z, j, u_acc)`` each [2, nwalkers/2], injected for parity
+runs) and ``init_pos`` ([nwalkers, ndim], replaces the initial Gaussian scatter
+of emcee.py:49-53).
+
+Waived reference behaviour: emcee.py:74 yields ``sample(-l, x, weight)`` -- the
+positional order of ``sample(x, lnl, weight)`` swapped, so ``run_chain`` labels
+columns wrongly there.  Here the yielded objects carry x / lnl in their proper
+fields; the row CONTENT (the lnl of the next position next to the old position)
+is reproduced.
+"""
+from collections import OrderedDict
+from math import ceil
+
+import numpy as np
+
+from .. import _lib as L
+from .. import dist
+from ..chains import ChainWriter
+from ..core import SlikSampler, arguments, sample
+from .utils import initialize_covariance, program_of
+
+
+class emcee(SlikSampler):
+    pool_chains = True    # run_chain joins all walkers into one Chain, as the reference does
+
+    def __init__(self, params, num_samples, nwalkers=100, cov_est=None, output_extra_params=None,
+                 output_file=None, output_freq=10, a=2.0, seed=None, streams=None, init_pos=None):
+        if output_extra_params is None:
+            output_extra_params = []
+        super().__init__(**arguments(exclude=["params"]))
+        if self.output_extra_params:
+            raise NotImplementedError("output_extra_params needs per-point Python evaluation")
+        self.output_extra_params = OrderedDict()
+        self.sampled = params.find_sampled()
+        self.x0 = [params[k].start for k in self.sampled]
+        self.cov_est = initialize_covariance(self.sampled, self.cov_est)
+        self.stats = {}
+
+    def initial_positions(self):
+        """Scatter of the walkers around the start point (emcee.py:49-53)."""
+        if self.init_pos is not None:
+            return np.ascontiguousarray(self.init_pos, dtype=float)
+        rs = np.random.RandomState(None if self.seed is None else int(self.seed) % (2 ** 32))
+        return rs.multivariate_normal([v.start for v in self.sampled.values()], self.cov_est, size=int(self.nwalkers))
+
+    def sample(self, lnl):
+        for blocks in self._run(program_of(lnl), emit=True):
+            for wid, rows in blocks:
+                for r in rows:
+                    s = sample(r[2:].copy(), r[0], r[1], None)
+                    s.chain = wid
+                    yield s
+
+    def run(self, lnl_or_program, nsteps=None):
+        prog = lnl_or_program if hasattr(lnl_or_program, "struct") else program_of(lnl_or_program)
+        for _ in self._run(prog, emit=False, nsteps=nsteps):
+            pass
+        return self.stats
+
+    def _run(self, prog, emit, nsteps=None):
+        torch, lib = prog.torch, prog.lib
+        dev = prog.device
+        nd = len(self.x0)
+        k = int(self.nwalkers)
+        if k % 2 or k < 2:
+            raise ValueError("nwalkers must be even")
+        h = k // 2
+        rank, size = dist.get_rank(), dist.get_size()
+        lo0, hi0 = dist.shard_bounds(h, rank, size)          # my slice of the first half
+        lo1, hi1 = dist.shard_bounds(k - h, rank, size)      # my slice of the second half
+        n0, n1 = hi0 - lo0, hi1 - lo1
+        W = n0 + n1
+        gid = np.concatenate([np.arange(lo0, hi0), h + np.arange(lo1, hi1)])   # global walker ids
+        if nsteps is None:
+            nsteps = int(ceil(self.num_samples / float(k)))
+        seed = int(self.seed) if self.seed is not None else int(np.random.SeedSequence().entropy & (2 ** 63 - 1))
+        kw = dict(dtype=torch.float64, device=dev)
+        rl = 2 + nd
+        cap = max(nsteps, 1)
+        pos_all = self.initial_positions()
+        if pos_all.shape != (k, nd):
+            raise ValueError("initial positions must be [nwalkers, ndim]")
+        pos = torch.from_numpy(pos_all[gid]).to(dev).contiguous()   # local: first-half slice then second-half slice
+        lnl_pos = prog.lnl(pos)
+        halves = [(0, n0, lo0, h), (n0, W, h + lo1, k - h)]          # (row0, row1, first global id, half size)
+        q = torch.empty_like(pos)
+        zz = torch.empty(W, **kw)
+        weight = torch.ones(W, **kw)
+        rows = torch.empty((W, cap, rl), **kw)
+        nrows = torch.zeros(W, dtype=torch.int32, device=dev)
+        accepted = torch.zeros(W, dtype=torch.uint8, device=dev)
+        pos_old = torch.empty_like(pos)
+        writer = None
+        if self.output_file is not None:
+            path = self.output_file if rank == 0 else "%s.rank%d" % (self.output_file, rank)
+            writer = ChainWriter(path, ["lnl", "weight"] + list(self.sampled), "list")
+        prev_n = np.zeros(W, dtype=np.int64)
+        st = L.stream_ptr()
+        timers = getattr(self, "timers", None)     # bench.py: CUDA-event pairs per stage
+        nacc = torch.zeros((), dtype=torch.int64, device=dev)
+        F = int(self.output_freq)
+        try:
+            for i in range(nsteps):
+                pos_old.copy_(pos)
+                inj = self.streams(i) if self.streams is not None else None
+                for hidx, (r0, r1, g0, hsize) in enumerate(halves):
+                    o0, o1, _, csize = halves[1 - hidx]
+                    comp = dist.all_gather_rows(pos[o0:o1], csize)    # the complementary half, all ranks' rows
+                    ns = r1 - r0
+                    if ns == 0:
+                        continue
+                    uz = jj = ua = None
+                    if inj is not None:
+                        sl = slice(g0 - (0 if hidx == 0 else h), g0 - (0 if hidx == 0 else h) + ns)
+                        uz = torch.from_numpy(np.ascontiguousarray(inj[0][hidx][sl], dtype=np.float64)).to(dev)
+                        jj = torch.from_numpy(np.ascontiguousarray(inj[1][hidx][sl], dtype=np.int64)).to(dev)
+                        ua = torch.from_numpy(np.ascontiguousarray(inj[2][hidx][sl], dtype=np.float64)).to(dev)
+                    s_view, l_view, q_view = pos[r0:r1], lnl_pos[r0:r1], q[r0:r1]
+                    L.check(lib.csl_stretch_propose(ns, csize, nd, s_view.data_ptr(), comp.data_ptr(), float(self.a),
+                                                    L.ptr(uz), L.ptr(jj), seed, i, hidx, g0, q_view.data_ptr(),
+                                                    zz[r0:r1].data_ptr(), st), "csl_stretch_propose")
+                    lnl_q = prog.lnl(q_view, timers=timers)
+                    L.check(lib.csl_stretch_accept(ns, csize, nd, s_view.data_ptr(), l_view.data_ptr(),
+                                                   q_view.data_ptr(), lnl_q.data_ptr(), zz[r0:r1].data_ptr(),
+                                                   L.ptr(ua), seed, i, hidx, g0, accepted[r0:r1].data_ptr(), st),
+                            "csl_stretch_accept")
+                nacc += accepted.sum()
+                L.check(lib.csl_emcee_rows(W, nd, pos_old.data_ptr(), pos.data_ptr(), lnl_pos.data_ptr(),
+                                           weight.data_ptr(), 1 if i == nsteps - 1 else 0, rows.data_ptr(),
+                                           nrows.data_ptr(), cap, st), "csl_emcee_rows")
+                if (emit or writer is not None) and ((i + 1) % F == 0 or i == nsteps - 1):
+                    n_now = nrows.cpu().numpy().astype(np.int64)
+                    a_, b_ = int(prev_n.min(initial=0)), int(n_now.max(initial=0))
+                    slab = rows[:, a_:b_].cpu().numpy() if b_ > a_ else np.zeros((W, 0, rl))
+                    blocks = [(int(gid[c]), slab[c, prev_n[c] - a_:n_now[c] - a_]) for c in range(W)]
+                    prev_n = n_now
+                    if writer is not None:
+                        for wid, r in blocks:
+                            for c0 in range(0, len(r), F):      # records of at most output_freq rows (emcee.py:80-84)
+                                writer.write(wid, r[c0:c0 + F])
+                        writer.flush()
+                    if emit:
+                        yield blocks
+        finally:
+            if writer is not None:
+                writer.close()
+        self.stats = dict(pos=pos, lnl=lnl_pos, weight=weight, rows=rows, nrows=nrows, nsteps=nsteps,
+                          walker_ids=gid, seed=seed, accepted=int(nacc.item()), evals=nsteps * W)

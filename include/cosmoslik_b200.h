@@ -1,0 +1,229 @@
+/*
+ * cosmoslik_b200 -- C ABI of the B200 hot path (libcosmoslik_b200.so).
+ *
+ * The reference (marius311/cosmoslik) is pure Python and has no FFI; the
+ * functions below are what a ctypes binding in the reference's plugins would
+ * call for the path "sampler step + priors + foreground model + window binning
+ * + Gaussian chi^2" (SURVEY.md section 8).  Each entry names the reference
+ * lines it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - no function allocates, frees or synchronises (except *_host variants,
+ *     which synchronise the given stream before returning);
+ *   - `stream` is a cudaStream_t passed as void*; 0 is the legacy default stream;
+ *   - return value 0 = success, otherwise a cudaError_t or a negative
+ *     CSL_E_* code; csl_last_error() gives a message for the calling thread;
+ *   - all floating point is IEEE binary64.
+ *   - walker-major arrays are row-major [W, ndim]; "rows" matrices are
+ *     [n_pad, ldr] with the WALKER index contiguous.
+ */
+#ifndef COSMOSLIK_B200_H
+#define COSMOSLIK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSL_ABI_VERSION 1
+
+/* error codes (negative; positive values are cudaError_t) */
+#define CSL_E_BADARG   (-1)
+#define CSL_E_TOOLARGE (-2)
+#define CSL_E_NODEVICE (-3)
+
+/* geometry the host must honour when it pads its tables */
+#define CSL_BM        64   /* rows per binning / TRSM row block            */
+#define CSL_BN       128   /* walkers per column tile                      */
+#define CSL_KC        16   /* ell (k) chunk                                */
+#define CSL_MAX_DIM   64   /* max sampled parameters                       */
+#define CSL_MAX_TERMS  8   /* template terms per spectrum                  */
+#define CSL_MAX_PLAW   4   /* power-law terms per spectrum                 */
+#define CSL_SPEC_STRIDE 64 /* int32 words per spectrum record              */
+#define CSL_TILE_STRIDE 32 /* int32 words per tile record                  */
+#define CSL_STACK     16   /* coefficient bytecode stack depth             */
+
+/* coefficient bytecode (one flat program; STORE pops into coef row `arg`) */
+enum {
+  CSL_OP_PUSHP = 0, CSL_OP_PUSHC = 1, CSL_OP_ADD = 2, CSL_OP_SUB = 3, CSL_OP_MUL = 4,
+  CSL_OP_DIV = 5, CSL_OP_NEG = 6, CSL_OP_EXP = 7, CSL_OP_LOG = 8, CSL_OP_POW = 9,
+  CSL_OP_SQRT = 10, CSL_OP_STORE = 11, CSL_OP_SQR = 12
+};
+
+/* spectrum record, int32 words (table spec_tab[nspec][CSL_SPEC_STRIDE]) */
+enum {
+  CSL_S_NLPAD = 0,   /* padded number of ell columns (multiple of CSL_KC)       */
+  CSL_S_NTERM = 1,   /* template terms: cl += coef[TERM_COEF[t]] * T[TERM_OFF[t] + l] */
+  CSL_S_NPLAW = 2,   /* power-law terms: cl += coef[amp] * M[l] * exp(coef[idx] * logB[l]) */
+  CSL_S_CAL   = 3,   /* coef row multiplying the data of this spectrum, -1 = 1.0 */
+  CSL_S_TERM_COEF = 8,  CSL_S_TERM_OFF = 16,
+  CSL_S_PLAW_AMP = 24, CSL_S_PLAW_IDX = 28, CSL_S_PLAW_LOGB = 32, CSL_S_PLAW_MUL = 36
+};
+
+/* tile record, int32 words (table tile_tab[ntile][CSL_TILE_STRIDE]) */
+enum {
+  CSL_T_ROW0 = 0,    /* first residual row of the tile                          */
+  CSL_T_NROWS = 1,   /* valid rows, 1..CSL_BM                                   */
+  CSL_T_SPEC = 2,
+  CSL_T_LBEGIN = 3,  /* first ell column (multiple of CSL_KC)                   */
+  CSL_T_LEND = 4,    /* one past the last column (multiple of CSL_KC)           */
+  CSL_T_WINOFF_LO = 5, CSL_T_WINOFF_HI = 6, /* offset (doubles) of the tile's first window row   */
+  CSL_T_WINLD = 7,   /* window row stride in doubles                            */
+  CSL_T_GLO = 8,     /* [8]: per 8-row group, first non-zero column chunk start */
+  CSL_T_GHI = 16     /* [8]: per 8-row group, one past last non-zero column     */
+};
+
+/*
+ * A compiled posterior ("device program").  Built on the host from the plugin
+ * tree; the struct itself lives in host memory, its pointers are device
+ * pointers.  It states, for W walkers at once, what Slik.evaluate computes
+ * for one (cosmoslik/cosmoslik.py:109-141):
+ *
+ *   prior  = likelihoods/priors.py:24-30   (box -> +inf, Gaussian penalties)
+ *   coef   = scalar functions of the parameters (bytecode)
+ *   lnl    = prior + sum_k coef[scalar_coef[k]] + 1/2 || L^-1 r ||^2
+ *   r      = cal * d - W . cl        (resid_mode 1; spt_lowl.py:132,171-182;
+ *                                     mspec_lnl.py:63-73)
+ *          = coef[direct_coef[i]] - d[i]   (resid_mode 2; dense Gaussian)
+ *   cl     = sum_t coef * T_t[l] + sum_p coef * M_p[l] * exp(coef * logB_p[l])
+ *            (spt_lowl.py:206-207; models/clust_poisson_egfs.py:14-17)
+ */
+typedef struct csl_program {
+  int32_t ndim, ncoef, ncode, nbox, ngauss, nscalar, nspec, ntile;
+  int32_t n, n_pad, resid_mode, reserved0;
+  const int32_t* code_op;   const int32_t* code_arg;  const double* code_val;
+  const int32_t* box_idx;   const double* box_lo;     const double* box_hi;
+  const int32_t* gauss_idx; const double* gauss_c;    const double* gauss_w;
+  const int32_t* scalar_coef;
+  const int32_t* spec_tab;  const int32_t* tile_tab;
+  const double* templates;  const double* windows;    const double* data;
+  const int32_t* direct_coef;
+  const double* Lmat;       /* [n_pad, n_pad] row-major lower factor, identity padded */
+  const double* Linv_diag;  /* [n_pad/CSL_BM][CSL_BM*CSL_BM] inverses of the diagonal blocks */
+} csl_program_t;
+
+int csl_abi_version(void);
+const char* csl_last_error(void);
+int csl_sizeof_program(void);
+/* device properties: out[0]=SM count, out[1]=cc major, out[2]=cc minor, out[3]=max smem/block optin */
+int csl_device_info(int device, int32_t* out4_host);
+
+/* ---- posterior evaluation (replaces Slik.evaluate, cosmoslik.py:109-141) ---------------- */
+
+/* priors (likelihoods/priors.py:24-30) + coefficient bytecode.
+ * x [W, ndim] -> coef [ncoef, ldc] (ldc >= W), prior [W] (+inf outside a box).
+ * Coefficient columns W..ldc-1 are filled with walker W-1's values (tile padding). */
+int csl_eval_prepare(const csl_program_t* p, int W, const double* x, double* coef, int ldc,
+                     double* prior, void* stream);
+
+/* foreground build in shared memory (spt_lowl.py:206-207, clust_poisson_egfs.py:14-17),
+ * window binning as an FP64 DMMA GEMM (spt_lowl.py:182) and the residual
+ * r = cal*d - b (spt_lowl.py:132) -> R [n_pad, ldr].  W must be a multiple of CSL_BN
+ * (pad with copies of a valid walker). */
+int csl_bin_residual(const csl_program_t* p, int W, const double* coef, int ldc, double* R, int ldr,
+                     void* stream);
+
+/* resid_mode 2: R[i, w] = coef[direct_coef[i], w] - data[i] (zero rows up to n_pad). */
+int csl_direct_residual(const csl_program_t* p, int W, const double* coef, int ldc, double* R, int ldr,
+                        void* stream);
+
+/* chi2[w] = || L^-1 R[:, w] ||^2 by a blocked triangular solve on DMMA
+ * (replaces cho_solve + dot, spt_lowl.py:133 / mspec_lnl.py:73).  R is overwritten by L^-1 R. */
+int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, double* chi2, void* stream);
+
+/* lnl[w] = prior[w] + sum scalar coefs + chi2[w]/2 ; +inf where prior is +inf (cosmoslik.py:135-141).
+ * chi2 may be NULL when the program has no quadratic form. */
+int csl_combine(const csl_program_t* p, int W, const double* coef, int ldc, const double* prior,
+                const double* chi2, double* lnl, void* stream);
+
+/* The four calls above in sequence.  Workspace (device, caller owned):
+ *   coef [ncoef, Wp], prior [Wp], R [n_pad, Wp], chi2 [Wp]  with Wp = W rounded up to CSL_BN. */
+int csl_lnl(const csl_program_t* p, int W, const double* x, double* lnl,
+            double* ws_coef, double* ws_prior, double* ws_R, double* ws_chi2, void* stream);
+
+/* End-to-end variant with HOST buffers (pinned or pageable): copies x_host -> x_dev, evaluates,
+ * copies lnl back and synchronises `stream`.  x_dev [Wp, ndim] and lnl_dev [Wp] are device scratch. */
+int csl_lnl_host(const csl_program_t* p, int W, const double* x_host, double* lnl_host,
+                 double* x_dev, double* lnl_dev,
+                 double* ws_coef, double* ws_prior, double* ws_R, double* ws_chi2, void* stream);
+
+/* ---- Metropolis-Hastings (samplers/metropolis_hastings.py) -------------------------------- */
+
+/* draw_x (:141-142) for all chains: test_x = cur_x + delta.
+ *   mode 0: delta = inj[w, :]                     (injected offsets; exact add)
+ *   mode 1: delta = inj[w, :] @ F                 (injected standard normals)
+ *   mode 2: delta = philox_normals(seed, step, chain0 + w) @ F
+ * F [ndim, ndim] row-major is the matrix numpy's multivariate_normal uses (host SVD). */
+int csl_mh_propose(int W, int ndim, const double* cur_x, double* test_x, int mode, const double* inj,
+                   const double* F, uint64_t seed, uint32_t step, uint32_t chain0, void* stream);
+
+/* accept test + weight bookkeeping + row emission (:154-164) for all chains.
+ *   u: injected uniforms [W] or NULL -> Philox(seed, step, chain0 + w).
+ *   rows [W, cap, 2+ndim] receives (lnl, weight, x...) at slot nrows[w]++ when the reference
+ *   would yield; accepted [W] (uint8) records the decision, margin [W] = log(u) - temp*(cur-test)
+ *   (for near-tie diagnostics; may be NULL). */
+int csl_mh_accept(int W, int ndim, double* cur_x, double* cur_lnl, double* cur_weight,
+                  const double* test_x, const double* test_lnl, const double* u,
+                  uint64_t seed, uint32_t step, uint32_t chain0, double temp, double max_weight,
+                  double* rows, int32_t* nrows, int cap, uint8_t* accepted, double* margin, void* stream);
+
+/* Whole MH run for a dense Gaussian posterior, one warp per chain, `nsteps` steps in ONE launch
+ * (draw_x + priors + x^T C^-1 x/2 by forward substitution + accept + rows); ndim <= 32.
+ *   Lfac: LOWER Cholesky factor [n, n] of the target covariance, mean [n]; residual row i is
+ *   x[perm[i]] - mean[i].  Priors are taken from p.
+ *   z/u: injected streams [nsteps, W, ndim] / [nsteps, W], or NULL for Philox.
+ *   z_is_delta: 1 -> z holds offsets. */
+int csl_mh_gauss_run(const csl_program_t* p, int W, int nsteps, const double* Lfac, const double* mean,
+                     const int32_t* perm, double* cur_x, double* cur_lnl, double* cur_weight,
+                     const double* z, int z_is_delta, const double* u, const double* F,
+                     uint64_t seed, uint32_t step0, uint32_t chain0, double temp, double max_weight,
+                     double* rows, int32_t* nrows, int cap, void* stream);
+
+/* get_new_cov (:249-253) sufficient statistics over the last half of every chain's rows:
+ * pass 1 (mean == NULL): out[0] = sum w, out[1..ndim] = sum w x.
+ * pass 2 (mean given):   out[1+ndim ..] = sum w (x-mean)(x-mean)^T  [ndim*ndim].
+ * partial [128, 1+ndim+ndim*ndim] is scratch; the reduction order is fixed (bitwise reproducible).
+ * Sums over ranks are one all-reduce of out. */
+int csl_mh_moments(int W, int ndim, const double* rows, const int32_t* nrows, int cap,
+                   const double* mean, double* partial, double* out, void* stream);
+
+/* ---- affine-invariant ensemble sampler (samplers/emcee.py + emcee 2.x stretch move) ------- */
+
+/* proposals for the Ns active walkers s [Ns, ndim] against the complementary half comp [Nc, ndim]:
+ *   z = ((a-1) u_z + 1)^2 / a ;  q = c_j - z (c_j - s)
+ * u_z [Ns], j [Ns] injected, or NULL -> Philox(seed, step, half, walker0 + k) with j over Nc.
+ * Writes q [Ns, ndim] and zz [Ns]. */
+int csl_stretch_propose(int Ns, int Nc, int ndim, const double* s, const double* comp, double a,
+                        const double* u_z, const int64_t* j, uint64_t seed, uint32_t step, uint32_t half,
+                        uint32_t walker0, double* q, double* zz, void* stream);
+
+/* accept iff (ndim-1) ln z + lnp(q) - lnp(s) > ln u_acc, lnp = -lnl; updates s, lnl_s in place. */
+int csl_stretch_accept(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q, const double* lnl_q,
+                       const double* zz, const double* u_acc, uint64_t seed, uint32_t step, uint32_t half,
+                       uint32_t walker0, uint8_t* accepted, void* stream);
+
+/* wrapper bookkeeping of samplers/emcee.py:70-88 after a full step: a walker that did not move
+ * gains weight; one that moved (or any walker on the last step) emits (lnl_next, weight, x_old). */
+int csl_emcee_rows(int W, int ndim, const double* pos_old, const double* pos_new, const double* lnl_new,
+                   double* weight, int last_step, double* rows, int32_t* nrows, int cap, void* stream);
+
+/* ---- convergence (new; nothing in the reference) ----------------------------------------- */
+
+/* per-chain weighted count / mean / variance over rows -> stats [W, 1+2*ndim] */
+int csl_chain_moments(int W, int ndim, const double* rows, const int32_t* nrows, int cap, int burn_rows,
+                      double* stats, void* stream);
+
+/* ---- test hooks --------------------------------------------------------------------------- */
+int csl_philox_mh(int W, int ndim, uint64_t seed, uint32_t step, uint32_t chain0, double* z, double* u,
+                  void* stream);
+int csl_philox_stretch(int Ns, int Nc, uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0,
+                       double* u_z, int64_t* j, double* u_acc, void* stream);
+/* plain FP64 DMMA GEMM C[M,N] = A[M,K] B[K,N] (row-major, M%64==0, N%128==0, K%16==0) for peak tests */
+int csl_dgemm_dmma(int M, int N, int K, const double* A, const double* B, double* C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSMOSLIK_B200_H */

@@ -116,7 +116,7 @@ def mh_lockstep(lnl_batch, x0, nsteps, cov_est, z=None, delta=None, u=None,
     (the matrix numpy's multivariate_normal uses, :141-142); alternatively
     ``delta[t, c, :]`` injects the offset itself.  ``u[t, c]`` is the accept
     uniform.  After every ``exchange`` steps, once more than
-    ``proposal_update_start`` steps have been taken, ``cov_est`` is replaced by
+    ``proposal_update_start`` steps have been taken (and steps remain), ``cov_est`` is replaced by
     ``pooled_new_cov`` of all rows emitted so far (the master's rule, :200-201).
 
     Returns per-chain lists of rows (lnl, weight, x), the final state and the
@@ -148,7 +148,7 @@ def mh_lockstep(lnl_batch, x0, nsteps, cov_est, z=None, delta=None, u=None,
                 if cur_w[c] >= max_weight:
                     rows[c].append((cur_lnl[c], cur_w[c], cur_x[c].copy()))
                     cur_w[c] = 0
-        if proposal_update and (t + 1) % exchange == 0 and (t + 1) > proposal_update_start:
+        if proposal_update and (t + 1) % exchange == 0 and proposal_update_start < (t + 1) < nsteps:
             xs = [np.array([r[2] for r in rc]) if rc else None for rc in rows]
             ws = [np.array([r[1] for r in rc]) if rc else None for rc in rows]
             cov_est = pooled_new_cov(xs, ws)

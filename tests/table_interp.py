@@ -1,0 +1,99 @@
+"""Numpy interpreter of the tables a CompiledProgram holds (TEST-ONLY).
+
+It walks exactly the data the CUDA kernels walk (bytecode, spectrum / tile records, padded
+windows, templates, factor), so CPU tests can check the host-side tracing and compilation
+against the oracle without a GPU.  It is not a product path."""
+import numpy as np
+import scipy.linalg as sla
+
+from cosmoslik_b200 import _lib as L
+
+
+def run_bytecode(cp, x):
+    t = cp.tables
+    coef = np.zeros(max(cp.meta["ncoef"], 1))
+    st = []
+    inv = {v: k for k, v in L.OP.items()}
+    for op, arg, val in zip(t["code_op"][:cp.meta["ncode"]], t["code_arg"], t["code_val"]):
+        name = inv[int(op)]
+        if name == "PUSHP": st.append(float(x[arg]))
+        elif name == "PUSHC": st.append(float(val))
+        elif name == "STORE": coef[arg] = st.pop()
+        elif name in ("NEG", "EXP", "LOG", "SQRT", "SQR"):
+            a = st.pop()
+            f = {"NEG": lambda: -a, "EXP": lambda: np.exp(a), "LOG": lambda: np.log(a), "SQRT": lambda: np.sqrt(a),
+                 "SQR": lambda: a * a}[name]
+            st.append(f())
+        else:
+            b = st.pop(); a = st.pop()
+            f = {"ADD": lambda: a + b, "SUB": lambda: a - b, "MUL": lambda: a * b, "DIV": lambda: a / b,
+                 "POW": lambda: a ** b}[name]
+            st.append(f())
+    assert not st
+    return coef
+
+
+def prior(cp, x):
+    t, m = cp.tables, cp.meta
+    for b in range(m["nbox"]):
+        v = x[t["box_idx"][b]]
+        if not (t["box_lo"][b] <= v <= t["box_hi"][b]):
+            return np.inf
+    s = 0.0
+    for k in range(m["ngauss"]):
+        d = x[t["gauss_idx"][k]] - t["gauss_c"][k]
+        s = s + d * d / 2 / (t["gauss_w"][k] * t["gauss_w"][k])
+    return s
+
+
+def residual(cp, coef):
+    t, m = cp.tables, cp.meta
+    r = np.zeros(m["n_pad"])
+    if m["resid_mode"] == 2:
+        for i in range(m["n"]):
+            r[i] = coef[t["direct_coef"][i]] - t["data"][i]
+        return r
+    for tile in t["tile_tab"][:m["ntile"]]:
+        spec = t["spec_tab"][tile[L.T_SPEC]]
+        l0, l1 = tile[L.T_LBEGIN], tile[L.T_LEND]
+        cl = np.zeros(l1 - l0)
+        for k in range(spec[L.S_NTERM]):
+            off = spec[L.S_TERM_OFF + k]
+            cl += coef[spec[L.S_TERM_COEF + k]] * t["templates"][off + l0: off + l1]
+        for k in range(spec[L.S_NPLAW]):
+            lb = t["templates"][spec[L.S_PLAW_LOGB + k] + l0: spec[L.S_PLAW_LOGB + k] + l1]
+            mu = t["templates"][spec[L.S_PLAW_MUL + k] + l0: spec[L.S_PLAW_MUL + k] + l1]
+            with np.errstate(over="ignore"):
+                cl += coef[spec[L.S_PLAW_AMP + k]] * mu * np.exp(coef[spec[L.S_PLAW_IDX + k]] * lb)
+        woff = (int(tile[L.T_WINOFF_HI]) << 32) | (int(tile[L.T_WINOFF_LO]) & 0xFFFFFFFF)
+        ld = tile[L.T_WINLD]
+        cal = 1.0 if spec[L.S_CAL] < 0 else coef[spec[L.S_CAL]]
+        for rr in range(tile[L.T_NROWS]):
+            w = t["windows"][woff + rr * ld + l0: woff + rr * ld + l1]
+            # the group range must cover every non-zero of the row
+            g = rr // 8
+            nz = np.flatnonzero(w)
+            if nz.size:
+                assert tile[L.T_GLO + g] <= l0 + nz[0] and l0 + nz[-1] < tile[L.T_GHI + g]
+            row = tile[L.T_ROW0] + rr
+            r[row] = cal * t["data"][row] - np.dot(w, cl)
+    return r
+
+
+def lnl(cp, x):
+    x = np.asarray(x, dtype=float)
+    m, t = cp.meta, cp.tables
+    pr = prior(cp, x)
+    if pr == np.inf:
+        return np.inf
+    coef = run_bytecode(cp, x)
+    like = 0.0
+    for k in range(m["nscalar"]):
+        like = like + coef[t["scalar_coef"][k]]
+    if m["resid_mode"]:
+        r = residual(cp, coef)
+        npad = m["n_pad"]
+        y = sla.solve_triangular(t["Lmat"].reshape(npad, npad), r, lower=True)
+        # diagonal-block inverses must be the inverses of the factor's diagonal blocks
+        like = like + 0.5 * float(y @ y)
+    return like + pr

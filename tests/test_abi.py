@@ -1,0 +1,54 @@
+"""The C-ABI library loads on a machine without a GPU and exports every symbol that
+include/cosmoslik_b200.h declares; the Python binding agrees with the header's constants."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+from cosmoslik_b200 import _lib
+
+
+def header():
+    with open(os.path.join(ROOT, "include", "cosmoslik_b200.h")) as f:
+        return f.read()
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = re.findall(r"^(?:int|const char\*)\s+(csl_\w+)\s*\(", header(), flags=re.M)
+    assert len(names) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+        assert n in _lib.SIGNATURES, "symbol %s has no ctypes signature" % n
+    assert set(_lib.SIGNATURES) == set(names)
+
+
+def test_constants_match_header():
+    h = header()
+    defs = dict(re.findall(r"#define\s+CSL_(\w+)\s+(-?\d+)", h))
+    assert int(defs["BM"]) == _lib.BM and int(defs["BN"]) == _lib.BN and int(defs["KC"]) == _lib.KC
+    assert int(defs["MAX_DIM"]) == _lib.MAX_DIM and int(defs["MAX_TERMS"]) == _lib.MAX_TERMS
+    assert int(defs["MAX_PLAW"]) == _lib.MAX_PLAW and int(defs["SPEC_STRIDE"]) == _lib.SPEC_STRIDE
+    assert int(defs["TILE_STRIDE"]) == _lib.TILE_STRIDE and int(defs["STACK"]) == _lib.STACK
+    enums = dict((k, int(v)) for k, v in re.findall(r"CSL_(\w+)\s*=\s*(\d+)", h))
+    for k, v in _lib.OP.items():
+        assert enums["OP_" + k] == v
+    for k in ("S_NLPAD", "S_NTERM", "S_NPLAW", "S_CAL", "S_TERM_COEF", "S_TERM_OFF", "S_PLAW_AMP", "S_PLAW_IDX",
+              "S_PLAW_LOGB", "S_PLAW_MUL", "T_ROW0", "T_NROWS", "T_SPEC", "T_LBEGIN", "T_LEND", "T_WINOFF_LO",
+              "T_WINOFF_HI", "T_WINLD", "T_GLO", "T_GHI"):
+        assert enums[k] == getattr(_lib, k), k
+
+
+def test_library_loads_and_struct_layout_agrees():
+    lib = _lib.lib()
+    assert lib.csl_abi_version() == 1
+    assert lib.csl_sizeof_program() == ctypes.sizeof(_lib.Program)
+
+
+def test_argument_validation_without_a_gpu():
+    """bad arguments are rejected before any CUDA call"""
+    lib = _lib.lib()
+    rc = lib.csl_dgemm_dmma(63, 128, 16, None, None, None, None)
+    assert rc == -1 and b"null" in lib.csl_last_error()
+    rc = lib.csl_mh_propose(0, 3, None, None, 0, None, None, 0, 0, 0, None)
+    assert rc == -1

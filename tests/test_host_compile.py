@@ -1,0 +1,171 @@
+"""Host-side tracing + compilation (no GPU): the tables handed to the kernels, interpreted in
+numpy by tests/table_interp.py, must reproduce the oracle / the reference's golden outputs."""
+import numpy as np
+import pytest
+
+from conftest import golden
+import b200_scripts as B
+import oracle_scripts as S
+import table_interp as TI
+from cosmoslik_b200 import Slik, SlikDict, param, SlikPlugin, likelihoods, models
+from cosmoslik_b200.program import CompiledProgram
+from cosmoslik_b200 import _lib as L
+from oracle import runtime as ort, likes as olikes
+
+
+def compiled(script_cls):
+    s = script_cls()
+    slik = Slik(s)
+    return slik, CompiledProgram(list(slik.get_sampled()), slik.params.priors, slik.trace())
+
+
+@pytest.mark.parametrize("which", ["s12", "k11"])
+def test_spt_lowl_tables_reproduce_reference(spt_data, which):
+    g = golden("spt_lowl_lnl.npz")
+    slik, cp = compiled(B.spt_script(spt_data, which, g["tt"]))
+    assert cp.names == list(g[which + "_names"])
+    got = np.array([TI.lnl(cp, x) for x in g[which + "_x"][:24]])
+    ref = g[which + "_lnl"][:24]
+    assert np.array_equal(np.isinf(got), np.isinf(ref))
+    f = np.isfinite(ref)
+    np.testing.assert_allclose(got[f], ref[f], rtol=1e-11)
+    assert cp.meta["n"] == 47 and cp.meta["n_pad"] == 64 and cp.meta["ntile"] == 1
+    assert cp.flops["bin_dense"] == 2 * 47 * 3251
+
+
+def test_quickstart_is_pure_bytecode():
+    slik, cp = compiled(B.quick_script())
+    assert cp.meta["resid_mode"] == 0 and cp.meta["nscalar"] == 1
+    for x in ([0.3, -1.2], [0, 0], [5, 7]):
+        assert TI.lnl(cp, x) == (x[0] ** 2 + x[1] ** 2) / 2
+
+
+def test_gaussian_plugin_tables():
+    A = np.random.RandomState(0).standard_normal((30, 30))
+    C = A @ A.T / 30 + np.eye(30)
+    slik, cp = compiled(B.gauss_script(C))
+    assert cp.gauss_direct is not None and list(cp.gauss_direct["perm"]) == list(range(30))
+    oslik = ort.Slik(S.gauss_script(C)())
+    xs = np.random.RandomState(1).standard_normal((8, 30))
+    for x in xs:
+        assert abs(TI.lnl(cp, x) - oslik.evaluate(*x)[0]) < 1e-12 * abs(oslik.evaluate(*x)[0])
+    # diagonal-block inverses really invert the factor's diagonal blocks
+    npad = cp.meta["n_pad"]
+    Lm = cp.tables["Lmat"].reshape(npad, npad)
+    inv = cp.tables["Linv_diag"].reshape(-1, L.BM, L.BM)
+    for b in range(npad // L.BM):
+        s = slice(b * L.BM, (b + 1) * L.BM)
+        np.testing.assert_allclose(inv[b] @ Lm[s, s], np.eye(L.BM), atol=1e-12)
+
+
+def make_mspec_problem(ns, seed=3, nspec=3, nbins=20, lmin=50, lmax=700, banded=False):
+    """A small multi-frequency bandpower problem on both the oracle and the product plugins."""
+    rs = np.random.RandomState(seed)
+    maps = ["T090", "T150", "T220"][:nspec]
+    keys = [(a, b) for i, a in enumerate(maps) for b in maps[i:]]
+    nl = lmax - lmin
+    ell = np.arange(lmax)
+    cmb = {"cl_TT": 4000.0 * np.exp(-(ell / 900.0) ** 1.1) + 20.0}
+    use, windows, signal = {}, {}, {}
+    for k in keys:
+        use[k] = (lmin, lmax)
+        centers = np.linspace(0, nl, nbins + 2)[1:-1]
+        w = np.exp(-0.5 * ((np.arange(nl)[None, :] - centers[:, None]) / (nl / nbins / 2.0)) ** 2)
+        w /= w.sum(1, keepdims=True)
+        if banded:
+            w[w < 1e-6] = 0.0
+        else:
+            w += 1e-10
+        windows[k] = w
+        signal[k] = w @ cmb["cl_TT"][lmin:lmax] * (1 + 0.02 * rs.standard_normal(nbins)) + 30
+    n = nbins * len(keys)
+    d = np.concatenate([signal[k] for k in sorted(keys)])
+    Acov = rs.standard_normal((n, n)) * 0.05
+    cov = np.diag((0.03 * d) ** 2) + (Acov @ Acov.T) * np.outer(0.03 * d, 0.03 * d)
+    return dict(maps=maps, keys=keys, use=use, windows=windows, signal=signal, cov=cov, cmb=cmb)
+
+
+def mspec_scripts(prob):
+    """(oracle script class, product script class) for the same problem"""
+    starts = dict(Aps=12.0, Acib=6.0, ncib=0.8, cal150=1.0, cal220=1.0, Acmb=1.0)
+
+    def build(ns_param, ns_Plugin, like_cls, egfs_cls):
+        class script(ns_Plugin):
+            def __init__(self):
+                super().__init__()
+                self.Aps = ns_param(start=starts["Aps"], scale=2, min=0)
+                self.Acib = ns_param(start=starts["Acib"], scale=1, min=0, max=50)
+                self.ncib = ns_param(start=starts["ncib"], scale=0.1, range=(0.1, 2.5))
+                self.cal150 = ns_param(start=1.0, scale=0.01, gaussian_prior=(1, 0.02))
+                self.cal220 = ns_param(start=1.0, scale=0.02, gaussian_prior=(1, 0.05))
+                self.Acmb = ns_param(start=1.0, scale=0.01)
+                self.egfs = egfs_cls()
+                self.like = like_cls(prob["use"], prob["windows"], prob["signal"], prob["cov"])
+                self.sampler = None
+
+            def __call__(self):
+                self.like.cal = {"T150": self.cal150, "T220": self.cal220}
+                cmb = {"cl_TT": self.Acmb * prob["cmb"]["cl_TT"]}
+                return self.like(cmb, self.egfs(Aps=self.Aps, Acib=self.Acib, ncib=self.ncib))
+        return script
+
+    o = build(ort.Param, ort.Plugin, olikes.MspecLike, olikes.ClustPoissonEgfs)
+    b = build(param, SlikPlugin, likelihoods.mspec_lnl, models.clust_poisson_egfs)
+    return o, b
+
+
+@pytest.mark.parametrize("banded", [False, True])
+def test_mspec_with_power_law_foregrounds(banded):
+    prob = make_mspec_problem(None, banded=banded)
+    o_cls, b_cls = mspec_scripts(prob)
+    oslik = ort.Slik(o_cls())
+    slik, cp = compiled(b_cls)
+    assert list(oslik.get_sampled()) == cp.names == ["Acib", "Acmb", "Aps", "cal150", "cal220", "ncib"]
+    rs = np.random.RandomState(4)
+    x0 = np.array([oslik.get_start()[k] for k in cp.names])
+    for i in range(10):
+        x = x0 * (1 + 0.05 * rs.standard_normal(len(x0)))
+        if i == 3: x[cp.names.index("Aps")] = -1.0
+        if i == 4: x[cp.names.index("ncib")] = 2.6
+        ref = oslik.evaluate(*x)[0]
+        got = TI.lnl(cp, x)
+        if np.isinf(ref):
+            assert np.isinf(got)
+        else:
+            assert abs(got - ref) <= 1e-11 * abs(ref)
+    if banded:
+        assert cp.flops["bin_exec"] < 0.7 * 2 * 64 * 656 * 6   # zero blocks are skipped
+    assert cp.meta["nspec"] == 6 and cp.meta["n"] == 120 and cp.meta["n_pad"] == 128
+
+
+def test_find_sampled_order_and_errors():
+    t = SlikDict(b=param(start=1, scale=1), a=SlikDict(z=param(start=2, scale=1), y=3), c=4)
+    assert list(t.find_sampled()) == ["a.z", "b"]
+    t["a.z"] = 5
+    assert t.a.z == 5 and t["a.z"] == 5 and "a.q" not in t and "a.y" in t
+    c = t.deepcopy()
+    c["a.y"] = 9
+    assert t.a.y == 3 and c.a.y == 9
+    with pytest.raises(ValueError):
+        t[3] = 1
+    slik = Slik(B.quick_script(sampler=lambda s: None)())
+    with pytest.raises(ValueError, match="Expected 2 parameters"):
+        slik._bind((1,), {})
+    with pytest.raises(ValueError, match="Missing"):
+        slik._bind((), {"a": 1})
+    with pytest.raises(ValueError, match="either"):
+        slik._bind((1, 2), {"a": 1})
+
+
+def test_untraceable_script_fails_loudly():
+    class bad(SlikPlugin):
+        def __init__(self):
+            super().__init__()
+            self.a = param(start=0, scale=1)
+            self.sampler = None
+
+        def __call__(self):
+            return np.exp(self.a)   # numpy ufunc on a symbolic parameter
+
+    with pytest.raises(TypeError, match="cannot be batched"):
+        Slik(bad()).trace()
