@@ -151,7 +151,7 @@ class emcee(SlikSampler):
                                            nrows.data_ptr(), cap, st), "csl_emcee_rows")
                 if (emit or writer is not None) and ((i + 1) % F == 0 or i == nsteps - 1):
                     n_now = nrows.cpu().numpy().astype(np.int64)
-                    a_, b_ = int(prev_n.min(initial=0)), int(n_now.max(initial=0))
+                    a_, b_ = (int(prev_n.min()), int(n_now.max())) if W else (0, 0)
                     slab = rows[:, a_:b_].cpu().numpy() if b_ > a_ else np.zeros((W, 0, rl))
                     blocks = [(int(gid[c]), slab[c, prev_n[c] - a_:n_now[c] - a_]) for c in range(W)]
                     prev_n = n_now

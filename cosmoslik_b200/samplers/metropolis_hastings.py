@@ -152,7 +152,9 @@ class metropolis_hastings(SlikSampler):
                                 "csl_mh_accept")
                 done += nb
                 # ---- pooled proposal update (metropolis_hastings.py:200-201, 249-253)
-                if self.proposal_update and done % S == 0 and done > self.proposal_update_start and done < steps:
+                # (ignored for a single chain, as the reference ignores it without MPI: docstring :69-72)
+                if (self.proposal_update and ntot > 1 and done % S == 0 and done > self.proposal_update_start
+                        and done < steps):
                     L.check(lib.csl_mh_moments(W, nd, rows.data_ptr(), nrows.data_ptr(), cap, None,
                                                mom_part.data_ptr(), mom.data_ptr(), st), "csl_mh_moments")
                     dist.all_reduce_sum(mom[:1 + nd])
@@ -169,7 +171,7 @@ class metropolis_hastings(SlikSampler):
                     n_now = nrows.cpu().numpy().astype(np.int64)
                     if n_now.max(initial=0) > cap:
                         raise RuntimeError("row buffer overflow")
-                    a, b = int(prev_n.min(initial=0)), int(n_now.max(initial=0))
+                    a, b = (int(prev_n.min()), int(n_now.max())) if W else (0, 0)
                     slab = rows[:, a:b].cpu().numpy() if b > a else np.zeros((W, 0, rl))
                     blocks = [(lo + c, slab[c, prev_n[c] - a:n_now[c] - a]) for c in range(W)]
                     prev_n = n_now

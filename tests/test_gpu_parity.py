@@ -174,8 +174,11 @@ def test_mh_exact_with_injected_offsets(torch):
     slik = Slik(B.quick_script(lambda s: samplers.metropolis_hastings(
         s, num_samples=n, streams=dict(delta=delta, u=g["u"][:, None])))())
     rows = [(s.lnl, s.weight, s.x) for s in slik.sample()]
-    x = check_rows(rows, g, lnl_exact=True)
+    x = check_rows(rows, g)
     np.testing.assert_array_equal(x, g["x"])
+    # lnl: the reference squares numpy scalars through libm pow(x, 2.0), which is not always the
+    # correctly rounded x*x the device computes -> agreement to 1 ulp, not bit for bit
+    np.testing.assert_allclose([r[0] for r in rows], g["lnl"], rtol=4e-16, atol=0)
 
 
 @pytest.mark.parametrize("fused", [True, False])
