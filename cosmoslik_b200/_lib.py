@@ -15,7 +15,8 @@ MAX_DIM, MAX_TERMS, MAX_PLAW = 64, 8, 4
 SPEC_STRIDE, TILE_STRIDE, STACK = 64, 32, 16
 OP = dict(PUSHP=0, PUSHC=1, ADD=2, SUB=3, MUL=4, DIV=5, NEG=6, EXP=7, LOG=8, POW=9, SQRT=10, STORE=11, SQR=12)
 S_NLPAD, S_NTERM, S_NPLAW, S_CAL = 0, 1, 2, 3
-S_TERM_COEF, S_TERM_OFF, S_PLAW_AMP, S_PLAW_IDX, S_PLAW_LOGB, S_PLAW_MUL = 8, 16, 24, 28, 32, 36
+S_LTAB, S_TERM_COEF, S_PLAW_AMP, S_PLAW_IDX = 4, 8, 24, 28
+MAX_CLASS = 8
 T_ROW0, T_NROWS, T_SPEC, T_LBEGIN, T_LEND, T_WINOFF_LO, T_WINOFF_HI, T_WINLD, T_GLO, T_GHI = 0, 1, 2, 3, 4, 5, 6, 7, 8, 16
 
 _i32p, _f64p, _vp = C.c_void_p, C.c_void_p, C.c_void_p
@@ -25,7 +26,8 @@ class Program(C.Structure):
     """csl_program_t"""
     _fields_ = ([(n, C.c_int32) for n in
                  ("ndim", "ncoef", "ncode", "nbox", "ngauss", "nscalar", "nspec", "ntile",
-                  "n", "n_pad", "resid_mode", "reserved0")] +
+                  "n", "n_pad", "resid_mode", "nclass")] +
+                [("cls", (C.c_int32 * 4) * 8)] +
                 [(n, C.c_void_p) for n in
                  ("code_op", "code_arg", "code_val", "box_idx", "box_lo", "box_hi",
                   "gauss_idx", "gauss_c", "gauss_w", "scalar_coef", "spec_tab", "tile_tab",

@@ -4,16 +4,25 @@
 //              mspec_lnl.py:50-73 (the same per cross-spectrum).
 // C[bins, walkers] = Wnd[bins, ell] * Cl[ell, walkers] runs on the FP64 tensor pipe (DMMA.8x8x4).
 // The Cl operand never exists in HBM: each CTA builds its [16 ell x 128 walker] chunk in shared
-// memory from the walker's coefficients (registers) and the templates (L1-broadcast loads).
+// memory from the walker's coefficients (registers) and the spectrum's ell-table, whose 16 rows for
+// the chunk are staged in shared memory by cp.async together with the window tile.
+//
+// ell-table row (doubles): [T_0 .. T_{NT-1}, (logB_q, M_q) for q < NP]
+//   cl[l] = sum_t coef_t T_t[l] + sum_q amp_q M_q[l] exp(idx_q logB_q[l])
+// The kernel is instantiated per padded class <NT, NP> so the build loop is branch-free and fully
+// unrolled; the host sorts the tiles by class (csl_program_t::cls).
 #include "common.cuh"
 
+template <int NT, int NP>
 __global__ void __launch_bounds__(CSL_THREADS, 2)
-k_bin_residual(csl_program_t p, int W, const double* __restrict__ coef, int ldc, double* __restrict__ R,
-               int ldr) {
+k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coef, int ldc,
+               double* __restrict__ R, int ldr) {
+  constexpr int LSTRIDE = NT + 2 * NP;
   extern __shared__ __align__(16) double smem[];
   double* As = smem;                       // [2][CSL_ASZ]
   double* Bs = smem + 2 * CSL_ASZ;         // [2][CSL_BSZ]
-  const int32_t* tile = p.tile_tab + (long long)blockIdx.x * CSL_TILE_STRIDE;
+  double* Ls = Bs + 2 * CSL_BSZ;           // [2][CSL_KC * LSTRIDE]
+  const int32_t* tile = p.tile_tab + (long long)(tile0 + blockIdx.x) * CSL_TILE_STRIDE;
   const int32_t* spec = p.spec_tab + (long long)tile[CSL_T_SPEC] * CSL_SPEC_STRIDE;
   const int c0 = blockIdx.y * CSL_BN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -22,39 +31,35 @@ k_bin_residual(csl_program_t p, int W, const double* __restrict__ coef, int ldc,
   const int l_begin = tile[CSL_T_LBEGIN], l_end = tile[CSL_T_LEND];
   const long long win_off = ((long long)tile[CSL_T_WINOFF_HI] << 32) | (unsigned)tile[CSL_T_WINOFF_LO];
   const long long win_ld = tile[CSL_T_WINLD];
-  const double* Wnd = p.windows + win_off;
+  const double* __restrict__ Wnd = p.windows + win_off;
+  const double* __restrict__ ltab = p.templates + spec[CSL_S_LTAB];
 
   // builder role: this thread owns walker c0 + wl and 8 of the 16 ell rows of a chunk
   const int wl = tid & (CSL_BN - 1), grp = tid >> 7;
-  const int nterm = spec[CSL_S_NTERM], nplaw = spec[CSL_S_NPLAW];
-  double cf[CSL_MAX_TERMS];
-  int toff[CSL_MAX_TERMS];
+  double cf[NT > 0 ? NT : 1], pamp[NP > 0 ? NP : 1], pidx[NP > 0 ? NP : 1];
 #pragma unroll
-  for (int t = 0; t < CSL_MAX_TERMS; ++t) {
-    cf[t] = (t < nterm) ? coef[(long long)spec[CSL_S_TERM_COEF + t] * ldc + c0 + wl] : 0.0;
-    toff[t] = (t < nterm) ? spec[CSL_S_TERM_OFF + t] : 0;
-  }
-  double pamp[CSL_MAX_PLAW], pidx[CSL_MAX_PLAW];
+  for (int t = 0; t < NT; ++t) cf[t] = coef[(long long)spec[CSL_S_TERM_COEF + t] * ldc + c0 + wl];
 #pragma unroll
-  for (int q = 0; q < CSL_MAX_PLAW; ++q) {
-    pamp[q] = (q < nplaw) ? coef[(long long)spec[CSL_S_PLAW_AMP + q] * ldc + c0 + wl] : 0.0;
-    pidx[q] = (q < nplaw) ? coef[(long long)spec[CSL_S_PLAW_IDX + q] * ldc + c0 + wl] : 0.0;
+  for (int q = 0; q < NP; ++q) {
+    pamp[q] = coef[(long long)spec[CSL_S_PLAW_AMP + q] * ldc + c0 + wl];
+    pidx[q] = coef[(long long)spec[CSL_S_PLAW_IDX + q] * ldc + c0 + wl];
   }
 
-  auto build_B = [&](double* B, int l0) {
+  // stage the 16 ell-table rows of a chunk (contiguous 16*LSTRIDE doubles) with 16-byte cp.async
+  auto load_L = [&](double* L, int l0) {
+    constexpr int NCH = CSL_KC * LSTRIDE / 2;
+    for (int c = tid; c < NCH; c += CSL_THREADS) cp_async16(L + 2 * c, ltab + (long long)l0 * LSTRIDE + 2 * c);
+  };
+  auto build_B = [&](double* B, const double* L) {
 #pragma unroll
     for (int r = 0; r < CSL_KC / 2; ++r) {
       const int kk = grp * (CSL_KC / 2) + r;
-      const int l = l0 + kk;
+      const double* row = L + kk * LSTRIDE;     // warp-uniform address -> shared-memory broadcast
       double v = 0.0;
 #pragma unroll
-      for (int t = 0; t < CSL_MAX_TERMS; ++t)
-        if (t < nterm) v = fma(cf[t], __ldg(p.templates + toff[t] + l), v);
-      for (int q = 0; q < nplaw; ++q) {
-        double lb = __ldg(p.templates + spec[CSL_S_PLAW_LOGB + q] + l);
-        double mu = __ldg(p.templates + spec[CSL_S_PLAW_MUL + q] + l);
-        v = fma(pamp[q] * mu, exp(pidx[q] * lb), v);
-      }
+      for (int t = 0; t < NT; ++t) v = fma(cf[t], row[t], v);
+#pragma unroll
+      for (int q = 0; q < NP; ++q) v = fma(pamp[q] * row[NT + 2 * q + 1], exp(pidx[q] * row[NT + 2 * q]), v);
       B[kk * CSL_LDB + wl] = v;
     }
   };
@@ -75,19 +80,26 @@ k_bin_residual(csl_program_t p, int W, const double* __restrict__ coef, int ldc,
 
   const int nchunk = (l_end - l_begin) / CSL_KC;
   if (nchunk > 0) {
+    // prologue: table rows of chunks 0 and 1, window tile of chunk 0; build B(0)
+    load_L(Ls, l_begin);
     load_A_tile_async(As, Wnd + l_begin, win_ld, tid);
     cp_async_commit();
-    build_B(Bs, l_begin);
+    if (nchunk > 1) load_L(Ls + CSL_KC * LSTRIDE, l_begin + CSL_KC);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    build_B(Bs, Ls);
     cp_async_wait<0>();
     __syncthreads();
     for (int c = 0; c < nchunk; ++c) {
       const int cur = c & 1;
       const int l0 = l_begin + c * CSL_KC;
-      if (c + 1 < nchunk) {
-        load_A_tile_async(As + (cur ^ 1) * CSL_ASZ, Wnd + l0 + CSL_KC, win_ld, tid);
-        cp_async_commit();
-        build_B(Bs + (cur ^ 1) * CSL_BSZ, l0 + CSL_KC);
-      }
+      // in flight during this iteration: window tile of chunk c+1, table rows of chunk c+2
+      // (Ls[cur] held chunk c's rows, consumed one iteration ago)
+      if (c + 1 < nchunk) load_A_tile_async(As + (cur ^ 1) * CSL_ASZ, Wnd + l0 + CSL_KC, win_ld, tid);
+      if (c + 2 < nchunk) load_L(Ls + cur * CSL_KC * LSTRIDE, l0 + 2 * CSL_KC);
+      cp_async_commit();
+      if (c + 1 < nchunk) build_B(Bs + (cur ^ 1) * CSL_BSZ, Ls + (cur ^ 1) * CSL_KC * LSTRIDE);
       unsigned mmask = 0;
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
@@ -131,25 +143,58 @@ __global__ void k_zero_pad_rows(double* __restrict__ R, int ldr, int n, int n_pa
   if (i < tot) R[(long long)n * ldr + i] = 0.0;
 }
 
-extern "C" int csl_bin_residual(const csl_program_t* p, int W, const double* coef, int ldc, double* R, int ldr,
-                                void* stream) {
-  CSL_REQUIRE(p && coef && R, "csl_bin_residual: null argument");
-  CSL_REQUIRE(p->resid_mode == 1 && p->ntile > 0, "csl_bin_residual: program has no binned spectra");
-  CSL_REQUIRE(W > 0 && W % CSL_BN == 0 && ldr >= W && ldc >= W && (ldr % 2) == 0,
-              "csl_bin_residual: W must be a positive multiple of 128 and ldr, ldc >= W");
+template <int NT, int NP>
+static int launch_class(const csl_program_t* p, int tile0, int ntile, int W, const double* coef, int ldc,
+                        double* R, int ldr, cudaStream_t s) {
   static bool attr_set = false;
-  const size_t smem = (size_t)(2 * CSL_ASZ + 2 * CSL_BSZ) * sizeof(double);
+  const size_t smem = (size_t)(2 * CSL_ASZ + 2 * CSL_BSZ + 2 * CSL_KC * (NT + 2 * NP)) * sizeof(double);
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_bin_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_bin_residual<NT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
     attr_set = true;
   }
+  dim3 grid(ntile, W / CSL_BN);
+  k_bin_residual<NT, NP><<<grid, CSL_THREADS, smem, s>>>(*p, tile0, W, coef, ldc, R, ldr);
+  return 0;
+}
+
+#define CSL_DISPATCH_NP(NTV)                                                                          \
+  switch (np) {                                                                                        \
+    case 0: return launch_class<NTV, 0>(p, tile0, ntile, W, coef, ldc, R, ldr, s);                     \
+    case 1: return launch_class<NTV, 1>(p, tile0, ntile, W, coef, ldc, R, ldr, s);                     \
+    case 2: return launch_class<NTV, 2>(p, tile0, ntile, W, coef, ldc, R, ldr, s);                     \
+    case 4: return launch_class<NTV, 4>(p, tile0, ntile, W, coef, ldc, R, ldr, s);                     \
+    default: return csl_fail(CSL_E_BADARG, "csl_bin_residual: power-law class must be 0, 1, 2 or 4");  \
+  }
+
+static int dispatch_class(int nt, int np, const csl_program_t* p, int tile0, int ntile, int W, const double* coef,
+                          int ldc, double* R, int ldr, cudaStream_t s) {
+  switch (nt) {
+    case 0: CSL_DISPATCH_NP(0)
+    case 2: CSL_DISPATCH_NP(2)
+    case 4: CSL_DISPATCH_NP(4)
+    case 8: CSL_DISPATCH_NP(8)
+    default: return csl_fail(CSL_E_BADARG, "csl_bin_residual: template class must be 0, 2, 4 or 8");
+  }
+}
+
+extern "C" int csl_bin_residual(const csl_program_t* p, int W, const double* coef, int ldc, double* R, int ldr,
+                                void* stream) {
+  CSL_REQUIRE(p && coef && R, "csl_bin_residual: null argument");
+  CSL_REQUIRE(p->resid_mode == 1 && p->ntile > 0 && p->nclass > 0 && p->nclass <= CSL_MAX_CLASS,
+              "csl_bin_residual: program has no binned spectra");
+  CSL_REQUIRE(W > 0 && W % CSL_BN == 0 && ldr >= W && ldc >= W && (ldr % 2) == 0,
+              "csl_bin_residual: W must be a positive multiple of 128 and ldr, ldc >= W");
   cudaStream_t s = (cudaStream_t)stream;
   if (p->n_pad > p->n) {
     long long tot = (long long)(p->n_pad - p->n) * ldr;
     k_zero_pad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(R, ldr, p->n, p->n_pad);
   }
-  dim3 grid(p->ntile, W / CSL_BN);
-  k_bin_residual<<<grid, CSL_THREADS, smem, s>>>(*p, W, coef, ldc, R, ldr);
+  for (int c = 0; c < p->nclass; ++c) {
+    const int32_t* k = p->cls[c];
+    CSL_REQUIRE(k[0] + 2 * k[1] > 0, "csl_bin_residual: empty spectrum class");
+    int rc = dispatch_class(k[0], k[1], p, k[2], k[3], W, coef, ldc, R, ldr, s);
+    if (rc) return rc;
+  }
   return csl_check_launch("k_bin_residual");
 }

@@ -84,7 +84,8 @@ class CompiledProgram(object):
             raise ValueError("number of sampled parameters must be in 1..%d" % L.MAX_DIM)
         self.tables = {}
         self.meta = dict(ndim=self.ndim, ncoef=0, ncode=0, nbox=0, ngauss=0, nscalar=0, nspec=0, ntile=0,
-                         n=0, n_pad=0, resid_mode=0)
+                         n=0, n_pad=0, resid_mode=0, nclass=0)
+        self.cls = np.zeros((L.MAX_CLASS, 4), np.int32)
         self.host = {}
         self.flops = {}
         self._build(priors, lnl_expr)
@@ -179,10 +180,15 @@ class CompiledProgram(object):
         nspec = len(q.blocks)
         spec_tab = np.zeros((nspec, L.SPEC_STRIDE), np.int32)
         tiles, templ, wins, data = [], [], [], []
-        toff = 0      # running offset into the template buffer (doubles)
+        toff = 0      # running offset into the ell-table buffer (doubles, kept even)
         woff = 0      # running offset into the window buffer
         row0 = 0
-        flops_dense = flops_exec = 0
+        flops_dense = flops_exec = flops_nnz = builds = 0
+        zero_row = None
+
+        def pad_class(k, sizes):
+            return next(s_ for s_ in sizes if s_ >= k)
+
         for s, blk in enumerate(q.blocks):
             nb, nl = blk.windows.shape
             if blk.data.shape != (nb,):
@@ -197,21 +203,32 @@ class CompiledProgram(object):
             terms += [(c, t[:nl]) for c, t in m.terms]
             if len(terms) > L.MAX_TERMS or len(m.plaws) > L.MAX_PLAW:
                 raise ValueError("spectrum %d: at most %d template and %d power-law terms" % (s, L.MAX_TERMS, L.MAX_PLAW))
+            NT, NP = pad_class(len(terms), (0, 2, 4, 8)), pad_class(len(m.plaws), (0, 1, 2, 4))
+            if NT + NP == 0:
+                NT = 2
+            if (len(terms) < NT or len(m.plaws) < NP) and zero_row is None:
+                zero_row = code.coef(Const(0.0))     # padding terms multiply an all-zero coefficient
+            stride = NT + 2 * NP
             rec = spec_tab[s]
-            rec[L.S_NLPAD], rec[L.S_NTERM], rec[L.S_NPLAW] = nlp, len(terms), len(m.plaws)
-            for t, (c, arr) in enumerate(terms):
-                buf = np.zeros(nlp); buf[:nl] = arr
-                rec[L.S_TERM_COEF + t] = code.coef(c); rec[L.S_TERM_OFF + t] = toff
-                templ.append(buf); toff += nlp
-            for k, (amp, idx_e, base, mul) in enumerate(m.plaws):
-                lb = np.zeros(nlp); mu = np.zeros(nlp)
-                with np.errstate(divide="ignore"):
-                    lg = np.log(base[:nl])
-                lb[:nl] = np.where(np.isneginf(lg), -1e300, lg)   # 0**n: 0 for n>0, 1 for n==0, inf for n<0
-                mu[:nl] = mul[:nl]
-                rec[L.S_PLAW_AMP + k] = code.coef(amp); rec[L.S_PLAW_IDX + k] = code.coef(idx_e)
-                rec[L.S_PLAW_LOGB + k] = toff; templ.append(lb); toff += nlp
-                rec[L.S_PLAW_MUL + k] = toff; templ.append(mu); toff += nlp
+            rec[L.S_NLPAD], rec[L.S_NTERM], rec[L.S_NPLAW], rec[L.S_LTAB] = nlp, NT, NP, toff
+            ltab = np.zeros((nlp, stride))
+            for t in range(NT):
+                if t < len(terms):
+                    rec[L.S_TERM_COEF + t] = code.coef(terms[t][0]); ltab[:nl, t] = terms[t][1]
+                else:
+                    rec[L.S_TERM_COEF + t] = zero_row
+            for k in range(NP):
+                if k < len(m.plaws):
+                    amp, idx_e, base, mul = m.plaws[k]
+                    with np.errstate(divide="ignore"):
+                        lg = np.log(base[:nl])
+                    # base 0: exp(idx * -1e300) gives 0**idx = 0 (idx>0), 1 (idx==0), inf (idx<0) like numpy
+                    ltab[:nl, NT + 2 * k] = np.where(np.isneginf(lg), -1e300, lg)
+                    ltab[:nl, NT + 2 * k + 1] = mul[:nl]
+                    rec[L.S_PLAW_AMP + k] = code.coef(amp); rec[L.S_PLAW_IDX + k] = code.coef(idx_e)
+                else:
+                    rec[L.S_PLAW_AMP + k] = rec[L.S_PLAW_IDX + k] = zero_row
+            templ.append(ltab.ravel()); toff += ltab.size
             cal = blk.cal
             if isinstance(cal, Expr) and not (isinstance(cal, Const) and cal.v == 1.0):
                 rec[L.S_CAL] = code.coef(cal)
@@ -238,8 +255,10 @@ class CompiledProgram(object):
                     rec_t[L.T_GLO + g8], rec_t[L.T_GHI + g8] = glo, ghi
                     nch = len([c for c in range(lo, hi, L.KC) if c + L.KC > glo and c < ghi])
                     flops_exec += 2 * 8 * L.KC * nch
-                tiles.append(rec_t)
+                builds += (hi - lo) * (len(terms) + 20 * len(m.plaws))
+                tiles.append(((NT, NP), rec_t))
             flops_dense += 2 * nb * nl
+            flops_nnz += 2 * int(np.count_nonzero(blk.windows))
             wins.append(wp.ravel()); woff += wp.size
             data.append(blk.data)
             row0 += nb
@@ -248,18 +267,28 @@ class CompiledProgram(object):
             raise ValueError("bandpower likelihood: covariance is %s, data vector has %d rows" % (q.cov.shape, n))
         self._factor(P, q.cov)
         d = np.zeros(self.n_pad); d[:n] = np.concatenate(data)
+        # tiles sorted by kernel class (stable): one launch of k_bin_residual<NT, NP> per class
+        classes = sorted(set(k for k, _ in tiles))
+        if len(classes) > L.MAX_CLASS:
+            raise ValueError("too many distinct spectrum classes")
+        ordered, cls = [], np.zeros((L.MAX_CLASS, 4), np.int32)
+        for ci, k in enumerate(classes):
+            mine = [r for kk, r in tiles if kk == k]
+            cls[ci] = (k[0], k[1], len(ordered), len(mine))
+            ordered += mine
         P['resid_mode'] = 1
-        P['nspec'], P['ntile'] = nspec, len(tiles)
+        P['nspec'], P['ntile'], P['nclass'] = nspec, len(ordered), len(classes)
+        self.cls = cls
         self._dev('spec_tab', spec_tab, np.int32)
-        self._dev('tile_tab', np.array(tiles), np.int32)
-        self._dev('templates', np.concatenate(templ) if templ else np.zeros(1), np.float64)
+        self._dev('tile_tab', np.array(ordered), np.int32)
+        self._dev('templates', np.concatenate(templ), np.float64)
         self._dev('windows', np.concatenate(wins), np.float64)
         self._dev('data', d, np.float64)
-        self.host["spec_tab"], self.host["tile_tab"] = spec_tab, np.array(tiles)
-        # algorithmic work per evaluation: dense windows, executed DMMA blocks, TRSM
-        self.flops = dict(bin_dense=flops_dense, bin_exec=flops_exec, trsm=self.n_pad * self.n_pad + self.n_pad * L.BM,
-                          trsm_alg=n * n)
-
+        self.host["spec_tab"], self.host["tile_tab"] = spec_tab, np.array(ordered)
+        # work per evaluation: dense windows, non-zero window entries, DMMA blocks that
+        # are actually executed, foreground-build FP64 ops (~1 per template term, ~20 per power law), TRSM
+        self.flops = dict(bin_dense=flops_dense, bin_nnz=flops_nnz, bin_exec=flops_exec, build_ops=2 * builds,
+                          trsm=self.n_pad * self.n_pad + self.n_pad * L.BM, trsm_alg=n * n)
 
 
 class DeviceProgram(CompiledProgram):
@@ -278,6 +307,9 @@ class DeviceProgram(CompiledProgram):
             setattr(P, k, int(v))
         for k in self._PTR_FIELDS:
             setattr(P, k, self.dev[k].data_ptr() if k in self.dev else None)
+        for ci in range(L.MAX_CLASS):
+            for j in range(4):
+                P.cls[ci][j] = int(self.cls[ci, j])
         self.struct = P
         if self.gauss_direct is not None:
             self.gauss_direct = {k: torch.from_numpy(v).to(self.device) for k, v in self.gauss_direct.items()}

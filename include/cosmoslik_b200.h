@@ -44,6 +44,7 @@ extern "C" {
 #define CSL_SPEC_STRIDE 64 /* int32 words per spectrum record              */
 #define CSL_TILE_STRIDE 32 /* int32 words per tile record                  */
 #define CSL_STACK     16   /* coefficient bytecode stack depth             */
+#define CSL_MAX_CLASS  8   /* distinct (NT, NP) spectrum classes per program */
 
 /* coefficient bytecode (one flat program; STORE pops into coef row `arg`) */
 enum {
@@ -55,11 +56,15 @@ enum {
 /* spectrum record, int32 words (table spec_tab[nspec][CSL_SPEC_STRIDE]) */
 enum {
   CSL_S_NLPAD = 0,   /* padded number of ell columns (multiple of CSL_KC)       */
-  CSL_S_NTERM = 1,   /* template terms: cl += coef[TERM_COEF[t]] * T[TERM_OFF[t] + l] */
-  CSL_S_NPLAW = 2,   /* power-law terms: cl += coef[amp] * M[l] * exp(coef[idx] * logB[l]) */
+  CSL_S_NTERM = 1,   /* NT: template terms, padded to the class size {0,1,2,4,8}   */
+  CSL_S_NPLAW = 2,   /* NP: power-law terms, padded to the class size {0,1,2,4}    */
   CSL_S_CAL   = 3,   /* coef row multiplying the data of this spectrum, -1 = 1.0 */
-  CSL_S_TERM_COEF = 8,  CSL_S_TERM_OFF = 16,
-  CSL_S_PLAW_AMP = 24, CSL_S_PLAW_IDX = 28, CSL_S_PLAW_LOGB = 32, CSL_S_PLAW_MUL = 36
+  CSL_S_LTAB  = 4,   /* offset (doubles) of the ell-table in `templates`: nl_pad rows of
+                        [T_0..T_{NT-1}, (logB_q, M_q) q<NP];
+                        cl[l] = sum_t coef[TERM_COEF[t]] T_t[l]
+                              + sum_q coef[PLAW_AMP[q]] M_q[l] exp(coef[PLAW_IDX[q]] logB_q[l])
+                        (padding terms point at an all-zero coefficient row / zero columns)  */
+  CSL_S_TERM_COEF = 8, CSL_S_PLAW_AMP = 24, CSL_S_PLAW_IDX = 28
 };
 
 /* tile record, int32 words (table tile_tab[ntile][CSL_TILE_STRIDE]) */
@@ -92,7 +97,8 @@ enum {
  */
 typedef struct csl_program {
   int32_t ndim, ncoef, ncode, nbox, ngauss, nscalar, nspec, ntile;
-  int32_t n, n_pad, resid_mode, reserved0;
+  int32_t n, n_pad, resid_mode, nclass;
+  int32_t cls[CSL_MAX_CLASS][4];   /* per class: NT, NP, first tile, number of tiles (tiles sorted by class) */
   const int32_t* code_op;   const int32_t* code_arg;  const double* code_val;
   const int32_t* box_idx;   const double* box_lo;     const double* box_hi;
   const int32_t* gauss_idx; const double* gauss_c;    const double* gauss_w;

@@ -56,15 +56,15 @@ def residual(cp, coef):
     for tile in t["tile_tab"][:m["ntile"]]:
         spec = t["spec_tab"][tile[L.T_SPEC]]
         l0, l1 = tile[L.T_LBEGIN], tile[L.T_LEND]
+        NT, NP = spec[L.S_NTERM], spec[L.S_NPLAW]
+        stride = NT + 2 * NP
+        ltab = t["templates"][spec[L.S_LTAB]: spec[L.S_LTAB] + spec[L.S_NLPAD] * stride].reshape(-1, stride)[l0:l1]
         cl = np.zeros(l1 - l0)
-        for k in range(spec[L.S_NTERM]):
-            off = spec[L.S_TERM_OFF + k]
-            cl += coef[spec[L.S_TERM_COEF + k]] * t["templates"][off + l0: off + l1]
-        for k in range(spec[L.S_NPLAW]):
-            lb = t["templates"][spec[L.S_PLAW_LOGB + k] + l0: spec[L.S_PLAW_LOGB + k] + l1]
-            mu = t["templates"][spec[L.S_PLAW_MUL + k] + l0: spec[L.S_PLAW_MUL + k] + l1]
+        for k in range(NT):
+            cl += coef[spec[L.S_TERM_COEF + k]] * ltab[:, k]
+        for k in range(NP):
             with np.errstate(over="ignore"):
-                cl += coef[spec[L.S_PLAW_AMP + k]] * mu * np.exp(coef[spec[L.S_PLAW_IDX + k]] * lb)
+                cl += coef[spec[L.S_PLAW_AMP + k]] * ltab[:, NT + 2 * k + 1] * np.exp(coef[spec[L.S_PLAW_IDX + k]] * ltab[:, NT + 2 * k])
         woff = (int(tile[L.T_WINOFF_HI]) << 32) | (int(tile[L.T_WINOFF_LO]) & 0xFFFFFFFF)
         ld = tile[L.T_WINLD]
         cal = 1.0 if spec[L.S_CAL] < 0 else coef[spec[L.S_CAL]]

@@ -33,8 +33,8 @@ def test_constants_match_header():
     enums = dict((k, int(v)) for k, v in re.findall(r"CSL_(\w+)\s*=\s*(\d+)", h))
     for k, v in _lib.OP.items():
         assert enums["OP_" + k] == v
-    for k in ("S_NLPAD", "S_NTERM", "S_NPLAW", "S_CAL", "S_TERM_COEF", "S_TERM_OFF", "S_PLAW_AMP", "S_PLAW_IDX",
-              "S_PLAW_LOGB", "S_PLAW_MUL", "T_ROW0", "T_NROWS", "T_SPEC", "T_LBEGIN", "T_LEND", "T_WINOFF_LO",
+    for k in ("S_NLPAD", "S_NTERM", "S_NPLAW", "S_CAL", "S_LTAB", "S_TERM_COEF", "S_PLAW_AMP", "S_PLAW_IDX",
+              "T_ROW0", "T_NROWS", "T_SPEC", "T_LBEGIN", "T_LEND", "T_WINOFF_LO",
               "T_WINOFF_HI", "T_WINLD", "T_GLO", "T_GHI"):
         assert enums[k] == getattr(_lib, k), k
 
