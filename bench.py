@@ -253,7 +253,7 @@ def run_b200(args):
     # SURVEY.md 8d); binning = 2*nnz(windows) + foreground build (2 flops per template FMA, a power law
     # counted as 20 FMAs) per walker.  "executed" adds padding / zero blocks actually issued.
     per_kernel = {}
-    for name, kern, alg, exe in (("chi2", "k_trsm_chi2", fl["trsm_alg"], fl["trsm"]),
+    for name, kern, alg, exe in (("chi2", "k_trigemm_chi2" if prog.meta.get("chi2_mode") else "k_trsm_chi2", fl["trsm_alg"], fl["trsm"]),
                                  ("bin_residual", "k_bin_residual", fl["bin_nnz"] + fl["build_ops"],
                                   fl["bin_exec"] + fl["build_ops"])):
         if name in stage_ms:

@@ -31,7 +31,8 @@ class Program(C.Structure):
                 [(n, C.c_void_p) for n in
                  ("code_op", "code_arg", "code_val", "box_idx", "box_lo", "box_hi",
                   "gauss_idx", "gauss_c", "gauss_w", "scalar_coef", "spec_tab", "tile_tab",
-                  "templates", "windows", "data", "direct_coef", "Lmat", "Linv_diag")])
+                  "templates", "windows", "data", "direct_coef", "Lmat", "Linv_diag", "Minv")] +
+                [("chi2_mode", C.c_int32), ("reserved1", C.c_int32)])
 
 
 _P = C.POINTER(Program)
@@ -46,10 +47,10 @@ SIGNATURES = {
     "csl_eval_prepare": (_int, [_P, _int, _vp, _vp, _int, _vp, _vp]),
     "csl_bin_residual": (_int, [_P, _int, _vp, _int, _vp, _int, _vp]),
     "csl_direct_residual": (_int, [_P, _int, _vp, _int, _vp, _int, _vp]),
-    "csl_chi2": (_int, [_P, _int, _vp, _int, _vp, _vp]),
+    "csl_chi2": (_int, [_P, _int, _vp, _int, _vp, _vp, _vp]),
     "csl_combine": (_int, [_P, _int, _vp, _int, _vp, _vp, _vp, _vp]),
-    "csl_lnl": (_int, [_P, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "csl_lnl_host": (_int, [_P, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "csl_lnl": (_int, [_P, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "csl_lnl_host": (_int, [_P, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "csl_mh_propose": (_int, [_int, _int, _vp, _vp, _int, _vp, _vp, _u64, _u32, _u32, _vp]),
     "csl_mh_accept": (_int, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _dbl, _dbl,
                              _vp, _vp, _int, _vp, _vp, _vp]),

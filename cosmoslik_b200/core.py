@@ -257,10 +257,13 @@ class Slik(object):
             raise TypeError("script __call__ returned %r; expected a likelihood term or parameter expression" % type(out))
         return out
 
-    def program(self):
-        if self._program is None:
+    def program(self, chi2_mode=None):
+        """The compiled device program (cached).  chi2_mode: 'auto' (default), 'trsm' or 'inverse' --
+        see program.CompiledProgram._factor."""
+        if self._program is None or (chi2_mode is not None and chi2_mode != self._program.chi2_mode):
             from .program import DeviceProgram
-            self._program = DeviceProgram(list(self._sampled), self.params.priors, self.trace())
+            self._program = DeviceProgram(list(self._sampled), self.params.priors, self.trace(),
+                                          chi2_mode=chi2_mode or "auto")
         return self._program
 
     # -- evaluation -----------------------------------------------------------

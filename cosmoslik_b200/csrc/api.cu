@@ -37,7 +37,7 @@ extern "C" int csl_device_info(int device, int32_t* out) {
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 extern "C" int csl_lnl(const csl_program_t* p, int W, const double* x, double* lnl, double* ws_coef,
-                       double* ws_prior, double* ws_R, double* ws_chi2, void* stream) {
+                       double* ws_prior, double* ws_R, double* ws_chi2, double* ws_part, void* stream) {
   CSL_REQUIRE(p && x && lnl && ws_prior && W > 0, "csl_lnl: null argument");
   const int Wp = round_up(W, CSL_BN);
   int rc = csl_eval_prepare(p, W, x, ws_coef, Wp, ws_prior, stream);
@@ -48,7 +48,7 @@ extern "C" int csl_lnl(const csl_program_t* p, int W, const double* x, double* l
     if (p->resid_mode == 1) rc = csl_bin_residual(p, Wp, ws_coef, Wp, ws_R, Wp, stream);
     else rc = csl_direct_residual(p, W, ws_coef, Wp, ws_R, Wp, stream);
     if (rc) return rc;
-    rc = csl_chi2(p, Wp, ws_R, Wp, ws_chi2, stream);
+    rc = csl_chi2(p, Wp, ws_R, Wp, ws_chi2, ws_part, stream);
     if (rc) return rc;
     chi2 = ws_chi2;
   }
@@ -57,12 +57,12 @@ extern "C" int csl_lnl(const csl_program_t* p, int W, const double* x, double* l
 
 extern "C" int csl_lnl_host(const csl_program_t* p, int W, const double* x_host, double* lnl_host, double* x_dev,
                             double* lnl_dev, double* ws_coef, double* ws_prior, double* ws_R, double* ws_chi2,
-                            void* stream) {
+                            double* ws_part, void* stream) {
   CSL_REQUIRE(p && x_host && lnl_host && x_dev && lnl_dev && W > 0, "csl_lnl_host: null argument");
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaMemcpyAsync(x_dev, x_host, (size_t)W * p->ndim * sizeof(double), cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-  int rc = csl_lnl(p, W, x_dev, lnl_dev, ws_coef, ws_prior, ws_R, ws_chi2, stream);
+  int rc = csl_lnl(p, W, x_dev, lnl_dev, ws_coef, ws_prior, ws_R, ws_chi2, ws_part, stream);
   if (rc) return rc;
   e = cudaMemcpyAsync(lnl_host, lnl_dev, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s);
   if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));

@@ -90,10 +90,84 @@ k_trsm_chi2(csl_program_t p, double* R, int ldr, double* __restrict__ chi2) {
   if (tid < CSL_BN) chi2[c0 + tid] = red[tid] + red[CSL_BN + tid];
 }
 
-extern "C" int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, double* chi2, void* stream) {
+// ---- explicit-inverse mode ---------------------------------------------------------------------------
+// Y = M R with M = L^-1 (lower triangular, inverted once on the host in extended precision and verified
+// against the substitution result before it is used).  Every 64-row block of Y is an independent tile
+// product over K = 64 (i+1) columns, so the grid is (column tiles x row blocks) with no sequential
+// dependency, two CTAs per SM, and the same flop count as the blocked solve (n^2 + 64 n).  Each CTA
+// writes the column sums of squares of its row block to part[i, :]; k_sum_partials adds the row blocks
+// in a fixed order.
+__global__ void __launch_bounds__(CSL_THREADS, 2)
+k_trigemm_chi2(csl_program_t p, const double* __restrict__ R, int ldr, double* __restrict__ part) {
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = As + 2 * CSL_ASZ;
+  double* red = Bs + 2 * CSL_BSZ;           // [2][128]
+  const int npad = p.n_pad, nblk = npad / CSL_BM;
+  // consecutive CTAs share a column tile (its R panel stays in L2); the longest row blocks go first
+  const int ct = blockIdx.x / nblk, i = nblk - 1 - (int)(blockIdx.x % nblk);
+  const int c0 = ct * CSL_BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 32;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  // rows >= n of M are identity rows acting on zero rows of R: skip their 8-row groups altogether
+  unsigned mmask = 0;
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+    if (i * CSL_BM + wm0 + mi * 8 < p.n) mmask |= 1u << mi;
+  const int kend = min((i + 1) * CSL_BM, (p.n + CSL_KC - 1) / CSL_KC * CSL_KC);
+  gemm_stream_AB(acc, p.Minv + (long long)i * CSL_BM * npad, npad, R + c0, ldr, kend / CSL_KC, As, Bs, tid, wm0, wn0,
+                 lane, mmask);
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double v = 0.0;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) v = fma(acc[mi][ni][e], acc[mi][ni][e], v);
+      v += shfl_xor_d(v, 4);
+      v += shfl_xor_d(v, 8);
+      v += shfl_xor_d(v, 16);
+      if (g == 0) red[(warp >> 2) * CSL_BN + wn0 + ni * 8 + 2 * t + e] = v;
+    }
+  __syncthreads();
+  if (tid < CSL_BN) part[(long long)i * ldr + c0 + tid] = red[tid] + red[CSL_BN + tid];
+}
+
+__global__ void k_sum_partials(int nblk, int W, int ldr, const double* __restrict__ part, double* __restrict__ chi2) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  double s = 0.0;
+  for (int i = 0; i < nblk; ++i) s += part[(long long)i * ldr + w];
+  chi2[w] = s;
+}
+
+extern "C" int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part,
+                        void* stream) {
   CSL_REQUIRE(p && R && chi2, "csl_chi2: null argument");
-  CSL_REQUIRE(p->n_pad > 0 && p->n_pad % CSL_BM == 0 && p->Lmat && p->Linv_diag, "csl_chi2: program has no factor");
+  CSL_REQUIRE(p->n_pad > 0 && p->n_pad % CSL_BM == 0, "csl_chi2: program has no factor");
   CSL_REQUIRE(W > 0 && W % CSL_BN == 0 && ldr >= W && (ldr % 2) == 0, "csl_chi2: W must be a positive multiple of 128");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->chi2_mode == 1) {
+    CSL_REQUIRE(p->Minv && ws_part, "csl_chi2: explicit-inverse mode needs Minv and the partial-sum workspace");
+    static bool attr1 = false;
+    const size_t smem1 = (size_t)(2 * CSL_ASZ + 2 * CSL_BSZ + 2 * CSL_BN) * sizeof(double);
+    if (!attr1) {
+      cudaError_t e = cudaFuncSetAttribute(k_trigemm_chi2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+      if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+      attr1 = true;
+    }
+    const int nblk = p->n_pad / CSL_BM;
+    k_trigemm_chi2<<<(W / CSL_BN) * nblk, CSL_THREADS, smem1, s>>>(*p, R, ldr, ws_part);
+    k_sum_partials<<<(W + 255) / 256, 256, 0, s>>>(nblk, W, ldr, ws_part, chi2);
+    return csl_check_launch("k_trigemm_chi2");
+  }
+  CSL_REQUIRE(p->Lmat && p->Linv_diag, "csl_chi2: program has no factor");
   static bool attr_set = false;
   const size_t smem = (size_t)CHI2_SMEM_DOUBLES * sizeof(double);
   if (!attr_set) {
@@ -101,7 +175,7 @@ extern "C" int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, doubl
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
     attr_set = true;
   }
-  k_trsm_chi2<<<W / CSL_BN, CSL_THREADS, smem, (cudaStream_t)stream>>>(*p, R, ldr, chi2);
+  k_trsm_chi2<<<W / CSL_BN, CSL_THREADS, smem, s>>>(*p, R, ldr, chi2);
   return csl_check_launch("k_trsm_chi2");
 }
 

@@ -91,7 +91,7 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xo
 __device__ __forceinline__ void gemm_stream_AB(double (&acc)[4][4][2], const double* __restrict__ A,
                                                long long lda, const double* __restrict__ B, long long ldb,
                                                int nchunk, double* As, double* Bs, int tid, int wm0, int wn0,
-                                               int lane) {
+                                               int lane, unsigned mmask = 0xFu) {
   if (nchunk <= 0) return;
   load_A_tile_async(As, A, lda, tid);
   load_B_tile_async(Bs, B, ldb, tid);
@@ -105,7 +105,7 @@ __device__ __forceinline__ void gemm_stream_AB(double (&acc)[4][4][2], const dou
       load_B_tile_async(Bs + (cur ^ 1) * CSL_BSZ, B + (long long)(c + 1) * CSL_KC * ldb, ldb, tid);
       cp_async_commit();
     }
-    warp_mma_chunk(acc, As + cur * CSL_ASZ, Bs + cur * CSL_BSZ, wm0, wn0, lane);
+    warp_mma_chunk(acc, As + cur * CSL_ASZ, Bs + cur * CSL_BSZ, wm0, wn0, lane, mmask);
     cp_async_wait<0>();
     __syncthreads();
   }

@@ -75,9 +75,10 @@ class CompiledProgram(object):
 
     _PTR_FIELDS = ("code_op", "code_arg", "code_val", "box_idx", "box_lo", "box_hi", "gauss_idx", "gauss_c",
                    "gauss_w", "scalar_coef", "spec_tab", "tile_tab", "templates", "windows", "data",
-                   "direct_coef", "Lmat", "Linv_diag")
+                   "direct_coef", "Lmat", "Linv_diag", "Minv")
 
-    def __init__(self, names, priors, lnl_expr):
+    def __init__(self, names, priors, lnl_expr, chi2_mode="auto"):
+        self.chi2_mode = chi2_mode
         self.names = list(names)
         self.ndim = len(self.names)
         if not (1 <= self.ndim <= L.MAX_DIM):
@@ -160,6 +161,25 @@ class CompiledProgram(object):
         self.host["L"] = Lf[:n, :n]
         self._dev('Lmat', Lf, np.float64)
         self._dev('Linv_diag', inv, np.float64)
+        # explicit inverse of the whole factor (chi2_mode 1): double-precision triangular solve, one step
+        # of Newton refinement with the residual in extended precision, and a check against forward
+        # substitution; used only if it reproduces the substitution chi^2 to 1e-13
+        self.meta['chi2_mode'] = 0
+        if self.chi2_mode in ("auto", "inverse") and n <= 4096:
+            M = sla.solve_triangular(Lf[:n, :n], np.eye(n), lower=True)
+            if n <= 1024:
+                Ll, Ml = Lf[:n, :n].astype(np.longdouble), M.astype(np.longdouble)
+                M = np.tril((Ml + Ml @ (np.eye(n, dtype=np.longdouble) - Ll @ Ml)).astype(np.float64))
+            rs = np.random.RandomState(12345)
+            probe = Lf[:n, :n] @ rs.standard_normal((n, 8)) + 0.01 * rs.standard_normal((n, 8))
+            y_sub = sla.solve_triangular(Lf[:n, :n], probe, lower=True)
+            y_inv = M @ probe
+            err = np.max(np.abs((y_inv ** 2).sum(0) - (y_sub ** 2).sum(0)) / (y_sub ** 2).sum(0))
+            self.host["inverse_check"] = float(err)
+            if err < 1e-13 or self.chi2_mode == "inverse":
+                Mp = np.eye(npad); Mp[:n, :n] = M
+                self._dev('Minv', Mp, np.float64)
+                self.meta['chi2_mode'] = 1
 
     def _build_gauss(self, P, code, q):
         n = len(q.values)
@@ -294,12 +314,12 @@ class CompiledProgram(object):
 class DeviceProgram(CompiledProgram):
     """A compiled posterior resident on one CUDA device."""
 
-    def __init__(self, names, priors, lnl_expr, device=None):
+    def __init__(self, names, priors, lnl_expr, device=None, chi2_mode="auto"):
         torch = L.require_cuda()
         self.lib = L.lib()
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        super().__init__(names, priors, lnl_expr)
+        super().__init__(names, priors, lnl_expr, chi2_mode=chi2_mode)
         self._ws = {}
         self.dev = {k: torch.from_numpy(v).to(self.device) for k, v in self.tables.items()}
         P = L.Program()
@@ -324,6 +344,7 @@ class DeviceProgram(CompiledProgram):
             ws = dict(coef=t.empty((max(self.ncoef, 1), Wp), **kw), prior=t.empty(Wp, **kw),
                       R=t.empty((max(self.n_pad, 1), Wp), **kw) if self.n_pad else None,
                       chi2=t.empty(Wp, **kw) if self.n_pad else None,
+                      part=t.empty((self.n_pad // L.BM, Wp), **kw) if self.n_pad else None,
                       x=t.empty((Wp, self.ndim), **kw), lnl=t.empty(Wp, **kw))
             self._ws[Wp] = ws
         return ws
@@ -343,7 +364,8 @@ class DeviceProgram(CompiledProgram):
         st = L.stream_ptr()
         if timers is None:
             L.check(self.lib.csl_lnl(C.byref(self.struct), W, x.data_ptr(), out.data_ptr(), ws["coef"].data_ptr(),
-                                     ws["prior"].data_ptr(), L.ptr(ws["R"]), L.ptr(ws["chi2"]), st), "csl_lnl")
+                                     ws["prior"].data_ptr(), L.ptr(ws["R"]), L.ptr(ws["chi2"]), L.ptr(ws["part"]), st),
+                    "csl_lnl")
             return out
         Wp = _rup(W, L.BN)
         P = C.byref(self.struct)
@@ -365,7 +387,8 @@ class DeviceProgram(CompiledProgram):
             stage("direct_residual", lambda: self.lib.csl_direct_residual(P, W, ws["coef"].data_ptr(), Wp,
                                                                           ws["R"].data_ptr(), Wp, st))
         if self.meta["resid_mode"]:
-            stage("chi2", lambda: self.lib.csl_chi2(P, Wp, ws["R"].data_ptr(), Wp, ws["chi2"].data_ptr(), st))
+            stage("chi2", lambda: self.lib.csl_chi2(P, Wp, ws["R"].data_ptr(), Wp, ws["chi2"].data_ptr(),
+                                                    ws["part"].data_ptr(), st))
             chi2 = ws["chi2"].data_ptr()
         stage("combine", lambda: self.lib.csl_combine(P, W, ws["coef"].data_ptr(), Wp, ws["prior"].data_ptr(), chi2,
                                                       out.data_ptr(), st))
@@ -380,6 +403,6 @@ class DeviceProgram(CompiledProgram):
             out_host = np.empty(W)
         L.check(self.lib.csl_lnl_host(C.byref(self.struct), W, x_host.ctypes.data, out_host.ctypes.data,
                                       ws["x"].data_ptr(), ws["lnl"].data_ptr(), ws["coef"].data_ptr(),
-                                      ws["prior"].data_ptr(), L.ptr(ws["R"]), L.ptr(ws["chi2"]), L.stream_ptr()),
-                "csl_lnl_host")
+                                      ws["prior"].data_ptr(), L.ptr(ws["R"]), L.ptr(ws["chi2"]), L.ptr(ws["part"]),
+                                      L.stream_ptr()), "csl_lnl_host")
         return out_host

@@ -108,6 +108,9 @@ typedef struct csl_program {
   const int32_t* direct_coef;
   const double* Lmat;       /* [n_pad, n_pad] row-major lower factor, identity padded */
   const double* Linv_diag;  /* [n_pad/CSL_BM][CSL_BM*CSL_BM] inverses of the diagonal blocks */
+  const double* Minv;       /* [n_pad, n_pad] row-major L^-1 (lower), or NULL                     */
+  int32_t chi2_mode;        /* 0: blocked forward substitution; 1: explicit-inverse tile product  */
+  int32_t reserved1;
 } csl_program_t;
 
 int csl_abi_version(void);
@@ -135,9 +138,11 @@ int csl_bin_residual(const csl_program_t* p, int W, const double* coef, int ldc,
 int csl_direct_residual(const csl_program_t* p, int W, const double* coef, int ldc, double* R, int ldr,
                         void* stream);
 
-/* chi2[w] = || L^-1 R[:, w] ||^2 by a blocked triangular solve on DMMA
- * (replaces cho_solve + dot, spt_lowl.py:133 / mspec_lnl.py:73).  R is overwritten by L^-1 R. */
-int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, double* chi2, void* stream);
+/* chi2[w] = || L^-1 R[:, w] ||^2 on DMMA (replaces cho_solve + dot, spt_lowl.py:133 / mspec_lnl.py:73).
+ *   chi2_mode 0: blocked forward substitution, 64-row blocks, R is overwritten by L^-1 R;
+ *   chi2_mode 1: tile products with the host-inverted factor Minv (chosen by the host only when the
+ *                inverse reproduces the substitution result to 1e-13); needs ws_part [n_pad/64, ldr]. */
+int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part, void* stream);
 
 /* lnl[w] = prior[w] + sum scalar coefs + chi2[w]/2 ; +inf where prior is +inf (cosmoslik.py:135-141).
  * chi2 may be NULL when the program has no quadratic form. */
@@ -145,15 +150,17 @@ int csl_combine(const csl_program_t* p, int W, const double* coef, int ldc, cons
                 const double* chi2, double* lnl, void* stream);
 
 /* The four calls above in sequence.  Workspace (device, caller owned):
- *   coef [ncoef, Wp], prior [Wp], R [n_pad, Wp], chi2 [Wp]  with Wp = W rounded up to CSL_BN. */
+ *   coef [ncoef, Wp], prior [Wp], R [n_pad, Wp], chi2 [Wp], part [n_pad/64, Wp]
+ *   with Wp = W rounded up to CSL_BN. */
 int csl_lnl(const csl_program_t* p, int W, const double* x, double* lnl,
-            double* ws_coef, double* ws_prior, double* ws_R, double* ws_chi2, void* stream);
+            double* ws_coef, double* ws_prior, double* ws_R, double* ws_chi2, double* ws_part, void* stream);
 
 /* End-to-end variant with HOST buffers (pinned or pageable): copies x_host -> x_dev, evaluates,
  * copies lnl back and synchronises `stream`.  x_dev [Wp, ndim] and lnl_dev [Wp] are device scratch. */
 int csl_lnl_host(const csl_program_t* p, int W, const double* x_host, double* lnl_host,
                  double* x_dev, double* lnl_dev,
-                 double* ws_coef, double* ws_prior, double* ws_R, double* ws_chi2, void* stream);
+                 double* ws_coef, double* ws_prior, double* ws_R, double* ws_chi2, double* ws_part,
+                 void* stream);
 
 /* ---- Metropolis-Hastings (samplers/metropolis_hastings.py) -------------------------------- */
 

@@ -115,6 +115,26 @@ def test_multispectrum_lnl_matches_the_oracle(torch, kind):
     assert relerr(got, ref) < RTOL
 
 
+@pytest.mark.parametrize("mode", ["trsm", "inverse"])
+def test_both_chi2_kernels_match_the_oracle(torch, spt_data, mode):
+    """blocked forward substitution (k_trsm_chi2) and the explicit-inverse tile product (k_trigemm_chi2)"""
+    prob = synthetic.planck_lite_problem(3)
+    oslik = ort.Slik(synthetic.build_script(ORACLE, prob)())
+    slik = Slik(synthetic.build_script(PRODUCT, prob)())
+    prog = slik.program(chi2_mode=mode)
+    assert prog.meta["chi2_mode"] == (1 if mode == "inverse" else 0)
+    names = list(slik.get_sampled())
+    x0 = np.array([prob["truth"][k] for k in names]); sc = np.array([prob["scales"][k] for k in names])
+    X = x0 + sc * np.random.RandomState(8).standard_normal((130, len(names))) * 3
+    ref = np.array([oslik.evaluate(*x)[0] for x in X])
+    assert relerr(slik.evaluate_batch(X), ref) < RTOL
+    # the real SPT covariance (47 bins) through the same kernel
+    g = golden("spt_lowl_lnl.npz")
+    s2 = Slik(B.spt_script(spt_data, "s12", g["tt"])())
+    s2.program(chi2_mode=mode)
+    assert relerr(s2.evaluate_batch(g["s12_x"]), g["s12_lnl"]) < RTOL
+
+
 def test_ragged_and_tiny_batches(torch, spt_data):
     """W not a multiple of the 128-walker tile, W = 1, and a batch where every walker is outside the prior"""
     g = golden("spt_lowl_lnl.npz")
