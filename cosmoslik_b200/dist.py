@@ -69,23 +69,26 @@ def all_reduce_sum(t):
 
 
 def all_gather_rows(local, total_rows):
-    """Concatenate the ranks' row blocks [n_r, ...] in rank order into [total_rows, ...].
-    Uses all_gather_into_tensor when every rank holds the same number of rows."""
+    """Concatenate the ranks' row blocks [n_r, ...] in rank order into [total_rows, ...]
+    (shares as given by shard_bounds).  Equal shares go through all_gather_into_tensor; ragged
+    shares are padded to the largest share, gathered and trimmed."""
     d = _dist()
     if not d:
         return local
     import torch
     size = d.get_world_size()
-    if total_rows % size == 0 and local.shape[0] * size == total_rows:
-        out = torch.empty((total_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    tail = tuple(local.shape[1:])
+    if total_rows % size == 0:
+        out = torch.empty((total_rows,) + tail, dtype=local.dtype, device=local.device)
         d.all_gather_into_tensor(out, local.contiguous())
         return out
-    parts = []
-    for r in range(size):
-        lo, hi = shard_bounds(total_rows, r, size)
-        parts.append(torch.empty((hi - lo,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device))
-    d.all_gather(parts, local.contiguous())
-    return torch.cat(parts, 0)
+    bounds = [shard_bounds(total_rows, r, size) for r in range(size)]
+    biggest = max(hi - lo for lo, hi in bounds)
+    padded = torch.zeros((biggest,) + tail, dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(size)]
+    d.all_gather(parts, padded)
+    return torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, bounds)], 0)
 
 
 def barrier():
