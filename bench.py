@@ -35,7 +35,7 @@ UNIT = "evals/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="planck_lite", choices=["planck_lite", "spt_multifreq"])
@@ -146,42 +146,58 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (NVML, 20 ms period; nvidia-smi fallback)."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("hw_power_brake", 0x80), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index, self.samples, self.stop = index, [], False
         self.thread = threading.Thread(target=self._run, daemon=True)
+        self.max_mhz = None
 
     def _run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [v.strip() for v in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self.stop:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((mhz, mask))
+                time.sleep(0.02)
+        except Exception:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+            while not self.stop:
+                try:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                         timeout=5).stdout
+                    f = [v.strip() for v in out.strip().split(",")]
+                    self.max_mhz = float(f[1])
+                    self.samples.append((float(f[0]), int(f[2], 16)))
+                except Exception:
+                    pass
+                time.sleep(0.1)
 
     def __enter__(self):
-        self.thread.start(); return self
+        self.thread.start(); time.sleep(0.05); return self
 
     def __exit__(self, *a):
         self.stop = True; self.thread.join(timeout=6)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        reasons = set()
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(s[0] for s in self.samples)
+        mask = 0
         for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons),
-                "samples": len(sm)}
+            mask |= s[1]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz,
+                "reasons": [n for n, bit in self.REASONS if mask & bit], "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------- B200 arm
@@ -245,6 +261,7 @@ def run_b200(args):
 
     # ---- per-kernel durations from the event pairs recorded inside the timed region
     stage_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in timers.items()}
+    host_ms = smp.stats.get("host_ms_per_step")
     stage_n = {k: len(v) for k, v in timers.items()}
     half = args.walkers // 2
     fl = prog.flops
@@ -298,7 +315,7 @@ def run_b200(args):
             "config": config_of(args, prob, k_total), "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps + 4,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
-            "acceptance": acc_frac,
+            "acceptance": acc_frac, "host_launch_ms_per_step": host_ms,
             "flops_per_eval": {"trsm_algorithmic": fl["trsm_alg"], "trsm_executed": fl["trsm"],
                                "binning_dense_windows": fl["bin_dense"], "binning_nonzero_windows": fl["bin_nnz"],
                                "binning_executed_dmma": fl["bin_exec"], "foreground_build": fl["build_ops"]}}

@@ -120,13 +120,20 @@ class emcee(SlikSampler):
         timers = getattr(self, "timers", None)     # bench.py: CUDA-event pairs per stage
         nacc = torch.zeros((), dtype=torch.int64, device=dev)
         F = int(self.output_freq)
+        import time as _time
+        t_host0 = _time.perf_counter()
         try:
             for i in range(nsteps):
                 pos_old.copy_(pos)
                 inj = self.streams(i) if self.streams is not None else None
                 for hidx, (r0, r1, g0, hsize) in enumerate(halves):
                     o0, o1, _, csize = halves[1 - hidx]
+                    if timers is not None:
+                        ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
                     comp = dist.all_gather_rows(pos[o0:o1], csize)    # the complementary half, all ranks' rows
+                    if timers is not None:
+                        ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
+                        timers.setdefault("all_gather", []).append((ev0, ev1))
                     ns = r1 - r0
                     if ns == 0:
                         continue
@@ -165,5 +172,6 @@ class emcee(SlikSampler):
         finally:
             if writer is not None:
                 writer.close()
-        self.stats = dict(pos=pos, lnl=lnl_pos, weight=weight, rows=rows, nrows=nrows, nsteps=nsteps,
+        host_ms = 1e3 * (_time.perf_counter() - t_host0) / max(nsteps, 1)   # CPU time to ENQUEUE one step
+        self.stats = dict(host_ms_per_step=host_ms, pos=pos, lnl=lnl_pos, weight=weight, rows=rows, nrows=nrows, nsteps=nsteps,
                           walker_ids=gid, seed=seed, accepted=int(nacc.item()), evals=nsteps * W)
