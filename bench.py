@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--walkers", type=int, default=65536, help="walkers per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--binning", default="auto", choices=["auto", "dmma", "segsum"],
+                    help="window-binning kernel: DMMA tile product, per-bin segmented sum, or by window structure")
+    ap.add_argument("--chi2", default="auto", choices=["auto", "trsm", "inverse"])
     return ap.parse_args()
 
 
@@ -51,7 +54,7 @@ def make_problem(name):
 
 
 def config_of(args, prob, nwalkers_total):
-    win = ("top-hat plik-lite bins (block-sparse window matrix; all-zero DMMA blocks skipped)"
+    win = ("top-hat plik-lite bins (block-sparse window matrix; binning kernel: %s)" % args.binning
            if args.workload == "planck_lite" else "Gaussian bumps + 1e-10 tails (numerically dense windows)")
     return {"workload": "BASELINE configs[3] planck_lite TT/TE/EE 613 bins" if args.workload == "planck_lite"
             else "BASELINE configs[2] spt_multifreq 6 spectra x 50 bins",
@@ -226,7 +229,7 @@ def run_b200(args):
     k_total = args.walkers * size
     sampler = lambda s: cb.samplers.emcee(s, num_samples=k_total, nwalkers=k_total, seed=1234)
     slik = cb.Slik(synthetic.build_script(ns, prob, sampler=sampler)())
-    prog = slik.program()
+    prog = slik.program(chi2_mode=args.chi2, binning=args.binning)
     smp = slik.sampler
     names = list(slik.get_sampled())
     # tight initial ball around the truth (a burnt-in ensemble), identical on every rank
@@ -271,7 +274,8 @@ def run_b200(args):
     # counted as 20 FMAs) per walker.  "executed" adds padding / zero blocks actually issued.
     per_kernel = {}
     for name, kern, alg, exe in (("chi2", "k_trigemm_chi2" if prog.meta.get("chi2_mode") else "k_trsm_chi2", fl["trsm_alg"], fl["trsm"]),
-                                 ("bin_residual", "k_bin_residual", fl["bin_nnz"] + fl["build_ops"],
+                                 ("bin_residual", "k_bin_segsum" if prog.meta.get("nsegclass") else "k_bin_residual",
+                                  fl["bin_nnz"] + fl["build_ops"],
                                   fl["bin_exec"] + fl["build_ops"])):
         if name in stage_ms:
             t = stage_ms[name] * 1e-3

@@ -234,6 +234,7 @@ class Slik(object):
             from .likelihoods.priors import priors
             params.priors = priors(params)
         self._program = None
+        self._program_options = {}
 
     def get_sampled(self):
         return self._sampled
@@ -257,13 +258,13 @@ class Slik(object):
             raise TypeError("script __call__ returned %r; expected a likelihood term or parameter expression" % type(out))
         return out
 
-    def program(self, chi2_mode=None):
-        """The compiled device program (cached).  chi2_mode: 'auto' (default), 'trsm' or 'inverse' --
-        see program.CompiledProgram._factor."""
-        if self._program is None or (chi2_mode is not None and chi2_mode != self._program.chi2_mode):
+    def program(self, **options):
+        """The compiled device program (cached).  Options (see program.CompiledProgram):
+        chi2_mode = 'auto' | 'trsm' | 'inverse';  binning = 'auto' | 'dmma' | 'segsum'."""
+        if self._program is None or (options and options != self._program_options):
             from .program import DeviceProgram
-            self._program = DeviceProgram(list(self._sampled), self.params.priors, self.trace(),
-                                          chi2_mode=chi2_mode or "auto")
+            self._program_options = dict(options)
+            self._program = DeviceProgram(list(self._sampled), self.params.priors, self.trace(), **options)
         return self._program
 
     # -- evaluation -----------------------------------------------------------

@@ -136,6 +136,89 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
   }
 }
 
+// ---- segmented-sum binning for block-sparse windows ----------------------------------------------------
+// One thread per walker, CSL_SEG_GROUP window rows per CTA row.  For each row only its non-zero support
+// [lo, hi) is visited: cl[l] is built once from the (warp-uniform) ell-table row and folded into the
+// bin with one extra FMA.  No shared memory, no barriers: the kernel is bound by the FP64 pipe.
+template <int NT, int NP>
+__global__ void __launch_bounds__(128)
+k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restrict__ coef, int ldc,
+             double* __restrict__ R, int ldr) {
+  constexpr int LSTRIDE = NT + 2 * NP;
+  const int w = blockIdx.x * 128 + threadIdx.x;
+  const int b_begin = bin0 + blockIdx.y * CSL_SEG_GROUP;
+  const int b_end = min(b_begin + CSL_SEG_GROUP, bin0 + nbins);
+  const int32_t* first = p.bin_tab + (long long)b_begin * CSL_BIN_STRIDE;
+  const int32_t* spec = p.spec_tab + (long long)first[CSL_B_SPEC] * CSL_SPEC_STRIDE;   // one spectrum per group
+  const double* __restrict__ ltab = p.templates + spec[CSL_S_LTAB];
+  double cf[NT > 0 ? NT : 1], pamp[NP > 0 ? NP : 1], pidx[NP > 0 ? NP : 1];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) cf[t] = coef[(long long)spec[CSL_S_TERM_COEF + t] * ldc + w];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    pamp[q] = coef[(long long)spec[CSL_S_PLAW_AMP + q] * ldc + w];
+    pidx[q] = coef[(long long)spec[CSL_S_PLAW_IDX + q] * ldc + w];
+  }
+  const int calrow = spec[CSL_S_CAL];
+  const double cal = calrow >= 0 ? coef[(long long)calrow * ldc + w] : 1.0;
+
+  auto cl_at = [&](const double* __restrict__ row) {
+    double v = 0.0;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) v = fma(cf[t], __ldg(row + t), v);
+#pragma unroll
+    for (int q = 0; q < NP; ++q)
+      v = fma(pamp[q] * __ldg(row + NT + 2 * q + 1), exp(pidx[q] * __ldg(row + NT + 2 * q)), v);
+    return v;
+  };
+
+  for (int b = b_begin; b < b_end; ++b) {
+    const int32_t* rec = p.bin_tab + (long long)b * CSL_BIN_STRIDE;
+    const int lo = rec[CSL_B_LO], hi = rec[CSL_B_HI], row = rec[CSL_B_ROW];
+    if (row < 0) continue;   // group padding
+    const long long woff = ((long long)rec[CSL_B_WINOFF_HI] << 32) | (unsigned)rec[CSL_B_WINOFF_LO];
+    const double* __restrict__ wrow = p.windows + woff;
+    double acc0 = 0.0, acc1 = 0.0;
+    int l = lo;
+    for (; l + 1 < hi; l += 2) {          // two independent elements in flight per thread
+      const double v0 = cl_at(ltab + (long long)l * LSTRIDE);
+      const double v1 = cl_at(ltab + (long long)(l + 1) * LSTRIDE);
+      acc0 = fma(__ldg(wrow + l), v0, acc0);
+      acc1 = fma(__ldg(wrow + l + 1), v1, acc1);
+    }
+    if (l < hi) acc0 = fma(__ldg(wrow + l), cl_at(ltab + (long long)l * LSTRIDE), acc0);
+    R[(long long)row * ldr + w] = __dsub_rn(__dmul_rn(cal, p.data[row]), acc0 + acc1);
+  }
+}
+
+template <int NT, int NP>
+static int launch_seg(const csl_program_t* p, int bin0, int nbins, int W, const double* coef, int ldc,
+                      double* R, int ldr, cudaStream_t s) {
+  dim3 grid(W / 128, (nbins + CSL_SEG_GROUP - 1) / CSL_SEG_GROUP);
+  k_bin_segsum<NT, NP><<<grid, 128, 0, s>>>(*p, bin0, nbins, W, coef, ldc, R, ldr);
+  return 0;
+}
+
+#define CSL_DISPATCH_SEG_NP(NTV)                                                                       \
+  switch (np) {                                                                                        \
+    case 0: return launch_seg<NTV, 0>(p, b0, nb, W, coef, ldc, R, ldr, s);                             \
+    case 1: return launch_seg<NTV, 1>(p, b0, nb, W, coef, ldc, R, ldr, s);                             \
+    case 2: return launch_seg<NTV, 2>(p, b0, nb, W, coef, ldc, R, ldr, s);                             \
+    case 4: return launch_seg<NTV, 4>(p, b0, nb, W, coef, ldc, R, ldr, s);                             \
+    default: return csl_fail(CSL_E_BADARG, "csl_bin_residual: power-law class must be 0, 1, 2 or 4");  \
+  }
+
+static int dispatch_seg(int nt, int np, const csl_program_t* p, int b0, int nb, int W, const double* coef, int ldc,
+                        double* R, int ldr, cudaStream_t s) {
+  switch (nt) {
+    case 0: CSL_DISPATCH_SEG_NP(0)
+    case 2: CSL_DISPATCH_SEG_NP(2)
+    case 4: CSL_DISPATCH_SEG_NP(4)
+    case 8: CSL_DISPATCH_SEG_NP(8)
+    default: return csl_fail(CSL_E_BADARG, "csl_bin_residual: template class must be 0, 2, 4 or 8");
+  }
+}
+
 // rows n .. n_pad of R are zero so the padded (identity) part of L contributes nothing
 __global__ void k_zero_pad_rows(double* __restrict__ R, int ldr, int n, int n_pad) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,7 +264,8 @@ static int dispatch_class(int nt, int np, const csl_program_t* p, int tile0, int
 extern "C" int csl_bin_residual(const csl_program_t* p, int W, const double* coef, int ldc, double* R, int ldr,
                                 void* stream) {
   CSL_REQUIRE(p && coef && R, "csl_bin_residual: null argument");
-  CSL_REQUIRE(p->resid_mode == 1 && p->ntile > 0 && p->nclass > 0 && p->nclass <= CSL_MAX_CLASS,
+  CSL_REQUIRE(p->resid_mode == 1 && (p->nclass > 0 || p->nsegclass > 0) && p->nclass <= CSL_MAX_CLASS &&
+                  p->nsegclass <= CSL_MAX_CLASS,
               "csl_bin_residual: program has no binned spectra");
   CSL_REQUIRE(W > 0 && W % CSL_BN == 0 && ldr >= W && ldc >= W && (ldr % 2) == 0,
               "csl_bin_residual: W must be a positive multiple of 128 and ldr, ldc >= W");
@@ -194,6 +278,12 @@ extern "C" int csl_bin_residual(const csl_program_t* p, int W, const double* coe
     const int32_t* k = p->cls[c];
     CSL_REQUIRE(k[0] + 2 * k[1] > 0, "csl_bin_residual: empty spectrum class");
     int rc = dispatch_class(k[0], k[1], p, k[2], k[3], W, coef, ldc, R, ldr, s);
+    if (rc) return rc;
+  }
+  for (int c = 0; c < p->nsegclass; ++c) {
+    const int32_t* k = p->segcls[c];
+    CSL_REQUIRE(k[0] + 2 * k[1] > 0 && p->bin_tab, "csl_bin_residual: empty segmented class");
+    int rc = dispatch_seg(k[0], k[1], p, k[2], k[3], W, coef, ldc, R, ldr, s);
     if (rc) return rc;
   }
   return csl_check_launch("k_bin_residual");

@@ -75,18 +75,20 @@ class CompiledProgram(object):
 
     _PTR_FIELDS = ("code_op", "code_arg", "code_val", "box_idx", "box_lo", "box_hi", "gauss_idx", "gauss_c",
                    "gauss_w", "scalar_coef", "spec_tab", "tile_tab", "templates", "windows", "data",
-                   "direct_coef", "Lmat", "Linv_diag", "Minv")
+                   "direct_coef", "Lmat", "Linv_diag", "Minv", "bin_tab")
 
-    def __init__(self, names, priors, lnl_expr, chi2_mode="auto"):
+    def __init__(self, names, priors, lnl_expr, chi2_mode="auto", binning="auto"):
         self.chi2_mode = chi2_mode
+        self.binning = binning      # 'auto' | 'dmma' | 'segsum' (see _build_bandpower)
         self.names = list(names)
         self.ndim = len(self.names)
         if not (1 <= self.ndim <= L.MAX_DIM):
             raise ValueError("number of sampled parameters must be in 1..%d" % L.MAX_DIM)
         self.tables = {}
         self.meta = dict(ndim=self.ndim, ncoef=0, ncode=0, nbox=0, ngauss=0, nscalar=0, nspec=0, ntile=0,
-                         n=0, n_pad=0, resid_mode=0, nclass=0)
+                         n=0, n_pad=0, resid_mode=0, nclass=0, nsegclass=0)
         self.cls = np.zeros((L.MAX_CLASS, 4), np.int32)
+        self.segcls = np.zeros((L.MAX_CLASS, 4), np.int32)
         self.host = {}
         self.flops = {}
         self._build(priors, lnl_expr)
@@ -199,7 +201,7 @@ class CompiledProgram(object):
     def _build_bandpower(self, P, code, q):
         nspec = len(q.blocks)
         spec_tab = np.zeros((nspec, L.SPEC_STRIDE), np.int32)
-        tiles, templ, wins, data = [], [], [], []
+        tiles, segbins, templ, wins, data = [], [], [], [], []
         toff = 0      # running offset into the ell-table buffer (doubles, kept even)
         woff = 0      # running offset into the window buffer
         row0 = 0
@@ -258,7 +260,28 @@ class CompiledProgram(object):
                 rec[L.S_CAL] = -1
             nbp = _rup(nb, L.BM)
             wp = np.zeros((nbp, nlp)); wp[:nb, :nl] = blk.windows
-            for t0 in range(0, nb, L.BM):
+            supports = [_support(wp[b:b + 1]) for b in range(nb)]
+            covered = sum(hi - lo for lo, hi in supports)
+            # rows whose supports barely overlap (top-hat bins): every cl[l] is needed by ~one row, so a
+            # per-row segmented sum does the minimum work; dense windows go to the DMMA tile product
+            seg = self.binning == "segsum" or (self.binning == "auto" and covered <= 2 * nl)
+            per_elem = len(terms) + 20 * len(m.plaws)
+            if seg:
+                for b in range(_rup(nb, L.SEG_GROUP)):
+                    rec_b = np.zeros(L.BIN_STRIDE, np.int32)
+                    if b < nb:
+                        off = woff + b * nlp
+                        lo32 = off & 0xFFFFFFFF
+                        rec_b[L.B_ROW], rec_b[L.B_SPEC] = row0 + b, s
+                        rec_b[L.B_LO], rec_b[L.B_HI] = supports[b]
+                        rec_b[L.B_WINOFF_LO] = lo32 - (1 << 32) if lo32 >= (1 << 31) else lo32
+                        rec_b[L.B_WINOFF_HI] = off >> 32
+                    else:
+                        rec_b[L.B_ROW], rec_b[L.B_SPEC] = -1, s     # group padding: skipped by the kernel
+                    segbins.append(((NT, NP), rec_b))
+                flops_exec += 2 * covered
+                builds += covered * per_elem
+            for t0 in (range(0, nb, L.BM) if not seg else ()):
                 nr = min(L.BM, nb - t0)
                 lo, hi = _support(wp[t0:t0 + nr])
                 lo, hi = lo // L.KC * L.KC, _rup(hi, L.KC)
@@ -275,7 +298,7 @@ class CompiledProgram(object):
                     rec_t[L.T_GLO + g8], rec_t[L.T_GHI + g8] = glo, ghi
                     nch = len([c for c in range(lo, hi, L.KC) if c + L.KC > glo and c < ghi])
                     flops_exec += 2 * 8 * L.KC * nch
-                builds += (hi - lo) * (len(terms) + 20 * len(m.plaws))
+                builds += (hi - lo) * per_elem
                 tiles.append(((NT, NP), rec_t))
             flops_dense += 2 * nb * nl
             flops_nnz += 2 * int(np.count_nonzero(blk.windows))
@@ -287,24 +310,30 @@ class CompiledProgram(object):
             raise ValueError("bandpower likelihood: covariance is %s, data vector has %d rows" % (q.cov.shape, n))
         self._factor(P, q.cov)
         d = np.zeros(self.n_pad); d[:n] = np.concatenate(data)
-        # tiles sorted by kernel class (stable): one launch of k_bin_residual<NT, NP> per class
-        classes = sorted(set(k for k, _ in tiles))
-        if len(classes) > L.MAX_CLASS:
-            raise ValueError("too many distinct spectrum classes")
-        ordered, cls = [], np.zeros((L.MAX_CLASS, 4), np.int32)
-        for ci, k in enumerate(classes):
-            mine = [r for kk, r in tiles if kk == k]
-            cls[ci] = (k[0], k[1], len(ordered), len(mine))
-            ordered += mine
+        # records sorted by kernel class (stable): one launch per class <NT, NP>
+        def by_class(records, width):
+            classes = sorted(set(k for k, _ in records))
+            if len(classes) > L.MAX_CLASS:
+                raise ValueError("too many distinct spectrum classes")
+            ordered, cls = [], np.zeros((L.MAX_CLASS, 4), np.int32)
+            for ci, k in enumerate(classes):
+                mine = [r for kk, r in records if kk == k]
+                cls[ci] = (k[0], k[1], len(ordered), len(mine))
+                ordered += mine
+            return (np.array(ordered) if ordered else np.zeros((1, width), np.int32)), cls, len(classes), len(ordered)
+
+        tile_arr, self.cls, nclass, ntile = by_class(tiles, L.TILE_STRIDE)
+        bin_arr, self.segcls, nsegclass, _ = by_class(segbins, L.BIN_STRIDE)
+        ordered = tile_arr
         P['resid_mode'] = 1
-        P['nspec'], P['ntile'], P['nclass'] = nspec, len(ordered), len(classes)
-        self.cls = cls
+        P['nspec'], P['ntile'], P['nclass'], P['nsegclass'] = nspec, ntile, nclass, nsegclass
         self._dev('spec_tab', spec_tab, np.int32)
-        self._dev('tile_tab', np.array(ordered), np.int32)
+        self._dev('tile_tab', tile_arr, np.int32)
+        self._dev('bin_tab', bin_arr, np.int32)
         self._dev('templates', np.concatenate(templ), np.float64)
         self._dev('windows', np.concatenate(wins), np.float64)
         self._dev('data', d, np.float64)
-        self.host["spec_tab"], self.host["tile_tab"] = spec_tab, np.array(ordered)
+        self.host["spec_tab"], self.host["tile_tab"], self.host["bin_tab"] = spec_tab, tile_arr, bin_arr
         # work per evaluation: dense windows, non-zero window entries, DMMA blocks that
         # are actually executed, foreground-build FP64 ops (~1 per template term, ~20 per power law), TRSM
         self.flops = dict(bin_dense=flops_dense, bin_nnz=flops_nnz, bin_exec=flops_exec, build_ops=2 * builds,
@@ -314,12 +343,12 @@ class CompiledProgram(object):
 class DeviceProgram(CompiledProgram):
     """A compiled posterior resident on one CUDA device."""
 
-    def __init__(self, names, priors, lnl_expr, device=None, chi2_mode="auto"):
+    def __init__(self, names, priors, lnl_expr, device=None, chi2_mode="auto", binning="auto"):
         torch = L.require_cuda()
         self.lib = L.lib()
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        super().__init__(names, priors, lnl_expr, chi2_mode=chi2_mode)
+        super().__init__(names, priors, lnl_expr, chi2_mode=chi2_mode, binning=binning)
         self._ws = {}
         self.dev = {k: torch.from_numpy(v).to(self.device) for k, v in self.tables.items()}
         P = L.Program()
@@ -330,6 +359,7 @@ class DeviceProgram(CompiledProgram):
         for ci in range(L.MAX_CLASS):
             for j in range(4):
                 P.cls[ci][j] = int(self.cls[ci, j])
+                P.segcls[ci][j] = int(self.segcls[ci, j])
         self.struct = P
         if self.gauss_direct is not None:
             self.gauss_direct = {k: torch.from_numpy(v).to(self.device) for k, v in self.gauss_direct.items()}

@@ -45,6 +45,8 @@ extern "C" {
 #define CSL_TILE_STRIDE 32 /* int32 words per tile record                  */
 #define CSL_STACK     16   /* coefficient bytecode stack depth             */
 #define CSL_MAX_CLASS  8   /* distinct (NT, NP) spectrum classes per program */
+#define CSL_BIN_STRIDE 8   /* int32 words per bin record (segmented-sum binning) */
+#define CSL_SEG_GROUP  8   /* bins per CTA row of the segmented-sum kernel    */
 
 /* coefficient bytecode (one flat program; STORE pops into coef row `arg`) */
 enum {
@@ -80,6 +82,16 @@ enum {
   CSL_T_GHI = 16     /* [8]: per 8-row group, one past last non-zero column     */
 };
 
+/* bin record, int32 words (table bin_tab[nsegbin][CSL_BIN_STRIDE]): one window row handled by the
+ * segmented-sum kernel (block-sparse windows: rows whose supports barely overlap) */
+enum {
+  CSL_B_ROW = 0,     /* residual row                                            */
+  CSL_B_SPEC = 1,
+  CSL_B_LO = 2,      /* first non-zero column                                   */
+  CSL_B_HI = 3,      /* one past the last non-zero column                       */
+  CSL_B_WINOFF_LO = 4, CSL_B_WINOFF_HI = 5   /* offset (doubles) of the window row */
+};
+
 /*
  * A compiled posterior ("device program").  Built on the host from the plugin
  * tree; the struct itself lives in host memory, its pointers are device
@@ -110,7 +122,9 @@ typedef struct csl_program {
   const double* Linv_diag;  /* [n_pad/CSL_BM][CSL_BM*CSL_BM] inverses of the diagonal blocks */
   const double* Minv;       /* [n_pad, n_pad] row-major L^-1 (lower), or NULL                     */
   int32_t chi2_mode;        /* 0: blocked forward substitution; 1: explicit-inverse tile product  */
-  int32_t reserved1;
+  int32_t nsegclass;        /* segmented-sum classes (spectra with block-sparse windows)          */
+  int32_t segcls[CSL_MAX_CLASS][4];  /* per class: NT, NP, first bin record, number of bin records */
+  const int32_t* bin_tab;
 } csl_program_t;
 
 int csl_abi_version(void);
@@ -128,9 +142,10 @@ int csl_eval_prepare(const csl_program_t* p, int W, const double* x, double* coe
                      double* prior, void* stream);
 
 /* foreground build in shared memory (spt_lowl.py:206-207, clust_poisson_egfs.py:14-17),
- * window binning as an FP64 DMMA GEMM (spt_lowl.py:182) and the residual
- * r = cal*d - b (spt_lowl.py:132) -> R [n_pad, ldr].  W must be a multiple of CSL_BN
- * (pad with copies of a valid walker). */
+ * window binning (spt_lowl.py:182) and the residual r = cal*d - b (spt_lowl.py:132) -> R [n_pad, ldr].
+ * Spectra with dense windows go through the FP64 DMMA tile product (tile_tab / cls); spectra whose
+ * window rows barely overlap (top-hat bins) through a per-bin segmented sum (bin_tab / segcls) that
+ * builds every cl[l] exactly once.  W must be a multiple of CSL_BN (pad with copies of a valid walker). */
 int csl_bin_residual(const csl_program_t* p, int W, const double* coef, int ldc, double* R, int ldr,
                      void* stream);
 

@@ -53,6 +53,26 @@ def residual(cp, coef):
         for i in range(m["n"]):
             r[i] = coef[t["direct_coef"][i]] - t["data"][i]
         return r
+    for ci in range(m.get("nsegclass", 0)):
+        NTc, NPc, b0, nb = cp.segcls[ci]
+        for rec in t["bin_tab"][b0:b0 + nb]:
+            if rec[L.B_ROW] < 0:
+                continue
+            spec = t["spec_tab"][rec[L.B_SPEC]]
+            NT, NP = spec[L.S_NTERM], spec[L.S_NPLAW]
+            assert (NT, NP) == (NTc, NPc)
+            stride = NT + 2 * NP
+            l0, l1 = rec[L.B_LO], rec[L.B_HI]
+            ltab = t["templates"][spec[L.S_LTAB]: spec[L.S_LTAB] + spec[L.S_NLPAD] * stride].reshape(-1, stride)[l0:l1]
+            cl = np.zeros(l1 - l0)
+            for k in range(NT):
+                cl += coef[spec[L.S_TERM_COEF + k]] * ltab[:, k]
+            for k in range(NP):
+                with np.errstate(over="ignore"):
+                    cl += coef[spec[L.S_PLAW_AMP + k]] * ltab[:, NT + 2 * k + 1] * np.exp(coef[spec[L.S_PLAW_IDX + k]] * ltab[:, NT + 2 * k])
+            woff = (int(rec[L.B_WINOFF_HI]) << 32) | (int(rec[L.B_WINOFF_LO]) & 0xFFFFFFFF)
+            cal = 1.0 if spec[L.S_CAL] < 0 else coef[spec[L.S_CAL]]
+            r[rec[L.B_ROW]] = cal * t["data"][rec[L.B_ROW]] - np.dot(t["windows"][woff + l0: woff + l1], cl)
     for tile in t["tile_tab"][:m["ntile"]]:
         spec = t["spec_tab"][tile[L.T_SPEC]]
         l0, l1 = tile[L.T_LBEGIN], tile[L.T_LEND]

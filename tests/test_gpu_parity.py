@@ -123,6 +123,7 @@ def test_both_chi2_kernels_match_the_oracle(torch, spt_data, mode):
     slik = Slik(synthetic.build_script(PRODUCT, prob)())
     prog = slik.program(chi2_mode=mode)
     assert prog.meta["chi2_mode"] == (1 if mode == "inverse" else 0)
+    assert slik.program(chi2_mode=mode) is prog
     names = list(slik.get_sampled())
     x0 = np.array([prob["truth"][k] for k in names]); sc = np.array([prob["scales"][k] for k in names])
     X = x0 + sc * np.random.RandomState(8).standard_normal((130, len(names))) * 3
@@ -133,6 +134,22 @@ def test_both_chi2_kernels_match_the_oracle(torch, spt_data, mode):
     s2 = Slik(B.spt_script(spt_data, "s12", g["tt"])())
     s2.program(chi2_mode=mode)
     assert relerr(s2.evaluate_batch(g["s12_x"]), g["s12_lnl"]) < RTOL
+
+
+@pytest.mark.parametrize("binning", ["dmma", "segsum"])
+def test_both_binning_kernels_match_the_oracle(torch, binning):
+    """top-hat (block-sparse) windows through the DMMA tile product with zero-block skipping and through
+    the per-bin segmented sum"""
+    prob = synthetic.planck_lite_problem(4)
+    oslik = ort.Slik(synthetic.build_script(ORACLE, prob)())
+    slik = Slik(synthetic.build_script(PRODUCT, prob)())
+    prog = slik.program(binning=binning)
+    assert (prog.meta["nsegclass"] > 0) == (binning == "segsum") and (prog.meta["nclass"] > 0) == (binning == "dmma")
+    names = list(slik.get_sampled())
+    x0 = np.array([prob["truth"][k] for k in names]); sc = np.array([prob["scales"][k] for k in names])
+    X = x0 + sc * np.random.RandomState(9).standard_normal((200, len(names))) * 3
+    ref = np.array([oslik.evaluate(*x)[0] for x in X])
+    assert relerr(slik.evaluate_batch(X), ref) < RTOL
 
 
 def test_ragged_and_tiny_batches(torch, spt_data):
