@@ -156,38 +156,46 @@ class ClockSampler(object):
     def __init__(self, index):
         self.index, self.samples, self.stop = index, [], False
         self.thread = threading.Thread(target=self._run, daemon=True)
-        self.max_mhz = None
-
-    def _run(self):
-        try:
+        self.max_mhz, self.nv, self.h = None, None, None
+        try:                                  # NVML is initialised BEFORE the timed region
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            while not self.stop:
-                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
-                except Exception:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                self.samples.append((mhz, mask))
-                time.sleep(0.02)
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.nv = nv
         except Exception:
-            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+            self.nv = None
+
+    def _run(self):
+        nv, h = self.nv, self.h
+        if nv is not None:
             while not self.stop:
                 try:
-                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                         timeout=5).stdout
-                    f = [v.strip() for v in out.strip().split(",")]
-                    self.max_mhz = float(f[1])
-                    self.samples.append((float(f[0]), int(f[2], 16)))
+                    mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    try:
+                        mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    self.samples.append((mhz, mask))
                 except Exception:
                     pass
-                time.sleep(0.1)
+                time.sleep(0.05)
+            return
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                self.max_mhz = float(f[1])
+                self.samples.append((float(f[0]), int(f[2], 16)))
+            except Exception:
+                pass
+            time.sleep(0.2)
 
     def __enter__(self):
-        self.thread.start(); time.sleep(0.05); return self
+        self.thread.start(); return self
 
     def __exit__(self, *a):
         self.stop = True; self.thread.join(timeout=6)
@@ -237,6 +245,7 @@ def run_b200(args):
     smp.init_pos = x0 + sc * np.random.RandomState(99).standard_normal((k_total, len(names)))
 
     # ---- device-resident timing: K full stretch steps, CUDA events, max over ranks
+    smp.row_capacity = args.steps            # same row buffer for the warm-up and the timed run
     smp.run(prog, nsteps=max(args.warmup, 3))
     smp.init_pos = np.zeros((k_total, len(names)))   # placeholder; replaced below by the warmed-up state
     full = dist.all_gather_rows(smp.stats["pos"][:args.walkers // 2], k_total // 2)
@@ -246,7 +255,8 @@ def run_b200(args):
     smp.timers = timers
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(dev) as clk:
+    sampler_clk = ClockSampler(dev)
+    with sampler_clk as clk:
         e0.record()
         smp.run(prog, nsteps=args.steps)
         e1.record()

@@ -17,8 +17,8 @@ OP = dict(PUSHP=0, PUSHC=1, ADD=2, SUB=3, MUL=4, DIV=5, NEG=6, EXP=7, LOG=8, POW
 S_NLPAD, S_NTERM, S_NPLAW, S_CAL = 0, 1, 2, 3
 S_LTAB, S_TERM_COEF, S_PLAW_AMP, S_PLAW_IDX = 4, 8, 24, 28
 MAX_CLASS = 8
-BIN_STRIDE, SEG_GROUP = 8, 8
-B_ROW, B_SPEC, B_LO, B_HI, B_WINOFF_LO, B_WINOFF_HI = 0, 1, 2, 3, 4, 5
+BIN_STRIDE, SEG_GROUP = 16, 8
+B_ROW, B_SPEC, B_LO, B_HI, B_WINOFF_LO, B_WINOFF_HI, B_DMAX = 0, 1, 2, 3, 4, 5, 8
 T_ROW0, T_NROWS, T_SPEC, T_LBEGIN, T_LEND, T_WINOFF_LO, T_WINOFF_HI, T_WINLD, T_GLO, T_GHI = 0, 1, 2, 3, 4, 5, 6, 7, 8, 16
 
 _i32p, _f64p, _vp = C.c_void_p, C.c_void_p, C.c_void_p

@@ -7,7 +7,7 @@
 // memory from the walker's coefficients (registers) and the spectrum's ell-table, whose 16 rows for
 // the chunk are staged in shared memory by cp.async together with the window tile.
 //
-// ell-table row (doubles): [T_0 .. T_{NT-1}, (logB_q, M_q) for q < NP]
+// ell-table row (doubles): [T_0 .. T_{NT-1}, (logB_q, M_q, D_q, 0) for q < NP],  D_q[l] = logB_q[l+1] - logB_q[l]
 //   cl[l] = sum_t coef_t T_t[l] + sum_q amp_q M_q[l] exp(idx_q logB_q[l])
 // The kernel is instantiated per padded class <NT, NP> so the build loop is branch-free and fully
 // unrolled; the host sorts the tiles by class (csl_program_t::cls).
@@ -17,7 +17,7 @@ template <int NT, int NP>
 __global__ void __launch_bounds__(CSL_THREADS, 2)
 k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coef, int ldc,
                double* __restrict__ R, int ldr) {
-  constexpr int LSTRIDE = NT + 2 * NP;
+  constexpr int LSTRIDE = NT + 4 * NP;
   extern __shared__ __align__(16) double smem[];
   double* As = smem;                       // [2][CSL_ASZ]
   double* Bs = smem + 2 * CSL_ASZ;         // [2][CSL_BSZ]
@@ -59,7 +59,7 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
 #pragma unroll
       for (int t = 0; t < NT; ++t) v = fma(cf[t], row[t], v);
 #pragma unroll
-      for (int q = 0; q < NP; ++q) v = fma(pamp[q] * row[NT + 2 * q + 1], exp(pidx[q] * row[NT + 2 * q]), v);
+      for (int q = 0; q < NP; ++q) v = fma(pamp[q] * row[NT + 4 * q + 1], exp(pidx[q] * row[NT + 4 * q]), v);
       B[kk * CSL_LDB + wl] = v;
     }
   };
@@ -137,20 +137,61 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
 }
 
 // ---- segmented-sum binning for block-sparse windows ----------------------------------------------------
-// One thread per walker, CSL_SEG_GROUP window rows per CTA row.  For each row only its non-zero support
-// [lo, hi) is visited: cl[l] is built once from the (warp-uniform) ell-table row and folded into the
-// bin with one extra FMA.  No shared memory, no barriers: the kernel is bound by the FP64 pipe.
+// One thread per walker, CSL_SEG_GROUP window rows per CTA.  For each row only its non-zero support
+// [lo, hi) is visited: cl[l] is built once and folded into the bin with one extra FMA.  The ell-table
+// rows and the window weights of the group's column span are staged in shared memory in chunks of
+// SEG_CH columns (coalesced loads), so the inner loop is 16-byte broadcast LDS + FP64 math only.
+//
+// Power laws along consecutive l:  E[l] = exp(idx logB[l]) obeys E[l+1] = E[l] exp(idx D[l]) with
+// D[l] = logB[l+1] - logB[l] (host, extended precision).  Within a bin the kernel takes one exact exp at
+// the first column and advances by a Taylor polynomial in y = idx D: degree 6 when |y| <= 0.012
+// (truncation y^7/7! < 7e-18), degree 10 when |y| <= 0.1 (y^11/11! < 3e-19), decided per warp from the
+// bin's max |D| (bin record) -- otherwise exp at every column.  The polynomials of different columns are
+// independent; only one multiply per column sits on the dependent chain.  Rounding grows by ~1 ulp per
+// column over a bin (<= a few 1e-15 relative), far inside the 1e-10 budget on lnL.
+template <int DEG>
+__device__ __forceinline__ double exp_taylor(double y) {
+  double p = (DEG == 10) ? 2.7557319223985893e-07 : 1.3888888888888889e-03;     // 1/10!  or 1/6!
+  if (DEG == 10) {
+    p = fma(p, y, 2.7557319223985888e-06);   // 1/9!
+    p = fma(p, y, 2.4801587301587302e-05);   // 1/8!
+    p = fma(p, y, 1.9841269841269841e-04);   // 1/7!
+    p = fma(p, y, 1.3888888888888889e-03);   // 1/6!
+  }
+  p = fma(p, y, 8.3333333333333332e-03);     // 1/5!
+  p = fma(p, y, 4.1666666666666664e-02);     // 1/4!
+  p = fma(p, y, 1.6666666666666666e-01);     // 1/3!
+  p = fma(p, y, 0.5);
+  p = fma(p, y, 1.0);
+  return fma(p, y, 1.0);
+}
+
 template <int NT, int NP>
 __global__ void __launch_bounds__(128)
 k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restrict__ coef, int ldc,
              double* __restrict__ R, int ldr) {
-  constexpr int LSTRIDE = NT + 2 * NP;
-  const int w = blockIdx.x * 128 + threadIdx.x;
+  constexpr int LSTRIDE = NT + 4 * NP;
+  constexpr int SEG_CH = LSTRIDE > 12 ? 128 : 256;     // keeps static shared memory under 48 KB
+  __shared__ __align__(16) double srow[SEG_CH * (LSTRIDE > 0 ? LSTRIDE : 1)];
+  __shared__ __align__(16) double swgt[CSL_SEG_GROUP][SEG_CH];
+  __shared__ int slo[CSL_SEG_GROUP], shi[CSL_SEG_GROUP], srw[CSL_SEG_GROUP];
+  __shared__ float sdmax[CSL_SEG_GROUP][CSL_MAX_PLAW];
+  __shared__ long long soff[CSL_SEG_GROUP];
+  const int tid = threadIdx.x;
+  const int w = blockIdx.x * 128 + tid;
   const int b_begin = bin0 + blockIdx.y * CSL_SEG_GROUP;
-  const int b_end = min(b_begin + CSL_SEG_GROUP, bin0 + nbins);
   const int32_t* first = p.bin_tab + (long long)b_begin * CSL_BIN_STRIDE;
   const int32_t* spec = p.spec_tab + (long long)first[CSL_B_SPEC] * CSL_SPEC_STRIDE;   // one spectrum per group
   const double* __restrict__ ltab = p.templates + spec[CSL_S_LTAB];
+  if (tid < CSL_SEG_GROUP) {
+    const int32_t* rec = first + tid * CSL_BIN_STRIDE;        // records are padded to whole groups
+    const bool live = (b_begin + tid < bin0 + nbins) && rec[CSL_B_ROW] >= 0;
+    slo[tid] = live ? rec[CSL_B_LO] : 0;
+    shi[tid] = live ? rec[CSL_B_HI] : 0;
+    srw[tid] = live ? rec[CSL_B_ROW] : -1;
+    soff[tid] = ((long long)rec[CSL_B_WINOFF_HI] << 32) | (unsigned)rec[CSL_B_WINOFF_LO];
+    for (int q = 0; q < CSL_MAX_PLAW; ++q) sdmax[tid][q] = __int_as_float(rec[CSL_B_DMAX + q]);
+  }
   double cf[NT > 0 ? NT : 1], pamp[NP > 0 ? NP : 1], pidx[NP > 0 ? NP : 1];
 #pragma unroll
   for (int t = 0; t < NT; ++t) cf[t] = coef[(long long)spec[CSL_S_TERM_COEF + t] * ldc + w];
@@ -161,33 +202,77 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
   }
   const int calrow = spec[CSL_S_CAL];
   const double cal = calrow >= 0 ? coef[(long long)calrow * ldc + w] : 1.0;
+  __syncthreads();
+  int glo = 0x7fffffff, ghi = 0;
+#pragma unroll
+  for (int b = 0; b < CSL_SEG_GROUP; ++b)
+    if (shi[b] > slo[b]) { glo = min(glo, slo[b]); ghi = max(ghi, shi[b]); }
 
-  auto cl_at = [&](const double* __restrict__ row) {
-    double v = 0.0;
+  double acc[CSL_SEG_GROUP];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) v = fma(cf[t], __ldg(row + t), v);
+  for (int b = 0; b < CSL_SEG_GROUP; ++b) acc[b] = 0.0;
+
+  // one column: x = sum_t cf T + sum_q (amp M) E_q ; then E_q advances to the next column
+  auto column = [&](const double* row, double wgt, double (&E)[NP > 0 ? NP : 1], double& a, auto advance) {
+    double x = 0.0;
 #pragma unroll
-    for (int q = 0; q < NP; ++q)
-      v = fma(pamp[q] * __ldg(row + NT + 2 * q + 1), exp(pidx[q] * __ldg(row + NT + 2 * q)), v);
-    return v;
+    for (int t = 0; t < NT; ++t) x = fma(cf[t], row[t], x);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) x = fma(pamp[q] * row[NT + 4 * q + 1], E[q], x);
+    a = fma(wgt, x, a);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) E[q] = advance(E[q], pidx[q], row + NT + 4 * q);
   };
 
-  for (int b = b_begin; b < b_end; ++b) {
-    const int32_t* rec = p.bin_tab + (long long)b * CSL_BIN_STRIDE;
-    const int lo = rec[CSL_B_LO], hi = rec[CSL_B_HI], row = rec[CSL_B_ROW];
-    if (row < 0) continue;   // group padding
-    const long long woff = ((long long)rec[CSL_B_WINOFF_HI] << 32) | (unsigned)rec[CSL_B_WINOFF_LO];
-    const double* __restrict__ wrow = p.windows + woff;
-    double acc0 = 0.0, acc1 = 0.0;
-    int l = lo;
-    for (; l + 1 < hi; l += 2) {          // two independent elements in flight per thread
-      const double v0 = cl_at(ltab + (long long)l * LSTRIDE);
-      const double v1 = cl_at(ltab + (long long)(l + 1) * LSTRIDE);
-      acc0 = fma(__ldg(wrow + l), v0, acc0);
-      acc1 = fma(__ldg(wrow + l + 1), v1, acc1);
+  for (int c0 = glo; c0 < ghi; c0 += SEG_CH) {
+    const int n = min(SEG_CH, ghi - c0);
+    {
+      const double2* __restrict__ src = reinterpret_cast<const double2*>(ltab + (long long)c0 * LSTRIDE);
+      double2* dst = reinterpret_cast<double2*>(srow);
+      for (int i = tid; i < n * LSTRIDE / 2; i += 128) dst[i] = __ldg(src + i);
+#pragma unroll
+      for (int b = 0; b < CSL_SEG_GROUP; ++b) {
+        const int l0 = max(slo[b], c0), l1 = min(shi[b], c0 + n);
+        const double* __restrict__ wr = p.windows + soff[b];
+        for (int l = l0 + tid; l < l1; l += 128) swgt[b][l - c0] = __ldg(wr + l);
+      }
     }
-    if (l < hi) acc0 = fma(__ldg(wrow + l), cl_at(ltab + (long long)l * LSTRIDE), acc0);
-    R[(long long)row * ldr + w] = __dsub_rn(__dmul_rn(cal, p.data[row]), acc0 + acc1);
+    __syncthreads();
+#pragma unroll 1
+    for (int b = 0; b < CSL_SEG_GROUP; ++b) {
+      const int l0 = max(slo[b], c0) - c0, l1 = min(shi[b], c0 + n) - c0;
+      if (l1 <= l0) continue;                   // block-uniform
+      double ymax = 0.0;
+#pragma unroll
+      for (int q = 0; q < NP; ++q) ymax = fmax(ymax, fabs(pidx[q]) * (double)sdmax[b][q]);
+      const bool t6 = __all_sync(0xffffffffu, ymax <= 0.012);
+      const bool t10 = __all_sync(0xffffffffu, ymax <= 0.1);
+      double E[NP > 0 ? NP : 1];
+#pragma unroll
+      for (int q = 0; q < NP; ++q) E[q] = exp(pidx[q] * srow[l0 * LSTRIDE + NT + 4 * q]);
+      double a = 0.0;
+      const double* wg = swgt[b];
+      if (t6) {
+        for (int l = l0; l < l1; ++l)
+          column(srow + l * LSTRIDE, wg[l], E, a,
+                 [](double e, double idx, const double* r) { return e * exp_taylor<6>(idx * r[2]); });
+      } else if (t10) {
+        for (int l = l0; l < l1; ++l)
+          column(srow + l * LSTRIDE, wg[l], E, a,
+                 [](double e, double idx, const double* r) { return e * exp_taylor<10>(idx * r[2]); });
+      } else {
+        for (int l = l0; l < l1; ++l)        // exact exp at every column (next column's logB is r[4 NP .. ])
+          column(srow + l * LSTRIDE, wg[l], E, a,
+                 [&](double e, double idx, const double* r) { return (l + 1 < l1) ? exp(idx * r[LSTRIDE]) : e; });
+      }
+      acc[b] += a;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int b = 0; b < CSL_SEG_GROUP; ++b) {
+    const int row = srw[b];
+    if (row >= 0) R[(long long)row * ldr + w] = __dsub_rn(__dmul_rn(cal, p.data[row]), acc[b]);
   }
 }
 
@@ -230,7 +315,7 @@ template <int NT, int NP>
 static int launch_class(const csl_program_t* p, int tile0, int ntile, int W, const double* coef, int ldc,
                         double* R, int ldr, cudaStream_t s) {
   static bool attr_set = false;
-  const size_t smem = (size_t)(2 * CSL_ASZ + 2 * CSL_BSZ + 2 * CSL_KC * (NT + 2 * NP)) * sizeof(double);
+  const size_t smem = (size_t)(2 * CSL_ASZ + 2 * CSL_BSZ + 2 * CSL_KC * (NT + 4 * NP)) * sizeof(double);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_bin_residual<NT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));

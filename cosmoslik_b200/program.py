@@ -230,7 +230,7 @@ class CompiledProgram(object):
                 NT = 2
             if (len(terms) < NT or len(m.plaws) < NP) and zero_row is None:
                 zero_row = code.coef(Const(0.0))     # padding terms multiply an all-zero coefficient
-            stride = NT + 2 * NP
+            stride = NT + 4 * NP
             rec = spec_tab[s]
             rec[L.S_NLPAD], rec[L.S_NTERM], rec[L.S_NPLAW], rec[L.S_LTAB] = nlp, NT, NP, toff
             ltab = np.zeros((nlp, stride))
@@ -245,8 +245,15 @@ class CompiledProgram(object):
                     with np.errstate(divide="ignore"):
                         lg = np.log(base[:nl])
                     # base 0: exp(idx * -1e300) gives 0**idx = 0 (idx>0), 1 (idx==0), inf (idx<0) like numpy
-                    ltab[:nl, NT + 2 * k] = np.where(np.isneginf(lg), -1e300, lg)
-                    ltab[:nl, NT + 2 * k + 1] = mul[:nl]
+                    ltab[:nl, NT + 4 * k] = np.where(np.isneginf(lg), -1e300, lg)
+                    ltab[:nl, NT + 4 * k + 1] = mul[:nl]
+                    # D[l] = logB[l+1] - logB[l] in extended precision (the kernels' power-law recurrence)
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        lgl = np.log(base[:nl].astype(np.longdouble))
+                        dl = np.zeros(nlp, dtype=np.longdouble)
+                        dl[:nl - 1] = lgl[1:] - lgl[:-1]
+                    dl = np.where(np.isfinite(dl), dl, 1e300).astype(np.float64)   # next to a zero base: never "small"
+                    ltab[:, NT + 4 * k + 2] = dl
                     rec[L.S_PLAW_AMP + k] = code.coef(amp); rec[L.S_PLAW_IDX + k] = code.coef(idx_e)
                 else:
                     rec[L.S_PLAW_AMP + k] = rec[L.S_PLAW_IDX + k] = zero_row
@@ -276,6 +283,12 @@ class CompiledProgram(object):
                         rec_b[L.B_LO], rec_b[L.B_HI] = supports[b]
                         rec_b[L.B_WINOFF_LO] = lo32 - (1 << 32) if lo32 >= (1 << 31) else lo32
                         rec_b[L.B_WINOFF_HI] = off >> 32
+                        lo_b, hi_b = supports[b]
+                        for k in range(len(m.plaws)):
+                            seg_d = np.abs(ltab[lo_b:max(hi_b - 1, lo_b), NT + 4 * k + 2])
+                            dmax = np.float32(min(seg_d.max() if seg_d.size else 0.0, 3e38))
+                            dmax = np.nextafter(dmax, np.float32(np.inf))            # round up
+                            rec_b[L.B_DMAX + k] = dmax.view(np.int32)
                     else:
                         rec_b[L.B_ROW], rec_b[L.B_SPEC] = -1, s     # group padding: skipped by the kernel
                     segbins.append(((NT, NP), rec_b))

@@ -97,7 +97,7 @@ class emcee(SlikSampler):
         seed = int(self.seed) if self.seed is not None else int(np.random.SeedSequence().entropy & (2 ** 63 - 1))
         kw = dict(dtype=torch.float64, device=dev)
         rl = 2 + nd
-        cap = max(nsteps, 1)
+        cap = max(nsteps, int(getattr(self, "row_capacity", 0)), 1)
         pos_all = self.initial_positions()
         if pos_all.shape != (k, nd):
             raise ValueError("initial positions must be [nwalkers, ndim]")
@@ -107,7 +107,11 @@ class emcee(SlikSampler):
         q = torch.empty_like(pos)
         zz = torch.empty(W, **kw)
         weight = torch.ones(W, **kw)
-        rows = torch.empty((W, cap, rl), **kw)
+        buf = getattr(self, "_buffers", None)           # reuse the big row buffer across runs of equal shape
+        if buf is None or buf[0] != (W, cap, rl, str(dev)):
+            buf = ((W, cap, rl, str(dev)), torch.empty((W, cap, rl), **kw))
+            dict.__setitem__(self, "_buffers", buf)
+        rows = buf[1]
         nrows = torch.zeros(W, dtype=torch.int32, device=dev)
         accepted = torch.zeros(W, dtype=torch.uint8, device=dev)
         pos_old = torch.empty_like(pos)

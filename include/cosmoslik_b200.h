@@ -45,7 +45,7 @@ extern "C" {
 #define CSL_TILE_STRIDE 32 /* int32 words per tile record                  */
 #define CSL_STACK     16   /* coefficient bytecode stack depth             */
 #define CSL_MAX_CLASS  8   /* distinct (NT, NP) spectrum classes per program */
-#define CSL_BIN_STRIDE 8   /* int32 words per bin record (segmented-sum binning) */
+#define CSL_BIN_STRIDE 16  /* int32 words per bin record (segmented-sum binning) */
 #define CSL_SEG_GROUP  8   /* bins per CTA row of the segmented-sum kernel    */
 
 /* coefficient bytecode (one flat program; STORE pops into coef row `arg`) */
@@ -62,7 +62,7 @@ enum {
   CSL_S_NPLAW = 2,   /* NP: power-law terms, padded to the class size {0,1,2,4}    */
   CSL_S_CAL   = 3,   /* coef row multiplying the data of this spectrum, -1 = 1.0 */
   CSL_S_LTAB  = 4,   /* offset (doubles) of the ell-table in `templates`: nl_pad rows of
-                        [T_0..T_{NT-1}, (logB_q, M_q) q<NP];
+                        [T_0..T_{NT-1}, (logB_q, M_q, D_q, 0) q<NP], D_q[l] = logB_q[l+1] - logB_q[l];
                         cl[l] = sum_t coef[TERM_COEF[t]] T_t[l]
                               + sum_q coef[PLAW_AMP[q]] M_q[l] exp(coef[PLAW_IDX[q]] logB_q[l])
                         (padding terms point at an all-zero coefficient row / zero columns)  */
@@ -89,7 +89,8 @@ enum {
   CSL_B_SPEC = 1,
   CSL_B_LO = 2,      /* first non-zero column                                   */
   CSL_B_HI = 3,      /* one past the last non-zero column                       */
-  CSL_B_WINOFF_LO = 4, CSL_B_WINOFF_HI = 5   /* offset (doubles) of the window row */
+  CSL_B_WINOFF_LO = 4, CSL_B_WINOFF_HI = 5,  /* offset (doubles) of the window row */
+  CSL_B_DMAX = 8     /* [CSL_MAX_PLAW]: float32 bits, max |D_q[l]| over [lo, hi) (see k_bin_segsum) */
 };
 
 /*

@@ -61,7 +61,7 @@ def residual(cp, coef):
             spec = t["spec_tab"][rec[L.B_SPEC]]
             NT, NP = spec[L.S_NTERM], spec[L.S_NPLAW]
             assert (NT, NP) == (NTc, NPc)
-            stride = NT + 2 * NP
+            stride = NT + 4 * NP
             l0, l1 = rec[L.B_LO], rec[L.B_HI]
             ltab = t["templates"][spec[L.S_LTAB]: spec[L.S_LTAB] + spec[L.S_NLPAD] * stride].reshape(-1, stride)[l0:l1]
             cl = np.zeros(l1 - l0)
@@ -69,7 +69,7 @@ def residual(cp, coef):
                 cl += coef[spec[L.S_TERM_COEF + k]] * ltab[:, k]
             for k in range(NP):
                 with np.errstate(over="ignore"):
-                    cl += coef[spec[L.S_PLAW_AMP + k]] * ltab[:, NT + 2 * k + 1] * np.exp(coef[spec[L.S_PLAW_IDX + k]] * ltab[:, NT + 2 * k])
+                    cl += coef[spec[L.S_PLAW_AMP + k]] * ltab[:, NT + 4 * k + 1] * np.exp(coef[spec[L.S_PLAW_IDX + k]] * ltab[:, NT + 4 * k])
             woff = (int(rec[L.B_WINOFF_HI]) << 32) | (int(rec[L.B_WINOFF_LO]) & 0xFFFFFFFF)
             cal = 1.0 if spec[L.S_CAL] < 0 else coef[spec[L.S_CAL]]
             r[rec[L.B_ROW]] = cal * t["data"][rec[L.B_ROW]] - np.dot(t["windows"][woff + l0: woff + l1], cl)
@@ -77,14 +77,14 @@ def residual(cp, coef):
         spec = t["spec_tab"][tile[L.T_SPEC]]
         l0, l1 = tile[L.T_LBEGIN], tile[L.T_LEND]
         NT, NP = spec[L.S_NTERM], spec[L.S_NPLAW]
-        stride = NT + 2 * NP
+        stride = NT + 4 * NP
         ltab = t["templates"][spec[L.S_LTAB]: spec[L.S_LTAB] + spec[L.S_NLPAD] * stride].reshape(-1, stride)[l0:l1]
         cl = np.zeros(l1 - l0)
         for k in range(NT):
             cl += coef[spec[L.S_TERM_COEF + k]] * ltab[:, k]
         for k in range(NP):
             with np.errstate(over="ignore"):
-                cl += coef[spec[L.S_PLAW_AMP + k]] * ltab[:, NT + 2 * k + 1] * np.exp(coef[spec[L.S_PLAW_IDX + k]] * ltab[:, NT + 2 * k])
+                cl += coef[spec[L.S_PLAW_AMP + k]] * ltab[:, NT + 4 * k + 1] * np.exp(coef[spec[L.S_PLAW_IDX + k]] * ltab[:, NT + 4 * k])
         woff = (int(tile[L.T_WINOFF_HI]) << 32) | (int(tile[L.T_WINOFF_LO]) & 0xFFFFFFFF)
         ld = tile[L.T_WINLD]
         cal = 1.0 if spec[L.S_CAL] < 0 else coef[spec[L.S_CAL]]
