@@ -122,7 +122,7 @@ k_trigemm_chi2(csl_program_t p, const double* __restrict__ R, int ldr, double* _
     if (i * CSL_BM + wm0 + mi * 8 < p.n) mmask |= 1u << mi;
   const int kend = min((i + 1) * CSL_BM, (p.n + CSL_KC - 1) / CSL_KC * CSL_KC);
   gemm_stream_AB(acc, p.Minv + (long long)i * CSL_BM * npad, npad, R + c0, ldr, kend / CSL_KC, As, Bs, tid, wm0, wn0,
-                 lane, mmask);
+                 lane, mmask, i * CSL_BM);
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni)
 #pragma unroll

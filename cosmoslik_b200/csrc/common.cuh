@@ -91,7 +91,9 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xo
 __device__ __forceinline__ void gemm_stream_AB(double (&acc)[4][4][2], const double* __restrict__ A,
                                                long long lda, const double* __restrict__ B, long long ldb,
                                                int nchunk, double* As, double* Bs, int tid, int wm0, int wn0,
-                                               int lane, unsigned mmask = 0xFu) {
+                                               int lane, unsigned mmask = 0xFu, int tri_row0 = -1) {
+  // tri_row0 >= 0: A is lower triangular and this tile's first row is global row tri_row0 (columns start
+  // at 0): 8-row groups that lie entirely above the diagonal of a chunk are skipped.
   if (nchunk <= 0) return;
   load_A_tile_async(As, A, lda, tid);
   load_B_tile_async(Bs, B, ldb, tid);
@@ -105,7 +107,13 @@ __device__ __forceinline__ void gemm_stream_AB(double (&acc)[4][4][2], const dou
       load_B_tile_async(Bs + (cur ^ 1) * CSL_BSZ, B + (long long)(c + 1) * CSL_KC * ldb, ldb, tid);
       cp_async_commit();
     }
-    warp_mma_chunk(acc, As + cur * CSL_ASZ, Bs + cur * CSL_BSZ, wm0, wn0, lane, mmask);
+    unsigned m = mmask;
+    if (tri_row0 >= 0) {
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+        if (tri_row0 + wm0 + mi * 8 + 7 < c * CSL_KC) m &= ~(1u << mi);
+    }
+    if (m) warp_mma_chunk(acc, As + cur * CSL_ASZ, Bs + cur * CSL_BSZ, wm0, wn0, lane, m);
     cp_async_wait<0>();
     __syncthreads();
   }

@@ -183,6 +183,20 @@ class CompiledProgram(object):
                 self._dev('Minv', Mp, np.float64)
                 self.meta['chi2_mode'] = 1
 
+    def _chi2_executed_flops(self):
+        """DMMA flops per walker the chi^2 kernel actually issues (8-row groups x 16-column chunks)"""
+        n, npad = self.n, self.n_pad
+        if not self.meta.get('chi2_mode'):
+            return npad * npad + npad * L.BM            # blocked solve: full blocks incl. the diagonal inverses
+        tot = 0
+        kmax = _rup(n, L.KC)
+        for r0 in range(0, npad, 8):
+            if r0 >= n:
+                continue
+            kend = min((r0 // L.BM + 1) * L.BM, kmax)
+            tot += sum(1 for k0 in range(0, kend, L.KC) if r0 + 7 >= k0) * 2 * 8 * L.KC
+        return tot
+
     def _build_gauss(self, P, code, q):
         n = len(q.values)
         if q.cov.shape != (n, n) or q.mean.shape != (n,):
@@ -350,7 +364,7 @@ class CompiledProgram(object):
         # work per evaluation: dense windows, non-zero window entries, DMMA blocks that
         # are actually executed, foreground-build FP64 ops (~1 per template term, ~20 per power law), TRSM
         self.flops = dict(bin_dense=flops_dense, bin_nnz=flops_nnz, bin_exec=flops_exec, build_ops=2 * builds,
-                          trsm=self.n_pad * self.n_pad + self.n_pad * L.BM, trsm_alg=n * n)
+                          trsm=self._chi2_executed_flops(), trsm_alg=n * n)
 
 
 class DeviceProgram(CompiledProgram):

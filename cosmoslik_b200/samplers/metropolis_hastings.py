@@ -73,6 +73,26 @@ class metropolis_hastings(SlikSampler):
             pass
         return self.stats
 
+    def gelman_rubin(self, burn_rows=0):
+        """Potential scale reduction R-hat per sampled parameter over ALL chains of the last run
+        (new functionality; the reference has no convergence statistic).  Per-chain weighted
+        count / mean / variance are reduced on the device (``csl_chain_moments``); with several
+        GPUs the per-chain moments are all-gathered; the O(nchains x ndim) combination is
+        chains.rhat_from_moments."""
+        from ..chains import rhat_from_moments
+        st = self.stats
+        if not st:
+            raise RuntimeError("gelman_rubin: run the sampler first")
+        rows, nrows = st["rows"], st["nrows"]
+        W, cap, rl = rows.shape
+        nd = rl - 2
+        torch = __import__("torch")
+        out = torch.empty((W, 1 + 2 * nd), dtype=torch.float64, device=rows.device)
+        L.check(L.lib().csl_chain_moments(W, nd, rows.data_ptr(), nrows.data_ptr(), cap, int(burn_rows),
+                                          out.data_ptr(), L.stream_ptr()), "csl_chain_moments")
+        allm = dist.all_gather_rows(out, int(self.nchains)).cpu().numpy()
+        return rhat_from_moments(allm[:, 0], allm[:, 1:1 + nd], allm[:, 1 + nd:])
+
     # ------------------------------------------------------------------
     def _run(self, prog, emit):
         torch, lib = prog.torch, prog.lib

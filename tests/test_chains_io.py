@@ -1,0 +1,116 @@
+"""Chain containers and the chain-file format (CPU): files written by this package load with the
+reference's own ``load_chain`` (when the reference tree is mounted), the reference's file loads here,
+and the statistics agree with the oracle."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden
+from cosmoslik_b200 import Chain, Chains, load_chain, get_covariance, combine_covs
+from cosmoslik_b200.chains import ChainWriter, gelman_rubin, rhat_from_moments
+from cosmoslik_b200.samplers.metropolis_hastings import _FileBlocks
+from oracle import refshim, runtime as ort, samplers as osamp
+
+
+def test_reference_chain_file_loads_here():
+    g = golden("mh_quick.npz")
+    c = load_chain(os.path.join(GOLDEN, "ref_mh.chain"))
+    assert isinstance(c, Chains) and len(c) == 1
+    assert list(c[0].keys()) == ["lnl", "weight", "a", "b"]
+    np.testing.assert_array_equal(c[0]["lnl"], g["file_lnl"])
+    np.testing.assert_array_equal(c[0]["weight"], g["file_weight"])
+    np.testing.assert_array_equal(c[0]["a"], g["file_a"])
+
+
+def test_single_process_block_structure_matches_the_reference(tmp_path):
+    """nchains == 1: records of mpi_comm_freq rows minus the last one (metropolis_hastings.py:237)"""
+    g = golden("mh_quick.npz")
+    rows = np.column_stack([g["lnl"], g["weight"], g["x"]])
+    path = str(tmp_path / "single.chain")
+    fb = _FileBlocks(path, ["lnl", "weight", "a", "b"], 100, single=True)
+    for i in range(0, len(rows), 37):          # rows arrive in arbitrary pieces
+        fb.add(0, rows[i:i + 37])
+    fb.finish()
+    with open(path, "rb") as f, open(os.path.join(GOLDEN, "ref_mh.chain"), "rb") as fr:
+        mine, ref = [], []
+        for fh, out in ((f, mine), (fr, ref)):
+            while True:
+                try:
+                    out.append(pickle.load(fh))
+                except EOFError:
+                    break
+    assert list(mine[0]) == list(ref[0])                       # header: ndarray of names
+    assert len(mine) == len(ref)
+    for (i1, r1), (i2, r2) in zip(mine[1:], ref[1:]):
+        assert i1 == i2 and r1.dtype == r2.dtype
+        np.testing.assert_array_equal(r1.view(float), r2.view(float))
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("header", ["ndarray", "list"])
+def test_files_written_here_load_with_the_reference_loader(tmp_path, header):
+    R = refshim.load()
+    rs = np.random.RandomState(0)
+    path = str(tmp_path / "multi.chain")
+    w = ChainWriter(path, ["lnl", "weight", "p.a", "p.b", "q"], header)
+    data = {}
+    for block in range(3):
+        for cid in (2, 0, 1):
+            r = rs.standard_normal((4 + cid, 5))
+            data.setdefault(cid, []).append(r)
+            w.write(cid, r)
+        w.flush()
+    w.close()
+    ref = R.chains.load_chain(path)
+    mine = load_chain(path)
+    assert len(ref) == len(mine) == 3
+    for cid in range(3):
+        full = np.concatenate(data[cid])
+        for k, name in enumerate(["lnl", "weight", "p.a", "p.b", "q"]):
+            np.testing.assert_array_equal(mine[cid][name], full[:, k])
+        # the reference loader iterates a set of ids; match by content
+        assert any(np.array_equal(rc["q"], full[:, 4]) for rc in ref)
+
+
+def test_chain_statistics():
+    rs = np.random.RandomState(1)
+    x = rs.standard_normal((500, 3)) @ rs.standard_normal((3, 3))
+    w = rs.randint(1, 8, 500).astype(float)
+    c = Chain({"lnl": rs.uniform(size=500), "weight": w, "a": x[:, 0], "b": x[:, 1], "c": x[:, 2]})
+    names = ["a", "b", "c"]
+    np.testing.assert_allclose(c.cov(names), ort.get_covariance(x, w), rtol=1e-13)
+    np.testing.assert_allclose(c.mean(names), np.average(x, axis=0, weights=w))
+    assert c.length() == 500 and c.length(unique=False) == w.sum()
+    assert abs(c.acceptance() - 1 / w.mean()) < 1e-15
+    b = c.burnin(100)
+    first = np.searchsorted(np.cumsum(w), 100)
+    assert b.length() == 500 - first
+    t = c.thin(10)
+    assert abs(t["weight"].sum() - np.ceil(w.sum() / 10)) <= 1
+    assert c.best_fit()["lnl"] == c["lnl"].min()
+    j = Chains([c, c]).join()
+    assert j.length() == 1000
+    g = c.add_gauss_prior("a", 0.0, 2.0)
+    np.testing.assert_allclose(g["lnl"] - c["lnl"], c["a"] ** 2 / 2 / 4)
+    assert "acceptance" in str(c)
+
+
+def test_combine_covs_and_get_covariance_match_the_reference_outputs():
+    g = golden("cov.npz")
+    np.testing.assert_allclose(get_covariance(g["dat"], g["wts"]), g["cov_w"], rtol=1e-14)
+    names, cov = combine_covs({"a": 2.0, "b": 0.5}, (["c", "a"], np.array([[4.0, 0.3], [0.3, 9.0]])))
+    idx = [names.index(k) for k in ("a", "b", "c")]
+    np.testing.assert_array_equal(cov[np.ix_(idx, idx)], g["init_cov"])
+
+
+def test_gelman_rubin_host():
+    rs = np.random.RandomState(2)
+    chains = Chains([Chain({"lnl": np.zeros(2000), "weight": rs.randint(1, 5, 2000).astype(float),
+                            "x": rs.standard_normal(2000), "y": rs.standard_normal(2000) * 3}) for _ in range(6)])
+    got = gelman_rubin(chains, ["x", "y"])
+    mom = [osamp.chain_moments(c.matrix(["x", "y"]), c["weight"]) for c in chains]
+    ref = osamp.gelman_rubin([m[0] for m in mom], [m[1] for m in mom], [m[2] for m in mom])
+    np.testing.assert_allclose(got, ref, rtol=1e-13)
+    assert set(chains.gelman_rubin()) == {"x", "y"}

@@ -300,6 +300,21 @@ def test_mh_device_streams_reproduce_the_oracle(torch):
             np.testing.assert_allclose([r[2] for r in got[c]], [r[2] for r in rows[c]], rtol=0, atol=1e-11)
 
 
+def test_gelman_rubin_on_device_matches_the_oracle(torch):
+    nd, nch, nsteps = 4, 16, 800
+    Cv = np.eye(nd) + 0.2
+    slik = Slik(B.gauss_script(Cv, lambda s: samplers.metropolis_hastings(
+        s, num_samples=nsteps * nch, nchains=nch, seed=77, proposal_update=False))())
+    st = slik.sampler.run(slik.evaluate)
+    rows, nrows = st["rows"].cpu().numpy(), st["nrows"].cpu().numpy()
+    burn = 20
+    mom = [osamp.chain_moments(rows[c, burn:nrows[c], 2:], rows[c, burn:nrows[c], 1]) for c in range(nch)]
+    ref = osamp.gelman_rubin([m[0] for m in mom], [m[1] for m in mom], [m[2] for m in mom])
+    got = slik.sampler.gelman_rubin(burn_rows=burn)
+    np.testing.assert_allclose(got, ref, rtol=1e-11)
+    assert np.all(got < 1.2)
+
+
 # ---------------------------------------------------------------- stretch move
 def test_stretch_move_matches_the_oracle(torch, tmp_path):
     prob = synthetic.spt_multifreq_problem(1, nbins=12, lmax=801)
