@@ -187,35 +187,59 @@ k_mh_gauss_run(csl_program_t p, int W, int nsteps, const double* __restrict__ Lf
 // ---------------------------------------------------------------------------------------------
 // get_new_cov sufficient statistics (metropolis_hastings.py:249-253, chains.py:507-512)
 // ---------------------------------------------------------------------------------------------
-#define MOM_BLOCKS 128
+#define MOM_BLOCKS 592      // 4 CTAs per SM on 148 SMs
+#define MOM_TILE 64         // rows staged per barrier pair
 // pass 1 (mean == nullptr): partial[b][0] = sum w, [1..nd] = sum w x.
 // pass 2: partial[b][1+nd + i*nd + k] = sum w (x_i - mean_i)(x_k - mean_k).
+// The last half of a chain's rows is contiguous in memory: tiles of MOM_TILE rows are staged in shared
+// memory with coalesced loads, then every thread owns a few (i,k) pairs and sweeps the tile.
 __global__ void __launch_bounds__(SAMP_THREADS)
 k_mh_moments(int W, int nd, const double* __restrict__ rows, const int32_t* __restrict__ nrows, int cap,
              const double* __restrict__ mean, double* __restrict__ partial) {
-  __shared__ double sx[CSL_MAX_DIM + 2];
+  extern __shared__ double sx[];            // [MOM_TILE][2 + nd]
   const int m = 1 + nd + nd * nd;
-  double acc[(CSL_MAX_DIM * CSL_MAX_DIM + SAMP_THREADS - 1) / SAMP_THREADS];
-#pragma unroll
-  for (int q = 0; q < (int)(sizeof(acc) / sizeof(double)); ++q) acc[q] = 0.0;
-  double a1 = 0.0;  // pass 1: thread i < 1+nd accumulates element i
   const int rl = 2 + nd;
+  constexpr int NACC = (CSL_MAX_DIM * CSL_MAX_DIM + SAMP_THREADS - 1) / SAMP_THREADS;
+  double acc[NACC];
+  int pi[NACC], pk[NACC];
+#pragma unroll
+  for (int q = 0; q < NACC; ++q) {
+    acc[q] = 0.0;
+    int e = threadIdx.x + q * SAMP_THREADS;
+    pi[q] = (e < nd * nd) ? e / nd : -1;
+    pk[q] = (e < nd * nd) ? e - (e / nd) * nd : 0;
+  }
+  double mi[NACC], mk[NACC];
+#pragma unroll
+  for (int q = 0; q < NACC; ++q) {
+    mi[q] = (mean && pi[q] >= 0) ? mean[pi[q]] : 0.0;
+    mk[q] = (mean && pi[q] >= 0) ? mean[pk[q]] : 0.0;
+  }
+  double a1 = 0.0;  // pass 1: thread i <= nd accumulates element i
   for (int w = blockIdx.x; w < W; w += MOM_BLOCKS) {
-    int nr = min(nrows[w], cap);
-    for (int r = nr / 2; r < nr; ++r) {
-      const double* row = rows + ((long long)w * cap + r) * rl;
+    const int nr = min(nrows[w], cap);
+    for (int t0 = nr / 2; t0 < nr; t0 += MOM_TILE) {
+      const int nt = min(MOM_TILE, nr - t0);
+      const double* src = rows + ((long long)w * cap + t0) * rl;
       __syncthreads();
-      if (threadIdx.x < rl) sx[threadIdx.x] = row[threadIdx.x];
+      for (int j = threadIdx.x; j < nt * rl; j += SAMP_THREADS) sx[j] = src[j];
       __syncthreads();
-      const double wt = sx[1];
       if (mean == nullptr) {
-        if (threadIdx.x == 0) a1 += wt;
-        else if (threadIdx.x <= nd) a1 = fma(wt, sx[1 + threadIdx.x], a1);
+        if (threadIdx.x <= nd) {
+          for (int r = 0; r < nt; ++r) {
+            const double wt = sx[r * rl + 1];
+            a1 = (threadIdx.x == 0) ? a1 + wt : fma(wt, sx[r * rl + 1 + threadIdx.x], a1);
+          }
+        }
       } else {
-        int q = 0;
-        for (int e = threadIdx.x; e < nd * nd; e += SAMP_THREADS, ++q) {
-          int i = e / nd, k = e - i * nd;
-          acc[q] = fma(wt * (sx[2 + i] - mean[i]), sx[2 + k] - mean[k], acc[q]);
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) {
+          if (pi[q] >= 0) {
+            double s_ = acc[q];
+            for (int r = 0; r < nt; ++r)
+              s_ = fma(sx[r * rl + 1] * (sx[r * rl + 2 + pi[q]] - mi[q]), sx[r * rl + 2 + pk[q]] - mk[q], s_);
+            acc[q] = s_;
+          }
         }
       }
     }
@@ -224,8 +248,9 @@ k_mh_moments(int W, int nd, const double* __restrict__ rows, const int32_t* __re
   if (mean == nullptr) {
     if (threadIdx.x <= nd) out[threadIdx.x] = a1;
   } else {
-    int q = 0;
-    for (int e = threadIdx.x; e < nd * nd; e += SAMP_THREADS, ++q) out[1 + nd + e] = acc[q];
+#pragma unroll
+    for (int q = 0; q < NACC; ++q)
+      if (pi[q] >= 0) out[1 + nd + threadIdx.x + q * SAMP_THREADS] = acc[q];
   }
 }
 
@@ -406,7 +431,7 @@ extern "C" int csl_mh_moments(int W, int ndim, const double* rows, const int32_t
   CSL_REQUIRE(W > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && rows && nrows && partial && out, "csl_mh_moments: bad argument");
   const int m = 1 + ndim + ndim * ndim;
   cudaStream_t s = (cudaStream_t)stream;
-  k_mh_moments<<<MOM_BLOCKS, SAMP_THREADS, 0, s>>>(W, ndim, rows, nrows, cap, mean, partial);
+  k_mh_moments<<<MOM_BLOCKS, SAMP_THREADS, (size_t)MOM_TILE * (2 + ndim) * sizeof(double), s>>>(W, ndim, rows, nrows, cap, mean, partial);
   int lo = mean ? 1 + ndim : 0, hi = mean ? m : 1 + ndim;
   k_reduce_partials<<<(hi - lo + 127) / 128, 128, 0, s>>>(m, lo, hi, partial, out);
   return csl_check_launch("k_mh_moments");

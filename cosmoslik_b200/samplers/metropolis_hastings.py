@@ -122,7 +122,7 @@ class metropolis_hastings(SlikSampler):
         accepted = torch.zeros(W, dtype=torch.uint8, device=dev)
         margin = torch.zeros(W, **kw)
         m = 1 + nd + nd * nd
-        mom_part = torch.empty((128, m), **kw)
+        mom_part = torch.empty((592, m), **kw)
         mom = torch.zeros(m, **kw)
         streams = self.streams or {}
         zs = streams.get("z"); ds = streams.get("delta"); us = streams.get("u")

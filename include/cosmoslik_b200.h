@@ -213,7 +213,7 @@ int csl_mh_gauss_run(const csl_program_t* p, int W, int nsteps, const double* Lf
 /* get_new_cov (:249-253) sufficient statistics over the last half of every chain's rows:
  * pass 1 (mean == NULL): out[0] = sum w, out[1..ndim] = sum w x.
  * pass 2 (mean given):   out[1+ndim ..] = sum w (x-mean)(x-mean)^T  [ndim*ndim].
- * partial [128, 1+ndim+ndim*ndim] is scratch; the reduction order is fixed (bitwise reproducible).
+ * partial [592, 1+ndim+ndim*ndim] is scratch; the reduction order is fixed (bitwise reproducible).
  * Sums over ranks are one all-reduce of out. */
 int csl_mh_moments(int W, int ndim, const double* rows, const int32_t* nrows, int cap,
                    const double* mean, double* partial, double* out, void* stream);
