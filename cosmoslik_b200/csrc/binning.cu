@@ -13,6 +13,26 @@
 // unrolled; the host sorts the tiles by class (csl_program_t::cls).
 #include "common.cuh"
 
+// exp(y) for small |y| by its Taylor polynomial: degree 6 for |y| <= 0.012 (truncation < 7e-18), degree 10
+// for |y| <= 0.1 (< 3e-19).  Used to advance a power law E[l] = exp(idx logB[l]) to the next column:
+// E[l+1] = E[l] exp(idx D[l]),  D[l] = logB[l+1] - logB[l] from the ell-table.
+template <int DEG>
+__device__ __forceinline__ double exp_taylor(double y) {
+  double p = (DEG == 10) ? 2.7557319223985893e-07 : 1.3888888888888889e-03;     // 1/10!  or 1/6!
+  if (DEG == 10) {
+    p = fma(p, y, 2.7557319223985888e-06);   // 1/9!
+    p = fma(p, y, 2.4801587301587302e-05);   // 1/8!
+    p = fma(p, y, 1.9841269841269841e-04);   // 1/7!
+    p = fma(p, y, 1.3888888888888889e-03);   // 1/6!
+  }
+  p = fma(p, y, 8.3333333333333332e-03);     // 1/5!
+  p = fma(p, y, 4.1666666666666664e-02);     // 1/4!
+  p = fma(p, y, 1.6666666666666666e-01);     // 1/3!
+  p = fma(p, y, 0.5);
+  p = fma(p, y, 1.0);
+  return fma(p, y, 1.0);
+}
+
 template <int NT, int NP>
 __global__ void __launch_bounds__(CSL_THREADS, 2)
 k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coef, int ldc,
@@ -50,17 +70,31 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
     constexpr int NCH = CSL_KC * LSTRIDE / 2;
     for (int c = tid; c < NCH; c += CSL_THREADS) cp_async16(L + 2 * c, ltab + (long long)l0 * LSTRIDE + 2 * c);
   };
+  // 8 consecutive columns per thread: one exact exp at the first, Taylor advances after it (warp votes pick
+  // the degree; a column pair with a large log-step falls back to exp)
   auto build_B = [&](double* B, const double* L) {
+    const double* row = L + grp * (CSL_KC / 2) * LSTRIDE;     // warp-uniform address -> shared-memory broadcast
+    double E[NP > 0 ? NP : 1];
 #pragma unroll
-    for (int r = 0; r < CSL_KC / 2; ++r) {
-      const int kk = grp * (CSL_KC / 2) + r;
-      const double* row = L + kk * LSTRIDE;     // warp-uniform address -> shared-memory broadcast
+    for (int q = 0; q < NP; ++q) E[q] = exp(pidx[q] * row[NT + 4 * q]);
+#pragma unroll 2
+    for (int r = 0; r < CSL_KC / 2; ++r, row += LSTRIDE) {
       double v = 0.0;
 #pragma unroll
       for (int t = 0; t < NT; ++t) v = fma(cf[t], row[t], v);
 #pragma unroll
-      for (int q = 0; q < NP; ++q) v = fma(pamp[q] * row[NT + 4 * q + 1], exp(pidx[q] * row[NT + 4 * q]), v);
-      B[kk * CSL_LDB + wl] = v;
+      for (int q = 0; q < NP; ++q) v = fma(pamp[q] * row[NT + 4 * q + 1], E[q], v);
+      B[(grp * (CSL_KC / 2) + r) * CSL_LDB + wl] = v;
+      if (r + 1 < CSL_KC / 2) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          const double y = pidx[q] * row[NT + 4 * q + 2];
+          const double ay = fabs(y);
+          if (__all_sync(0xffffffffu, ay <= 0.012)) E[q] *= exp_taylor<6>(y);
+          else if (__all_sync(0xffffffffu, ay <= 0.1)) E[q] *= exp_taylor<10>(y);
+          else E[q] = exp(pidx[q] * row[LSTRIDE + NT + 4 * q]);
+        }
+      }
     }
   };
 
@@ -149,23 +183,6 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
 // bin's max |D| (bin record) -- otherwise exp at every column.  The polynomials of different columns are
 // independent; only one multiply per column sits on the dependent chain.  Rounding grows by ~1 ulp per
 // column over a bin (<= a few 1e-15 relative), far inside the 1e-10 budget on lnL.
-template <int DEG>
-__device__ __forceinline__ double exp_taylor(double y) {
-  double p = (DEG == 10) ? 2.7557319223985893e-07 : 1.3888888888888889e-03;     // 1/10!  or 1/6!
-  if (DEG == 10) {
-    p = fma(p, y, 2.7557319223985888e-06);   // 1/9!
-    p = fma(p, y, 2.4801587301587302e-05);   // 1/8!
-    p = fma(p, y, 1.9841269841269841e-04);   // 1/7!
-    p = fma(p, y, 1.3888888888888889e-03);   // 1/6!
-  }
-  p = fma(p, y, 8.3333333333333332e-03);     // 1/5!
-  p = fma(p, y, 4.1666666666666664e-02);     // 1/4!
-  p = fma(p, y, 1.6666666666666666e-01);     // 1/3!
-  p = fma(p, y, 0.5);
-  p = fma(p, y, 1.0);
-  return fma(p, y, 1.0);
-}
-
 template <int NT, int NP>
 __global__ void __launch_bounds__(128)
 k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restrict__ coef, int ldc,
