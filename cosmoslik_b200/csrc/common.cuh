@@ -34,25 +34,51 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // One k-chunk (CSL_KC columns) of the CTA tile product on a warp tile of 32 x 32:
 // acc[mi][ni][2] += A[wm0 + 8 mi .., :] * B[:, wn0 + 8 ni ..]
-// As: [CSL_BM][CSL_LDA], Bs: [CSL_KC][CSL_LDB].  mmask bit mi = 0 skips an all-zero 8-row group.
-__device__ __forceinline__ void warp_mma_chunk(double (&acc)[4][4][2], const double* __restrict__ As,
-                                               const double* __restrict__ Bs, int wm0, int wn0, int lane,
-                                               unsigned mmask = 0xFu) {
+// As: [CSL_BM][CSL_LDA], Bs: [CSL_KC][CSL_LDB].  Bit mi of MASK = 0 drops an all-zero 8-row group at
+// COMPILE time: a predicated-off DMMA still occupies the FP64 pipe (measured), a removed one does not.
+template <unsigned MASK>
+__device__ __forceinline__ void warp_mma_chunk_m(double (&acc)[4][4][2], const double* __restrict__ As,
+                                                 const double* __restrict__ Bs, int wm0, int wn0, int lane) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int ks = 0; ks < CSL_KC / 4; ++ks) {
     double a[4], b[4];
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) a[mi] = As[(wm0 + mi * 8 + g) * CSL_LDA + ks * 4 + t];
+    for (int mi = 0; mi < 4; ++mi)
+      if (MASK & (1u << mi)) a[mi] = As[(wm0 + mi * 8 + g) * CSL_LDA + ks * 4 + t];
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(ks * 4 + t) * CSL_LDB + wn0 + ni * 8 + g];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
-      if (mmask & (1u << mi)) {
+      if (MASK & (1u << mi)) {
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
       }
     }
+  }
+}
+
+// runtime mask -> one of the 16 compile-time variants (warp-uniform switch, a real branch)
+__device__ __forceinline__ void warp_mma_chunk(double (&acc)[4][4][2], const double* __restrict__ As,
+                                               const double* __restrict__ Bs, int wm0, int wn0, int lane,
+                                               unsigned mmask = 0xFu) {
+  switch (mmask & 0xFu) {
+    case 0xF: warp_mma_chunk_m<0xF>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0xE: warp_mma_chunk_m<0xE>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0xC: warp_mma_chunk_m<0xC>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0x8: warp_mma_chunk_m<0x8>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0x7: warp_mma_chunk_m<0x7>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0x3: warp_mma_chunk_m<0x3>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0x1: warp_mma_chunk_m<0x1>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0x6: warp_mma_chunk_m<0x6>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0x4: warp_mma_chunk_m<0x4>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0x2: warp_mma_chunk_m<0x2>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0x0: break;
+    case 0x5: warp_mma_chunk_m<0x5>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0x9: warp_mma_chunk_m<0x9>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0xA: warp_mma_chunk_m<0xA>(acc, As, Bs, wm0, wn0, lane); break;
+    case 0xB: warp_mma_chunk_m<0xB>(acc, As, Bs, wm0, wn0, lane); break;
+    default: warp_mma_chunk_m<0xD>(acc, As, Bs, wm0, wn0, lane); break;
   }
 }
 
