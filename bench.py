@@ -326,7 +326,7 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": size, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_of(args, prob, k_total), "e2e": e2e,
+            "config": dict(config_of(args, prob, k_total), exchange=smp.stats.get("exchange")), "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps + 4,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
             "acceptance": acc_frac, "host_launch_ms_per_step": host_ms,

@@ -292,11 +292,17 @@ k_stretch_propose(int Ns, int Nc, int nd, const double* __restrict__ s, const do
   if (lane == 0) zz[k] = z;
 }
 
+// Accept + publish.  With walkers sharded over several GPUs every rank keeps a replica of ALL walkers'
+// positions (`gath`, symmetric memory).  The accept kernel itself stores each local walker's final
+// position into every rank's replica over NVLink -- peer pointers (st.global on mapped peer memory) or
+// one multimem.st through the NVSwitch multicast address -- so the "all-gather of the complementary
+// half" is fused into the accept step; a device-side barrier follows on the stream.
 __global__ void __launch_bounds__(SAMP_THREADS)
 k_stretch_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ lnl_s, const double* __restrict__ q,
                  const double* __restrict__ lnl_q, const double* __restrict__ zz, const double* __restrict__ u_acc,
                  uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0, uint32_t Nc,
-                 uint8_t* __restrict__ accepted) {
+                 uint8_t* __restrict__ accepted, const unsigned long long* __restrict__ peers, int npeers,
+                 unsigned long long mc_ptr, long long dst_row0) {
   const int k = warp_global(), lane = threadIdx.x & 31;
   if (k >= Ns) return;
   double ua;
@@ -306,13 +312,28 @@ k_stretch_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ ln
   const double newlnp = -lnl_q[k], lnp0 = -lnl_s[k];
   const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)nd - 1.0, log(zz[k])), newlnp), lnp0);
   const bool acc = lnpdiff > log(ua);
+  const long long b = (long long)k * nd;
+  double v0 = 0.0, v1 = 0.0;
+  if (lane < nd) v0 = acc ? q[b + lane] : s[b + lane];
+  if (lane + 32 < nd) v1 = acc ? q[b + lane + 32] : s[b + lane + 32];
   if (acc) {
-    const long long b = (long long)k * nd;
-    if (lane < nd) s[b + lane] = q[b + lane];
-    if (lane + 32 < nd) s[b + lane + 32] = q[b + lane + 32];
+    if (lane < nd) s[b + lane] = v0;
+    if (lane + 32 < nd) s[b + lane + 32] = v1;
     if (lane == 0) lnl_s[k] = lnl_q[k];
   }
   if (lane == 0 && accepted) accepted[k] = acc ? 1 : 0;
+  const long long drow = (dst_row0 + k) * nd;
+  if (mc_ptr) {
+    double* dst = reinterpret_cast<double*>(mc_ptr) + drow;
+    if (lane < nd) asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" :: "l"(dst + lane), "d"(v0) : "memory");
+    if (lane + 32 < nd) asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" :: "l"(dst + lane + 32), "d"(v1) : "memory");
+  } else {
+    for (int r = 0; r < npeers; ++r) {
+      double* dst = reinterpret_cast<double*>(peers[r]) + drow;
+      if (lane < nd) dst[lane] = v0;
+      if (lane + 32 < nd) dst[lane + 32] = v1;
+    }
+  }
 }
 
 // wrapper bookkeeping, samplers/emcee.py:70-88
@@ -448,15 +469,35 @@ extern "C" int csl_stretch_propose(int Ns, int Nc, int ndim, const double* s, co
   return csl_check_launch("k_stretch_propose");
 }
 
+static int stretch_accept_impl(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q, const double* lnl_q,
+                               const double* zz, const double* u_acc, uint64_t seed, uint32_t step, uint32_t half,
+                               uint32_t walker0, uint8_t* accepted, const unsigned long long* peers, int npeers,
+                               unsigned long long mc_ptr, long long dst_row0, void* stream) {
+  CSL_REQUIRE(Ns > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && s && lnl_s && q && lnl_q && zz,
+              "csl_stretch_accept: bad argument");
+  CSL_REQUIRE(npeers == 0 || peers || mc_ptr, "csl_stretch_accept: peer pointers missing");
+  k_stretch_accept<<<warp_grid(Ns), SAMP_THREADS, 0, (cudaStream_t)stream>>>(
+      Ns, ndim, s, lnl_s, q, lnl_q, zz, u_acc, seed, step, half, walker0, (uint32_t)Nc, accepted, peers, npeers, mc_ptr,
+      dst_row0);
+  return csl_check_launch("k_stretch_accept");
+}
+
 extern "C" int csl_stretch_accept(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q,
                                   const double* lnl_q, const double* zz, const double* u_acc, uint64_t seed,
                                   uint32_t step, uint32_t half, uint32_t walker0, uint8_t* accepted, void* stream) {
-  CSL_REQUIRE(Ns > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && s && lnl_s && q && lnl_q && zz,
-              "csl_stretch_accept: bad argument");
-  k_stretch_accept<<<warp_grid(Ns), SAMP_THREADS, 0, (cudaStream_t)stream>>>(Ns, ndim, s, lnl_s, q, lnl_q, zz, u_acc,
-                                                                            seed, step, half, walker0, (uint32_t)Nc,
-                                                                            accepted);
-  return csl_check_launch("k_stretch_accept");
+  return stretch_accept_impl(Ns, Nc, ndim, s, lnl_s, q, lnl_q, zz, u_acc, seed, step, half, walker0, accepted, nullptr,
+                             0, 0ull, 0, stream);
+}
+
+extern "C" int csl_stretch_accept_publish(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q,
+                                          const double* lnl_q, const double* zz, const double* u_acc, uint64_t seed,
+                                          uint32_t step, uint32_t half, uint32_t walker0, uint8_t* accepted,
+                                          const uint64_t* peer_ptrs, int npeers, uint64_t multicast_ptr,
+                                          int64_t dst_row0, void* stream) {
+  CSL_REQUIRE(npeers > 0 && (peer_ptrs || multicast_ptr), "csl_stretch_accept_publish: no peers given");
+  return stretch_accept_impl(Ns, Nc, ndim, s, lnl_s, q, lnl_q, zz, u_acc, seed, step, half, walker0, accepted,
+                             reinterpret_cast<const unsigned long long*>(peer_ptrs), npeers,
+                             (unsigned long long)multicast_ptr, (long long)dst_row0, stream);
 }
 
 extern "C" int csl_emcee_rows(int W, int ndim, const double* pos_old, const double* pos_new, const double* lnl_new,

@@ -95,3 +95,44 @@ def barrier():
     d = _dist()
     if d:
         d.barrier()
+
+
+class EnsembleReplica(object):
+    """Every rank's copy of ALL walkers' positions in NVLink symmetric memory
+    (torch.distributed._symmetric_memory): the stretch-move accept kernel stores each local walker's
+    final position straight into every rank's copy (csl_stretch_accept_publish), so no all-gather
+    collective is issued; `barrier()` is a device-side barrier on the current stream.
+    Only with the NCCL backend and one rank per GPU; `EnsembleReplica.create` returns None otherwise
+    and the sampler falls back to NCCL all_gather."""
+
+    def __init__(self, tensor, handle, peers_dev, multicast):
+        self.tensor, self.handle, self.peers_dev, self.multicast = tensor, handle, peers_dev, multicast
+        self.npeers = handle.world_size
+        self._chan = 0
+
+    @classmethod
+    def create(cls, nrows, ndim, device):
+        d = _dist()
+        if d is None or d.get_world_size() == 1 or d.get_backend() != "nccl":
+            return None
+        if os.environ.get("COSMOSLIK_B200_NO_SYMM", "0") == "1":
+            return None
+        try:
+            import torch
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty((nrows, ndim), dtype=torch.float64, device=device)
+            h = symm.rendezvous(t, d.group.WORLD)
+            ptrs = torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64, device=device)
+            mc = 0
+            if os.environ.get("COSMOSLIK_B200_MULTICAST", "0") == "1" and h.has_multicast_support(
+                    h.device.type if hasattr(h, "device") else "cuda", device.index):
+                mc = int(h.multicast_ptr)
+            return cls(t, h, ptrs, mc)
+        except Exception as e:      # symmetric memory unavailable on this system
+            if get_rank() == 0:
+                print("cosmoslik_b200: symmetric-memory replica unavailable (%s); using NCCL all_gather" % e)
+            return None
+
+    def barrier(self):
+        self.handle.barrier(channel=self._chan)
+        self._chan ^= 1

@@ -104,6 +104,13 @@ class emcee(SlikSampler):
         pos = torch.from_numpy(pos_all[gid]).to(dev).contiguous()   # local: first-half slice then second-half slice
         lnl_pos = prog.lnl(pos)
         halves = [(0, n0, lo0, h), (n0, W, h + lo1, k - h)]          # (row0, row1, first global id, half size)
+        # several GPUs: a replica of the whole ensemble in NVLink symmetric memory, updated by the accept
+        # kernel itself (fused exchange); otherwise NCCL all_gather of the complementary half
+        replica = dist.EnsembleReplica.create(k, nd, dev) if size > 1 else None
+        if replica is not None:
+            replica.tensor.copy_(torch.from_numpy(pos_all).to(dev))
+            torch.cuda.synchronize()
+            dist.barrier()
         q = torch.empty_like(pos)
         zz = torch.empty(W, **kw)
         weight = torch.ones(W, **kw)
@@ -134,12 +141,18 @@ class emcee(SlikSampler):
                     o0, o1, _, csize = halves[1 - hidx]
                     if timers is not None:
                         ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
-                    comp = dist.all_gather_rows(pos[o0:o1], csize)    # the complementary half, all ranks' rows
+                    if replica is not None:
+                        cbase = 0 if hidx == 1 else h                 # global row of the complementary half
+                        comp = replica.tensor[cbase:cbase + csize]
+                    else:
+                        comp = dist.all_gather_rows(pos[o0:o1], csize)    # the complementary half, all ranks' rows
                     if timers is not None:
                         ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
                         timers.setdefault("all_gather", []).append((ev0, ev1))
                     ns = r1 - r0
                     if ns == 0:
+                        if replica is not None:
+                            replica.barrier()
                         continue
                     uz = jj = ua = None
                     if inj is not None:
@@ -152,10 +165,18 @@ class emcee(SlikSampler):
                                                     L.ptr(uz), L.ptr(jj), seed, i, hidx, g0, q_view.data_ptr(),
                                                     zz[r0:r1].data_ptr(), st), "csl_stretch_propose")
                     lnl_q = prog.lnl(q_view, timers=timers)
-                    L.check(lib.csl_stretch_accept(ns, csize, nd, s_view.data_ptr(), l_view.data_ptr(),
-                                                   q_view.data_ptr(), lnl_q.data_ptr(), zz[r0:r1].data_ptr(),
-                                                   L.ptr(ua), seed, i, hidx, g0, accepted[r0:r1].data_ptr(), st),
-                            "csl_stretch_accept")
+                    if replica is None:
+                        L.check(lib.csl_stretch_accept(ns, csize, nd, s_view.data_ptr(), l_view.data_ptr(),
+                                                       q_view.data_ptr(), lnl_q.data_ptr(), zz[r0:r1].data_ptr(),
+                                                       L.ptr(ua), seed, i, hidx, g0, accepted[r0:r1].data_ptr(), st),
+                                "csl_stretch_accept")
+                    else:
+                        L.check(lib.csl_stretch_accept_publish(
+                            ns, csize, nd, s_view.data_ptr(), l_view.data_ptr(), q_view.data_ptr(), lnl_q.data_ptr(),
+                            zz[r0:r1].data_ptr(), L.ptr(ua), seed, i, hidx, g0, accepted[r0:r1].data_ptr(),
+                            replica.peers_dev.data_ptr(), replica.npeers, replica.multicast, g0, st),
+                            "csl_stretch_accept_publish")
+                        replica.barrier()      # every rank's stores have landed before anyone proposes again
                 nacc += accepted.sum()
                 L.check(lib.csl_emcee_rows(W, nd, pos_old.data_ptr(), pos.data_ptr(), lnl_pos.data_ptr(),
                                            weight.data_ptr(), 1 if i == nsteps - 1 else 0, rows.data_ptr(),
@@ -177,5 +198,8 @@ class emcee(SlikSampler):
             if writer is not None:
                 writer.close()
         host_ms = 1e3 * (_time.perf_counter() - t_host0) / max(nsteps, 1)   # CPU time to ENQUEUE one step
-        self.stats = dict(host_ms_per_step=host_ms, pos=pos, lnl=lnl_pos, weight=weight, rows=rows, nrows=nrows, nsteps=nsteps,
+        exchange = ("none" if size == 1 else "nccl all_gather" if replica is None else
+                    "accept kernel stores to every rank's replica over NVLink (%s) + device barrier"
+                    % ("multimem.st multicast" if replica.multicast else "peer pointers"))
+        self.stats = dict(exchange=exchange, host_ms_per_step=host_ms, pos=pos, lnl=lnl_pos, weight=weight, rows=rows, nrows=nrows, nsteps=nsteps,
                           walker_ids=gid, seed=seed, accepted=int(nacc.item()), evals=nsteps * W)

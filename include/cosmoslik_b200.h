@@ -233,6 +233,18 @@ int csl_stretch_accept(int Ns, int Nc, int ndim, double* s, double* lnl_s, const
                        const double* zz, const double* u_acc, uint64_t seed, uint32_t step, uint32_t half,
                        uint32_t walker0, uint8_t* accepted, void* stream);
 
+/* Accept fused with the exchange step of the sharded ensemble (replaces the mpi_map pool round trip,
+ * mpi/mpi.py:40-64): besides updating s / lnl_s, every walker's final position is stored into row
+ * dst_row0 + k of EVERY rank's replica of the ensemble -- peer_ptrs[npeers] are the device addresses of
+ * the replicas (peer-mapped symmetric memory, this rank included) or, if multicast_ptr != 0, one
+ * multimem.st through the NVSwitch multicast address.  The caller issues a device-side barrier on the
+ * stream afterwards. */
+int csl_stretch_accept_publish(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q,
+                               const double* lnl_q, const double* zz, const double* u_acc, uint64_t seed,
+                               uint32_t step, uint32_t half, uint32_t walker0, uint8_t* accepted,
+                               const uint64_t* peer_ptrs, int npeers, uint64_t multicast_ptr, int64_t dst_row0,
+                               void* stream);
+
 /* wrapper bookkeeping of samplers/emcee.py:70-88 after a full step: a walker that did not move
  * gains weight; one that moved (or any walker on the last step) emits (lnl_next, weight, x_old). */
 int csl_emcee_rows(int W, int ndim, const double* pos_old, const double* pos_new, const double* lnl_new,
