@@ -336,6 +336,29 @@ k_stretch_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ ln
   }
 }
 
+// Device-side barrier across the ranks of one NVLink domain, launched on the compute stream right after
+// the publishing accept kernel.  flags[r] (one per rank, symmetric memory, uint64[world]) holds the last
+// epoch each peer has reached.  Thread r signals peer r with a system-scope release store (cumulative:
+// the previous kernel's peer stores are ordered before it) and spins on its own slot r with acquire
+// loads.  The host never blocks.  A bounded spin (~4 s) guards against a dead peer.
+__global__ void k_peer_barrier(const unsigned long long* __restrict__ flag_ptrs, int rank, int world,
+                               unsigned long long epoch) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  __threadfence_system();
+  unsigned long long* theirs = reinterpret_cast<unsigned long long*>(flag_ptrs[r]) + rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(theirs), "l"(epoch) : "memory");
+  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(flag_ptrs[rank]) + r;
+  unsigned long long seen = 0;
+  const long long t0 = clock64();
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+    if (seen >= epoch) break;
+    __nanosleep(40);
+  } while (clock64() - t0 < 8000000000ll);
+  __threadfence_system();
+}
+
 // wrapper bookkeeping, samplers/emcee.py:70-88
 __global__ void __launch_bounds__(SAMP_THREADS)
 k_emcee_rows(int W, int nd, const double* __restrict__ pos_old, const double* __restrict__ pos_new,
@@ -498,6 +521,13 @@ extern "C" int csl_stretch_accept_publish(int Ns, int Nc, int ndim, double* s, d
   return stretch_accept_impl(Ns, Nc, ndim, s, lnl_s, q, lnl_q, zz, u_acc, seed, step, half, walker0, accepted,
                              reinterpret_cast<const unsigned long long*>(peer_ptrs), npeers,
                              (unsigned long long)multicast_ptr, (long long)dst_row0, stream);
+}
+
+extern "C" int csl_peer_barrier(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, void* stream) {
+  CSL_REQUIRE(flag_ptrs && world > 0 && world <= 32 && rank >= 0 && rank < world, "csl_peer_barrier: bad argument");
+  k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(flag_ptrs), rank, world,
+                                                      (unsigned long long)epoch);
+  return csl_check_launch("k_peer_barrier");
 }
 
 extern "C" int csl_emcee_rows(int W, int ndim, const double* pos_old, const double* pos_new, const double* lnl_new,

@@ -105,10 +105,11 @@ class EnsembleReplica(object):
     Only with the NCCL backend and one rank per GPU; `EnsembleReplica.create` returns None otherwise
     and the sampler falls back to NCCL all_gather."""
 
-    def __init__(self, tensor, handle, peers_dev, multicast):
+    def __init__(self, tensor, handle, peers_dev, multicast, flags=None, flag_handle=None, flag_ptrs=None):
         self.tensor, self.handle, self.peers_dev, self.multicast = tensor, handle, peers_dev, multicast
         self.npeers = handle.world_size
-        self._chan = 0
+        self.flags, self.flag_handle, self.flag_ptrs = flags, flag_handle, flag_ptrs
+        self._epoch = 0
 
     @classmethod
     def create(cls, nrows, ndim, device):
@@ -124,15 +125,27 @@ class EnsembleReplica(object):
             h = symm.rendezvous(t, d.group.WORLD)
             ptrs = torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64, device=device)
             mc = 0
-            if os.environ.get("COSMOSLIK_B200_MULTICAST", "0") == "1" and h.has_multicast_support(
-                    h.device.type if hasattr(h, "device") else "cuda", device.index):
-                mc = int(h.multicast_ptr)
-            return cls(t, h, ptrs, mc)
+            if os.environ.get("COSMOSLIK_B200_MULTICAST", "0") == "1":
+                try:                       # NVSwitch multicast address (NVLS), when the fabric offers one
+                    mc = int(h.multicast_ptr or 0)
+                except Exception:
+                    mc = 0
+            # flags for the device-side barrier (csl_peer_barrier): uint64[world] per rank, zeroed
+            f = symm.empty((h.world_size,), dtype=torch.int64, device=device)
+            f.zero_()
+            fh = symm.rendezvous(f, d.group.WORLD)
+            fptrs = torch.tensor([int(p) for p in fh.buffer_ptrs], dtype=torch.int64, device=device)
+            torch.cuda.synchronize()
+            d.barrier()
+            return cls(t, h, ptrs, mc, f, fh, fptrs)
         except Exception as e:      # symmetric memory unavailable on this system
             if get_rank() == 0:
                 print("cosmoslik_b200: symmetric-memory replica unavailable (%s); using NCCL all_gather" % e)
             return None
 
     def barrier(self):
-        self.handle.barrier(channel=self._chan)
-        self._chan ^= 1
+        """device-side barrier on the current stream; the host does not wait"""
+        from . import _lib as L
+        self._epoch += 1
+        L.check(L.lib().csl_peer_barrier(self.flag_ptrs.data_ptr(), self.handle.rank, self.npeers, self._epoch,
+                                         L.stream_ptr()), "csl_peer_barrier")

@@ -106,7 +106,14 @@ class emcee(SlikSampler):
         halves = [(0, n0, lo0, h), (n0, W, h + lo1, k - h)]          # (row0, row1, first global id, half size)
         # several GPUs: a replica of the whole ensemble in NVLink symmetric memory, updated by the accept
         # kernel itself (fused exchange); otherwise NCCL all_gather of the complementary half
-        replica = dist.EnsembleReplica.create(k, nd, dev) if size > 1 else None
+        replica = None
+        if size > 1:                        # the rendezvous is expensive: one replica per sampler and shape
+            cached = getattr(self, "_replica", None)
+            if cached is not None and cached[0] == (k, nd, str(dev)):
+                replica = cached[1]
+            else:
+                replica = dist.EnsembleReplica.create(k, nd, dev)
+                dict.__setitem__(self, "_replica", ((k, nd, str(dev)), replica))
         if replica is not None:
             replica.tensor.copy_(torch.from_numpy(pos_all).to(dev))
             torch.cuda.synchronize()
@@ -161,9 +168,14 @@ class emcee(SlikSampler):
                         jj = torch.from_numpy(np.ascontiguousarray(inj[1][hidx][sl], dtype=np.int64)).to(dev)
                         ua = torch.from_numpy(np.ascontiguousarray(inj[2][hidx][sl], dtype=np.float64)).to(dev)
                     s_view, l_view, q_view = pos[r0:r1], lnl_pos[r0:r1], q[r0:r1]
+                    if timers is not None:
+                        ep0 = torch.cuda.Event(enable_timing=True); ep0.record()
                     L.check(lib.csl_stretch_propose(ns, csize, nd, s_view.data_ptr(), comp.data_ptr(), float(self.a),
                                                     L.ptr(uz), L.ptr(jj), seed, i, hidx, g0, q_view.data_ptr(),
                                                     zz[r0:r1].data_ptr(), st), "csl_stretch_propose")
+                    if timers is not None:
+                        ep1 = torch.cuda.Event(enable_timing=True); ep1.record()
+                        timers.setdefault("propose", []).append((ep0, ep1))
                     lnl_q = prog.lnl(q_view, timers=timers)
                     if replica is None:
                         L.check(lib.csl_stretch_accept(ns, csize, nd, s_view.data_ptr(), l_view.data_ptr(),
@@ -171,12 +183,20 @@ class emcee(SlikSampler):
                                                        L.ptr(ua), seed, i, hidx, g0, accepted[r0:r1].data_ptr(), st),
                                 "csl_stretch_accept")
                     else:
+                        if timers is not None:
+                            ea = torch.cuda.Event(enable_timing=True); ea.record()
                         L.check(lib.csl_stretch_accept_publish(
                             ns, csize, nd, s_view.data_ptr(), l_view.data_ptr(), q_view.data_ptr(), lnl_q.data_ptr(),
                             zz[r0:r1].data_ptr(), L.ptr(ua), seed, i, hidx, g0, accepted[r0:r1].data_ptr(),
                             replica.peers_dev.data_ptr(), replica.npeers, replica.multicast, g0, st),
                             "csl_stretch_accept_publish")
+                        if timers is not None:
+                            eb = torch.cuda.Event(enable_timing=True); eb.record()
                         replica.barrier()      # every rank's stores have landed before anyone proposes again
+                        if timers is not None:
+                            ec = torch.cuda.Event(enable_timing=True); ec.record()
+                            timers.setdefault("accept_publish", []).append((ea, eb))
+                            timers.setdefault("replica_barrier", []).append((eb, ec))
                 nacc += accepted.sum()
                 L.check(lib.csl_emcee_rows(W, nd, pos_old.data_ptr(), pos.data_ptr(), lnl_pos.data_ptr(),
                                            weight.data_ptr(), 1 if i == nsteps - 1 else 0, rows.data_ptr(),

@@ -245,6 +245,11 @@ int csl_stretch_accept_publish(int Ns, int Nc, int ndim, double* s, double* lnl_
                                const uint64_t* peer_ptrs, int npeers, uint64_t multicast_ptr, int64_t dst_row0,
                                void* stream);
 
+/* Device-side barrier over the ranks of one NVLink domain, on `stream` (the host does not block).
+ * flag_ptrs[world]: device addresses of every rank's uint64[world] flag array (symmetric memory, zeroed
+ * once); epoch must increase by one per call.  Orders the peer stores of the preceding kernel. */
+int csl_peer_barrier(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, void* stream);
+
 /* wrapper bookkeeping of samplers/emcee.py:70-88 after a full step: a walker that did not move
  * gains weight; one that moved (or any walker on the last step) emits (lnl_next, weight, x_old). */
 int csl_emcee_rows(int W, int ndim, const double* pos_old, const double* pos_new, const double* lnl_new,
