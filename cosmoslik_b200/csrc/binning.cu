@@ -16,21 +16,16 @@
 // exp(y) for small |y| by its Taylor polynomial: degree 6 for |y| <= 0.012 (truncation < 7e-18), degree 10
 // for |y| <= 0.1 (< 3e-19).  Used to advance a power law E[l] = exp(idx logB[l]) to the next column:
 // E[l+1] = E[l] exp(idx D[l]),  D[l] = logB[l+1] - logB[l] from the ell-table.
+// 1/k! in constant memory: DFMA takes the coefficient as a constant-bank operand, no moves needed
+__constant__ double c_inv_fact[11] = {1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02,
+                                      8.3333333333333332e-03, 1.3888888888888889e-03, 1.9841269841269841e-04,
+                                      2.4801587301587302e-05, 2.7557319223985888e-06, 2.7557319223985893e-07};
 template <int DEG>
 __device__ __forceinline__ double exp_taylor(double y) {
-  double p = (DEG == 10) ? 2.7557319223985893e-07 : 1.3888888888888889e-03;     // 1/10!  or 1/6!
-  if (DEG == 10) {
-    p = fma(p, y, 2.7557319223985888e-06);   // 1/9!
-    p = fma(p, y, 2.4801587301587302e-05);   // 1/8!
-    p = fma(p, y, 1.9841269841269841e-04);   // 1/7!
-    p = fma(p, y, 1.3888888888888889e-03);   // 1/6!
-  }
-  p = fma(p, y, 8.3333333333333332e-03);     // 1/5!
-  p = fma(p, y, 4.1666666666666664e-02);     // 1/4!
-  p = fma(p, y, 1.6666666666666666e-01);     // 1/3!
-  p = fma(p, y, 0.5);
-  p = fma(p, y, 1.0);
-  return fma(p, y, 1.0);
+  double p = c_inv_fact[DEG];
+#pragma unroll
+  for (int k = DEG - 1; k >= 0; --k) p = fma(p, y, c_inv_fact[k]);
+  return p;
 }
 
 template <int NT, int NP>
@@ -270,10 +265,12 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
       double a = 0.0;
       const double* wg = swgt[b];
       if (t6) {
+#pragma unroll 4
         for (int l = l0; l < l1; ++l)
           column(srow + l * LSTRIDE, wg[l], E, a,
                  [](double e, double idx, const double* r) { return e * exp_taylor<6>(idx * r[2]); });
       } else if (t10) {
+#pragma unroll 2
         for (int l = l0; l < l1; ++l)
           column(srow + l * LSTRIDE, wg[l], E, a,
                  [](double e, double idx, const double* r) { return e * exp_taylor<10>(idx * r[2]); });
