@@ -1,3 +1,4 @@
 from .metropolis_hastings import metropolis_hastings
 from .emcee import emcee
+from .priors import priors
 from .utils import initialize_covariance, proposal_factor

@@ -211,6 +211,25 @@ def main():
         out["chain_x%d" % c] = chain_x[c]
         out["chain_w%d" % c] = chain_w[c]
     np.savez_compressed(os.path.join(OUT, "cov.npz"), **out)
+
+    # ---------------- samplers.priors: i.i.d. draws from the uniform priors (samplers/priors.py:11-47) ----
+    import cosmoslik_plugins.samplers.priors as ref_priors
+
+    class boxed(core.SlikPlugin):
+        def __init__(self):
+            super().__init__()
+            self.a = core.param(start=0, scale=1, range=(-2, 3))
+            self.b = core.param(start=0, scale=1, uniform_prior=(0.5, 1.5), gaussian_prior=(1.0, 0.2))
+            self.sampler = ref_priors.priors(self, num_samples=200, reseed=False)
+
+        def __call__(self):
+            return (self.a ** 2 + self.b ** 2) / 2
+
+    np.random.seed(4242)
+    rows = [(r.lnl, r.weight, np.array(r.x, dtype=float)) for r in core.Slik(boxed()).sample()]
+    lnl, w, x = pack_rows(rows)
+    np.savez_compressed(os.path.join(OUT, "prior_sampler.npz"), seed=4242, lnl=lnl, weight=w, x=x)
+    print("prior_sampler rows", len(rows))
     print("wrote", sorted(os.listdir(OUT)))
 
 

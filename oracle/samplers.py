@@ -157,6 +157,26 @@ def mh_lockstep(lnl_batch, x0, nsteps, cov_est, z=None, delta=None, u=None,
     return rows, (cur_x, cur_lnl, cur_w), adapt
 
 
+def prior_sampler(lnl, sampled_names, uniform_priors, nsamples, uniform):
+    """samplers/priors.py:11-47: i.i.d. draws from the uniform priors, every row weight 1.
+    ``uniform_priors`` is the list the priors plugin builds (likelihoods/priors.py:6-16); per parameter the
+    FIRST box is used, more than two boxes or none is an error (:27-33).  ``uniform(lo, hi)`` is drawn
+    parameter by parameter in sorted-name order, sample by sample (:38-39).  PINNED by
+    tests/golden/prior_sampler.npz."""
+    box = {}
+    for k in sampled_names:
+        pr = [(n, lo, hi) for (n, lo, hi) in uniform_priors if n == k]
+        if len(pr) > 2:
+            raise Exception("Can't sample prior for parameters with multiple priors at once.")
+        if not pr:
+            raise Exception("Prior for parameter '%s' is improper." % k)
+        box[k] = pr[0][1:]
+    for _ in range(int(nsamples)):
+        x = [uniform(*box[k]) for k in sampled_names]
+        val, extra = lnl(*x)
+        yield Row(x, val, 1, extra)
+
+
 # --------------------------------------------------------------------------
 # affine-invariant ensemble sampler (third-party emcee 2.x, restated)
 # --------------------------------------------------------------------------

@@ -315,6 +315,39 @@ def test_gelman_rubin_on_device_matches_the_oracle(torch):
     assert np.all(got < 1.2)
 
 
+def test_prior_sampler_matches_the_reference(torch):
+    from cosmoslik_b200 import SlikPlugin, param
+    g = golden("prior_sampler.npz")
+
+    class boxed(SlikPlugin):
+        def __init__(self):
+            super().__init__()
+            self.a = param(start=0, scale=1, range=(-2, 3))
+            self.b = param(start=0, scale=1, uniform_prior=(0.5, 1.5), gaussian_prior=(1.0, 0.2))
+            self.sampler = samplers.priors(self, num_samples=200, reseed=False)
+
+        def __call__(self):
+            return (self.a ** 2 + self.b ** 2) / 2
+
+    np.random.seed(int(g["seed"]))
+    rows = [(s.lnl, s.weight, s.x) for s in Slik(boxed()).sample()]
+    np.testing.assert_array_equal([r[2] for r in rows], g["x"])          # same points, bit for bit
+    np.testing.assert_array_equal([r[1] for r in rows], g["weight"])
+    np.testing.assert_allclose([r[0] for r in rows], g["lnl"], rtol=4e-16)
+
+    class improper(SlikPlugin):
+        def __init__(self):
+            super().__init__()
+            self.a = param(start=0, scale=1)
+            self.sampler = samplers.priors(self, num_samples=2)
+
+        def __call__(self):
+            return self.a ** 2
+
+    with pytest.raises(Exception, match="improper"):
+        improper()
+
+
 # ---------------------------------------------------------------- stretch move
 def test_stretch_move_matches_the_oracle(torch, tmp_path):
     prob = synthetic.spt_multifreq_problem(1, nbins=12, lmax=801)
