@@ -53,3 +53,14 @@ def test_argument_validation_without_a_gpu():
     assert rc == -1 and b"null" in lib.csl_last_error()
     rc = lib.csl_mh_propose(0, 3, None, None, 0, None, None, 0, 0, 0, None)
     assert rc == -1
+
+
+def test_integration_md_struct_matches_the_binding():
+    """the ctypes stub shown to reference maintainers is the real layout"""
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        src = f.read()
+    code = src[src.index("class csl_program_t(C.Structure):"):src.index("lib.csl_lnl.restype")]
+    ns = {"C": ctypes}
+    exec(code, ns)
+    assert ctypes.sizeof(ns["csl_program_t"]) == ctypes.sizeof(_lib.Program)
+    assert [f[0] for f in ns["csl_program_t"]._fields_] == [f[0] for f in _lib.Program._fields_]
