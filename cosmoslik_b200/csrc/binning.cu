@@ -178,19 +178,69 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
 // bin's max |D| (bin record) -- otherwise exp at every column.  The polynomials of different columns are
 // independent; only one multiply per column sits on the dependent chain.  Rounding grows by ~1 ulp per
 // column over a bin (<= a few 1e-15 relative), far inside the 1e-10 budget on lnL.
+#define SEG_WPT 2      // walkers per thread: table rows / weights / loop control are amortised over both
+
+// One window row over columns [l0, l1) of the staged chunk, for the SEG_WPT walkers of a thread:
+//   x = sum_t cf T + sum_q (amp M) E_q ;  a += weight x ;  E_q advances to the next column.
+// MODE 0 / 1: Taylor degree 6 / 10 in y = idx D;  MODE 2: exact exp at every column.
+template <int NT, int NP, int MODE>
+__device__ __forceinline__ void seg_row(const double* __restrict__ srow, const double* __restrict__ wg, int l0, int l1,
+                                        const double (&cf)[SEG_WPT][NT > 0 ? NT : 1],
+                                        const double (&pamp)[SEG_WPT][NP > 0 ? NP : 1],
+                                        const double (&pidx)[SEG_WPT][NP > 0 ? NP : 1],
+                                        double (&E)[SEG_WPT][NP > 0 ? NP : 1], double (&a)[SEG_WPT]) {
+  constexpr int LSTRIDE = NT + 4 * NP;
+  const double* row = srow + l0 * LSTRIDE;
+  for (int l = l0; l < l1; ++l, row += LSTRIDE) {
+    const double wgt = wg[l];
+    double T[NT > 0 ? NT : 1], M[NP > 0 ? NP : 1], D[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) T[t] = row[t];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) { M[q] = row[NT + 4 * q + 1]; D[q] = row[NT + 4 * q + 2]; }
+#pragma unroll
+    for (int j = 0; j < SEG_WPT; ++j) {
+      double x = 0.0;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) x = fma(cf[j][t], T[t], x);
+#pragma unroll
+      for (int q = 0; q < NP; ++q) x = fma(pamp[j][q] * M[q], E[j][q], x);
+      a[j] = fma(wgt, x, a[j]);
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+#pragma unroll
+      for (int j = 0; j < SEG_WPT; ++j) {
+        if (MODE == 0) E[j][q] *= exp_taylor<6>(pidx[j][q] * D[q]);
+        else if (MODE == 1) E[j][q] *= exp_taylor<10>(pidx[j][q] * D[q]);
+        else if (l + 1 < l1) E[j][q] = exp(pidx[j][q] * row[LSTRIDE + NT + 4 * q]);   // next column's logB
+      }
+    }
+  }
+}
+
 template <int NT, int NP>
 __global__ void __launch_bounds__(128)
 k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restrict__ coef, int ldc,
              double* __restrict__ R, int ldr) {
   constexpr int LSTRIDE = NT + 4 * NP;
-  constexpr int SEG_CH = LSTRIDE > 12 ? 128 : 256;     // keeps static shared memory under 48 KB
+  constexpr int SEG_CH = LSTRIDE > 12 ? 96 : (LSTRIDE > 8 ? 160 : 224);   // static shared memory < 48 KB
+  constexpr int NPX = NP > 0 ? NP : 1, NTX = NT > 0 ? NT : 1;
   __shared__ __align__(16) double srow[SEG_CH * (LSTRIDE > 0 ? LSTRIDE : 1)];
   __shared__ __align__(16) double swgt[CSL_SEG_GROUP][SEG_CH];
   __shared__ int slo[CSL_SEG_GROUP], shi[CSL_SEG_GROUP], srw[CSL_SEG_GROUP];
   __shared__ float sdmax[CSL_SEG_GROUP][CSL_MAX_PLAW];
+  __shared__ double sacc[CSL_SEG_GROUP][SEG_WPT * 128];  // partial sums of bins that span several chunks
   __shared__ long long soff[CSL_SEG_GROUP];
   const int tid = threadIdx.x;
-  const int w = blockIdx.x * 128 + tid;
+  int w[SEG_WPT];
+  bool live_w[SEG_WPT];
+#pragma unroll
+  for (int j = 0; j < SEG_WPT; ++j) {
+    w[j] = blockIdx.x * (SEG_WPT * 128) + j * 128 + tid;
+    live_w[j] = w[j] < W;
+    if (!live_w[j]) w[j] = W - 1;             // replay a valid walker, never stored
+  }
   const int b_begin = bin0 + blockIdx.y * CSL_SEG_GROUP;
   const int32_t* first = p.bin_tab + (long long)b_begin * CSL_BIN_STRIDE;
   const int32_t* spec = p.spec_tab + (long long)first[CSL_B_SPEC] * CSL_SPEC_STRIDE;   // one spectrum per group
@@ -204,37 +254,28 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
     soff[tid] = ((long long)rec[CSL_B_WINOFF_HI] << 32) | (unsigned)rec[CSL_B_WINOFF_LO];
     for (int q = 0; q < CSL_MAX_PLAW; ++q) sdmax[tid][q] = __int_as_float(rec[CSL_B_DMAX + q]);
   }
-  double cf[NT > 0 ? NT : 1], pamp[NP > 0 ? NP : 1], pidx[NP > 0 ? NP : 1];
-#pragma unroll
-  for (int t = 0; t < NT; ++t) cf[t] = coef[(long long)spec[CSL_S_TERM_COEF + t] * ldc + w];
-#pragma unroll
-  for (int q = 0; q < NP; ++q) {
-    pamp[q] = coef[(long long)spec[CSL_S_PLAW_AMP + q] * ldc + w];
-    pidx[q] = coef[(long long)spec[CSL_S_PLAW_IDX + q] * ldc + w];
-  }
+  double cf[SEG_WPT][NTX], pamp[SEG_WPT][NPX], pidx[SEG_WPT][NPX], cal[SEG_WPT];
   const int calrow = spec[CSL_S_CAL];
-  const double cal = calrow >= 0 ? coef[(long long)calrow * ldc + w] : 1.0;
+#pragma unroll
+  for (int j = 0; j < SEG_WPT; ++j) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) cf[j][t] = coef[(long long)spec[CSL_S_TERM_COEF + t] * ldc + w[j]];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      pamp[j][q] = coef[(long long)spec[CSL_S_PLAW_AMP + q] * ldc + w[j]];
+      pidx[j][q] = coef[(long long)spec[CSL_S_PLAW_IDX + q] * ldc + w[j]];
+    }
+    cal[j] = calrow >= 0 ? coef[(long long)calrow * ldc + w[j]] : 1.0;
+  }
   __syncthreads();
   int glo = 0x7fffffff, ghi = 0;
 #pragma unroll
   for (int b = 0; b < CSL_SEG_GROUP; ++b)
     if (shi[b] > slo[b]) { glo = min(glo, slo[b]); ghi = max(ghi, shi[b]); }
-
-  double acc[CSL_SEG_GROUP];
 #pragma unroll
-  for (int b = 0; b < CSL_SEG_GROUP; ++b) acc[b] = 0.0;
-
-  // one column: x = sum_t cf T + sum_q (amp M) E_q ; then E_q advances to the next column
-  auto column = [&](const double* row, double wgt, double (&E)[NP > 0 ? NP : 1], double& a, auto advance) {
-    double x = 0.0;
+  for (int b = 0; b < CSL_SEG_GROUP; ++b)
 #pragma unroll
-    for (int t = 0; t < NT; ++t) x = fma(cf[t], row[t], x);
-#pragma unroll
-    for (int q = 0; q < NP; ++q) x = fma(pamp[q] * row[NT + 4 * q + 1], E[q], x);
-    a = fma(wgt, x, a);
-#pragma unroll
-    for (int q = 0; q < NP; ++q) E[q] = advance(E[q], pidx[q], row + NT + 4 * q);
-  };
+    for (int j = 0; j < SEG_WPT; ++j) sacc[b][j * 128 + tid] = 0.0;
 
   for (int c0 = glo; c0 < ghi; c0 += SEG_CH) {
     const int n = min(SEG_CH, ghi - c0);
@@ -256,44 +297,53 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
       if (l1 <= l0) continue;                   // block-uniform
       double ymax = 0.0;
 #pragma unroll
-      for (int q = 0; q < NP; ++q) ymax = fmax(ymax, fabs(pidx[q]) * (double)sdmax[b][q]);
+      for (int j = 0; j < SEG_WPT; ++j)
+#pragma unroll
+        for (int q = 0; q < NP; ++q) ymax = fmax(ymax, fabs(pidx[j][q]) * (double)sdmax[b][q]);
       const bool t6 = __all_sync(0xffffffffu, ymax <= 0.012);
       const bool t10 = __all_sync(0xffffffffu, ymax <= 0.1);
-      double E[NP > 0 ? NP : 1];
+      double E[SEG_WPT][NPX], a[SEG_WPT];
 #pragma unroll
-      for (int q = 0; q < NP; ++q) E[q] = exp(pidx[q] * srow[l0 * LSTRIDE + NT + 4 * q]);
-      double a = 0.0;
-      const double* wg = swgt[b];
-      if (t6) {
-#pragma unroll 4
-        for (int l = l0; l < l1; ++l)
-          column(srow + l * LSTRIDE, wg[l], E, a,
-                 [](double e, double idx, const double* r) { return e * exp_taylor<6>(idx * r[2]); });
-      } else if (t10) {
-#pragma unroll 2
-        for (int l = l0; l < l1; ++l)
-          column(srow + l * LSTRIDE, wg[l], E, a,
-                 [](double e, double idx, const double* r) { return e * exp_taylor<10>(idx * r[2]); });
-      } else {
-        for (int l = l0; l < l1; ++l)        // exact exp at every column (next column's logB is r[4 NP .. ])
-          column(srow + l * LSTRIDE, wg[l], E, a,
-                 [&](double e, double idx, const double* r) { return (l + 1 < l1) ? exp(idx * r[LSTRIDE]) : e; });
+      for (int j = 0; j < SEG_WPT; ++j) {
+        a[j] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) E[j][q] = exp(pidx[j][q] * srow[l0 * LSTRIDE + NT + 4 * q]);
       }
-      acc[b] += a;
+      const double* wg = swgt[b];
+      if (t6) seg_row<NT, NP, 0>(srow, wg, l0, l1, cf, pamp, pidx, E, a);
+      else if (t10) seg_row<NT, NP, 1>(srow, wg, l0, l1, cf, pamp, pidx, E, a);
+      else seg_row<NT, NP, 2>(srow, wg, l0, l1, cf, pamp, pidx, E, a);
+      const bool done = shi[b] <= c0 + n;       // the bin ends in this chunk: r = cal * d - b  (spt_lowl.py:132)
+      const int row = srw[b];
+      const double d = p.data[row];
+#pragma unroll
+      for (int j = 0; j < SEG_WPT; ++j) {
+        const double tot = a[j] + sacc[b][j * 128 + tid];        // own slot: no hazard with other threads
+        if (done) {
+          if (live_w[j]) R[(long long)row * ldr + w[j]] = __dsub_rn(__dmul_rn(cal[j], d), tot);
+        } else {
+          sacc[b][j * 128 + tid] = tot;
+        }
+      }
     }
     __syncthreads();
   }
-#pragma unroll
+  // rows whose window is empty (no columns at all) still owe r = cal * d
+#pragma unroll 1
   for (int b = 0; b < CSL_SEG_GROUP; ++b) {
     const int row = srw[b];
-    if (row >= 0) R[(long long)row * ldr + w] = __dsub_rn(__dmul_rn(cal, p.data[row]), acc[b]);
+    if (row >= 0 && shi[b] <= slo[b]) {
+#pragma unroll
+      for (int j = 0; j < SEG_WPT; ++j)
+        if (live_w[j]) R[(long long)row * ldr + w[j]] = __dmul_rn(cal[j], p.data[row]);
+    }
   }
 }
 
 template <int NT, int NP>
 static int launch_seg(const csl_program_t* p, int bin0, int nbins, int W, const double* coef, int ldc,
                       double* R, int ldr, cudaStream_t s) {
-  dim3 grid(W / 128, (nbins + CSL_SEG_GROUP - 1) / CSL_SEG_GROUP);
+  dim3 grid((W + SEG_WPT * 128 - 1) / (SEG_WPT * 128), (nbins + CSL_SEG_GROUP - 1) / CSL_SEG_GROUP);
   k_bin_segsum<NT, NP><<<grid, 128, 0, s>>>(*p, bin0, nbins, W, coef, ldc, R, ldr);
   return 0;
 }
