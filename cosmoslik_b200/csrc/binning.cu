@@ -178,6 +178,7 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
 // bin's max |D| (bin record) -- otherwise exp at every column.  The polynomials of different columns are
 // independent; only one multiply per column sits on the dependent chain.  Rounding grows by ~1 ulp per
 // column over a bin (<= a few 1e-15 relative), far inside the 1e-10 budget on lnL.
+#define SEG_TPB 128    // threads per CTA
 #define SEG_WPT 2      // walkers per thread: table rows / weights / loop control are amortised over both
 
 // One window row over columns [l0, l1) of the staged chunk, for the SEG_WPT walkers of a thread:
@@ -220,7 +221,7 @@ __device__ __forceinline__ void seg_row(const double* __restrict__ srow, const d
 }
 
 template <int NT, int NP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SEG_TPB)
 k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restrict__ coef, int ldc,
              double* __restrict__ R, int ldr) {
   constexpr int LSTRIDE = NT + 4 * NP;
@@ -230,14 +231,14 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
   __shared__ __align__(16) double swgt[CSL_SEG_GROUP][SEG_CH];
   __shared__ int slo[CSL_SEG_GROUP], shi[CSL_SEG_GROUP], srw[CSL_SEG_GROUP];
   __shared__ float sdmax[CSL_SEG_GROUP][CSL_MAX_PLAW];
-  __shared__ double sacc[CSL_SEG_GROUP][SEG_WPT * 128];  // partial sums of bins that span several chunks
+  __shared__ double sacc[CSL_SEG_GROUP][SEG_WPT * SEG_TPB];  // partial sums of bins that span several chunks
   __shared__ long long soff[CSL_SEG_GROUP];
   const int tid = threadIdx.x;
   int w[SEG_WPT];
   bool live_w[SEG_WPT];
 #pragma unroll
   for (int j = 0; j < SEG_WPT; ++j) {
-    w[j] = blockIdx.x * (SEG_WPT * 128) + j * 128 + tid;
+    w[j] = blockIdx.x * (SEG_WPT * SEG_TPB) + j * SEG_TPB + tid;
     live_w[j] = w[j] < W;
     if (!live_w[j]) w[j] = W - 1;             // replay a valid walker, never stored
   }
@@ -275,19 +276,19 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
 #pragma unroll
   for (int b = 0; b < CSL_SEG_GROUP; ++b)
 #pragma unroll
-    for (int j = 0; j < SEG_WPT; ++j) sacc[b][j * 128 + tid] = 0.0;
+    for (int j = 0; j < SEG_WPT; ++j) sacc[b][j * SEG_TPB + tid] = 0.0;
 
   for (int c0 = glo; c0 < ghi; c0 += SEG_CH) {
     const int n = min(SEG_CH, ghi - c0);
     {
       const double2* __restrict__ src = reinterpret_cast<const double2*>(ltab + (long long)c0 * LSTRIDE);
       double2* dst = reinterpret_cast<double2*>(srow);
-      for (int i = tid; i < n * LSTRIDE / 2; i += 128) dst[i] = __ldg(src + i);
+      for (int i = tid; i < n * LSTRIDE / 2; i += SEG_TPB) dst[i] = __ldg(src + i);
 #pragma unroll
       for (int b = 0; b < CSL_SEG_GROUP; ++b) {
         const int l0 = max(slo[b], c0), l1 = min(shi[b], c0 + n);
         const double* __restrict__ wr = p.windows + soff[b];
-        for (int l = l0 + tid; l < l1; l += 128) swgt[b][l - c0] = __ldg(wr + l);
+        for (int l = l0 + tid; l < l1; l += SEG_TPB) swgt[b][l - c0] = __ldg(wr + l);
       }
     }
     __syncthreads();
@@ -318,11 +319,11 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
       const double d = p.data[row];
 #pragma unroll
       for (int j = 0; j < SEG_WPT; ++j) {
-        const double tot = a[j] + sacc[b][j * 128 + tid];        // own slot: no hazard with other threads
+        const double tot = a[j] + sacc[b][j * SEG_TPB + tid];        // own slot: no hazard with other threads
         if (done) {
           if (live_w[j]) R[(long long)row * ldr + w[j]] = __dsub_rn(__dmul_rn(cal[j], d), tot);
         } else {
-          sacc[b][j * 128 + tid] = tot;
+          sacc[b][j * SEG_TPB + tid] = tot;
         }
       }
     }
@@ -343,8 +344,8 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
 template <int NT, int NP>
 static int launch_seg(const csl_program_t* p, int bin0, int nbins, int W, const double* coef, int ldc,
                       double* R, int ldr, cudaStream_t s) {
-  dim3 grid((W + SEG_WPT * 128 - 1) / (SEG_WPT * 128), (nbins + CSL_SEG_GROUP - 1) / CSL_SEG_GROUP);
-  k_bin_segsum<NT, NP><<<grid, 128, 0, s>>>(*p, bin0, nbins, W, coef, ldc, R, ldr);
+  dim3 grid((W + SEG_WPT * SEG_TPB - 1) / (SEG_WPT * SEG_TPB), (nbins + CSL_SEG_GROUP - 1) / CSL_SEG_GROUP);
+  k_bin_segsum<NT, NP><<<grid, SEG_TPB, 0, s>>>(*p, bin0, nbins, W, coef, ldc, R, ldr);
   return 0;
 }
 
