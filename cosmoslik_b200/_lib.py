@@ -63,9 +63,9 @@ SIGNATURES = {
     "csl_stretch_propose": (_int, [_int, _int, _int, _vp, _vp, _dbl, _vp, _vp, _u64, _u32, _u32, _u32,
                                    _vp, _vp, _vp]),
     "csl_stretch_accept": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _u32,
-                                  _vp, _vp]),
+                                  _vp, _vp, _vp]),
     "csl_stretch_accept_publish": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _u32,
-                                          _vp, _vp, _int, _u64, C.c_int64, _vp]),
+                                          _vp, _vp, _vp, _int, _u64, C.c_int64, _vp]),
     "csl_peer_barrier": (_int, [_vp, _int, _int, _u64, _vp]),
     "csl_emcee_rows": (_int, [_int, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _vp]),
     "csl_chain_moments": (_int, [_int, _int, _vp, _vp, _int, _int, _vp, _vp]),

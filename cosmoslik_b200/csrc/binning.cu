@@ -369,13 +369,6 @@ static int dispatch_seg(int nt, int np, const csl_program_t* p, int b0, int nb, 
   }
 }
 
-// rows n .. n_pad of R are zero so the padded (identity) part of L contributes nothing
-__global__ void k_zero_pad_rows(double* __restrict__ R, int ldr, int n, int n_pad) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long tot = (long long)(n_pad - n) * ldr;
-  if (i < tot) R[(long long)n * ldr + i] = 0.0;
-}
-
 template <int NT, int NP>
 static int launch_class(const csl_program_t* p, int tile0, int ntile, int W, const double* coef, int ldc,
                         double* R, int ldr, cudaStream_t s) {
@@ -420,10 +413,8 @@ extern "C" int csl_bin_residual(const csl_program_t* p, int W, const double* coe
   CSL_REQUIRE(W > 0 && W % CSL_BN == 0 && ldr >= W && ldc >= W && (ldr % 2) == 0,
               "csl_bin_residual: W must be a positive multiple of 128 and ldr, ldc >= W");
   cudaStream_t s = (cudaStream_t)stream;
-  if (p->n_pad > p->n) {
-    long long tot = (long long)(p->n_pad - p->n) * ldr;
-    k_zero_pad_rows<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(R, ldr, p->n, p->n_pad);
-  }
+  // rows n .. n_pad are written (as zeros) by the kernels too: the host appends records with an empty
+  // window and zero data for them (program.py), so no separate clearing pass is needed
   for (int c = 0; c < p->nclass; ++c) {
     const int32_t* k = p->cls[c];
     CSL_REQUIRE(k[0] + 2 * k[1] > 0, "csl_bin_residual: empty spectrum class");

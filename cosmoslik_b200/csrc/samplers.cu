@@ -302,9 +302,12 @@ k_stretch_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ ln
                  const double* __restrict__ lnl_q, const double* __restrict__ zz, const double* __restrict__ u_acc,
                  uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0, uint32_t Nc,
                  uint8_t* __restrict__ accepted, const unsigned long long* __restrict__ peers, int npeers,
-                 unsigned long long mc_ptr, long long dst_row0) {
+                 unsigned long long mc_ptr, long long dst_row0, unsigned long long* __restrict__ nacc) {
   const int k = warp_global(), lane = threadIdx.x & 31;
-  if (k >= Ns) return;
+  if (k >= Ns) {                               // whole warps only; keep them for the block-wide count
+    if (nacc) __syncthreads_count(0);
+    return;
+  }
   double ua;
   if (u_acc) ua = u_acc[k];
   else { double uz; int64_t j; philox_stretch(seed, walker0 + (uint32_t)k, half, step, Nc, uz, j, ua); }
@@ -322,6 +325,10 @@ k_stretch_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ ln
     if (lane == 0) lnl_s[k] = lnl_q[k];
   }
   if (lane == 0 && accepted) accepted[k] = acc ? 1 : 0;
+  if (nacc) {                                   // one atomic per CTA
+    const int c = __syncthreads_count(lane == 0 && acc);
+    if (threadIdx.x == 0 && c) atomicAdd(nacc, (unsigned long long)c);
+  }
   const long long drow = (dst_row0 + k) * nd;
   if (mc_ptr) {
     double* dst = reinterpret_cast<double*>(mc_ptr) + drow;
@@ -361,7 +368,7 @@ __global__ void k_peer_barrier(const unsigned long long* __restrict__ flag_ptrs,
 
 // wrapper bookkeeping, samplers/emcee.py:70-88
 __global__ void __launch_bounds__(SAMP_THREADS)
-k_emcee_rows(int W, int nd, const double* __restrict__ pos_old, const double* __restrict__ pos_new,
+k_emcee_rows(int W, int nd, double* __restrict__ pos_old, const double* __restrict__ pos_new,
              const double* __restrict__ lnl_new, double* __restrict__ weight, int last_step,
              double* __restrict__ rows, int32_t* __restrict__ nrows, int cap) {
   const int w = warp_global(), lane = threadIdx.x & 31;
@@ -376,6 +383,9 @@ k_emcee_rows(int W, int nd, const double* __restrict__ pos_old, const double* __
   } else {
     emit_row(rows, nrows, cap, w, nd, lane, lnl_new[w], wt, o0, o1);
     if (lane == 0) weight[w] = 1.0;
+    // this step's positions are the next step's "old" ones
+    if (lane < nd) pos_old[b + lane] = n0;
+    if (lane + 32 < nd) pos_old[b + lane + 32] = n1;
   }
 }
 
@@ -495,32 +505,34 @@ extern "C" int csl_stretch_propose(int Ns, int Nc, int ndim, const double* s, co
 static int stretch_accept_impl(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q, const double* lnl_q,
                                const double* zz, const double* u_acc, uint64_t seed, uint32_t step, uint32_t half,
                                uint32_t walker0, uint8_t* accepted, const unsigned long long* peers, int npeers,
-                               unsigned long long mc_ptr, long long dst_row0, void* stream) {
+                               unsigned long long mc_ptr, long long dst_row0, unsigned long long* nacc, void* stream) {
   CSL_REQUIRE(Ns > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && s && lnl_s && q && lnl_q && zz,
               "csl_stretch_accept: bad argument");
   CSL_REQUIRE(npeers == 0 || peers || mc_ptr, "csl_stretch_accept: peer pointers missing");
   k_stretch_accept<<<warp_grid(Ns), SAMP_THREADS, 0, (cudaStream_t)stream>>>(
       Ns, ndim, s, lnl_s, q, lnl_q, zz, u_acc, seed, step, half, walker0, (uint32_t)Nc, accepted, peers, npeers, mc_ptr,
-      dst_row0);
+      dst_row0, nacc);
   return csl_check_launch("k_stretch_accept");
 }
 
 extern "C" int csl_stretch_accept(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q,
                                   const double* lnl_q, const double* zz, const double* u_acc, uint64_t seed,
-                                  uint32_t step, uint32_t half, uint32_t walker0, uint8_t* accepted, void* stream) {
+                                  uint32_t step, uint32_t half, uint32_t walker0, uint8_t* accepted,
+                                  uint64_t* naccepted, void* stream) {
   return stretch_accept_impl(Ns, Nc, ndim, s, lnl_s, q, lnl_q, zz, u_acc, seed, step, half, walker0, accepted, nullptr,
-                             0, 0ull, 0, stream);
+                             0, 0ull, 0, reinterpret_cast<unsigned long long*>(naccepted), stream);
 }
 
 extern "C" int csl_stretch_accept_publish(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q,
                                           const double* lnl_q, const double* zz, const double* u_acc, uint64_t seed,
                                           uint32_t step, uint32_t half, uint32_t walker0, uint8_t* accepted,
-                                          const uint64_t* peer_ptrs, int npeers, uint64_t multicast_ptr,
-                                          int64_t dst_row0, void* stream) {
+                                          uint64_t* naccepted, const uint64_t* peer_ptrs, int npeers,
+                                          uint64_t multicast_ptr, int64_t dst_row0, void* stream) {
   CSL_REQUIRE(npeers > 0 && (peer_ptrs || multicast_ptr), "csl_stretch_accept_publish: no peers given");
   return stretch_accept_impl(Ns, Nc, ndim, s, lnl_s, q, lnl_q, zz, u_acc, seed, step, half, walker0, accepted,
                              reinterpret_cast<const unsigned long long*>(peer_ptrs), npeers,
-                             (unsigned long long)multicast_ptr, (long long)dst_row0, stream);
+                             (unsigned long long)multicast_ptr, (long long)dst_row0,
+                             reinterpret_cast<unsigned long long*>(naccepted), stream);
 }
 
 extern "C" int csl_peer_barrier(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, void* stream) {
@@ -530,7 +542,7 @@ extern "C" int csl_peer_barrier(const uint64_t* flag_ptrs, int rank, int world, 
   return csl_check_launch("k_peer_barrier");
 }
 
-extern "C" int csl_emcee_rows(int W, int ndim, const double* pos_old, const double* pos_new, const double* lnl_new,
+extern "C" int csl_emcee_rows(int W, int ndim, double* pos_old, const double* pos_new, const double* lnl_new,
                               double* weight, int last_step, double* rows, int32_t* nrows, int cap, void* stream) {
   CSL_REQUIRE(W > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && pos_old && pos_new && lnl_new && weight && rows && nrows,
               "csl_emcee_rows: bad argument");

@@ -337,6 +337,27 @@ class CompiledProgram(object):
             raise ValueError("bandpower likelihood: covariance is %s, data vector has %d rows" % (q.cov.shape, n))
         self._factor(P, q.cov)
         d = np.zeros(self.n_pad); d[:n] = np.concatenate(data)
+        # rows n .. n_pad of R must read zero (identity padding of the factor): give them records with an
+        # empty window and zero data, so the binning kernels themselves write the zeros
+        if self.n_pad > n:
+            last_spec = nspec - 1
+            key = (int(spec_tab[last_spec][L.S_NTERM]), int(spec_tab[last_spec][L.S_NPLAW]))
+            if segbins:
+                key = segbins[-1][0]
+                last_spec = int(segbins[-1][1][L.B_SPEC])
+                for i in range(_rup(self.n_pad - n, L.SEG_GROUP)):
+                    rec_b = np.zeros(L.BIN_STRIDE, np.int32)
+                    rec_b[L.B_ROW] = n + i if n + i < self.n_pad else -1
+                    rec_b[L.B_SPEC] = last_spec
+                    segbins.append((key, rec_b))
+            elif tiles and tiles[-1][1][L.T_ROW0] + tiles[-1][1][L.T_NROWS] == n and \
+                    tiles[-1][1][L.T_NROWS] + (self.n_pad - n) <= L.BM:
+                tiles[-1][1][L.T_NROWS] += self.n_pad - n      # the last tile's zero-padded window rows
+            else:
+                rec_t = np.zeros(L.TILE_STRIDE, np.int32)
+                rec_t[L.T_ROW0], rec_t[L.T_NROWS], rec_t[L.T_SPEC] = n, self.n_pad - n, last_spec
+                tiles.append((key, rec_t))
+
         # records sorted by kernel class (stable): one launch per class <NT, NP>
         def by_class(records, width):
             classes = sorted(set(k for k, _ in records))

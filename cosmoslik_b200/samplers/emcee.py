@@ -128,7 +128,7 @@ class emcee(SlikSampler):
         rows = buf[1]
         nrows = torch.zeros(W, dtype=torch.int32, device=dev)
         accepted = torch.zeros(W, dtype=torch.uint8, device=dev)
-        pos_old = torch.empty_like(pos)
+        pos_old = pos.clone()                        # refreshed by csl_emcee_rows at the end of every step
         writer = None
         if self.output_file is not None:
             path = self.output_file if rank == 0 else "%s.rank%d" % (self.output_file, rank)
@@ -142,7 +142,6 @@ class emcee(SlikSampler):
         t_host0 = _time.perf_counter()
         try:
             for i in range(nsteps):
-                pos_old.copy_(pos)
                 inj = self.streams(i) if self.streams is not None else None
                 for hidx, (r0, r1, g0, hsize) in enumerate(halves):
                     o0, o1, _, csize = halves[1 - hidx]
@@ -180,7 +179,8 @@ class emcee(SlikSampler):
                     if replica is None:
                         L.check(lib.csl_stretch_accept(ns, csize, nd, s_view.data_ptr(), l_view.data_ptr(),
                                                        q_view.data_ptr(), lnl_q.data_ptr(), zz[r0:r1].data_ptr(),
-                                                       L.ptr(ua), seed, i, hidx, g0, accepted[r0:r1].data_ptr(), st),
+                                                       L.ptr(ua), seed, i, hidx, g0, accepted[r0:r1].data_ptr(),
+                                                       nacc.data_ptr(), st),
                                 "csl_stretch_accept")
                     else:
                         if timers is not None:
@@ -188,7 +188,7 @@ class emcee(SlikSampler):
                         L.check(lib.csl_stretch_accept_publish(
                             ns, csize, nd, s_view.data_ptr(), l_view.data_ptr(), q_view.data_ptr(), lnl_q.data_ptr(),
                             zz[r0:r1].data_ptr(), L.ptr(ua), seed, i, hidx, g0, accepted[r0:r1].data_ptr(),
-                            replica.peers_dev.data_ptr(), replica.npeers, replica.multicast, g0, st),
+                            nacc.data_ptr(), replica.peers_dev.data_ptr(), replica.npeers, replica.multicast, g0, st),
                             "csl_stretch_accept_publish")
                         if timers is not None:
                             eb = torch.cuda.Event(enable_timing=True); eb.record()
@@ -197,7 +197,6 @@ class emcee(SlikSampler):
                             ec = torch.cuda.Event(enable_timing=True); ec.record()
                             timers.setdefault("accept_publish", []).append((ea, eb))
                             timers.setdefault("replica_barrier", []).append((eb, ec))
-                nacc += accepted.sum()
                 L.check(lib.csl_emcee_rows(W, nd, pos_old.data_ptr(), pos.data_ptr(), lnl_pos.data_ptr(),
                                            weight.data_ptr(), 1 if i == nsteps - 1 else 0, rows.data_ptr(),
                                            nrows.data_ptr(), cap, st), "csl_emcee_rows")

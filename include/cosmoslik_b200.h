@@ -228,10 +228,12 @@ int csl_stretch_propose(int Ns, int Nc, int ndim, const double* s, const double*
                         const double* u_z, const int64_t* j, uint64_t seed, uint32_t step, uint32_t half,
                         uint32_t walker0, double* q, double* zz, void* stream);
 
-/* accept iff (ndim-1) ln z + lnp(q) - lnp(s) > ln u_acc, lnp = -lnl; updates s, lnl_s in place. */
+/* accept iff (ndim-1) ln z + lnp(q) - lnp(s) > ln u_acc, lnp = -lnl; updates s, lnl_s in place.
+ * accepted [Ns] (uint8) and *naccepted (device counter, incremented by the number of accepted moves)
+ * may be NULL. */
 int csl_stretch_accept(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q, const double* lnl_q,
                        const double* zz, const double* u_acc, uint64_t seed, uint32_t step, uint32_t half,
-                       uint32_t walker0, uint8_t* accepted, void* stream);
+                       uint32_t walker0, uint8_t* accepted, uint64_t* naccepted, void* stream);
 
 /* Accept fused with the exchange step of the sharded ensemble (replaces the mpi_map pool round trip,
  * mpi/mpi.py:40-64): besides updating s / lnl_s, every walker's final position is stored into row
@@ -242,8 +244,8 @@ int csl_stretch_accept(int Ns, int Nc, int ndim, double* s, double* lnl_s, const
 int csl_stretch_accept_publish(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q,
                                const double* lnl_q, const double* zz, const double* u_acc, uint64_t seed,
                                uint32_t step, uint32_t half, uint32_t walker0, uint8_t* accepted,
-                               const uint64_t* peer_ptrs, int npeers, uint64_t multicast_ptr, int64_t dst_row0,
-                               void* stream);
+                               uint64_t* naccepted, const uint64_t* peer_ptrs, int npeers, uint64_t multicast_ptr,
+                               int64_t dst_row0, void* stream);
 
 /* Device-side barrier over the ranks of one NVLink domain, on `stream` (the host does not block).
  * flag_ptrs[world]: device addresses of every rank's uint64[world] flag array (symmetric memory, zeroed
@@ -251,8 +253,9 @@ int csl_stretch_accept_publish(int Ns, int Nc, int ndim, double* s, double* lnl_
 int csl_peer_barrier(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, void* stream);
 
 /* wrapper bookkeeping of samplers/emcee.py:70-88 after a full step: a walker that did not move
- * gains weight; one that moved (or any walker on the last step) emits (lnl_next, weight, x_old). */
-int csl_emcee_rows(int W, int ndim, const double* pos_old, const double* pos_new, const double* lnl_new,
+ * gains weight; one that moved (or any walker on the last step) emits (lnl_next, weight, x_old) and its
+ * pos_old row is refreshed to pos_new (ready for the next step). */
+int csl_emcee_rows(int W, int ndim, double* pos_old, const double* pos_new, const double* lnl_new,
                    double* weight, int last_step, double* rows, int32_t* nrows, int cap, void* stream);
 
 /* ---- convergence (new; nothing in the reference) ----------------------------------------- */

@@ -48,8 +48,10 @@ def prior(cp, x):
 
 def residual(cp, coef):
     t, m = cp.tables, cp.meta
-    r = np.zeros(m["n_pad"])
+    r = np.full(m["n_pad"], np.nan)          # every row, padding included, must be written by some record
+    written = np.zeros(m["n_pad"], bool)
     if m["resid_mode"] == 2:
+        r[:] = 0.0
         for i in range(m["n"]):
             r[i] = coef[t["direct_coef"][i]] - t["data"][i]
         return r
@@ -73,6 +75,7 @@ def residual(cp, coef):
             woff = (int(rec[L.B_WINOFF_HI]) << 32) | (int(rec[L.B_WINOFF_LO]) & 0xFFFFFFFF)
             cal = 1.0 if spec[L.S_CAL] < 0 else coef[spec[L.S_CAL]]
             r[rec[L.B_ROW]] = cal * t["data"][rec[L.B_ROW]] - np.dot(t["windows"][woff + l0: woff + l1], cl)
+            written[rec[L.B_ROW]] = True
     for tile in t["tile_tab"][:m["ntile"]]:
         spec = t["spec_tab"][tile[L.T_SPEC]]
         l0, l1 = tile[L.T_LBEGIN], tile[L.T_LEND]
@@ -97,6 +100,8 @@ def residual(cp, coef):
                 assert tile[L.T_GLO + g] <= l0 + nz[0] and l0 + nz[-1] < tile[L.T_GHI + g]
             row = tile[L.T_ROW0] + rr
             r[row] = cal * t["data"][row] - np.dot(w, cl)
+            written[row] = True
+    assert written.all(), "residual rows %s are written by no tile / bin record" % np.flatnonzero(~written)
     return r
 
 
