@@ -293,8 +293,15 @@ def run_b200(args):
                                 "algorithmic_tflops": alg * half / t / 1e12, "executed_tflops": exe * half / t / 1e12,
                                 "frac_of_fp64_peak": alg * half / t / 1e12 / peak}
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_launch"])
+    traffic = None     # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f).get(dom)
+        if tj and tj["walkers_per_launch"] == half:
+            traffic = tj["dram_bytes_per_launch"]
     roofline = {"bound": "tensor", "kernel": dom, "achieved": per_kernel[dom]["algorithmic_tflops"], "peak": peak,
-                "unit": "TFLOP/s", "frac": per_kernel[dom]["frac_of_fp64_peak"], "traffic": None,
+                "unit": "TFLOP/s", "frac": per_kernel[dom]["frac_of_fp64_peak"], "traffic": traffic,
                 "peak_source": peak_src, "kernels": per_kernel,
                 "other_stages_ms": {k: v for k, v in stage_ms.items() if k not in ("chi2", "bin_residual")}}
 
