@@ -15,7 +15,7 @@ MAX_DIM, MAX_TERMS, MAX_PLAW = 64, 8, 4
 SPEC_STRIDE, TILE_STRIDE, STACK = 64, 32, 16
 OP = dict(PUSHP=0, PUSHC=1, ADD=2, SUB=3, MUL=4, DIV=5, NEG=6, EXP=7, LOG=8, POW=9, SQRT=10, STORE=11, SQR=12)
 S_NLPAD, S_NTERM, S_NPLAW, S_CAL = 0, 1, 2, 3
-S_LTAB, S_TERM_COEF, S_PLAW_AMP, S_PLAW_IDX = 4, 8, 24, 28
+S_LTAB, S_CALMODE, S_TERM_COEF, S_PLAW_AMP, S_PLAW_IDX = 4, 5, 8, 24, 28
 MAX_CLASS = 8
 BIN_STRIDE, SEG_GROUP = 16, 8
 B_ROW, B_SPEC, B_LO, B_HI, B_WINOFF_LO, B_WINOFF_HI, B_DMAX = 0, 1, 2, 3, 4, 5, 8
@@ -35,7 +35,7 @@ class Program(C.Structure):
                   "gauss_idx", "gauss_c", "gauss_w", "scalar_coef", "spec_tab", "tile_tab",
                   "templates", "windows", "data", "direct_coef", "Lmat", "Linv_diag", "Minv")] +
                 [("chi2_mode", C.c_int32), ("nsegclass", C.c_int32), ("segcls", (C.c_int32 * 4) * 8),
-                 ("bin_tab", C.c_void_p)])
+                 ("bin_tab", C.c_void_p), ("Sigma", C.c_void_p), ("n_base", C.c_int32), ("nmode", C.c_int32)])
 
 
 _P = C.POINTER(Program)
@@ -51,6 +51,7 @@ SIGNATURES = {
     "csl_bin_residual": (_int, [_P, _int, _vp, _int, _vp, _int, _vp]),
     "csl_direct_residual": (_int, [_P, _int, _vp, _int, _vp, _int, _vp]),
     "csl_chi2": (_int, [_P, _int, _vp, _int, _vp, _vp, _vp]),
+    "csl_cov_chi2": (_int, [_P, _int, _vp, _int, _vp, _vp]),
     "csl_combine": (_int, [_P, _int, _vp, _int, _vp, _vp, _vp, _vp]),
     "csl_lnl": (_int, [_P, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "csl_lnl_host": (_int, [_P, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

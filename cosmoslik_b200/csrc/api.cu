@@ -45,10 +45,11 @@ extern "C" int csl_lnl(const csl_program_t* p, int W, const double* x, double* l
   const double* chi2 = nullptr;
   if (p->resid_mode != 0) {
     CSL_REQUIRE(ws_R && ws_chi2 && ws_coef, "csl_lnl: workspace missing for the quadratic form");
-    if (p->resid_mode == 1) rc = csl_bin_residual(p, Wp, ws_coef, Wp, ws_R, Wp, stream);
+    if (p->resid_mode == 1 || p->resid_mode == 3) rc = csl_bin_residual(p, Wp, ws_coef, Wp, ws_R, Wp, stream);
     else rc = csl_direct_residual(p, W, ws_coef, Wp, ws_R, Wp, stream);
     if (rc) return rc;
-    rc = csl_chi2(p, Wp, ws_R, Wp, ws_chi2, ws_part, stream);
+    if (p->resid_mode == 3) rc = csl_cov_chi2(p, W, ws_R, Wp, ws_chi2, stream);
+    else rc = csl_chi2(p, Wp, ws_R, Wp, ws_chi2, ws_part, stream);
     if (rc) return rc;
     chi2 = ws_chi2;
   }

@@ -143,6 +143,7 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
   const int g = lane >> 2, t = lane & 3;
   const int row0 = tile[CSL_T_ROW0], nrows = tile[CSL_T_NROWS];
   const int calrow = spec[CSL_S_CAL];
+  const bool cal_on_model = spec[CSL_S_CALMODE] != 0;      // r = d - cal*b  (SPTSZ_lowl.py:68)
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) {
     const int col = c0 + wn0 + ni * 8 + 2 * t;
@@ -157,8 +158,13 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
       if (rl < nrows) {
         const double d = p.data[row0 + rl];
         double2 out;
-        out.x = __dsub_rn(__dmul_rn(cal0, d), acc[mi][ni][0]);
-        out.y = __dsub_rn(__dmul_rn(cal1, d), acc[mi][ni][1]);
+        if (cal_on_model) {
+          out.x = __dsub_rn(d, __dmul_rn(acc[mi][ni][0], cal0));
+          out.y = __dsub_rn(d, __dmul_rn(acc[mi][ni][1], cal1));
+        } else {
+          out.x = __dsub_rn(__dmul_rn(cal0, d), acc[mi][ni][0]);
+          out.y = __dsub_rn(__dmul_rn(cal1, d), acc[mi][ni][1]);
+        }
         *reinterpret_cast<double2*>(R + (long long)(row0 + rl) * ldr + col) = out;
       }
     }
@@ -257,6 +263,7 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
   }
   double cf[SEG_WPT][NTX], pamp[SEG_WPT][NPX], pidx[SEG_WPT][NPX], cal[SEG_WPT];
   const int calrow = spec[CSL_S_CAL];
+  const bool cal_on_model = spec[CSL_S_CALMODE] != 0;      // r = d - cal*b  (SPTSZ_lowl.py:68)
 #pragma unroll
   for (int j = 0; j < SEG_WPT; ++j) {
 #pragma unroll
@@ -321,7 +328,9 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
       for (int j = 0; j < SEG_WPT; ++j) {
         const double tot = a[j] + sacc[b][j * SEG_TPB + tid];        // own slot: no hazard with other threads
         if (done) {
-          if (live_w[j]) R[(long long)row * ldr + w[j]] = __dsub_rn(__dmul_rn(cal[j], d), tot);
+          if (live_w[j])
+            R[(long long)row * ldr + w[j]] = cal_on_model ? __dsub_rn(d, __dmul_rn(tot, cal[j]))
+                                                          : __dsub_rn(__dmul_rn(cal[j], d), tot);
         } else {
           sacc[b][j * SEG_TPB + tid] = tot;
         }
@@ -336,7 +345,7 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
     if (row >= 0 && shi[b] <= slo[b]) {
 #pragma unroll
       for (int j = 0; j < SEG_WPT; ++j)
-        if (live_w[j]) R[(long long)row * ldr + w[j]] = __dmul_rn(cal[j], p.data[row]);
+        if (live_w[j]) R[(long long)row * ldr + w[j]] = cal_on_model ? p.data[row] : __dmul_rn(cal[j], p.data[row]);
     }
   }
 }
@@ -407,7 +416,8 @@ static int dispatch_class(int nt, int np, const csl_program_t* p, int tile0, int
 extern "C" int csl_bin_residual(const csl_program_t* p, int W, const double* coef, int ldc, double* R, int ldr,
                                 void* stream) {
   CSL_REQUIRE(p && coef && R, "csl_bin_residual: null argument");
-  CSL_REQUIRE(p->resid_mode == 1 && (p->nclass > 0 || p->nsegclass > 0) && p->nclass <= CSL_MAX_CLASS &&
+  CSL_REQUIRE((p->resid_mode == 1 || p->resid_mode == 3) && (p->nclass > 0 || p->nsegclass > 0) &&
+                  p->nclass <= CSL_MAX_CLASS &&
                   p->nsegclass <= CSL_MAX_CLASS,
               "csl_bin_residual: program has no binned spectra");
   CSL_REQUIRE(W > 0 && W % CSL_BN == 0 && ldr >= W && ldc >= W && (ldr % 2) == 0,

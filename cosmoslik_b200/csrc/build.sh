@@ -6,5 +6,5 @@ OUT="$HERE/../libcosmoslik_b200.so"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared \
   ${CSL_PTXAS_V:+-Xptxas -v} \
-  -o "$OUT" "$HERE/api.cu" "$HERE/prepare.cu" "$HERE/binning.cu" "$HERE/chi2.cu" "$HERE/samplers.cu"
+  -o "$OUT" "$HERE/api.cu" "$HERE/prepare.cu" "$HERE/binning.cu" "$HERE/chi2.cu" "$HERE/covchi2.cu" "$HERE/samplers.cu"
 echo "built $OUT"

@@ -12,7 +12,8 @@ import numpy as np
 import scipy.linalg as sla
 
 from . import _lib as L
-from .symbolic import (BandpowerTerm, Bin, Const, Expr, GaussTerm, LnlSum, LnlTerm, Par, Un)
+from .symbolic import (BandpowerTerm, Bin, Const, Expr, GaussTerm, LnlSum, LnlTerm, LowRankCovBandpowerTerm, Par,
+                       SpectrumBlock, Un)
 
 
 def _rup(v, m):
@@ -75,7 +76,7 @@ class CompiledProgram(object):
 
     _PTR_FIELDS = ("code_op", "code_arg", "code_val", "box_idx", "box_lo", "box_hi", "gauss_idx", "gauss_c",
                    "gauss_w", "scalar_coef", "spec_tab", "tile_tab", "templates", "windows", "data",
-                   "direct_coef", "Lmat", "Linv_diag", "Minv", "bin_tab")
+                   "direct_coef", "Lmat", "Linv_diag", "Minv", "bin_tab", "Sigma")
 
     def __init__(self, names, priors, lnl_expr, chi2_mode="auto", binning="auto"):
         self.chi2_mode = chi2_mode
@@ -86,7 +87,7 @@ class CompiledProgram(object):
             raise ValueError("number of sampled parameters must be in 1..%d" % L.MAX_DIM)
         self.tables = {}
         self.meta = dict(ndim=self.ndim, ncoef=0, ncode=0, nbox=0, ngauss=0, nscalar=0, nspec=0, ntile=0,
-                         n=0, n_pad=0, resid_mode=0, nclass=0, nsegclass=0)
+                         n=0, n_pad=0, resid_mode=0, nclass=0, nsegclass=0, n_base=0, nmode=0)
         self.cls = np.zeros((L.MAX_CLASS, 4), np.int32)
         self.segcls = np.zeros((L.MAX_CLASS, 4), np.int32)
         self.host = {}
@@ -105,7 +106,7 @@ class CompiledProgram(object):
         parts = lnl_expr.parts if isinstance(lnl_expr, LnlSum) else [lnl_expr]
         scalars, quad = [], []
         for part in parts:
-            if isinstance(part, (BandpowerTerm, GaussTerm)):
+            if isinstance(part, (BandpowerTerm, GaussTerm, LowRankCovBandpowerTerm)):
                 quad.append(part)
             elif isinstance(part, LnlTerm):
                 raise TypeError("unsupported likelihood term %r" % (part,))
@@ -134,6 +135,8 @@ class CompiledProgram(object):
             q = quad[0]
             if isinstance(q, BandpowerTerm):
                 self._build_bandpower(P, code, q)
+            elif isinstance(q, LowRankCovBandpowerTerm):
+                self._build_lowrank(P, code, q)
             else:
                 self._build_gauss(P, code, q)
         P['n'], P['n_pad'] = self.n, self.n_pad
@@ -167,7 +170,7 @@ class CompiledProgram(object):
         # of Newton refinement with the residual in extended precision, and a check against forward
         # substitution; used only if it reproduces the substitution chi^2 to 1e-13
         self.meta['chi2_mode'] = 0
-        if self.chi2_mode in ("auto", "inverse") and n <= 4096:
+        if self.chi2_mode in ("auto", "inverse") and n <= 8192:
             M = sla.solve_triangular(Lf[:n, :n], np.eye(n), lower=True)
             if n <= 1024:
                 Ll, Ml = Lf[:n, :n].astype(np.longdouble), M.astype(np.longdouble)
@@ -212,7 +215,27 @@ class CompiledProgram(object):
             self.gauss_direct = dict(perm=np.array([v.index for v in q.values], np.int32),
                                      L=np.ascontiguousarray(self.host["L"]), mean=np.ascontiguousarray(q.mean))
 
-    def _build_bandpower(self, P, code, q):
+    def _build_lowrank(self, P, code, q):
+        """model-dependent covariance C = Sigma + V V^T: the residual vector stacks r and the K mode
+        vectors V_k = (W diag(b_k)) . cl, all binned by the ordinary binning kernels (the mode rows are
+        just more window rows with zero data); chi^2 by a per-walker Cholesky (csl_cov_chi2)."""
+        n, nl = q.windows.shape
+        K = q.modes.shape[0]
+        if q.sigma.shape != (n, n) or q.data.shape != (n,) or q.modes.shape[1] != nl:
+            raise ValueError("low-rank covariance likelihood: shape mismatch")
+        if n > 64 or K > 32:
+            raise ValueError("low-rank covariance likelihood: at most 64 bandpowers and 32 modes")
+        wm = (q.windows[None, :, :] * q.modes[:, None, :]).reshape(K * n, nl)
+        blocks = [SpectrumBlock(q.model, q.windows, q.data, q.cal, cal_on_model=True)]
+        if K:
+            blocks.append(SpectrumBlock(q.model, wm, np.zeros(K * n), 1.0))
+        self._build_bandpower(P, code, BandpowerTerm(blocks, None), factor=False)
+        P['resid_mode'] = 3
+        P['n_base'], P['nmode'] = n, K
+        self._dev('Sigma', q.sigma, np.float64)
+        self.flops.update(cov_chol=2 * (n * (n + 1) // 2 * K + n ** 3 // 6 + n * n // 2))
+
+    def _build_bandpower(self, P, code, q, factor=True):
         nspec = len(q.blocks)
         spec_tab = np.zeros((nspec, L.SPEC_STRIDE), np.int32)
         tiles, segbins, templ, wins, data = [], [], [], [], []
@@ -247,6 +270,7 @@ class CompiledProgram(object):
             stride = NT + 4 * NP
             rec = spec_tab[s]
             rec[L.S_NLPAD], rec[L.S_NTERM], rec[L.S_NPLAW], rec[L.S_LTAB] = nlp, NT, NP, toff
+            rec[L.S_CALMODE] = 1 if blk.cal_on_model else 0
             ltab = np.zeros((nlp, stride))
             for t in range(NT):
                 if t < len(terms):
@@ -333,9 +357,12 @@ class CompiledProgram(object):
             data.append(blk.data)
             row0 += nb
         n = row0
-        if q.cov.shape != (n, n):
-            raise ValueError("bandpower likelihood: covariance is %s, data vector has %d rows" % (q.cov.shape, n))
-        self._factor(P, q.cov)
+        if factor:
+            if q.cov.shape != (n, n):
+                raise ValueError("bandpower likelihood: covariance is %s, data vector has %d rows" % (q.cov.shape, n))
+            self._factor(P, q.cov)
+        else:
+            self.n, self.n_pad = n, _rup(n, L.BM)
         d = np.zeros(self.n_pad); d[:n] = np.concatenate(data)
         # rows n .. n_pad of R must read zero (identity padding of the factor): give them records with an
         # empty window and zero data, so the binning kernels themselves write the zeros
@@ -385,7 +412,7 @@ class CompiledProgram(object):
         # work per evaluation: dense windows, non-zero window entries, DMMA blocks that
         # are actually executed, foreground-build FP64 ops (~1 per template term, ~20 per power law), TRSM
         self.flops = dict(bin_dense=flops_dense, bin_nnz=flops_nnz, bin_exec=flops_exec, build_ops=2 * builds,
-                          trsm=self._chi2_executed_flops(), trsm_alg=n * n)
+                          trsm=self._chi2_executed_flops() if factor else 0, trsm_alg=n * n if factor else 0)
 
 
 class DeviceProgram(CompiledProgram):
@@ -458,13 +485,16 @@ class DeviceProgram(CompiledProgram):
         stage("prepare", lambda: self.lib.csl_eval_prepare(P, W, x.data_ptr(), ws["coef"].data_ptr(), Wp,
                                                            ws["prior"].data_ptr(), st))
         chi2 = None
-        if self.meta["resid_mode"] == 1:
+        if self.meta["resid_mode"] in (1, 3):
             stage("bin_residual", lambda: self.lib.csl_bin_residual(P, Wp, ws["coef"].data_ptr(), Wp,
                                                                     ws["R"].data_ptr(), Wp, st))
         elif self.meta["resid_mode"] == 2:
             stage("direct_residual", lambda: self.lib.csl_direct_residual(P, W, ws["coef"].data_ptr(), Wp,
                                                                           ws["R"].data_ptr(), Wp, st))
-        if self.meta["resid_mode"]:
+        if self.meta["resid_mode"] == 3:
+            stage("cov_chi2", lambda: self.lib.csl_cov_chi2(P, W, ws["R"].data_ptr(), Wp, ws["chi2"].data_ptr(), st))
+            chi2 = ws["chi2"].data_ptr()
+        elif self.meta["resid_mode"]:
             stage("chi2", lambda: self.lib.csl_chi2(P, Wp, ws["R"].data_ptr(), Wp, ws["chi2"].data_ptr(),
                                                     ws["part"].data_ptr(), st))
             chi2 = ws["chi2"].data_ptr()

@@ -277,9 +277,10 @@ class LnlSum(LnlTerm):
 class SpectrumBlock(object):
     """One binned spectrum of a bandpower likelihood: windows [nbins, nl] applied
     to model columns [lmin, lmin+nl), data [nbins], calibration multiplying the data."""
-    def __init__(self, model, windows, data, cal=1.0):
+    def __init__(self, model, windows, data, cal=1.0, cal_on_model=False):
         self.model, self.windows, self.data, self.cal = model, np.asarray(windows, dtype=float), \
             np.asarray(data, dtype=float), cal
+        self.cal_on_model = cal_on_model      # False: r = cal*d - b (spt_lowl, mspec); True: r = d - cal*b (SPTSZ)
 
 
 class BandpowerTerm(LnlTerm):
@@ -287,6 +288,16 @@ class BandpowerTerm(LnlTerm):
     covariance (spt_lowl.py:112-133; mspec_lnl.py:63-73)."""
     def __init__(self, blocks, cov):
         self.blocks, self.cov = list(blocks), np.asarray(cov, dtype=float)
+
+
+class LowRankCovBandpowerTerm(LnlTerm):
+    """1/2 r^T (Sigma + V V^T)^-1 r  with  r = d - cal * W.cl  and  V_k = (W diag(b_k)).cl:
+    a bandpower likelihood whose covariance depends on the model through rank-one beam modes
+    (SPTSZ_lowl.py:62-81, beam_cov = W (B o dl dl^T) W^T with B = sum_k b_k b_k^T)."""
+    def __init__(self, model, windows, data, cal, sigma, modes):
+        self.model, self.cal = model, cal
+        self.windows, self.data = np.asarray(windows, dtype=float), np.asarray(data, dtype=float)
+        self.sigma, self.modes = np.asarray(sigma, dtype=float), np.asarray(modes, dtype=float)
 
 
 class GaussTerm(LnlTerm):

@@ -141,6 +141,11 @@ def _model_cl(prob, key, p, lmax):
         if a[0] != b[0]:
             return p["A_cmb"] * tilt * t["te"][:lmax] + (0.3 * p["A_dust"]) * t["dust"][:lmax]
         return p["A_cmb"] * tilt * t["ee"][:lmax] + p["A_dust"] * t["dust"][:lmax]
+    if prob["kind"] == "unbinned":
+        tilt = (np.maximum(ell, 1.0) / prob["lpivot"]) ** p["n_tilt"]
+        if a[0] == "T" and b[0] == "T":
+            return p["A_cmb"] * tilt * t["tt"][:lmax] + p["A_ps"] * (ell / 3000.0) ** 2
+        return p["A_cmb"] * tilt * (t["te"] if a[0] != b[0] else t["ee"])[:lmax]
     x = ell / 3000.0
     fa, fb = a[1:], b[1:]
     return (p["A_cmb"] * t["tt"][:lmax] + p["Aps_%s_%s" % (fa, fb)] * x ** 2
@@ -168,6 +173,7 @@ def build_script(ns, prob, sampler=None):
     t = prob["templates"]
     truth, scales = prob["truth"], prob["scales"]
     planck = prob["kind"] == "planck_lite"
+    unbinned = prob["kind"] == "unbinned"
 
     class foregrounds(ns.egfs):
         """per-spectrum foreground model; called by mspec_lnl as
@@ -176,6 +182,8 @@ def build_script(ns, prob, sampler=None):
         def get_egfs(self, spectra, lmax, spec, **p):
             a, b = spec
             ell = np.arange(lmax) / 3000.0
+            if unbinned:
+                return {"ps": p["A_ps"] * ell ** 2} if (a[0] == "T" and b[0] == "T") else {}
             if planck:
                 if a[0] == "T" and b[0] == "T":
                     return {"ps": p["A_ps"] * ell ** 2, "cib": p["A_cib"] * ell ** p["n_cib"],
@@ -208,7 +216,7 @@ def build_script(ns, prob, sampler=None):
         def __call__(self):
             p = {k: self[k] for k in truth}
             lmax = max(v[1] for v in prob["use"].values())
-            if planck:
+            if planck or unbinned:
                 tilt = (np.maximum(np.arange(lmax), 1.0) / prob["lpivot"]) ** p["n_tilt"]
                 cmb = {"cl_TT": p["A_cmb"] * (tilt * t["tt"][:lmax]), "cl_TE": p["A_cmb"] * (tilt * t["te"][:lmax]),
                        "cl_EE": p["A_cmb"] * (tilt * t["ee"][:lmax])}
@@ -220,3 +228,37 @@ def build_script(ns, prob, sampler=None):
             return self.like(cmb, self.fg(**p))
 
     return script
+
+
+def unbinned_problem(lmax=2501, seed=0):
+    """BASELINE config 5: UNBINNED TT/TE/EE over ell = 2..lmax-1 (3 x 2499 = 7497 data points at
+    lmax = 2501), identity windows, dense covariance (banded + low rank, stored dense)."""
+    rs = np.random.RandomState(seed)
+    tt, te, ee = _cmb_templates(lmax)
+    T, E = "T143", "E143"
+    nl = lmax - 2
+    use = {(T, T): (2, lmax), (T, E): (2, lmax), (E, E): (2, lmax)}
+    windows = {k: np.eye(nl) for k in use}
+    truth = OrderedDict(A_cmb=1.0, n_tilt=0.0, A_ps=60.0, y_cal=1.0)
+    scales = OrderedDict(A_cmb=0.001, n_tilt=0.001, A_ps=2.0, y_cal=0.001)
+    prob = dict(kind="unbinned", maps=(T, E), use=use, windows=windows, truth=truth, scales=scales,
+                templates=dict(tt=tt, te=te, ee=ee), lpivot=1000.0, lmax=lmax)
+    m = model_vector(prob, truth)
+    n = m.size
+    sig = 0.05 * np.abs(m) + 1.0
+    cov = np.zeros((n, n))
+    idx = np.arange(n)
+    cov[idx, idx] = 1.0
+    cov[idx[:-1], idx[:-1] + 1] = cov[idx[:-1] + 1, idx[:-1]] = 0.2
+    cov[idx[:-nl], idx[:-nl] + nl] = cov[idx[:-nl] + nl, idx[:-nl]] = 0.05
+    u = rs.standard_normal((n, 3)) * 0.05
+    cov += u @ u.T
+    cov *= np.outer(sig, sig)
+    d = m + np.linalg.cholesky(cov) @ rs.standard_normal(n)
+    prob["cov"], prob["n"] = cov, n
+    signal, i = {}, 0
+    for key in sorted(use):
+        signal[key] = d[i:i + nl]
+        i += nl
+    prob["signal"] = signal
+    return prob

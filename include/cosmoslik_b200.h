@@ -61,6 +61,7 @@ enum {
   CSL_S_NTERM = 1,   /* NT: template terms, padded to the class size {0,1,2,4,8}   */
   CSL_S_NPLAW = 2,   /* NP: power-law terms, padded to the class size {0,1,2,4}    */
   CSL_S_CAL   = 3,   /* coef row multiplying the data of this spectrum, -1 = 1.0 */
+  CSL_S_CALMODE = 5, /* 0: r = cal*d - b (spt_lowl.py:132, mspec);  1: r = d - cal*b (SPTSZ_lowl.py:68) */
   CSL_S_LTAB  = 4,   /* offset (doubles) of the ell-table in `templates`: nl_pad rows of
                         [T_0..T_{NT-1}, (logB_q, M_q, D_q, 0) q<NP], D_q[l] = logB_q[l+1] - logB_q[l];
                         cl[l] = sum_t coef[TERM_COEF[t]] T_t[l]
@@ -105,6 +106,7 @@ enum {
  *   r      = cal * d - W . cl        (resid_mode 1; spt_lowl.py:132,171-182;
  *                                     mspec_lnl.py:63-73)
  *          = coef[direct_coef[i]] - d[i]   (resid_mode 2; dense Gaussian)
+ *   resid_mode 3: r = d - cal * W.cl and V_k = W_k.cl, lnl = 1/2 r^T (Sigma + V V^T)^-1 r
  *   cl     = sum_t coef * T_t[l] + sum_p coef * M_p[l] * exp(coef * logB_p[l])
  *            (spt_lowl.py:206-207; models/clust_poisson_egfs.py:14-17)
  */
@@ -126,6 +128,11 @@ typedef struct csl_program {
   int32_t nsegclass;        /* segmented-sum classes (spectra with block-sparse windows)          */
   int32_t segcls[CSL_MAX_CLASS][4];  /* per class: NT, NP, first bin record, number of bin records */
   const int32_t* bin_tab;
+  /* resid_mode 3: model-dependent covariance C = Sigma + V V^T (SPTSZ_lowl.py:62-81).  The residual
+   * vector stacks r (n_base rows) and the nmode columns of V (n_base rows each); chi^2 = r^T C^-1 r by a
+   * per-walker Cholesky factorisation (csl_cov_chi2). */
+  const double* Sigma;      /* [n_base, n_base] row-major */
+  int32_t n_base, nmode;
 } csl_program_t;
 
 int csl_abi_version(void);
@@ -159,6 +166,11 @@ int csl_direct_residual(const csl_program_t* p, int W, const double* coef, int l
  *   chi2_mode 1: tile products with the host-inverted factor Minv (chosen by the host only when the
  *                inverse reproduces the substitution result to 1e-13); needs ws_part [n_pad/64, ldr]. */
 int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part, void* stream);
+
+/* resid_mode 3 (replaces cho_factor(beam_cov + sigma) + cho_solve per call, SPTSZ_lowl.py:66-69):
+ * R [(1 + nmode) * n_base (padded), ldr] holds r and the columns of V for every walker; one warp per
+ * walker builds C = Sigma + V V^T in shared memory, factors it and solves.  n_base <= 64, nmode <= 32. */
+int csl_cov_chi2(const csl_program_t* p, int W, const double* R, int ldr, double* chi2, void* stream);
 
 /* lnl[w] = prior[w] + sum scalar coefs + chi2[w]/2 ; +inf where prior is +inf (cosmoslik.py:135-141).
  * chi2 may be NULL when the program has no quadratic form. */

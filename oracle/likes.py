@@ -103,6 +103,33 @@ class SptLowl(Plugin):
         return np.dot(dcl, cho_solve(self.cho_sigma, dcl)) / 2
 
 
+class SptszLowl(Plugin):
+    """likelihoods/SPTSZ_lowl_2017/SPTSZ_lowl.py:62-81 from arrays (the loader :25-57 and the beam-grid
+    reader :95-145 cannot run: py2 bytes/str at :31, cwd-relative path :35-36, SPTSZ_beam_errors.tar
+    missing).  PARITY UNPINNED against the reference itself; the arithmetic below is the reference's,
+    line for line:  dl (:74-77), db = W dl and beam_cov = W (beam_corr o dl dl^T) W^T (:81),
+    cho_factor(beam_cov + sigma) on every call (:67), deldb = spec - db*cal (:68), no log-det (:69)."""
+
+    def __init__(self, spec, sigma, windows, lmin_window, beam_corr, egfs, cal=1):
+        super().__init__()
+        self.spec, self.sigma = np.asarray(spec), np.asarray(sigma)
+        self.windows = np.asarray(windows)
+        self.windowrange = slice(int(lmin_window), int(lmin_window) + self.windows.shape[1])
+        self.lmax = self.windowrange.stop
+        self.beam_corr = np.asarray(beam_corr)
+        self.egfs, self.cal = egfs, cal
+
+    def __call__(self, cmb):
+        eg = self.egfs(lmax=self.lmax)[:self.lmax]
+        tt = cmb["TT"][:self.lmax]
+        dl = tt[self.windowrange] + eg[self.windowrange]
+        db = np.dot(self.windows, dl)
+        beam_cov = np.dot(self.windows, np.dot(self.beam_corr * np.outer(dl, dl), self.windows.T))
+        cho = cho_factor(beam_cov + self.sigma)
+        deldb = self.spec - db * self.cal
+        return np.dot(deldb, cho_solve(cho, deldb)) / 2.0
+
+
 class MspecLike(Plugin):
     """likelihoods/mspec_lnl.py:11-73 with the external ``mspec`` container
     replaced by plain dicts:

@@ -55,6 +55,8 @@ def residual(cp, coef):
         for i in range(m["n"]):
             r[i] = coef[t["direct_coef"][i]] - t["data"][i]
         return r
+    if m["resid_mode"] == 3:
+        pass
     for ci in range(m.get("nsegclass", 0)):
         NTc, NPc, b0, nb = cp.segcls[ci]
         for rec in t["bin_tab"][b0:b0 + nb]:
@@ -74,7 +76,9 @@ def residual(cp, coef):
                     cl += coef[spec[L.S_PLAW_AMP + k]] * ltab[:, NT + 4 * k + 1] * np.exp(coef[spec[L.S_PLAW_IDX + k]] * ltab[:, NT + 4 * k])
             woff = (int(rec[L.B_WINOFF_HI]) << 32) | (int(rec[L.B_WINOFF_LO]) & 0xFFFFFFFF)
             cal = 1.0 if spec[L.S_CAL] < 0 else coef[spec[L.S_CAL]]
-            r[rec[L.B_ROW]] = cal * t["data"][rec[L.B_ROW]] - np.dot(t["windows"][woff + l0: woff + l1], cl)
+            bval = np.dot(t["windows"][woff + l0: woff + l1], cl)
+            dval = t["data"][rec[L.B_ROW]]
+            r[rec[L.B_ROW]] = dval - cal * bval if spec[L.S_CALMODE] else cal * dval - bval
             written[rec[L.B_ROW]] = True
     for tile in t["tile_tab"][:m["ntile"]]:
         spec = t["spec_tab"][tile[L.T_SPEC]]
@@ -99,7 +103,7 @@ def residual(cp, coef):
             if nz.size:
                 assert tile[L.T_GLO + g] <= l0 + nz[0] and l0 + nz[-1] < tile[L.T_GHI + g]
             row = tile[L.T_ROW0] + rr
-            r[row] = cal * t["data"][row] - np.dot(w, cl)
+            r[row] = t["data"][row] - cal * np.dot(w, cl) if spec[L.S_CALMODE] else cal * t["data"][row] - np.dot(w, cl)
             written[row] = True
     assert written.all(), "residual rows %s are written by no tile / bin record" % np.flatnonzero(~written)
     return r
@@ -115,7 +119,14 @@ def lnl(cp, x):
     like = 0.0
     for k in range(m["nscalar"]):
         like = like + coef[t["scalar_coef"][k]]
-    if m["resid_mode"]:
+    if m["resid_mode"] == 3:
+        r = residual(cp, coef)
+        n, K = m["n_base"], m["nmode"]
+        V = r[n:n + n * K].reshape(K, n).T
+        C = t["Sigma"].reshape(n, n) + V @ V.T
+        y = sla.solve_triangular(np.linalg.cholesky(C), r[:n], lower=True)
+        like = like + 0.5 * float(y @ y)
+    elif m["resid_mode"]:
         r = residual(cp, coef)
         npad = m["n_pad"]
         y = sla.solve_triangular(t["Lmat"].reshape(npad, npad), r, lower=True)

@@ -33,7 +33,7 @@ def test_constants_match_header():
     enums = dict((k, int(v)) for k, v in re.findall(r"CSL_(\w+)\s*=\s*(\d+)", h))
     for k, v in _lib.OP.items():
         assert enums["OP_" + k] == v
-    for k in ("S_NLPAD", "S_NTERM", "S_NPLAW", "S_CAL", "S_LTAB", "S_TERM_COEF", "S_PLAW_AMP", "S_PLAW_IDX",
+    for k in ("S_NLPAD", "S_NTERM", "S_NPLAW", "S_CAL", "S_LTAB", "S_CALMODE", "S_TERM_COEF", "S_PLAW_AMP", "S_PLAW_IDX",
               "T_ROW0", "T_NROWS", "T_SPEC", "T_LBEGIN", "T_LEND", "T_WINOFF_LO",
               "T_WINOFF_HI", "T_WINLD", "T_GLO", "T_GHI", "B_ROW", "B_SPEC", "B_LO", "B_HI", "B_WINOFF_LO", "B_WINOFF_HI",
               "B_DMAX"):

@@ -169,3 +169,19 @@ def test_untraceable_script_fails_loudly():
 
     with pytest.raises(TypeError, match="cannot be batched"):
         Slik(bad()).trace()
+
+
+@pytest.mark.parametrize("by_modes", [False, True])
+def test_model_dependent_covariance_tables(by_modes):
+    """SPTSZ-style likelihood: C = sigma + V V^T with the beam modes as extra window rows"""
+    import sptsz_problem as SP
+    o_cls, b_cls = SP.scripts(nmode=5)
+    oslik = ort.Slik(o_cls())
+    slik = Slik(b_cls(by_modes))
+    cp = CompiledProgram(list(slik.get_sampled()), slik.params.priors, slik.trace())
+    assert cp.meta["resid_mode"] == 3 and cp.meta["n_base"] == 47 and cp.meta["nmode"] == 5
+    assert cp.meta["n"] == 6 * 47 and cp.names == list(oslik.get_sampled())
+    x0 = np.array([oslik.get_start()[k] for k in cp.names])
+    for f in (1.0, 1.03, 0.95):
+        ref = oslik.evaluate(*(x0 * f))[0]
+        assert abs(TI.lnl(cp, x0 * f) - ref) <= 1e-11 * abs(ref)
