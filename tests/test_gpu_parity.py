@@ -152,6 +152,50 @@ def test_both_binning_kernels_match_the_oracle(torch, binning):
     assert relerr(slik.evaluate_batch(X), ref) < RTOL
 
 
+def test_segmented_binning_with_ragged_walker_counts(torch):
+    """walker counts that leave the last 256-walker CTA of k_bin_segsum half empty"""
+    prob = synthetic.planck_lite_problem(5)
+    oslik = ort.Slik(synthetic.build_script(ORACLE, prob)())
+    slik = Slik(synthetic.build_script(PRODUCT, prob)())
+    names = list(slik.get_sampled())
+    x0 = np.array([prob["truth"][k] for k in names]); sc = np.array([prob["scales"][k] for k in names])
+    X = x0 + sc * np.random.RandomState(10).standard_normal((700, len(names)))
+    ref = np.array([oslik.evaluate(*x)[0] for x in X[:40]] + [oslik.evaluate(*x)[0] for x in X[-40:]])
+    for W in (700, 300, 129):
+        got = slik.evaluate_batch(X[:W])
+        assert relerr(got[:40], ref[:40]) < RTOL
+        if W == 700:
+            assert relerr(got[-40:], ref[40:]) < RTOL
+
+
+def test_script_file_runs_through_the_launcher(torch, tmp_path):
+    """python -m cosmoslik_b200 script.py --num_samples N  (load_script + argparse + drained sampler)"""
+    import subprocess, sys as _sys
+    from conftest import ROOT
+    script = tmp_path / "myscript.py"
+    out = tmp_path / "my.chain"
+    script.write_text("""
+from cosmoslik_b200 import *
+
+class myscript(SlikPlugin):
+    def __init__(self, ndim, num_samples=1000):
+        super().__init__()
+        ndim = self.ndim = int(ndim)
+        for i in range(ndim):
+            self["param%i" % i] = param(start=0, scale=1)
+        self.sampler = samplers.metropolis_hastings(self, num_samples=num_samples, output_file="OUTFILE", nchains=8)
+
+    def __call__(self):
+        return sum([self["param%i" % i] ** 2 for i in range(self.ndim)]) / 2
+""".replace("OUTFILE", str(out)))
+    r = subprocess.run([_sys.executable, "-m", "cosmoslik_b200", str(script), "3", "--num_samples", "2400"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    chains = load_chain(str(out))
+    assert len(chains) == 8 and set(chains[0].keys()) == {"lnl", "weight", "param0", "param1", "param2"}
+    assert sum(c["weight"].sum() for c in chains) > 0.9 * 2400
+
+
 def test_ragged_and_tiny_batches(torch, spt_data):
     """W not a multiple of the 128-walker tile, W = 1, and a batch where every walker is outside the prior"""
     g = golden("spt_lowl_lnl.npz")
