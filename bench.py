@@ -246,11 +246,7 @@ def run_b200(args):
 
     # ---- device-resident timing: K full stretch steps, CUDA events, max over ranks
     smp.row_capacity = args.steps            # same row buffer for the warm-up and the timed run
-    smp.run(prog, nsteps=max(args.warmup, 3))
-    smp.init_pos = np.zeros((k_total, len(names)))   # placeholder; replaced below by the warmed-up state
-    full = dist.all_gather_rows(smp.stats["pos"][:args.walkers // 2], k_total // 2)
-    full2 = dist.all_gather_rows(smp.stats["pos"][args.walkers // 2:], k_total - k_total // 2)
-    smp.init_pos = torch.cat([full, full2], 0).cpu().numpy()
+    smp.run(prog, nsteps=max(args.warmup, 3))      # warm-up: start positions evaluated, replica built
     timers = {}
     smp.timers = timers
     dist.barrier(); torch.cuda.synchronize()
@@ -258,13 +254,11 @@ def run_b200(args):
     sampler_clk = ClockSampler(dev)
     with sampler_clk as clk:
         e0.record()
-        smp.run(prog, nsteps=args.steps)
+        smp.run(prog, nsteps=args.steps, resume=True)     # exactly K steps, continuing the warmed-up ensemble
         e1.record()
         torch.cuda.synchronize()
     dist.barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    # smp.run() includes the initial lnl of the start positions (one extra evaluation sweep, as
-    # emcee does); it is inside the timed region and NOT counted as evaluations.
     if size > 1:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
     ms = float(ms.item())
@@ -306,7 +300,7 @@ def run_b200(args):
                 "other_stages_ms": {k: v for k, v in stage_ms.items() if k not in ("chi2", "bin_residual")}}
 
     # ---- end to end through the plugin API with HOST buffers (Slik.evaluate_batch -> csl_lnl_host)
-    Xh = torch.from_numpy(smp.init_pos[rank * args.walkers:(rank + 1) * args.walkers].copy()).pin_memory()
+    Xh = smp.stats["pos"].cpu().pin_memory()           # this rank's walkers, as a host array
     Oh = torch.empty(args.walkers, dtype=torch.float64).pin_memory()
     xh, oh = Xh.numpy(), Oh.numpy()
     for _ in range(3):
@@ -328,13 +322,15 @@ def run_b200(args):
     cpu = None
     if size == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_single(args.workload, args.cpu_seconds)
-    # my kernels per stretch step: per half-update propose, prepare, zero_pad, bin, chi2, combine, accept; + rows
-    launches_per_step = 2 * 7 + 1
+    # my kernels per stretch step: per half-update propose, prepare, one binning launch per spectrum class,
+    # chi2 (+ partial-sum reduce), combine, accept (+ peer barrier when sharded); + the row bookkeeping
+    nbin = int(prog.meta.get("nclass", 0)) + int(prog.meta.get("nsegclass", 0))
+    launches_per_step = 2 * (2 + nbin + (2 if prog.meta.get("chi2_mode") else 1) + 1 + 1 + (1 if size > 1 else 0)) + 1
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": size, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(config_of(args, prob, k_total), exchange=smp.stats.get("exchange")), "e2e": e2e,
-            "gpu_launches": launches_per_step * args.steps + 4,
+            "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
             "acceptance": acc_frac, "host_launch_ms_per_step": host_ms,
             "flops_per_eval": {"trsm_algorithmic": fl["trsm_alg"], "trsm_executed": fl["trsm"],

@@ -72,13 +72,16 @@ class emcee(SlikSampler):
                     s.chain = wid
                     yield s
 
-    def run(self, lnl_or_program, nsteps=None):
+    def run(self, lnl_or_program, nsteps=None, resume=False):
+        """Batched entry point: advance the ensemble `nsteps` steps and return the state dict.
+        ``resume=True`` continues from the state the previous call left (positions, lnl, weights)
+        without re-evaluating the start positions."""
         prog = lnl_or_program if hasattr(lnl_or_program, "struct") else program_of(lnl_or_program)
-        for _ in self._run(prog, emit=False, nsteps=nsteps):
+        for _ in self._run(prog, emit=False, nsteps=nsteps, resume=resume):
             pass
         return self.stats
 
-    def _run(self, prog, emit, nsteps=None):
+    def _run(self, prog, emit, nsteps=None, resume=False):
         torch, lib = prog.torch, prog.lib
         dev = prog.device
         nd = len(self.x0)
@@ -98,11 +101,15 @@ class emcee(SlikSampler):
         kw = dict(dtype=torch.float64, device=dev)
         rl = 2 + nd
         cap = max(nsteps, int(getattr(self, "row_capacity", 0)), 1)
-        pos_all = self.initial_positions()
-        if pos_all.shape != (k, nd):
-            raise ValueError("initial positions must be [nwalkers, ndim]")
-        pos = torch.from_numpy(pos_all[gid]).to(dev).contiguous()   # local: first-half slice then second-half slice
-        lnl_pos = prog.lnl(pos)
+        prev = self.stats if (resume and self.stats and tuple(self.stats["pos"].shape) == (W, nd)) else None
+        if prev is None:
+            pos_all = self.initial_positions()
+            if pos_all.shape != (k, nd):
+                raise ValueError("initial positions must be [nwalkers, ndim]")
+            pos = torch.from_numpy(pos_all[gid]).to(dev).contiguous()   # local: first-half then second-half slice
+            lnl_pos = prog.lnl(pos)
+        else:
+            pos, lnl_pos = prev["pos"], prev["lnl"]
         halves = [(0, n0, lo0, h), (n0, W, h + lo1, k - h)]          # (row0, row1, first global id, half size)
         # several GPUs: a replica of the whole ensemble in NVLink symmetric memory, updated by the accept
         # kernel itself (fused exchange); otherwise NCCL all_gather of the complementary half
@@ -114,13 +121,15 @@ class emcee(SlikSampler):
             else:
                 replica = dist.EnsembleReplica.create(k, nd, dev)
                 dict.__setitem__(self, "_replica", ((k, nd, str(dev)), replica))
-        if replica is not None:
+        if replica is not None and prev is None:
             replica.tensor.copy_(torch.from_numpy(pos_all).to(dev))
             torch.cuda.synchronize()
             dist.barrier()
+        elif replica is None and size > 1:
+            pass                                   # NCCL path gathers the complementary half every half-step
         q = torch.empty_like(pos)
         zz = torch.empty(W, **kw)
-        weight = torch.ones(W, **kw)
+        weight = prev["weight"] if prev is not None else torch.ones(W, **kw)
         buf = getattr(self, "_buffers", None)           # reuse the big row buffer across runs of equal shape
         if buf is None or buf[0] != (W, cap, rl, str(dev)):
             buf = ((W, cap, rl, str(dev)), torch.empty((W, cap, rl), **kw))
