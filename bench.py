@@ -251,8 +251,7 @@ def run_b200(args):
     smp.timers = timers
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler_clk = ClockSampler(dev)
-    with sampler_clk as clk:
+    with ClockSampler(dev) as clk:
         e0.record()
         smp.run(prog, nsteps=args.steps, resume=True)     # exactly K steps, continuing the warmed-up ensemble
         e1.record()

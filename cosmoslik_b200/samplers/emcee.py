@@ -29,6 +29,7 @@ columns wrongly there.  Here the yielded objects carry x / lnl in their proper
 fields; the row CONTENT (the lnl of the next position next to the old position)
 is reproduced.
 """
+import time
 from collections import OrderedDict
 from math import ceil
 
@@ -125,8 +126,6 @@ class emcee(SlikSampler):
             replica.tensor.copy_(torch.from_numpy(pos_all).to(dev))
             torch.cuda.synchronize()
             dist.barrier()
-        elif replica is None and size > 1:
-            pass                                   # NCCL path gathers the complementary half every half-step
         q = torch.empty_like(pos)
         zz = torch.empty(W, **kw)
         weight = prev["weight"] if prev is not None else torch.ones(W, **kw)
@@ -147,23 +146,40 @@ class emcee(SlikSampler):
         timers = getattr(self, "timers", None)     # bench.py: CUDA-event pairs per stage
         nacc = torch.zeros((), dtype=torch.int64, device=dev)
         F = int(self.output_freq)
-        import time as _time
-        t_host0 = _time.perf_counter()
+        t_host0 = time.perf_counter()
+        step0 = int(prev["steps_done"]) if prev is not None else 0       # Philox step counter continues on resume
+
+        class timed(object):
+            """CUDA-event pair around a stage, appended to timers[name] (bench.py); no-op without timers"""
+            def __init__(self, name):
+                self.name = name
+
+            def __enter__(self):
+                if timers is not None:
+                    self.a = torch.cuda.Event(enable_timing=True)
+                    self.a.record()
+
+            def __exit__(self, *exc):
+                if timers is not None:
+                    b_ev = torch.cuda.Event(enable_timing=True)
+                    b_ev.record()
+                    timers.setdefault(self.name, []).append((self.a, b_ev))
+
+        def to_dev(arr, dtype):
+            return torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(dev)
+
         try:
             for i in range(nsteps):
-                inj = self.streams(i) if self.streams is not None else None
+                step = step0 + i
+                inj = self.streams(step) if self.streams is not None else None
                 for hidx, (r0, r1, g0, hsize) in enumerate(halves):
                     o0, o1, _, csize = halves[1 - hidx]
-                    if timers is not None:
-                        ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
-                    if replica is not None:
-                        cbase = 0 if hidx == 1 else h                 # global row of the complementary half
-                        comp = replica.tensor[cbase:cbase + csize]
-                    else:
-                        comp = dist.all_gather_rows(pos[o0:o1], csize)    # the complementary half, all ranks' rows
-                    if timers is not None:
-                        ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
-                        timers.setdefault("all_gather", []).append((ev0, ev1))
+                    with timed("all_gather"):
+                        if replica is not None:
+                            cbase = 0 if hidx == 1 else h                 # global row of the complementary half
+                            comp = replica.tensor[cbase:cbase + csize]
+                        else:
+                            comp = dist.all_gather_rows(pos[o0:o1], csize)    # the complementary half, all ranks' rows
                     ns = r1 - r0
                     if ns == 0:
                         if replica is not None:
@@ -171,41 +187,33 @@ class emcee(SlikSampler):
                         continue
                     uz = jj = ua = None
                     if inj is not None:
-                        sl = slice(g0 - (0 if hidx == 0 else h), g0 - (0 if hidx == 0 else h) + ns)
-                        uz = torch.from_numpy(np.ascontiguousarray(inj[0][hidx][sl], dtype=np.float64)).to(dev)
-                        jj = torch.from_numpy(np.ascontiguousarray(inj[1][hidx][sl], dtype=np.int64)).to(dev)
-                        ua = torch.from_numpy(np.ascontiguousarray(inj[2][hidx][sl], dtype=np.float64)).to(dev)
+                        first = g0 - (0 if hidx == 0 else h)              # index of my first walker within its half
+                        uz = to_dev(inj[0][hidx][first:first + ns], np.float64)
+                        jj = to_dev(inj[1][hidx][first:first + ns], np.int64)
+                        ua = to_dev(inj[2][hidx][first:first + ns], np.float64)
                     s_view, l_view, q_view = pos[r0:r1], lnl_pos[r0:r1], q[r0:r1]
-                    if timers is not None:
-                        ep0 = torch.cuda.Event(enable_timing=True); ep0.record()
-                    L.check(lib.csl_stretch_propose(ns, csize, nd, s_view.data_ptr(), comp.data_ptr(), float(self.a),
-                                                    L.ptr(uz), L.ptr(jj), seed, i, hidx, g0, q_view.data_ptr(),
-                                                    zz[r0:r1].data_ptr(), st), "csl_stretch_propose")
-                    if timers is not None:
-                        ep1 = torch.cuda.Event(enable_timing=True); ep1.record()
-                        timers.setdefault("propose", []).append((ep0, ep1))
+                    with timed("propose"):
+                        L.check(lib.csl_stretch_propose(ns, csize, nd, s_view.data_ptr(), comp.data_ptr(),
+                                                        float(self.a), L.ptr(uz), L.ptr(jj), seed, step, hidx, g0,
+                                                        q_view.data_ptr(), zz[r0:r1].data_ptr(), st),
+                                "csl_stretch_propose")
                     lnl_q = prog.lnl(q_view, timers=timers)
                     if replica is None:
-                        L.check(lib.csl_stretch_accept(ns, csize, nd, s_view.data_ptr(), l_view.data_ptr(),
-                                                       q_view.data_ptr(), lnl_q.data_ptr(), zz[r0:r1].data_ptr(),
-                                                       L.ptr(ua), seed, i, hidx, g0, accepted[r0:r1].data_ptr(),
-                                                       nacc.data_ptr(), st),
-                                "csl_stretch_accept")
+                        with timed("accept"):
+                            L.check(lib.csl_stretch_accept(ns, csize, nd, s_view.data_ptr(), l_view.data_ptr(),
+                                                           q_view.data_ptr(), lnl_q.data_ptr(), zz[r0:r1].data_ptr(),
+                                                           L.ptr(ua), seed, step, hidx, g0,
+                                                           accepted[r0:r1].data_ptr(), nacc.data_ptr(), st),
+                                    "csl_stretch_accept")
                     else:
-                        if timers is not None:
-                            ea = torch.cuda.Event(enable_timing=True); ea.record()
-                        L.check(lib.csl_stretch_accept_publish(
-                            ns, csize, nd, s_view.data_ptr(), l_view.data_ptr(), q_view.data_ptr(), lnl_q.data_ptr(),
-                            zz[r0:r1].data_ptr(), L.ptr(ua), seed, i, hidx, g0, accepted[r0:r1].data_ptr(),
-                            nacc.data_ptr(), replica.peers_dev.data_ptr(), replica.npeers, replica.multicast, g0, st),
-                            "csl_stretch_accept_publish")
-                        if timers is not None:
-                            eb = torch.cuda.Event(enable_timing=True); eb.record()
-                        replica.barrier()      # every rank's stores have landed before anyone proposes again
-                        if timers is not None:
-                            ec = torch.cuda.Event(enable_timing=True); ec.record()
-                            timers.setdefault("accept_publish", []).append((ea, eb))
-                            timers.setdefault("replica_barrier", []).append((eb, ec))
+                        with timed("accept_publish"):
+                            L.check(lib.csl_stretch_accept_publish(
+                                ns, csize, nd, s_view.data_ptr(), l_view.data_ptr(), q_view.data_ptr(),
+                                lnl_q.data_ptr(), zz[r0:r1].data_ptr(), L.ptr(ua), seed, step, hidx, g0,
+                                accepted[r0:r1].data_ptr(), nacc.data_ptr(), replica.peers_dev.data_ptr(),
+                                replica.npeers, replica.multicast, g0, st), "csl_stretch_accept_publish")
+                        with timed("replica_barrier"):
+                            replica.barrier()      # every rank's stores have landed before anyone proposes again
                 L.check(lib.csl_emcee_rows(W, nd, pos_old.data_ptr(), pos.data_ptr(), lnl_pos.data_ptr(),
                                            weight.data_ptr(), 1 if i == nsteps - 1 else 0, rows.data_ptr(),
                                            nrows.data_ptr(), cap, st), "csl_emcee_rows")
@@ -225,9 +233,10 @@ class emcee(SlikSampler):
         finally:
             if writer is not None:
                 writer.close()
-        host_ms = 1e3 * (_time.perf_counter() - t_host0) / max(nsteps, 1)   # CPU time to ENQUEUE one step
+        host_ms = 1e3 * (time.perf_counter() - t_host0) / max(nsteps, 1)   # CPU time to ENQUEUE one step
         exchange = ("none" if size == 1 else "nccl all_gather" if replica is None else
                     "accept kernel stores to every rank's replica over NVLink (%s) + device barrier"
                     % ("multimem.st multicast" if replica.multicast else "peer pointers"))
-        self.stats = dict(exchange=exchange, host_ms_per_step=host_ms, pos=pos, lnl=lnl_pos, weight=weight, rows=rows, nrows=nrows, nsteps=nsteps,
-                          walker_ids=gid, seed=seed, accepted=int(nacc.item()), evals=nsteps * W)
+        self.stats = dict(exchange=exchange, host_ms_per_step=host_ms, pos=pos, lnl=lnl_pos, weight=weight, rows=rows,
+                          nrows=nrows, nsteps=nsteps, steps_done=step0 + nsteps, walker_ids=gid, seed=seed,
+                          accepted=int(nacc.item()), evals=nsteps * W)

@@ -139,18 +139,6 @@ def sqrt(x):
     return Un("sqrt", x) if isinstance(x, Expr) and not isinstance(x, Const) else math.sqrt(float(x))
 
 
-def evaluate(e, x):
-    """Host evaluation of an expression at a numeric vector (used for unit tests
-    of the tracer only -- never on a sampling path)."""
-    if isinstance(e, Const): return e.v
-    if isinstance(e, Par): return float(x[e.index])
-    if isinstance(e, Un):
-        a = evaluate(e.a, x)
-        return {"neg": lambda: -a, "sqr": lambda: a * a, "exp": lambda: math.exp(a),
-                "log": lambda: math.log(a), "sqrt": lambda: math.sqrt(a)}[e.op]()
-    return _fold(e.op, evaluate(e.a, x), evaluate(e.b, x))
-
-
 class Spectrum(object):
     """A spectrum that is linear in template arrays with symbolic coefficients:
 

@@ -19,7 +19,6 @@ What is produced (all from the reference's own code paths, via oracle/refshim.py
   ref_mh.chain        a chain file written by the reference (pickle stream)
 """
 import os
-import pickle
 import sys
 
 import numpy as np

@@ -2,7 +2,7 @@
 (cosmoslik_b200) exactly as a CosmoSlik user would write them."""
 import numpy as np
 
-from cosmoslik_b200 import SlikPlugin, param, likelihoods, models, samplers  # noqa: F401
+from cosmoslik_b200 import SlikPlugin, param, likelihoods
 
 
 def synthetic_tt(n=6000):

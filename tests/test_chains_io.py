@@ -9,7 +9,7 @@ import pytest
 
 from conftest import GOLDEN, golden
 from cosmoslik_b200 import Chain, Chains, load_chain, get_covariance, combine_covs
-from cosmoslik_b200.chains import ChainWriter, gelman_rubin, rhat_from_moments
+from cosmoslik_b200.chains import ChainWriter, gelman_rubin
 from cosmoslik_b200.samplers.metropolis_hastings import _FileBlocks
 from oracle import refshim, runtime as ort, samplers as osamp
 

@@ -30,7 +30,6 @@ def test_dist_helpers_world_size_3():
 
 @pytest.mark.gpu
 def test_sharded_stretch_move_is_bitwise_the_single_process_run(tmp_path):
-    import torch
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from namespaces import PRODUCT
     from cosmoslik_b200 import Slik, samplers, synthetic

@@ -1,9 +1,6 @@
 """Parity of the CUDA path (through the C ABI) with the CPU oracle and with the golden outputs of
 the unmodified reference.  Tolerances: lnL 1e-10 relative (BASELINE.json north_star); positions,
 weights and accept/reject decisions exact."""
-import ctypes as C
-import os
-
 import numpy as np
 import pytest
 
