@@ -247,8 +247,9 @@ def run_b200(args):
     # ---- device-resident timing: K full stretch steps, CUDA events, max over ranks
     smp.row_capacity = args.steps            # same row buffer for the warm-up and the timed run
     smp.run(prog, nsteps=max(args.warmup, 3))      # warm-up: start positions evaluated, replica built
-    timers = {}
-    smp.timers = timers
+    smp.python_loop = True                          # ... and the instrumented Python loop's code paths
+    smp.run(prog, nsteps=3, resume=True)
+    del smp["python_loop"]
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(dev) as clk:
@@ -263,11 +264,21 @@ def run_b200(args):
     ms = float(ms.item())
     value = k_total * args.steps / (ms * 1e-3)
     acc_frac = smp.stats["accepted"] / float(smp.stats["evals"])
+    host_ms = smp.stats.get("host_ms_per_step")
+    # ---- second pass of K more steps with a CUDA-event pair around every stage (this disables the C-side
+    # step loop: each stage is launched from Python between events), for the per-kernel durations
+    timers = {}
+    smp.timers = timers
+    dist.barrier(); torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    smp.run(prog, nsteps=args.steps, resume=True)
+    f1.record(); torch.cuda.synchronize()
+    ms_instrumented = f0.elapsed_time(f1) / args.steps
     del smp["timers"]
 
     # ---- per-kernel durations from the event pairs recorded inside the timed region
     stage_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in timers.items()}
-    host_ms = smp.stats.get("host_ms_per_step")
     stage_n = {k: len(v) for k, v in timers.items()}
     half = args.walkers // 2
     fl = prog.flops
@@ -331,7 +342,8 @@ def run_b200(args):
             "config": dict(config_of(args, prob, k_total), exchange=smp.stats.get("exchange")), "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
-            "acceptance": acc_frac, "host_launch_ms_per_step": host_ms,
+            "acceptance": acc_frac, "host_enqueue_ms_per_step": host_ms,
+            "ms_per_step_instrumented_pass": ms_instrumented,
             "flops_per_eval": {"trsm_algorithmic": fl["trsm_alg"], "trsm_executed": fl["trsm"],
                                "binning_dense_windows": fl["bin_dense"], "binning_nonzero_windows": fl["bin_nnz"],
                                "binning_executed_dmma": fl["bin_exec"], "foreground_build": fl["build_ops"]}}

@@ -38,6 +38,17 @@ class Program(C.Structure):
                  ("bin_tab", C.c_void_p), ("Sigma", C.c_void_p), ("n_base", C.c_int32), ("nmode", C.c_int32)])
 
 
+class Ensemble(C.Structure):
+    """csl_ensemble_t"""
+    _fields_ = ([(n, C.c_int32) for n in ("ndim", "n0", "n1", "h0", "h1")] +
+                [("gid0", C.c_uint32), ("gid1", C.c_uint32), ("cap", C.c_int32), ("a", C.c_double),
+                 ("seed", C.c_uint64)] +
+                [(n, C.c_void_p) for n in ("pos", "lnl", "q", "lnl_q", "zz", "weight", "pos_old", "rows", "nrows",
+                                           "accepted", "naccepted", "ws_coef", "ws_prior", "ws_R", "ws_chi2",
+                                           "ws_part", "replica", "peer_ptrs", "flag_ptrs")] +
+                [("multicast_ptr", C.c_uint64), ("epoch", C.c_uint64), ("npeers", C.c_int32), ("rank", C.c_int32)])
+
+
 _P = C.POINTER(Program)
 _int, _u64, _u32, _dbl = C.c_int, C.c_uint64, C.c_uint32, C.c_double
 
@@ -46,6 +57,7 @@ SIGNATURES = {
     "csl_abi_version": (_int, []),
     "csl_last_error": (C.c_char_p, []),
     "csl_sizeof_program": (_int, []),
+    "csl_sizeof_ensemble": (_int, []),
     "csl_device_info": (_int, [_int, _vp]),
     "csl_eval_prepare": (_int, [_P, _int, _vp, _vp, _int, _vp, _vp]),
     "csl_bin_residual": (_int, [_P, _int, _vp, _int, _vp, _int, _vp]),
@@ -68,6 +80,7 @@ SIGNATURES = {
     "csl_stretch_accept_publish": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _u32,
                                           _vp, _vp, _vp, _int, _u64, C.c_int64, _vp]),
     "csl_peer_barrier": (_int, [_vp, _int, _int, _u64, _vp]),
+    "csl_stretch_run": (_int, [_P, C.POINTER(Ensemble), _int, _u32, C.c_int64, _vp]),
     "csl_emcee_rows": (_int, [_int, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _vp]),
     "csl_chain_moments": (_int, [_int, _int, _vp, _vp, _int, _int, _vp, _vp]),
     "csl_philox_mh": (_int, [_int, _int, _u64, _u32, _u32, _vp, _vp, _vp]),
@@ -95,8 +108,8 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             f = getattr(L, name)
             f.restype, f.argtypes = res, args
-        if L.csl_sizeof_program() != C.sizeof(Program):
-            raise ImportError("cosmoslik_b200: csl_program_t layout mismatch between header and binding")
+        if L.csl_sizeof_program() != C.sizeof(Program) or L.csl_sizeof_ensemble() != C.sizeof(Ensemble):
+            raise ImportError("cosmoslik_b200: struct layout mismatch between header and binding")
         _lib = L
     return _lib
 

@@ -21,6 +21,7 @@ int csl_check_launch(const char* what) {
 extern "C" int csl_abi_version(void) { return CSL_ABI_VERSION; }
 extern "C" const char* csl_last_error(void) { return csl_err_buf; }
 extern "C" int csl_sizeof_program(void) { return (int)sizeof(csl_program_t); }
+extern "C" int csl_sizeof_ensemble(void) { return (int)sizeof(csl_ensemble_t); }
 
 extern "C" int csl_device_info(int device, int32_t* out) {
   CSL_REQUIRE(out, "csl_device_info: null output");
@@ -69,5 +70,55 @@ extern "C" int csl_lnl_host(const csl_program_t* p, int W, const double* x_host,
   if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
   e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+  return 0;
+}
+
+// ---- whole stretch-move steps enqueued from C -------------------------------------------------------------
+extern "C" int csl_stretch_run(const csl_program_t* p, csl_ensemble_t* e, int nsteps, uint32_t step0, int64_t last_step,
+                               void* stream) {
+  CSL_REQUIRE(p && e && nsteps >= 0, "csl_stretch_run: null argument");
+  CSL_REQUIRE(e->ndim == p->ndim && e->n0 >= 0 && e->n1 >= 0 && e->h0 > 0 && e->h1 > 0, "csl_stretch_run: bad ensemble");
+  CSL_REQUIRE(e->pos && e->lnl && e->q && e->lnl_q && e->zz && e->weight && e->pos_old && e->rows && e->nrows,
+              "csl_stretch_run: ensemble buffer missing");
+  CSL_REQUIRE(e->replica == nullptr || (e->peer_ptrs && e->flag_ptrs && e->npeers > 0),
+              "csl_stretch_run: replica given without peer / flag pointers");
+  const int nd = e->ndim, W = e->n0 + e->n1;
+  for (int i = 0; i < nsteps; ++i) {
+    const uint32_t step = step0 + (uint32_t)i;
+    for (int h = 0; h < 2; ++h) {
+      const int ns = h == 0 ? e->n0 : e->n1, r0 = h == 0 ? 0 : e->n0;
+      const int csize = h == 0 ? e->h1 : e->h0;
+      const uint32_t g0 = h == 0 ? e->gid0 : e->gid1;
+      // the complementary half: all walkers of the other colour (replica), or the local other slice
+      const double* comp = e->replica ? e->replica + (long long)(h == 0 ? e->h0 : 0) * nd
+                                      : e->pos + (long long)(h == 0 ? e->n0 : 0) * nd;
+      int rc = 0;
+      if (ns > 0) {
+        double* s = e->pos + (long long)r0 * nd;
+        double* q = e->q + (long long)r0 * nd;
+        rc = csl_stretch_propose(ns, csize, nd, s, comp, e->a, nullptr, nullptr, e->seed, step, (uint32_t)h, g0, q,
+                                 e->zz + r0, stream);
+        if (rc) return rc;
+        rc = csl_lnl(p, ns, q, e->lnl_q, e->ws_coef, e->ws_prior, e->ws_R, e->ws_chi2, e->ws_part, stream);
+        if (rc) return rc;
+        uint8_t* acc = e->accepted ? e->accepted + r0 : nullptr;
+        if (e->replica)
+          rc = csl_stretch_accept_publish(ns, csize, nd, s, e->lnl + r0, q, e->lnl_q, e->zz + r0, nullptr, e->seed, step,
+                                          (uint32_t)h, g0, acc, e->naccepted, e->peer_ptrs, e->npeers, e->multicast_ptr,
+                                          (int64_t)g0, stream);
+        else
+          rc = csl_stretch_accept(ns, csize, nd, s, e->lnl + r0, q, e->lnl_q, e->zz + r0, nullptr, e->seed, step,
+                                  (uint32_t)h, g0, acc, e->naccepted, stream);
+        if (rc) return rc;
+      }
+      if (e->replica) {
+        rc = csl_peer_barrier(e->flag_ptrs, e->rank, e->npeers, ++e->epoch, stream);
+        if (rc) return rc;
+      }
+    }
+    int rc = csl_emcee_rows(W, nd, e->pos_old, e->pos, e->lnl, e->weight, (int64_t)step == last_step ? 1 : 0, e->rows,
+                            e->nrows, e->cap, stream);
+    if (rc) return rc;
+  }
   return 0;
 }

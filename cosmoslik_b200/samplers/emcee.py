@@ -29,6 +29,7 @@ columns wrongly there.  Here the yielded objects carry x / lnl in their proper
 fields; the row CONTENT (the lnl of the next position next to the old position)
 is reproduced.
 """
+import ctypes as C
 import time
 from collections import OrderedDict
 from math import ceil
@@ -72,6 +73,15 @@ class emcee(SlikSampler):
                     s = sample(r[2:].copy(), r[0], r[1], None)
                     s.chain = wid
                     yield s
+
+    @staticmethod
+    def _collect_rows(rows, nrows, prev_n, gid, rl):
+        """device row buffer -> [(global walker id, new rows)] since the previous collection"""
+        W = rows.shape[0]
+        n_now = nrows.cpu().numpy().astype(np.int64)
+        a_, b_ = (int(prev_n.min()), int(n_now.max())) if W else (0, 0)
+        slab = rows[:, a_:b_].cpu().numpy() if b_ > a_ else np.zeros((W, 0, rl))
+        return [(int(gid[c]), slab[c, prev_n[c] - a_:n_now[c] - a_]) for c in range(W)], n_now
 
     def run(self, lnl_or_program, nsteps=None, resume=False):
         """Batched entry point: advance the ensemble `nsteps` steps and return the state dict.
@@ -168,8 +178,45 @@ class emcee(SlikSampler):
         def to_dev(arr, dtype):
             return torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(dev)
 
+        # Fast path: whole steps are enqueued from C (csl_stretch_run) -- no Python between the ~17 kernel
+        # launches of a step.  Needs device streams and either one GPU or the symmetric-memory replica.
+        native = self.streams is None and timers is None and (size == 1 or replica is not None) \
+            and not getattr(self, "python_loop", False)
+        ens = None
+        if native:
+            ws = prog.workspace(max(n0, n1, 1))
+            ens = L.Ensemble(ndim=nd, n0=n0, n1=n1, h0=h, h1=k - h, gid0=lo0, gid1=h + lo1, cap=cap, a=float(self.a),
+                             seed=seed, pos=pos.data_ptr(), lnl=lnl_pos.data_ptr(), q=q.data_ptr(),
+                             lnl_q=ws["lnl"].data_ptr(), zz=zz.data_ptr(), weight=weight.data_ptr(),
+                             pos_old=pos_old.data_ptr(), rows=rows.data_ptr(), nrows=nrows.data_ptr(),
+                             accepted=accepted.data_ptr(), naccepted=nacc.data_ptr(), ws_coef=ws["coef"].data_ptr(),
+                             ws_prior=ws["prior"].data_ptr(), ws_R=L.ptr(ws["R"]), ws_chi2=L.ptr(ws["chi2"]),
+                             ws_part=L.ptr(ws["part"]))
+            if replica is not None:
+                ens.replica, ens.peer_ptrs = replica.tensor.data_ptr(), replica.peers_dev.data_ptr()
+                ens.flag_ptrs, ens.multicast_ptr = replica.flag_ptrs.data_ptr(), replica.multicast
+                ens.epoch, ens.npeers, ens.rank = replica._epoch, replica.npeers, replica.handle.rank
+
         try:
-            for i in range(nsteps):
+            i = 0
+            while native and i < nsteps:
+                # one call per output block (or for the whole run when nobody consumes rows)
+                nb = min(F - (i % F), nsteps - i) if (emit or writer is not None) else nsteps - i
+                L.check(lib.csl_stretch_run(C.byref(prog.struct), C.byref(ens), nb, step0 + i, step0 + nsteps - 1, st),
+                        "csl_stretch_run")
+                if replica is not None:
+                    replica._epoch = int(ens.epoch)
+                i += nb
+                if (emit or writer is not None) and (i % F == 0 or i == nsteps):
+                    blocks, prev_n = self._collect_rows(rows, nrows, prev_n, gid, rl)
+                    if writer is not None:
+                        for wid, r in blocks:
+                            for c0 in range(0, len(r), F):
+                                writer.write(wid, r[c0:c0 + F])
+                        writer.flush()
+                    if emit:
+                        yield blocks
+            for i in (range(nsteps) if not native else ()):
                 step = step0 + i
                 inj = self.streams(step) if self.streams is not None else None
                 for hidx, (r0, r1, g0, hsize) in enumerate(halves):
@@ -218,11 +265,7 @@ class emcee(SlikSampler):
                                            weight.data_ptr(), 1 if i == nsteps - 1 else 0, rows.data_ptr(),
                                            nrows.data_ptr(), cap, st), "csl_emcee_rows")
                 if (emit or writer is not None) and ((i + 1) % F == 0 or i == nsteps - 1):
-                    n_now = nrows.cpu().numpy().astype(np.int64)
-                    a_, b_ = (int(prev_n.min()), int(n_now.max())) if W else (0, 0)
-                    slab = rows[:, a_:b_].cpu().numpy() if b_ > a_ else np.zeros((W, 0, rl))
-                    blocks = [(int(gid[c]), slab[c, prev_n[c] - a_:n_now[c] - a_]) for c in range(W)]
-                    prev_n = n_now
+                    blocks, prev_n = self._collect_rows(rows, nrows, prev_n, gid, rl)
                     if writer is not None:
                         for wid, r in blocks:
                             for c0 in range(0, len(r), F):      # records of at most output_freq rows (emcee.py:80-84)

@@ -138,6 +138,7 @@ typedef struct csl_program {
 int csl_abi_version(void);
 const char* csl_last_error(void);
 int csl_sizeof_program(void);
+int csl_sizeof_ensemble(void);
 /* device properties: out[0]=SM count, out[1]=cc major, out[2]=cc minor, out[3]=max smem/block optin */
 int csl_device_info(int device, int32_t* out4_host);
 
@@ -269,6 +270,37 @@ int csl_peer_barrier(const uint64_t* flag_ptrs, int rank, int world, uint64_t ep
  * pos_old row is refreshed to pos_new (ready for the next step). */
 int csl_emcee_rows(int W, int ndim, double* pos_old, const double* pos_new, const double* lnl_new,
                    double* weight, int last_step, double* rows, int32_t* nrows, int cap, void* stream);
+
+/* State of one rank's share of a stretch-move ensemble, for csl_stretch_run.  Local walkers are stored
+ * first-half slice then second-half slice: rows [0, n0) and [n0, n0+n1) of pos / lnl / q / zz / weight. */
+typedef struct csl_ensemble {
+  int32_t ndim, n0, n1;          /* local walkers in the first / second half                          */
+  int32_t h0, h1;                /* global sizes of the two halves                                      */
+  uint32_t gid0, gid1;           /* global walker id of local row 0 and of local row n0                 */
+  int32_t cap;                   /* row-buffer capacity per walker                                      */
+  double a;                      /* stretch scale (emcee default 2)                                     */
+  uint64_t seed;                 /* Philox key                                                          */
+  double *pos, *lnl, *q, *lnl_q, *zz, *weight, *pos_old, *rows;
+  int32_t* nrows;
+  uint8_t* accepted;
+  uint64_t* naccepted;
+  double *ws_coef, *ws_prior, *ws_R, *ws_chi2, *ws_part;     /* csl_lnl workspace for max(n0, n1) walkers */
+  /* sharded ensembles: replica of ALL positions in symmetric memory (NULL on a single GPU) */
+  double* replica;               /* this rank's replica [h0 + h1, ndim]                                 */
+  const uint64_t* peer_ptrs;     /* device array [npeers] of every rank's replica address               */
+  const uint64_t* flag_ptrs;     /* device array [npeers] of every rank's barrier flags (uint64[npeers]) */
+  uint64_t multicast_ptr;        /* NVSwitch multicast address of the replica, or 0                     */
+  uint64_t epoch;                /* barrier epoch, advanced by csl_stretch_run                          */
+  int32_t npeers, rank;
+} csl_ensemble_t;
+
+/* `nsteps` full stretch-move steps (both half-updates: propose, priors, foregrounds, binning, chi^2,
+ * accept [+ publish + peer barrier], then the wrapper's row bookkeeping) enqueued on `stream` from C --
+ * one call replaces ~20 Python-level launches per step (the loop of samplers/emcee.py:66-88 around
+ * emcee's EnsembleSampler.sample).  Steps are numbered step0, step0+1, ...; the step whose number equals
+ * last_step emits every walker's row (emcee.py:70).  Device Philox streams only. */
+int csl_stretch_run(const csl_program_t* p, csl_ensemble_t* e, int nsteps, uint32_t step0, int64_t last_step,
+                    void* stream);
 
 /* ---- convergence (new; nothing in the reference) ----------------------------------------- */
 
