@@ -18,7 +18,7 @@ from itertools import chain as _iterchain
 import numpy as np
 
 __all__ = ["Chain", "Chains", "get_covariance", "get_correlation", "combine_covs", "load_chain",
-           "ChainWriter", "gelman_rubin"]
+           "ChainWriter", "gelman_rubin", "device_summary"]
 
 
 def _is_listlike(v):
@@ -248,6 +248,32 @@ def rhat_from_moments(n, mu, var):
     W = var.mean(0)
     B_over_n = ((mu - mu.mean(0)) ** 2).sum(0) / (m - 1)
     return np.sqrt(((nbar - 1) / nbar * W + B_over_n) / W)
+
+
+def device_summary(stats, burn_rows=0):
+    """Weighted mean and covariance of ALL chains / walkers of a finished sampler run, reduced on the
+    device from its row buffer (`stats` = what ``sampler.run`` returned) -- the numbers
+    ``Chains.join().mean()`` / ``.cov()`` give (chains.py:78-96, 345-355; covariance denominator
+    sum(w) - 1), without copying the rows to the host.  With several GPUs the sums are all-reduced."""
+    import torch
+    from . import _lib as L
+    from . import dist
+    rows, nrows = stats["rows"], stats["nrows"]
+    W, cap, rl = rows.shape
+    nd = rl - 2
+    m = 1 + nd + nd * nd
+    part = torch.empty((592, m), dtype=torch.float64, device=rows.device)
+    out = torch.zeros(m, dtype=torch.float64, device=rows.device)
+    lib, st = L.lib(), L.stream_ptr()
+    L.check(lib.csl_rows_moments(W, nd, rows.data_ptr(), nrows.data_ptr(), cap, int(burn_rows), None,
+                                 part.data_ptr(), out.data_ptr(), st), "csl_rows_moments")
+    dist.all_reduce_sum(out[:1 + nd])
+    mean = (out[1:1 + nd] / out[0]).contiguous()
+    L.check(lib.csl_rows_moments(W, nd, rows.data_ptr(), nrows.data_ptr(), cap, int(burn_rows), mean.data_ptr(),
+                                 part.data_ptr(), out.data_ptr(), st), "csl_rows_moments")
+    dist.all_reduce_sum(out[1 + nd:])
+    h = out.cpu().numpy()
+    return dict(weight=h[0], mean=h[1:1 + nd] / h[0], cov=h[1 + nd:].reshape(nd, nd) / (h[0] - 1))
 
 
 # --------------------------------------------------------------------------

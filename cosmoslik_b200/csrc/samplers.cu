@@ -195,7 +195,7 @@ k_mh_gauss_run(csl_program_t p, int W, int nsteps, const double* __restrict__ Lf
 // memory with coalesced loads, then every thread owns a few (i,k) pairs and sweeps the tile.
 __global__ void __launch_bounds__(SAMP_THREADS)
 k_mh_moments(int W, int nd, const double* __restrict__ rows, const int32_t* __restrict__ nrows, int cap,
-             const double* __restrict__ mean, double* __restrict__ partial) {
+             const double* __restrict__ mean, double* __restrict__ partial, int burn) {
   extern __shared__ double sx[];            // [MOM_TILE][2 + nd]
   const int m = 1 + nd + nd * nd;
   const int rl = 2 + nd;
@@ -218,7 +218,8 @@ k_mh_moments(int W, int nd, const double* __restrict__ rows, const int32_t* __re
   double a1 = 0.0;  // pass 1: thread i <= nd accumulates element i
   for (int w = blockIdx.x; w < W; w += MOM_BLOCKS) {
     const int nr = min(nrows[w], cap);
-    for (int t0 = nr / 2; t0 < nr; t0 += MOM_TILE) {
+    // burn < 0: the last half of the chain's rows (get_new_cov); burn >= 0: rows from `burn` on
+    for (int t0 = (burn < 0 ? nr / 2 : min(burn, nr)); t0 < nr; t0 += MOM_TILE) {
       const int nt = min(MOM_TILE, nr - t0);
       const double* src = rows + ((long long)w * cap + t0) * rl;
       __syncthreads();
@@ -480,15 +481,26 @@ extern "C" int csl_mh_gauss_run(const csl_program_t* p, int W, int nsteps, const
   return csl_check_launch("k_mh_gauss_run");
 }
 
-extern "C" int csl_mh_moments(int W, int ndim, const double* rows, const int32_t* nrows, int cap,
-                              const double* mean, double* partial, double* out, void* stream) {
+static int moments_impl(int W, int ndim, const double* rows, const int32_t* nrows, int cap, const double* mean,
+                        double* partial, double* out, int burn, void* stream) {
   CSL_REQUIRE(W > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && rows && nrows && partial && out, "csl_mh_moments: bad argument");
   const int m = 1 + ndim + ndim * ndim;
   cudaStream_t s = (cudaStream_t)stream;
-  k_mh_moments<<<MOM_BLOCKS, SAMP_THREADS, (size_t)MOM_TILE * (2 + ndim) * sizeof(double), s>>>(W, ndim, rows, nrows, cap, mean, partial);
+  k_mh_moments<<<MOM_BLOCKS, SAMP_THREADS, (size_t)MOM_TILE * (2 + ndim) * sizeof(double), s>>>(W, ndim, rows, nrows, cap, mean, partial, burn);
   int lo = mean ? 1 + ndim : 0, hi = mean ? m : 1 + ndim;
   k_reduce_partials<<<(hi - lo + 127) / 128, 128, 0, s>>>(m, lo, hi, partial, out);
   return csl_check_launch("k_mh_moments");
+}
+
+extern "C" int csl_mh_moments(int W, int ndim, const double* rows, const int32_t* nrows, int cap,
+                              const double* mean, double* partial, double* out, void* stream) {
+  return moments_impl(W, ndim, rows, nrows, cap, mean, partial, out, -1, stream);
+}
+
+extern "C" int csl_rows_moments(int W, int ndim, const double* rows, const int32_t* nrows, int cap, int burn_rows,
+                                const double* mean, double* partial, double* out, void* stream) {
+  CSL_REQUIRE(burn_rows >= 0, "csl_rows_moments: burn_rows must be >= 0");
+  return moments_impl(W, ndim, rows, nrows, cap, mean, partial, out, burn_rows, stream);
 }
 
 extern "C" int csl_stretch_propose(int Ns, int Nc, int ndim, const double* s, const double* comp, double a,

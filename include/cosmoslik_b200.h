@@ -231,6 +231,11 @@ int csl_mh_gauss_run(const csl_program_t* p, int W, int nsteps, const double* Lf
 int csl_mh_moments(int W, int ndim, const double* rows, const int32_t* nrows, int cap,
                    const double* mean, double* partial, double* out, void* stream);
 
+/* The same two-pass weighted moments over ALL chains' rows from row `burn_rows` on: the device side of
+ * Chain.mean / Chain.cov on the joined chains (chains.py:78-96, 345-355) without a host round trip. */
+int csl_rows_moments(int W, int ndim, const double* rows, const int32_t* nrows, int cap, int burn_rows,
+                     const double* mean, double* partial, double* out, void* stream);
+
 /* ---- affine-invariant ensemble sampler (samplers/emcee.py + emcee 2.x stretch move) ------- */
 
 /* proposals for the Ns active walkers s [Ns, ndim] against the complementary half comp [Nc, ndim]:

@@ -389,6 +389,26 @@ def test_prior_sampler_matches_the_reference(torch):
         improper()
 
 
+def test_device_summary_matches_chain_statistics(torch):
+    """weighted mean / covariance of all chains reduced on the device == Chains.join().mean() / .cov()"""
+    from cosmoslik_b200 import Chain, Chains
+    from cosmoslik_b200.chains import device_summary
+    nd, nch, nsteps = 4, 12, 500
+    Cv = np.eye(nd) + 0.3
+    slik = Slik(B.gauss_script(Cv, lambda s: samplers.metropolis_hastings(
+        s, num_samples=nsteps * nch, nchains=nch, seed=21, proposal_update=False))())
+    st = slik.sampler.run(slik.evaluate)
+    rows, nrows = st["rows"].cpu().numpy(), st["nrows"].cpu().numpy()
+    names = list(slik.get_sampled())
+    burn = 15
+    chains = Chains([Chain(dict(zip(["lnl", "weight"] + names, rows[c, burn:nrows[c]].T))) for c in range(nch)])
+    joined = chains.join()
+    got = device_summary(st, burn_rows=burn)
+    np.testing.assert_allclose(got["mean"], joined.mean(names), rtol=1e-12)
+    np.testing.assert_allclose(got["cov"], joined.cov(names), rtol=1e-10)
+    assert got["weight"] == joined["weight"].sum()
+
+
 # ---------------------------------------------------------------- stretch move
 def test_stretch_move_matches_the_oracle(torch, tmp_path):
     prob = synthetic.spt_multifreq_problem(1, nbins=12, lmax=801)
