@@ -386,19 +386,28 @@ class CompiledProgram(object):
                 tiles.append((key, rec_t))
 
         # records sorted by kernel class (stable): one launch per class <NT, NP>
-        def by_class(records, width):
+        # Within a class the launch order is free (every record names its output row), so the groups that
+        # become one CTA are sorted longest first: the hardware hands CTAs out in index order, and short
+        # CTAs at the end keep the tail of the launch short (plik-lite bins widen 6x from ell 30 to 2500).
+        def by_class(records, width, group=1, work=None):
             classes = sorted(set(k for k, _ in records))
             if len(classes) > L.MAX_CLASS:
                 raise ValueError("too many distinct spectrum classes")
             ordered, cls = [], np.zeros((L.MAX_CLASS, 4), np.int32)
             for ci, k in enumerate(classes):
                 mine = [r for kk, r in records if kk == k]
+                if work is not None:
+                    assert len(mine) % group == 0
+                    chunks = [mine[i:i + group] for i in range(0, len(mine), group)]
+                    chunks.sort(key=lambda c: -sum(work(r) for r in c))      # stable
+                    mine = [r for c in chunks for r in c]
                 cls[ci] = (k[0], k[1], len(ordered), len(mine))
                 ordered += mine
             return (np.array(ordered) if ordered else np.zeros((1, width), np.int32)), cls, len(classes), len(ordered)
 
         tile_arr, self.cls, nclass, ntile = by_class(tiles, L.TILE_STRIDE)
-        bin_arr, self.segcls, nsegclass, _ = by_class(segbins, L.BIN_STRIDE)
+        bin_arr, self.segcls, nsegclass, _ = by_class(segbins, L.BIN_STRIDE, L.SEG_GROUP,
+                                                      lambda r: int(r[L.B_HI]) - int(r[L.B_LO]))
         ordered = tile_arr
         P['resid_mode'] = 1
         P['nspec'], P['ntile'], P['nclass'], P['nsegclass'] = nspec, ntile, nclass, nsegclass
