@@ -172,58 +172,69 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
 }
 
 // ---- segmented-sum binning for block-sparse windows ----------------------------------------------------
-// One thread per walker, CSL_SEG_GROUP window rows per CTA.  For each row only its non-zero support
-// [lo, hi) is visited: cl[l] is built once and folded into the bin with one extra FMA.  The ell-table
-// rows and the window weights of the group's column span are staged in shared memory in chunks of
-// SEG_CH columns (coalesced loads), so the inner loop is 16-byte broadcast LDS + FP64 math only.
+// One thread per walker (SEG_WPT walkers per thread), CSL_SEG_GROUP window rows per CTA.  For each row only
+// its non-zero support [lo, hi) is visited.  The columns of the group's rows are staged in shared memory
+// back to back, ALREADY MULTIPLIED by the window weight (the weight is the same for every walker, so the
+// CTA pays for it once instead of once per walker and column):
+//     staged row = [w T_0 .. w T_{NT-1},  w M_0 .. w M_{NP-1},  D_0 .. D_{NP-1}]          (RS doubles)
+// and the inner loop is broadcast LDS + FP64 FMAs only:
+//     b += sum_t coef_t (w T_t) + sum_q (w M_q) Ehat_q ,      Ehat_q = amp_q exp(idx_q logB_q[l]).
 //
 // Power laws along consecutive l:  E[l] = exp(idx logB[l]) obeys E[l+1] = E[l] exp(idx D[l]) with
 // D[l] = logB[l+1] - logB[l] (host, extended precision).  Within a bin the kernel takes one exact exp at
-// the first column and advances by a Taylor polynomial in y = idx D: degree 6 when |y| <= 0.012
-// (truncation y^7/7! < 7e-18), degree 10 when |y| <= 0.1 (y^11/11! < 3e-19), decided per warp from the
-// bin's max |D| (bin record) -- otherwise exp at every column.  The polynomials of different columns are
-// independent; only one multiply per column sits on the dependent chain.  Rounding grows by ~1 ulp per
-// column over a bin (<= a few 1e-15 relative), far inside the 1e-10 budget on lnL.
+// the first column (times the amplitude) and advances by a Taylor polynomial in y = idx D: degree 5 when
+// |y| <= 0.0035 (truncation y^6/6! < 3e-18), 6 when |y| <= 0.012 (< 7e-18), 10 when |y| <= 0.1 (< 3e-19),
+// decided per warp from the bin's max |D| (bin record) -- otherwise exp at every column.  Rounding grows by
+// ~1 ulp per column over a bin (<= a few 1e-15 relative), far inside the 1e-10 budget on lnL.
+//
+// A group whose columns exceed the staging capacity is processed in several passes; the bins are walked in
+// order, so a bin cut by a pass boundary simply keeps its running sum and power-law state in registers.
 #define SEG_TPB 128    // threads per CTA
-#define SEG_WPT 2      // walkers per thread: table rows / weights / loop control are amortised over both
+#define SEG_WPT 2      // walkers per thread: staged rows / loop control are amortised over both
+#define SEG_SMEM_DOUBLES 3072   // staged columns x RS (24 KB)
 
-// One window row over columns [l0, l1) of the staged chunk, for the SEG_WPT walkers of a thread:
-//   x = sum_t cf T + sum_q (amp M) E_q ;  a += weight x ;  E_q advances to the next column.
-// MODE 0 / 1: Taylor degree 6 / 10 in y = idx D;  MODE 2: exact exp at every column.
+// ncol staged columns starting at `row`, for the SEG_WPT walkers of a thread.
+// MODE 0 / 1 / 2: Taylor degree 5 / 6 / 10 in y = idx D;  MODE 3: exact exp at every column (ltab, l = ell
+// index of the first column, give the next column's logB; lend = one past the bin's last column).
 template <int NT, int NP, int MODE>
-__device__ __forceinline__ void seg_row(const double* __restrict__ srow, const double* __restrict__ wg, int l0, int l1,
-                                        const double (&cf)[SEG_WPT][NT > 0 ? NT : 1],
-                                        const double (&pamp)[SEG_WPT][NP > 0 ? NP : 1],
-                                        const double (&pidx)[SEG_WPT][NP > 0 ? NP : 1],
-                                        double (&E)[SEG_WPT][NP > 0 ? NP : 1], double (&a)[SEG_WPT]) {
-  constexpr int LSTRIDE = NT + 4 * NP;
-  const double* row = srow + l0 * LSTRIDE;
-  for (int l = l0; l < l1; ++l, row += LSTRIDE) {
-    const double wgt = wg[l];
+__device__ __forceinline__ void seg_cols(const double* __restrict__ row, int ncol,
+                                         const double (&cf)[SEG_WPT][NT > 0 ? NT : 1],
+                                         const double (&pamp)[SEG_WPT][NP > 0 ? NP : 1],
+                                         const double (&pidx)[SEG_WPT][NP > 0 ? NP : 1],
+                                         double (&E)[SEG_WPT][NP > 0 ? NP : 1], double (&at)[SEG_WPT],
+                                         double (&ap)[SEG_WPT], const double* __restrict__ ltab, int l, int lend) {
+  constexpr int RS = NT + 2 * NP, LSTRIDE = NT + 4 * NP;
+  auto column = [&](const double* __restrict__ r, int lcur) {
     double T[NT > 0 ? NT : 1], M[NP > 0 ? NP : 1], D[NP > 0 ? NP : 1];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) T[t] = row[t];
+    for (int t = 0; t < NT; ++t) T[t] = r[t];
 #pragma unroll
-    for (int q = 0; q < NP; ++q) { M[q] = row[NT + 4 * q + 1]; D[q] = row[NT + 4 * q + 2]; }
+    for (int q = 0; q < NP; ++q) { M[q] = r[NT + q]; D[q] = r[NT + NP + q]; }
 #pragma unroll
     for (int j = 0; j < SEG_WPT; ++j) {
-      double x = 0.0;
 #pragma unroll
-      for (int t = 0; t < NT; ++t) x = fma(cf[j][t], T[t], x);
+      for (int t = 0; t < NT; ++t) at[j] = fma(cf[j][t], T[t], at[j]);
 #pragma unroll
-      for (int q = 0; q < NP; ++q) x = fma(pamp[j][q] * M[q], E[j][q], x);
-      a[j] = fma(wgt, x, a[j]);
+      for (int q = 0; q < NP; ++q) ap[j] = fma(M[q], E[j][q], ap[j]);
     }
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
 #pragma unroll
       for (int j = 0; j < SEG_WPT; ++j) {
-        if (MODE == 0) E[j][q] *= exp_taylor<6>(pidx[j][q] * D[q]);
-        else if (MODE == 1) E[j][q] *= exp_taylor<10>(pidx[j][q] * D[q]);
-        else if (l + 1 < l1) E[j][q] = exp(pidx[j][q] * row[LSTRIDE + NT + 4 * q]);   // next column's logB
+        if (MODE == 0) E[j][q] *= exp_taylor<5>(pidx[j][q] * D[q]);
+        else if (MODE == 1) E[j][q] *= exp_taylor<6>(pidx[j][q] * D[q]);
+        else if (MODE == 2) E[j][q] *= exp_taylor<10>(pidx[j][q] * D[q]);
+        else if (lcur + 1 < lend)
+          E[j][q] = pamp[j][q] * exp(pidx[j][q] * __ldg(ltab + (long long)(lcur + 1) * LSTRIDE + NT + 4 * q));
       }
     }
+  };
+  int c = 0;
+  for (; c + 2 <= ncol; c += 2, row += 2 * RS) {
+    column(row, l + c);
+    column(row + RS, l + c + 1);
   }
+  if (c < ncol) column(row, l + c);
 }
 
 template <int NT, int NP>
@@ -231,13 +242,12 @@ __global__ void __launch_bounds__(SEG_TPB)
 k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restrict__ coef, int ldc,
              double* __restrict__ R, int ldr) {
   constexpr int LSTRIDE = NT + 4 * NP;
-  constexpr int SEG_CH = LSTRIDE > 12 ? 96 : (LSTRIDE > 8 ? 160 : 224);   // static shared memory < 48 KB
+  constexpr int RS = NT + 2 * NP;                    // > 0: the host never emits an empty class
+  constexpr int CAP = SEG_SMEM_DOUBLES / (RS > 0 ? RS : 1);
   constexpr int NPX = NP > 0 ? NP : 1, NTX = NT > 0 ? NT : 1;
-  __shared__ __align__(16) double srow[SEG_CH * (LSTRIDE > 0 ? LSTRIDE : 1)];
-  __shared__ __align__(16) double swgt[CSL_SEG_GROUP][SEG_CH];
-  __shared__ int slo[CSL_SEG_GROUP], shi[CSL_SEG_GROUP], srw[CSL_SEG_GROUP];
+  __shared__ __align__(16) double srow[SEG_SMEM_DOUBLES];
+  __shared__ int slo[CSL_SEG_GROUP], srw[CSL_SEG_GROUP], spre[CSL_SEG_GROUP + 1];
   __shared__ float sdmax[CSL_SEG_GROUP][CSL_MAX_PLAW];
-  __shared__ double sacc[CSL_SEG_GROUP][SEG_WPT * SEG_TPB];  // partial sums of bins that span several chunks
   __shared__ long long soff[CSL_SEG_GROUP];
   const int tid = threadIdx.x;
   int w[SEG_WPT];
@@ -252,14 +262,19 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
   const int32_t* first = p.bin_tab + (long long)b_begin * CSL_BIN_STRIDE;
   const int32_t* spec = p.spec_tab + (long long)first[CSL_B_SPEC] * CSL_SPEC_STRIDE;   // one spectrum per group
   const double* __restrict__ ltab = p.templates + spec[CSL_S_LTAB];
-  if (tid < CSL_SEG_GROUP) {
-    const int32_t* rec = first + tid * CSL_BIN_STRIDE;        // records are padded to whole groups
-    const bool live = (b_begin + tid < bin0 + nbins) && rec[CSL_B_ROW] >= 0;
-    slo[tid] = live ? rec[CSL_B_LO] : 0;
-    shi[tid] = live ? rec[CSL_B_HI] : 0;
-    srw[tid] = live ? rec[CSL_B_ROW] : -1;
-    soff[tid] = ((long long)rec[CSL_B_WINOFF_HI] << 32) | (unsigned)rec[CSL_B_WINOFF_LO];
-    for (int q = 0; q < CSL_MAX_PLAW; ++q) sdmax[tid][q] = __int_as_float(rec[CSL_B_DMAX + q]);
+  if (tid == 0) {
+    int pre = 0;                                               // columns of the group, back to back
+    for (int b = 0; b < CSL_SEG_GROUP; ++b) {
+      const int32_t* rec = first + b * CSL_BIN_STRIDE;        // records are padded to whole groups
+      const bool live = (b_begin + b < bin0 + nbins) && rec[CSL_B_ROW] >= 0;
+      slo[b] = live ? rec[CSL_B_LO] : 0;
+      srw[b] = live ? rec[CSL_B_ROW] : -1;
+      soff[b] = ((long long)rec[CSL_B_WINOFF_HI] << 32) | (unsigned)rec[CSL_B_WINOFF_LO];
+      for (int q = 0; q < CSL_MAX_PLAW; ++q) sdmax[b][q] = __int_as_float(rec[CSL_B_DMAX + q]);
+      spre[b] = pre;
+      pre += live ? max(rec[CSL_B_HI] - rec[CSL_B_LO], 0) : 0;
+    }
+    spre[CSL_SEG_GROUP] = pre;
   }
   double cf[SEG_WPT][NTX], pamp[SEG_WPT][NPX], pidx[SEG_WPT][NPX], cal[SEG_WPT];
   const int calrow = spec[CSL_S_CAL];
@@ -276,63 +291,70 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
     cal[j] = calrow >= 0 ? coef[(long long)calrow * ldc + w[j]] : 1.0;
   }
   __syncthreads();
-  int glo = 0x7fffffff, ghi = 0;
+  const int total = spre[CSL_SEG_GROUP];
+  double E[SEG_WPT][NPX], at[SEG_WPT], ap[SEG_WPT];       // running state of the bin being summed
 #pragma unroll
-  for (int b = 0; b < CSL_SEG_GROUP; ++b)
-    if (shi[b] > slo[b]) { glo = min(glo, slo[b]); ghi = max(ghi, shi[b]); }
+  for (int j = 0; j < SEG_WPT; ++j) {
+    at[j] = ap[j] = 0.0;
 #pragma unroll
-  for (int b = 0; b < CSL_SEG_GROUP; ++b)
-#pragma unroll
-    for (int j = 0; j < SEG_WPT; ++j) sacc[b][j * SEG_TPB + tid] = 0.0;
+    for (int q = 0; q < NPX; ++q) E[j][q] = 0.0;
+  }
 
-  for (int c0 = glo; c0 < ghi; c0 += SEG_CH) {
-    const int n = min(SEG_CH, ghi - c0);
-    {
-      const double2* __restrict__ src = reinterpret_cast<const double2*>(ltab + (long long)c0 * LSTRIDE);
-      double2* dst = reinterpret_cast<double2*>(srow);
-      for (int i = tid; i < n * LSTRIDE / 2; i += SEG_TPB) dst[i] = __ldg(src + i);
+  for (int p0 = 0; p0 < total; p0 += CAP) {
+    const int p1 = min(p0 + CAP, total);
+    // stage columns p0 .. p1 of the group, weighted
+    for (int i = tid; i < p1 - p0; i += SEG_TPB) {
+      const int ci = p0 + i;
+      int b = 0;
 #pragma unroll
-      for (int b = 0; b < CSL_SEG_GROUP; ++b) {
-        const int l0 = max(slo[b], c0), l1 = min(shi[b], c0 + n);
-        const double* __restrict__ wr = p.windows + soff[b];
-        for (int l = l0 + tid; l < l1; l += SEG_TPB) swgt[b][l - c0] = __ldg(wr + l);
+      for (int k = 1; k < CSL_SEG_GROUP; ++k) b += (ci >= spre[k]) ? 1 : 0;   // spre is non-decreasing
+      const int l = slo[b] + (ci - spre[b]);
+      const double wgt = __ldg(p.windows + soff[b] + l);
+      const double* __restrict__ src = ltab + (long long)l * LSTRIDE;
+      double* dst = srow + i * RS;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) dst[t] = wgt * __ldg(src + t);
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        dst[NT + q] = wgt * __ldg(src + NT + 4 * q + 1);
+        dst[NT + NP + q] = __ldg(src + NT + 4 * q + 2);
       }
     }
     __syncthreads();
 #pragma unroll 1
     for (int b = 0; b < CSL_SEG_GROUP; ++b) {
-      const int l0 = max(slo[b], c0) - c0, l1 = min(shi[b], c0 + n) - c0;
-      if (l1 <= l0) continue;                   // block-uniform
+      const int s0 = max(spre[b], p0), s1 = min(spre[b + 1], p1);
+      if (s1 <= s0) continue;                   // block-uniform
+      const int l = slo[b] + (s0 - spre[b]);
+      if (s0 == spre[b]) {                      // the bin starts here
+#pragma unroll
+        for (int j = 0; j < SEG_WPT; ++j) {
+          at[j] = ap[j] = 0.0;
+#pragma unroll
+          for (int q = 0; q < NP; ++q)
+            E[j][q] = pamp[j][q] * exp(pidx[j][q] * __ldg(ltab + (long long)l * LSTRIDE + NT + 4 * q));
+        }
+      }
       double ymax = 0.0;
 #pragma unroll
       for (int j = 0; j < SEG_WPT; ++j)
 #pragma unroll
         for (int q = 0; q < NP; ++q) ymax = fmax(ymax, fabs(pidx[j][q]) * (double)sdmax[b][q]);
-      const bool t6 = __all_sync(0xffffffffu, ymax <= 0.012);
-      const bool t10 = __all_sync(0xffffffffu, ymax <= 0.1);
-      double E[SEG_WPT][NPX], a[SEG_WPT];
+      const double* rows = srow + (s0 - p0) * RS;
+      const int lend = slo[b] + (spre[b + 1] - spre[b]);
+      if (__all_sync(0xffffffffu, ymax <= 0.0035)) seg_cols<NT, NP, 0>(rows, s1 - s0, cf, pamp, pidx, E, at, ap, ltab, l, lend);
+      else if (__all_sync(0xffffffffu, ymax <= 0.012)) seg_cols<NT, NP, 1>(rows, s1 - s0, cf, pamp, pidx, E, at, ap, ltab, l, lend);
+      else if (__all_sync(0xffffffffu, ymax <= 0.1)) seg_cols<NT, NP, 2>(rows, s1 - s0, cf, pamp, pidx, E, at, ap, ltab, l, lend);
+      else seg_cols<NT, NP, 3>(rows, s1 - s0, cf, pamp, pidx, E, at, ap, ltab, l, lend);
+      if (s1 == spre[b + 1]) {                  // the bin ends here: r = cal * d - b  (spt_lowl.py:132)
+        const int row = srw[b];
+        const double d = p.data[row];
 #pragma unroll
-      for (int j = 0; j < SEG_WPT; ++j) {
-        a[j] = 0.0;
-#pragma unroll
-        for (int q = 0; q < NP; ++q) E[j][q] = exp(pidx[j][q] * srow[l0 * LSTRIDE + NT + 4 * q]);
-      }
-      const double* wg = swgt[b];
-      if (t6) seg_row<NT, NP, 0>(srow, wg, l0, l1, cf, pamp, pidx, E, a);
-      else if (t10) seg_row<NT, NP, 1>(srow, wg, l0, l1, cf, pamp, pidx, E, a);
-      else seg_row<NT, NP, 2>(srow, wg, l0, l1, cf, pamp, pidx, E, a);
-      const bool done = shi[b] <= c0 + n;       // the bin ends in this chunk: r = cal * d - b  (spt_lowl.py:132)
-      const int row = srw[b];
-      const double d = p.data[row];
-#pragma unroll
-      for (int j = 0; j < SEG_WPT; ++j) {
-        const double tot = a[j] + sacc[b][j * SEG_TPB + tid];        // own slot: no hazard with other threads
-        if (done) {
+        for (int j = 0; j < SEG_WPT; ++j) {
+          const double tot = at[j] + ap[j];
           if (live_w[j])
             R[(long long)row * ldr + w[j]] = cal_on_model ? __dsub_rn(d, __dmul_rn(tot, cal[j]))
                                                           : __dsub_rn(__dmul_rn(cal[j], d), tot);
-        } else {
-          sacc[b][j * SEG_TPB + tid] = tot;
         }
       }
     }
@@ -342,7 +364,7 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
 #pragma unroll 1
   for (int b = 0; b < CSL_SEG_GROUP; ++b) {
     const int row = srw[b];
-    if (row >= 0 && shi[b] <= slo[b]) {
+    if (row >= 0 && spre[b + 1] == spre[b]) {
 #pragma unroll
       for (int j = 0; j < SEG_WPT; ++j)
         if (live_w[j]) R[(long long)row * ldr + w[j]] = cal_on_model ? p.data[row] : __dmul_rn(cal[j], p.data[row]);
