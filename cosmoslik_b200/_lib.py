@@ -18,7 +18,7 @@ S_NLPAD, S_NTERM, S_NPLAW, S_CAL = 0, 1, 2, 3
 S_LTAB, S_CALMODE, S_TERM_COEF, S_PLAW_AMP, S_PLAW_IDX = 4, 5, 8, 24, 28
 MAX_CLASS = 8
 BIN_STRIDE, SEG_GROUP = 16, 8
-B_ROW, B_SPEC, B_LO, B_HI, B_WINOFF_LO, B_WINOFF_HI, B_DMAX = 0, 1, 2, 3, 4, 5, 8
+B_ROW, B_SPEC, B_LO, B_HI, B_WINOFF_LO, B_WINOFF_HI, B_TABOFF_LO, B_TABOFF_HI, B_DMAX = 0, 1, 2, 3, 4, 5, 6, 7, 8
 T_ROW0, T_NROWS, T_SPEC, T_LBEGIN, T_LEND, T_WINOFF_LO, T_WINOFF_HI, T_WINLD, T_GLO, T_GHI = 0, 1, 2, 3, 4, 5, 6, 7, 8, 16
 
 _i32p, _f64p, _vp = C.c_void_p, C.c_void_p, C.c_void_p

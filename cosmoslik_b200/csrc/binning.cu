@@ -12,6 +12,7 @@
 // The kernel is instantiated per padded class <NT, NP> so the build loop is branch-free and fully
 // unrolled; the host sorts the tiles by class (csl_program_t::cls).
 #include "common.cuh"
+#include <type_traits>
 
 // exp(y) for small |y| by its Taylor polynomial: degree 6 for |y| <= 0.012 (truncation < 7e-18), degree 10
 // for |y| <= 0.1 (< 3e-19).  Used to advance a power law E[l] = exp(idx logB[l]) to the next column:
@@ -173,9 +174,9 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
 
 // ---- segmented-sum binning for block-sparse windows ----------------------------------------------------
 // One thread per walker (SEG_WPT walkers per thread), CSL_SEG_GROUP window rows per CTA.  For each row only
-// its non-zero support [lo, hi) is visited.  The columns of the group's rows are staged in shared memory
-// back to back, ALREADY MULTIPLIED by the window weight (the weight is the same for every walker, so the
-// CTA pays for it once instead of once per walker and column):
+// its non-zero support [lo, hi) is visited.  The columns of the group's rows lie back to back in a table the
+// host builds once (after the ell-tables in `templates`, bin record word CSL_B_TABOFF), ALREADY MULTIPLIED by
+// the window weight -- the weight is the same for every walker -- so staging is one contiguous cp.async copy:
 //     staged row = [w T_0 .. w T_{NT-1},  w M_0 .. w M_{NP-1},  D_0 .. D_{NP-1}]          (RS doubles)
 // and the inner loop is broadcast LDS + FP64 FMAs only:
 //     b += sum_t coef_t (w T_t) + sum_q (w M_q) Ehat_q ,      Ehat_q = amp_q exp(idx_q logB_q[l]).
@@ -184,8 +185,10 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
 // D[l] = logB[l+1] - logB[l] (host, extended precision).  Within a bin the kernel takes one exact exp at
 // the first column (times the amplitude) and advances by a Taylor polynomial in y = idx D: degree 5 when
 // |y| <= 0.0035 (truncation y^6/6! < 3e-18), 6 when |y| <= 0.012 (< 7e-18), 10 when |y| <= 0.1 (< 3e-19),
-// decided per warp from the bin's max |D| (bin record) -- otherwise exp at every column.  Rounding grows by
-// ~1 ulp per column over a bin (<= a few 1e-15 relative), far inside the 1e-10 budget on lnL.
+// decided per warp from the largest |D| of the group's bins (bin records) -- otherwise exp at every column.
+// A bin that begins at the column where the previous bin of the group ended (top-hat bins) inherits the
+// state instead of taking a new exp.  Rounding grows by ~1 ulp per column (<= 8 bins x a few tens of
+// columns: a few 1e-14 relative at worst), far inside the 1e-10 budget on lnL.
 //
 // A group whose columns exceed the staging capacity is processed in several passes; the bins are walked in
 // order, so a bin cut by a pass boundary simply keeps its running sum and power-law state in registers.
@@ -245,10 +248,13 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
   constexpr int RS = NT + 2 * NP;                    // > 0: the host never emits an empty class
   constexpr int CAP = SEG_SMEM_DOUBLES / (RS > 0 ? RS : 1);
   constexpr int NPX = NP > 0 ? NP : 1, NTX = NT > 0 ? NT : 1;
+  static_assert(RS % 2 == 0, "staged rows are copied in 16-byte pieces");
   __shared__ __align__(16) double srow[SEG_SMEM_DOUBLES];
   __shared__ int slo[CSL_SEG_GROUP], srw[CSL_SEG_GROUP], spre[CSL_SEG_GROUP + 1];
-  __shared__ float sdmax[CSL_SEG_GROUP][CSL_MAX_PLAW];
-  __shared__ long long soff[CSL_SEG_GROUP];
+  __shared__ float sgmax[CSL_MAX_PLAW];              // max |D_q| over the group's bins
+  __shared__ int scont[CSL_SEG_GROUP];               // bin starts at the column where the previous bin ended
+  __shared__ double slogb[CSL_SEG_GROUP][NPX];       // logB_q at each bin's first column
+  __shared__ long long sbase;
   const int tid = threadIdx.x;
   int w[SEG_WPT];
   bool live_w[SEG_WPT];
@@ -263,18 +269,32 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
   const int32_t* spec = p.spec_tab + (long long)first[CSL_B_SPEC] * CSL_SPEC_STRIDE;   // one spectrum per group
   const double* __restrict__ ltab = p.templates + spec[CSL_S_LTAB];
   if (tid == 0) {
-    int pre = 0;                                               // columns of the group, back to back
+    int pre = 0, prev_hi = -1;                                 // columns of the group, back to back
+    long long base = -1;
+    float gmax[CSL_MAX_PLAW] = {0.f, 0.f, 0.f, 0.f};
     for (int b = 0; b < CSL_SEG_GROUP; ++b) {
       const int32_t* rec = first + b * CSL_BIN_STRIDE;        // records are padded to whole groups
       const bool live = (b_begin + b < bin0 + nbins) && rec[CSL_B_ROW] >= 0;
+      const int ncol = live ? max(rec[CSL_B_HI] - rec[CSL_B_LO], 0) : 0;
       slo[b] = live ? rec[CSL_B_LO] : 0;
       srw[b] = live ? rec[CSL_B_ROW] : -1;
-      soff[b] = ((long long)rec[CSL_B_WINOFF_HI] << 32) | (unsigned)rec[CSL_B_WINOFF_LO];
-      for (int q = 0; q < CSL_MAX_PLAW; ++q) sdmax[b][q] = __int_as_float(rec[CSL_B_DMAX + q]);
+      if (ncol > 0 && base < 0) base = ((long long)rec[CSL_B_TABOFF_HI] << 32) | (unsigned)rec[CSL_B_TABOFF_LO];
+      scont[b] = ncol > 0 && rec[CSL_B_LO] == prev_hi;
+      if (ncol > 0) {
+        prev_hi = rec[CSL_B_HI];
+        for (int q = 0; q < CSL_MAX_PLAW; ++q) gmax[q] = fmaxf(gmax[q], __int_as_float(rec[CSL_B_DMAX + q]));
+      }
       spre[b] = pre;
-      pre += live ? max(rec[CSL_B_HI] - rec[CSL_B_LO], 0) : 0;
+      pre += ncol;
     }
     spre[CSL_SEG_GROUP] = pre;
+    sbase = base < 0 ? 0 : base;
+    for (int q = 0; q < CSL_MAX_PLAW; ++q) sgmax[q] = gmax[q];
+  }
+  if (NP > 0 && tid < CSL_SEG_GROUP * NP) {                    // independent of tid 0's loop: the records again
+    const int b = tid / NPX, q = tid % NPX;
+    const int32_t* rec = first + b * CSL_BIN_STRIDE;
+    slogb[b][q] = __ldg(ltab + (long long)max(rec[CSL_B_LO], 0) * LSTRIDE + NT + 4 * q);
   }
   double cf[SEG_WPT][NTX], pamp[SEG_WPT][NPX], pidx[SEG_WPT][NPX], cal[SEG_WPT];
   const int calrow = spec[CSL_S_CAL];
@@ -299,64 +319,65 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
 #pragma unroll
     for (int q = 0; q < NPX; ++q) E[j][q] = 0.0;
   }
+  // Taylor degree of the whole group, from the largest |D| of its bins (warp-uniform)
+  double ymax = 0.0;
+#pragma unroll
+  for (int j = 0; j < SEG_WPT; ++j)
+#pragma unroll
+    for (int q = 0; q < NP; ++q) ymax = fmax(ymax, fabs(pidx[j][q]) * (double)sgmax[q]);
+  const int mode = __all_sync(0xffffffffu, ymax <= 0.0035) ? 0 : __all_sync(0xffffffffu, ymax <= 0.012) ? 1
+                   : __all_sync(0xffffffffu, ymax <= 0.1) ? 2 : 3;
 
   for (int p0 = 0; p0 < total; p0 += CAP) {
     const int p1 = min(p0 + CAP, total);
-    // stage columns p0 .. p1 of the group, weighted
-    for (int i = tid; i < p1 - p0; i += SEG_TPB) {
-      const int ci = p0 + i;
-      int b = 0;
-#pragma unroll
-      for (int k = 1; k < CSL_SEG_GROUP; ++k) b += (ci >= spre[k]) ? 1 : 0;   // spre is non-decreasing
-      const int l = slo[b] + (ci - spre[b]);
-      const double wgt = __ldg(p.windows + soff[b] + l);
-      const double* __restrict__ src = ltab + (long long)l * LSTRIDE;
-      double* dst = srow + i * RS;
-#pragma unroll
-      for (int t = 0; t < NT; ++t) dst[t] = wgt * __ldg(src + t);
-#pragma unroll
-      for (int q = 0; q < NP; ++q) {
-        dst[NT + q] = wgt * __ldg(src + NT + 4 * q + 1);
-        dst[NT + NP + q] = __ldg(src + NT + 4 * q + 2);
-      }
+    // stage columns p0 .. p1 of the group (weighted rows, contiguous in the host-built table)
+    {
+      const double* __restrict__ gsrc = p.templates + sbase + (long long)p0 * RS;
+      const int n16 = (p1 - p0) * RS / 2;
+      for (int i = tid; i < n16; i += SEG_TPB) cp_async16(srow + 2 * i, gsrc + 2 * i);
+      cp_async_commit();
+      cp_async_wait<0>();
     }
     __syncthreads();
+    auto run_bins = [&](auto tag) {
+      constexpr int MODE = decltype(tag)::value;
 #pragma unroll 1
-    for (int b = 0; b < CSL_SEG_GROUP; ++b) {
-      const int s0 = max(spre[b], p0), s1 = min(spre[b + 1], p1);
-      if (s1 <= s0) continue;                   // block-uniform
-      const int l = slo[b] + (s0 - spre[b]);
-      if (s0 == spre[b]) {                      // the bin starts here
+      for (int b = 0; b < CSL_SEG_GROUP; ++b) {
+        const int s0 = max(spre[b], p0), s1 = min(spre[b + 1], p1);
+        if (s1 <= s0) continue;                   // block-uniform
+        const int l = slo[b] + (s0 - spre[b]);
+        if (s0 == spre[b]) {                      // the bin starts here
 #pragma unroll
-        for (int j = 0; j < SEG_WPT; ++j) {
-          at[j] = ap[j] = 0.0;
+          for (int j = 0; j < SEG_WPT; ++j) at[j] = ap[j] = 0.0;
+          // a bin that begins where the previous one ended inherits its power-law state: the update
+          // after a bin's last column has already advanced E to this column
+          if (MODE == 3 || !scont[b]) {
 #pragma unroll
-          for (int q = 0; q < NP; ++q)
-            E[j][q] = pamp[j][q] * exp(pidx[j][q] * __ldg(ltab + (long long)l * LSTRIDE + NT + 4 * q));
+            for (int j = 0; j < SEG_WPT; ++j)
+#pragma unroll
+              for (int q = 0; q < NP; ++q) E[j][q] = pamp[j][q] * exp(pidx[j][q] * slogb[b][q]);
+          }
+        }
+        const int lend = slo[b] + (spre[b + 1] - spre[b]);
+        seg_cols<NT, NP, MODE>(srow + (s0 - p0) * RS, s1 - s0, cf, pamp, pidx, E, at, ap, ltab, l, lend);
+        if (s1 == spre[b + 1]) {                  // the bin ends here: r = cal * d - b  (spt_lowl.py:132)
+          const int row = srw[b];
+          const double d = p.data[row];
+#pragma unroll
+          for (int j = 0; j < SEG_WPT; ++j) {
+            const double tot = at[j] + ap[j];
+            if (live_w[j])
+              R[(long long)row * ldr + w[j]] = cal_on_model ? __dsub_rn(d, __dmul_rn(tot, cal[j]))
+                                                            : __dsub_rn(__dmul_rn(cal[j], d), tot);
+          }
         }
       }
-      double ymax = 0.0;
-#pragma unroll
-      for (int j = 0; j < SEG_WPT; ++j)
-#pragma unroll
-        for (int q = 0; q < NP; ++q) ymax = fmax(ymax, fabs(pidx[j][q]) * (double)sdmax[b][q]);
-      const double* rows = srow + (s0 - p0) * RS;
-      const int lend = slo[b] + (spre[b + 1] - spre[b]);
-      if (__all_sync(0xffffffffu, ymax <= 0.0035)) seg_cols<NT, NP, 0>(rows, s1 - s0, cf, pamp, pidx, E, at, ap, ltab, l, lend);
-      else if (__all_sync(0xffffffffu, ymax <= 0.012)) seg_cols<NT, NP, 1>(rows, s1 - s0, cf, pamp, pidx, E, at, ap, ltab, l, lend);
-      else if (__all_sync(0xffffffffu, ymax <= 0.1)) seg_cols<NT, NP, 2>(rows, s1 - s0, cf, pamp, pidx, E, at, ap, ltab, l, lend);
-      else seg_cols<NT, NP, 3>(rows, s1 - s0, cf, pamp, pidx, E, at, ap, ltab, l, lend);
-      if (s1 == spre[b + 1]) {                  // the bin ends here: r = cal * d - b  (spt_lowl.py:132)
-        const int row = srw[b];
-        const double d = p.data[row];
-#pragma unroll
-        for (int j = 0; j < SEG_WPT; ++j) {
-          const double tot = at[j] + ap[j];
-          if (live_w[j])
-            R[(long long)row * ldr + w[j]] = cal_on_model ? __dsub_rn(d, __dmul_rn(tot, cal[j]))
-                                                          : __dsub_rn(__dmul_rn(cal[j], d), tot);
-        }
-      }
+    };
+    switch (mode) {
+      case 0: run_bins(std::integral_constant<int, 0>{}); break;
+      case 1: run_bins(std::integral_constant<int, 1>{}); break;
+      case 2: run_bins(std::integral_constant<int, 2>{}); break;
+      default: run_bins(std::integral_constant<int, 3>{}); break;
     }
     __syncthreads();
   }

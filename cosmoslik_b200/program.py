@@ -239,6 +239,7 @@ class CompiledProgram(object):
         nspec = len(q.blocks)
         spec_tab = np.zeros((nspec, L.SPEC_STRIDE), np.int32)
         tiles, segbins, templ, wins, data = [], [], [], [], []
+        segtabs, segoff = [], 0     # weighted column rows of the segmented-sum bins (appended after the ell-tables)
         toff = 0      # running offset into the ell-table buffer (doubles, kept even)
         woff = 0      # running offset into the window buffer
         row0 = 0
@@ -322,6 +323,14 @@ class CompiledProgram(object):
                         rec_b[L.B_WINOFF_LO] = lo32 - (1 << 32) if lo32 >= (1 << 31) else lo32
                         rec_b[L.B_WINOFF_HI] = off >> 32
                         lo_b, hi_b = supports[b]
+                        # the bin's columns as the kernel consumes them: [w T_t.., w M_q.., D_q..] per column
+                        wrow = wp[b, lo_b:hi_b, None]
+                        cols = np.empty((hi_b - lo_b, NT + 2 * NP))
+                        cols[:, :NT] = wrow * ltab[lo_b:hi_b, :NT]
+                        cols[:, NT:NT + NP] = wrow * ltab[lo_b:hi_b, NT + 1::4][:, :NP]
+                        cols[:, NT + NP:] = ltab[lo_b:hi_b, NT + 2::4][:, :NP]
+                        rec_b[L.B_TABOFF_LO], rec_b[L.B_TABOFF_HI] = segoff, 0      # relative; rebased below
+                        segtabs.append(cols.ravel()); segoff += cols.size
                         for k in range(len(m.plaws)):
                             seg_d = np.abs(ltab[lo_b:max(hi_b - 1, lo_b), NT + 4 * k + 2])
                             dmax = np.float32(min(seg_d.max() if seg_d.size else 0.0, 3e38))
@@ -386,6 +395,16 @@ class CompiledProgram(object):
                 tiles.append((key, rec_t))
 
         # records sorted by kernel class (stable): one launch per class <NT, NP>
+        if segtabs:
+            base = toff + (toff & 1)                         # 16-byte aligned start of the weighted rows
+            templ.append(np.zeros(base - toff))
+            templ += segtabs
+            for _, r in segbins:
+                if r[L.B_ROW] >= 0 and r[L.B_HI] > r[L.B_LO]:
+                    off = base + int(r[L.B_TABOFF_LO])
+                    lo32 = off & 0xFFFFFFFF
+                    r[L.B_TABOFF_LO] = lo32 - (1 << 32) if lo32 >= (1 << 31) else lo32
+                    r[L.B_TABOFF_HI] = off >> 32
         # Within a class the launch order is free (every record names its output row), so the groups that
         # become one CTA are sorted longest first: the hardware hands CTAs out in index order, and short
         # CTAs at the end keep the tail of the launch short (plik-lite bins widen 6x from ell 30 to 2500).

@@ -91,6 +91,9 @@ enum {
   CSL_B_LO = 2,      /* first non-zero column                                   */
   CSL_B_HI = 3,      /* one past the last non-zero column                       */
   CSL_B_WINOFF_LO = 4, CSL_B_WINOFF_HI = 5,  /* offset (doubles) of the window row */
+  CSL_B_TABOFF_LO = 6, CSL_B_TABOFF_HI = 7,  /* offset (doubles, in `templates`) of the bin's weighted column rows
+                                                [w T_0..w T_{NT-1}, w M_q.., D_q..] for l in [lo, hi); the bins of a
+                                                group are contiguous there, in record order */
   CSL_B_DMAX = 8     /* [CSL_MAX_PLAW]: float32 bits, max |D_q[l]| over [lo, hi) (see k_bin_segsum) */
 };
 
