@@ -284,12 +284,14 @@ def run_b200(args):
     fl = prog.flops
     peak, peak_src = fp64_peak()
     # algorithmic FP64 work per launch (DESIGN.md "Kernels"): chi2 = n^2 per walker (one triangular solve,
-    # SURVEY.md 8d); binning = 2*nnz(windows) + foreground build (2 flops per template FMA, a power law
-    # counted as 20 FMAs) per walker.  "executed" adds padding / zero blocks actually issued.
+    # SURVEY.md 8d); DMMA binning = 2*nnz(windows) + foreground build (2 flops per template FMA, a power law
+    # counted as 20 FMAs) per walker, "executed" adds padding / zero blocks actually issued; segmented-sum
+    # binning = 2 x the FP64 instructions it issues per walker (program.flops["seg_flops"]).
     per_kernel = {}
     for name, kern, alg, exe in (("chi2", "k_trigemm_chi2" if prog.meta.get("chi2_mode") else "k_trsm_chi2", fl["trsm_alg"], fl["trsm"]),
-                                 ("bin_residual", "k_bin_segsum" if prog.meta.get("nsegclass") else "k_bin_residual",
-                                  fl["bin_nnz"] + fl["build_ops"],
+                                 ("bin_residual", "k_bin_segsum", fl["seg_flops"], fl["seg_flops"])
+                                 if prog.meta.get("nsegclass") and not prog.meta.get("nclass") else
+                                 ("bin_residual", "k_bin_residual", fl["bin_nnz"] + fl["build_ops"],
                                   fl["bin_exec"] + fl["build_ops"])):
         if name in stage_ms:
             t = stage_ms[name] * 1e-3
@@ -346,7 +348,8 @@ def run_b200(args):
             "ms_per_step_instrumented_pass": ms_instrumented,
             "flops_per_eval": {"trsm_algorithmic": fl["trsm_alg"], "trsm_executed": fl["trsm"],
                                "binning_dense_windows": fl["bin_dense"], "binning_nonzero_windows": fl["bin_nnz"],
-                               "binning_executed_dmma": fl["bin_exec"], "foreground_build": fl["build_ops"]}}
+                               "binning_executed_dmma": fl["bin_exec"], "foreground_build": fl["build_ops"],
+                               "segsum_fp64_instructions_x2": fl.get("seg_flops", 0)}}
     print(json.dumps(line))
 
 

@@ -255,6 +255,7 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
   __shared__ int scont[CSL_SEG_GROUP];               // bin starts at the column where the previous bin ended
   __shared__ double slogb[CSL_SEG_GROUP][NPX];       // logB_q at each bin's first column
   __shared__ long long sbase;
+  __shared__ double sdat[CSL_SEG_GROUP];             // data value of each bin's residual row
   const int tid = threadIdx.x;
   int w[SEG_WPT];
   bool live_w[SEG_WPT];
@@ -295,6 +296,10 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
     const int b = tid / NPX, q = tid % NPX;
     const int32_t* rec = first + b * CSL_BIN_STRIDE;
     slogb[b][q] = __ldg(ltab + (long long)max(rec[CSL_B_LO], 0) * LSTRIDE + NT + 4 * q);
+  }
+  if (tid >= 64 && tid < 64 + CSL_SEG_GROUP) {
+    const int row = first[(tid - 64) * CSL_BIN_STRIDE + CSL_B_ROW];
+    sdat[tid - 64] = row >= 0 ? __ldg(p.data + row) : 0.0;
   }
   double cf[SEG_WPT][NTX], pamp[SEG_WPT][NPX], pidx[SEG_WPT][NPX], cal[SEG_WPT];
   const int calrow = spec[CSL_S_CAL];
@@ -362,7 +367,7 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
         seg_cols<NT, NP, MODE>(srow + (s0 - p0) * RS, s1 - s0, cf, pamp, pidx, E, at, ap, ltab, l, lend);
         if (s1 == spre[b + 1]) {                  // the bin ends here: r = cal * d - b  (spt_lowl.py:132)
           const int row = srw[b];
-          const double d = p.data[row];
+          const double d = sdat[b];
 #pragma unroll
           for (int j = 0; j < SEG_WPT; ++j) {
             const double tot = at[j] + ap[j];
@@ -388,7 +393,7 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
     if (row >= 0 && spre[b + 1] == spre[b]) {
 #pragma unroll
       for (int j = 0; j < SEG_WPT; ++j)
-        if (live_w[j]) R[(long long)row * ldr + w[j]] = cal_on_model ? p.data[row] : __dmul_rn(cal[j], p.data[row]);
+        if (live_w[j]) R[(long long)row * ldr + w[j]] = cal_on_model ? sdat[b] : __dmul_rn(cal[j], sdat[b]);
     }
   }
 }

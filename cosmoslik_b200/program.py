@@ -243,7 +243,7 @@ class CompiledProgram(object):
         toff = 0      # running offset into the ell-table buffer (doubles, kept even)
         woff = 0      # running offset into the window buffer
         row0 = 0
-        flops_dense = flops_exec = flops_nnz = builds = 0
+        flops_dense = flops_exec = flops_nnz = builds = seg_ops = 0
         zero_row = None
 
         def pad_class(k, sizes):
@@ -341,6 +341,10 @@ class CompiledProgram(object):
                     segbins.append(((NT, NP), rec_b))
                 flops_exec += 2 * covered
                 builds += covered * per_elem
+                # FP64 instructions k_bin_segsum issues per column and walker: NT template FMAs, and per power
+                # law 1 FMA + the advance (y = idx D, degree-6 Horner, E *= P: 8; degree 5 / 10 when |y| allows /
+                # demands); the window weight is folded into the host-built column table
+                seg_ops += covered * (NT + 9 * NP)
             for t0 in (range(0, nb, L.BM) if not seg else ()):
                 nr = min(L.BM, nb - t0)
                 lo, hi = _support(wp[t0:t0 + nr])
@@ -439,7 +443,7 @@ class CompiledProgram(object):
         self.host["spec_tab"], self.host["tile_tab"], self.host["bin_tab"] = spec_tab, tile_arr, bin_arr
         # work per evaluation: dense windows, non-zero window entries, DMMA blocks that
         # are actually executed, foreground-build FP64 ops (~1 per template term, ~20 per power law), TRSM
-        self.flops = dict(bin_dense=flops_dense, bin_nnz=flops_nnz, bin_exec=flops_exec, build_ops=2 * builds,
+        self.flops = dict(bin_dense=flops_dense, bin_nnz=flops_nnz, bin_exec=flops_exec, build_ops=2 * builds, seg_flops=2 * seg_ops,
                           trsm=self._chi2_executed_flops() if factor else 0, trsm_alg=n * n if factor else 0)
 
 
