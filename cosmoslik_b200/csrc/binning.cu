@@ -192,9 +192,19 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
 //
 // A group whose columns exceed the staging capacity is processed in several passes; the bins are walked in
 // order, so a bin cut by a pass boundary simply keeps its running sum and power-law state in registers.
+#ifndef SEG_TPB
 #define SEG_TPB 128    // threads per CTA
+#endif
 #define SEG_WPT 2      // walkers per thread: staged rows / loop control are amortised over both
+#ifndef SEG_SMEM_DOUBLES
 #define SEG_SMEM_DOUBLES 3072   // staged columns x RS (24 KB)
+#endif
+#ifndef SEG_MINB
+#define SEG_MINB 1
+#endif
+#ifndef SEG_UNROLL
+#define SEG_UNROLL 2
+#endif
 
 // ncol staged columns starting at `row`, for the SEG_WPT walkers of a thread.
 // MODE 0 / 1 / 2: Taylor degree 5 / 6 / 10 in y = idx D;  MODE 3: exact exp at every column (ltab, l = ell
@@ -233,15 +243,16 @@ __device__ __forceinline__ void seg_cols(const double* __restrict__ row, int nco
     }
   };
   int c = 0;
-  for (; c + 2 <= ncol; c += 2, row += 2 * RS) {
-    column(row, l + c);
-    column(row + RS, l + c + 1);
+  for (; c + SEG_UNROLL <= ncol; c += SEG_UNROLL, row += SEG_UNROLL * RS) {
+#pragma unroll
+    for (int u = 0; u < SEG_UNROLL; ++u) column(row + u * RS, l + c + u);
   }
-  if (c < ncol) column(row, l + c);
+#pragma unroll 1
+  for (; c < ncol; ++c, row += RS) column(row, l + c);
 }
 
 template <int NT, int NP>
-__global__ void __launch_bounds__(SEG_TPB)
+__global__ void __launch_bounds__(SEG_TPB, SEG_MINB)
 k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restrict__ coef, int ldc,
              double* __restrict__ R, int ldr) {
   constexpr int LSTRIDE = NT + 4 * NP;
