@@ -144,7 +144,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------- clocks
@@ -350,7 +350,7 @@ def run_b200(args):
                                "binning_dense_windows": fl["bin_dense"], "binning_nonzero_windows": fl["bin_nnz"],
                                "binning_executed_dmma": fl["bin_exec"], "foreground_build": fl["build_ops"],
                                "segsum_fp64_instructions_x2": fl.get("seg_flops", 0)}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_gauss30(args):
@@ -416,7 +416,7 @@ def run_gauss30(args):
                                  "kernel is latency/issue bound, not HBM bound"},
             "gpu_launches": args.steps + 2 * len(slik.sampler.adaptations) * 2 + 4, "clocks": clk.summary(),
             "acceptance": nrows / float(nch * args.steps * block)}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_unbinned(args):
@@ -480,11 +480,35 @@ def run_unbinned(args):
                          "frac": ach / peak, "traffic": None, "peak_source": peak_src, "stages_ms": stage_ms,
                          "executed_tflops": fl["trsm"] * per_gpu / (stage_ms["chi2"] * 1e-3) / 1e12},
             "gpu_launches": 8 * args.steps, "clocks": clk.summary()}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that print banners there (NCCL's version line under
+    # NCCL_DEBUG=VERSION, for one) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return _main(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+        if _LINES:
+            sys.stdout.write("\n".join(_LINES) + "\n")
+            sys.stdout.flush()
+
+
+_LINES = []
+
+
+def emit(line):
+    _LINES.append(json.dumps(line))
+
+
+def _main(args):
     if args.workload == "gauss30_mh" and args.impl == "b200":
         return run_gauss30(args)
     if args.workload == "unbinned_mh" and args.impl == "b200":
