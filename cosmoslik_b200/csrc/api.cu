@@ -1,6 +1,7 @@
 // C-ABI glue: error reporting, device info and the composed posterior evaluation.
 #include <string.h>
 #include "common.cuh"
+#include <stdlib.h>
 
 thread_local char csl_err_buf[256] = "";
 
@@ -83,6 +84,8 @@ extern "C" int csl_stretch_run(const csl_program_t* p, csl_ensemble_t* e, int ns
   CSL_REQUIRE(e->replica == nullptr || (e->peer_ptrs && e->flag_ptrs && e->npeers > 0),
               "csl_stretch_run: replica given without peer / flag pointers");
   const int nd = e->ndim, W = e->n0 + e->n1;
+  // binned bandpower likelihoods take the fused stages; everything else the staged ones
+  const bool fused = p->resid_mode == 1 && e->ws_coef && e->ws_R && e->ws_chi2 && getenv("CSL_NO_FUSE") == nullptr;
   for (int i = 0; i < nsteps; ++i) {
     const uint32_t step = step0 + (uint32_t)i;
     for (int h = 0; h < 2; ++h) {
@@ -96,12 +99,35 @@ extern "C" int csl_stretch_run(const csl_program_t* p, csl_ensemble_t* e, int ns
       if (ns > 0) {
         double* s = e->pos + (long long)r0 * nd;
         double* q = e->q + (long long)r0 * nd;
+        uint8_t* acc = e->accepted ? e->accepted + r0 : nullptr;
+        if (fused) {
+          // propose+prepare | residual | chi^2 (partials) | combine+accept(+publish): 2 + nclass launches per half
+          const int Wp = round_up(ns, CSL_BN);
+          rc = csl_fused_propose_prepare(p, ns, Wp, csize, s, comp, e->a, e->seed, step, (uint32_t)h, g0, q,
+                                         e->zz + r0, e->ws_coef, Wp, e->ws_prior, stream);
+          if (rc) return rc;
+          rc = csl_bin_residual(p, Wp, e->ws_coef, Wp, e->ws_R, Wp, stream);
+          if (rc) return rc;
+          rc = csl_chi2_impl(p, Wp, e->ws_R, Wp, e->ws_chi2, e->ws_part, false, stream);
+          if (rc) return rc;
+          const bool parts = p->chi2_mode == 1;
+          rc = csl_fused_combine_accept(p, ns, csize, nd, s, e->lnl + r0, q, e->lnl_q, e->zz + r0, e->seed, step,
+                                        (uint32_t)h, g0, acc, e->naccepted, e->replica ? e->peer_ptrs : nullptr,
+                                        e->replica ? e->npeers : 0, e->replica ? e->multicast_ptr : 0, (int64_t)g0,
+                                        e->ws_coef, Wp, e->ws_prior, parts ? nullptr : e->ws_chi2,
+                                        parts ? e->ws_part : nullptr, p->n_pad / CSL_BM, Wp, stream);
+          if (rc) return rc;
+          if (e->replica) {
+            rc = csl_peer_barrier(e->flag_ptrs, e->rank, e->npeers, ++e->epoch, stream);
+            if (rc) return rc;
+          }
+          continue;
+        }
         rc = csl_stretch_propose(ns, csize, nd, s, comp, e->a, nullptr, nullptr, e->seed, step, (uint32_t)h, g0, q,
                                  e->zz + r0, stream);
         if (rc) return rc;
         rc = csl_lnl(p, ns, q, e->lnl_q, e->ws_coef, e->ws_prior, e->ws_R, e->ws_chi2, e->ws_part, stream);
         if (rc) return rc;
-        uint8_t* acc = e->accepted ? e->accepted + r0 : nullptr;
         if (e->replica)
           rc = csl_stretch_accept_publish(ns, csize, nd, s, e->lnl + r0, q, e->lnl_q, e->zz + r0, nullptr, e->seed, step,
                                           (uint32_t)h, g0, acc, e->naccepted, e->peer_ptrs, e->npeers, e->multicast_ptr,

@@ -157,6 +157,13 @@ __global__ void k_sum_partials(int nblk, int W, int ldr, const double* __restric
 
 extern "C" int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part,
                         void* stream) {
+  return csl_chi2_impl(p, W, R, ldr, chi2, ws_part, true, stream);
+}
+
+// sum_partials = false (explicit-inverse mode only): leave the per-row-block column sums in ws_part[i, :]
+// for a consumer that adds them itself (the fused accept kernel of csl_stretch_run)
+int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part, bool sum_partials,
+                  void* stream) {
   CSL_REQUIRE(p && R && chi2, "csl_chi2: null argument");
   CSL_REQUIRE(p->n_pad > 0 && p->n_pad % CSL_BM == 0, "csl_chi2: program has no factor");
   CSL_REQUIRE(W > 0 && W % CSL_BN == 0 && ldr >= W && (ldr % 2) == 0, "csl_chi2: W must be a positive multiple of 128");
@@ -178,7 +185,7 @@ extern "C" int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, doubl
     grp = grp < 1 ? 1 : (grp > 256 ? 256 : grp);
     if (const char* e = getenv("CSL_TRIGEMM_GROUP")) grp = atoi(e) > 0 ? atoi(e) : grp;
     k_trigemm_chi2<<<(W / CSL_BN) * nblk, CSL_THREADS, smem1, s>>>(*p, R, ldr, ws_part, grp);
-    k_sum_partials<<<(W + 255) / 256, 256, 0, s>>>(nblk, W, ldr, ws_part, chi2);
+    if (sum_partials) k_sum_partials<<<(W + 255) / 256, 256, 0, s>>>(nblk, W, ldr, ws_part, chi2);
     return csl_check_launch("k_trigemm_chi2");
   }
   CSL_REQUIRE(p->Lmat && p->Linv_diag, "csl_chi2: program has no factor");

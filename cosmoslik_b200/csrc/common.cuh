@@ -14,6 +14,19 @@ extern thread_local char csl_err_buf[256];
 int csl_fail(int code, const char* msg);
 int csl_check_launch(const char* what);
 
+// internal (C++ linkage, not in the C ABI): fused stages of csl_stretch_run and the chi^2 partial sums
+int csl_fused_propose_prepare(const csl_program_t* p, int Ns, int Wp, int Nc, const double* s, const double* comp,
+                              double a, uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0, double* q,
+                              double* zz, double* coef, int ldc, double* prior, void* stream);
+int csl_fused_combine_accept(const csl_program_t* p, int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q,
+                             double* lnl_q, const double* zz, uint64_t seed, uint32_t step, uint32_t half,
+                             uint32_t walker0, uint8_t* accepted, uint64_t* naccepted, const uint64_t* peer_ptrs,
+                             int npeers, uint64_t multicast_ptr, int64_t dst_row0, const double* coef, int ldc,
+                             const double* prior, const double* chi2, const double* part, int nblk, int ldp,
+                             void* stream);
+int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part, bool sum_partials,
+                  void* stream);
+
 #define CSL_REQUIRE(cond, msg) do { if (!(cond)) return csl_fail(CSL_E_BADARG, msg); } while (0)
 
 // D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor pipe (SASS: DMMA.8x8x4).

@@ -1,6 +1,6 @@
 // Priors + coefficient bytecode for W walkers, and the final lnl combine.
 //   reference: cosmoslik_plugins/likelihoods/priors.py:24-30 ; cosmoslik/cosmoslik.py:135-141
-#include "common.cuh"
+#include "eval_device.cuh"
 
 #define PREP_THREADS 128
 
@@ -24,42 +24,7 @@ k_prepare(csl_program_t p, int W, int Wp, const double* __restrict__ x, double* 
   const double* xr = sx + threadIdx.x * lds;
   const int w = w0 + threadIdx.x;
 
-  // priors.py:26-28: first box that fails `lo <= x <= hi` (NaN fails) gives +inf
-  bool out = false;
-  for (int b = 0; b < p.nbox; ++b) {
-    double v = xr[p.box_idx[b]];
-    if (!(p.box_lo[b] <= v && v <= p.box_hi[b])) out = true;
-  }
-  // priors.py:30: sum((x-c)**2./2/w**2), python sum from 0 in list order
-  double pr = 0.0;
-  for (int k = 0; k < p.ngauss; ++k) {
-    double d = __dsub_rn(xr[p.gauss_idx[k]], p.gauss_c[k]);
-    double wv = p.gauss_w[k];
-    pr = __dadd_rn(pr, __ddiv_rn(__ddiv_rn(__dmul_rn(d, d), 2.0), __dmul_rn(wv, wv)));
-  }
-  if (w < W) prior[w] = out ? CUDART_INF : pr;
-
-  double st[CSL_STACK];
-  int sp = 0;
-  for (int pc = 0; pc < p.ncode; ++pc) {
-    const int op = p.code_op[pc];
-    switch (op) {
-      case CSL_OP_PUSHP: st[sp++] = xr[p.code_arg[pc]]; break;
-      case CSL_OP_PUSHC: st[sp++] = p.code_val[pc]; break;
-      case CSL_OP_ADD: --sp; st[sp - 1] = __dadd_rn(st[sp - 1], st[sp]); break;
-      case CSL_OP_SUB: --sp; st[sp - 1] = __dsub_rn(st[sp - 1], st[sp]); break;
-      case CSL_OP_MUL: --sp; st[sp - 1] = __dmul_rn(st[sp - 1], st[sp]); break;
-      case CSL_OP_DIV: --sp; st[sp - 1] = __ddiv_rn(st[sp - 1], st[sp]); break;
-      case CSL_OP_NEG: st[sp - 1] = -st[sp - 1]; break;
-      case CSL_OP_EXP: st[sp - 1] = exp(st[sp - 1]); break;
-      case CSL_OP_LOG: st[sp - 1] = log(st[sp - 1]); break;
-      case CSL_OP_POW: --sp; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
-      case CSL_OP_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
-      case CSL_OP_SQR: st[sp - 1] = __dmul_rn(st[sp - 1], st[sp - 1]); break;
-      case CSL_OP_STORE: coef[(long long)p.code_arg[pc] * ldc + w] = st[--sp]; break;
-      default: break;
-    }
-  }
+  prepare_walker(p, xr, w, W, coef, ldc, prior);
 }
 
 // lnl = like + prior with like = sum scalar coefs (+ chi2/2), cosmoslik.py:141; +inf on a hard prior (:135-137)
@@ -68,19 +33,7 @@ __global__ void k_combine(csl_program_t p, int W, const double* __restrict__ coe
                           double* __restrict__ lnl) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
-  double pr = prior[w];
-  double like = 0.0;
-  bool first = true;
-  for (int k = 0; k < p.nscalar; ++k) {
-    double v = coef[(long long)p.scalar_coef[k] * ldc + w];
-    like = first ? v : __dadd_rn(like, v);
-    first = false;
-  }
-  if (chi2 != nullptr) {
-    double h = chi2[w] * 0.5;
-    like = first ? h : __dadd_rn(like, h);
-  }
-  lnl[w] = (pr == CUDART_INF) ? CUDART_INF : __dadd_rn(like, pr);
+  lnl[w] = combine_walker(p, w, coef, ldc, prior[w], chi2 != nullptr, chi2 != nullptr ? chi2[w] : 0.0);
 }
 
 // resid_mode 2: R[i, w] = coef[direct_coef[i], w] - data[i]; rows n..n_pad are zero

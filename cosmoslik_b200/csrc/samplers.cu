@@ -4,7 +4,7 @@
 // One warp per walker: lane i owns parameter i (and i+32), so every global access to a walker's
 // row is one coalesced 8*ndim-byte segment.  These kernels are HBM-bound: ~(24 ndim + 32) B per
 // walker per step.
-#include "common.cuh"
+#include "eval_device.cuh"
 #include "philox.cuh"
 
 #define SAMP_THREADS 256
@@ -293,17 +293,59 @@ k_stretch_propose(int Ns, int Nc, int nd, const double* __restrict__ s, const do
   if (lane == 0) zz[k] = z;
 }
 
+// Proposal + priors + coefficient bytecode in one launch (the native step loop, csl_stretch_run): one
+// thread per walker computes its proposal row (same arithmetic as k_stretch_propose), keeps it in shared
+// memory and runs prepare_walker on it.  Columns Ns..Wp-1 of the coefficient tile replay walker Ns-1.
+#define SPP_THREADS 128
+__global__ void __launch_bounds__(SPP_THREADS)
+k_stretch_propose_prepare(csl_program_t p, int Ns, int Wp, int Nc, const double* __restrict__ s,
+                          const double* __restrict__ comp, double a, uint64_t seed, uint32_t step, uint32_t half,
+                          uint32_t walker0, double* __restrict__ q, double* __restrict__ zz,
+                          double* __restrict__ coef, int ldc, double* __restrict__ prior) {
+  extern __shared__ double sq[];
+  const int nd = p.ndim, lds = nd + 1;
+  const int w = blockIdx.x * SPP_THREADS + threadIdx.x;
+  if (w >= Wp) return;
+  const int k = min(w, Ns - 1);
+  double uz, ua;
+  int64_t j;
+  philox_stretch(seed, walker0 + (uint32_t)k, half, step, (uint32_t)Nc, uz, j, ua);
+  // zz = ((a - 1.) * u + 1) ** 2. / a
+  const double tq = __dadd_rn(__dmul_rn(a - 1.0, uz), 1.0);
+  const double z = __ddiv_rn(__dmul_rn(tq, tq), a);
+  const long long sb = (long long)k * nd, cb = (long long)j * nd;
+  double* qr = sq + threadIdx.x * lds;
+  for (int i = 0; i < nd; ++i) {
+    const double c = comp[cb + i];
+    const double v = __dsub_rn(c, __dmul_rn(z, __dsub_rn(c, s[sb + i])));     // q = c - zz * (c - s)
+    qr[i] = v;
+    if (w < Ns) q[sb + i] = v;
+  }
+  if (w < Ns) zz[w] = z;
+  prepare_walker(p, qr, w, Ns, coef, ldc, prior);
+}
+
 // Accept + publish.  With walkers sharded over several GPUs every rank keeps a replica of ALL walkers'
 // positions (`gath`, symmetric memory).  The accept kernel itself stores each local walker's final
 // position into every rank's replica over NVLink -- peer pointers (st.global on mapped peer memory) or
 // one multimem.st through the NVSwitch multicast address -- so the "all-gather of the complementary
 // half" is fused into the accept step; a device-side barrier follows on the stream.
+// what the fused variant needs to assemble lnl(q) itself
+struct csl_fused_combine {
+  csl_program_t p;
+  const double* coef; int ldc;
+  const double* prior; const double* chi2; const double* part; int nblk, ldp;
+  double* lnl_q;
+};
+
+template <bool FUSED>
 __global__ void __launch_bounds__(SAMP_THREADS)
 k_stretch_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ lnl_s, const double* __restrict__ q,
                  const double* __restrict__ lnl_q, const double* __restrict__ zz, const double* __restrict__ u_acc,
                  uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0, uint32_t Nc,
                  uint8_t* __restrict__ accepted, const unsigned long long* __restrict__ peers, int npeers,
-                 unsigned long long mc_ptr, long long dst_row0, unsigned long long* __restrict__ nacc) {
+                 unsigned long long mc_ptr, long long dst_row0, unsigned long long* __restrict__ nacc,
+                 csl_fused_combine fc) {
   const int k = warp_global(), lane = threadIdx.x & 31;
   if (k >= Ns) {                               // whole warps only; keep them for the block-wide count
     if (nacc) __syncthreads_count(0);
@@ -312,8 +354,23 @@ k_stretch_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ ln
   double ua;
   if (u_acc) ua = u_acc[k];
   else { double uz; int64_t j; philox_stretch(seed, walker0 + (uint32_t)k, half, step, Nc, uz, j, ua); }
+  double lq;
+  if (FUSED) {
+    // the proposal's lnl is assembled here (k_sum_partials + k_combine folded in; same order of additions)
+    double v = 0.0;
+    if (lane == 0) {
+      double chi2 = 0.0;
+      if (fc.part) for (int i = 0; i < fc.nblk; ++i) chi2 += fc.part[(long long)i * fc.ldp + k];
+      else if (fc.chi2) chi2 = fc.chi2[k];
+      v = combine_walker(fc.p, k, fc.coef, fc.ldc, fc.prior[k], fc.part != nullptr || fc.chi2 != nullptr, chi2);
+      fc.lnl_q[k] = v;
+    }
+    lq = shfl_d(v, 0);
+  } else {
+    lq = lnl_q[k];
+  }
   // lnpdiff = (dim - 1.) * log(zz) + newlnprob - lnprob0 ; accept = lnpdiff > log(u)
-  const double newlnp = -lnl_q[k], lnp0 = -lnl_s[k];
+  const double newlnp = -lq, lnp0 = -lnl_s[k];
   const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)nd - 1.0, log(zz[k])), newlnp), lnp0);
   const bool acc = lnpdiff > log(ua);
   const long long b = (long long)k * nd;
@@ -323,7 +380,7 @@ k_stretch_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ ln
   if (acc) {
     if (lane < nd) s[b + lane] = v0;
     if (lane + 32 < nd) s[b + lane + 32] = v1;
-    if (lane == 0) lnl_s[k] = lnl_q[k];
+    if (lane == 0) lnl_s[k] = lq;
   }
   if (lane == 0 && accepted) accepted[k] = acc ? 1 : 0;
   if (nacc) {                                   // one atomic per CTA
@@ -521,10 +578,36 @@ static int stretch_accept_impl(int Ns, int Nc, int ndim, double* s, double* lnl_
   CSL_REQUIRE(Ns > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && s && lnl_s && q && lnl_q && zz,
               "csl_stretch_accept: bad argument");
   CSL_REQUIRE(npeers == 0 || peers || mc_ptr, "csl_stretch_accept: peer pointers missing");
-  k_stretch_accept<<<warp_grid(Ns), SAMP_THREADS, 0, (cudaStream_t)stream>>>(
+  k_stretch_accept<false><<<warp_grid(Ns), SAMP_THREADS, 0, (cudaStream_t)stream>>>(
       Ns, ndim, s, lnl_s, q, lnl_q, zz, u_acc, seed, step, half, walker0, (uint32_t)Nc, accepted, peers, npeers, mc_ptr,
-      dst_row0, nacc);
+      dst_row0, nacc, csl_fused_combine());
   return csl_check_launch("k_stretch_accept");
+}
+
+// ---- fused stages of the native step loop (api.cu: csl_stretch_run); not part of the C ABI -----------------
+int csl_fused_propose_prepare(const csl_program_t* p, int Ns, int Wp, int Nc, const double* s, const double* comp,
+                              double a, uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0, double* q,
+                              double* zz, double* coef, int ldc, double* prior, void* stream) {
+  const size_t smem = (size_t)SPP_THREADS * (p->ndim + 1) * sizeof(double);
+  k_stretch_propose_prepare<<<(Wp + SPP_THREADS - 1) / SPP_THREADS, SPP_THREADS, smem, (cudaStream_t)stream>>>(
+      *p, Ns, Wp, Nc, s, comp, a, seed, step, half, walker0, q, zz, coef, ldc, prior);
+  return csl_check_launch("k_stretch_propose_prepare");
+}
+
+int csl_fused_combine_accept(const csl_program_t* p, int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q,
+                             double* lnl_q, const double* zz, uint64_t seed, uint32_t step, uint32_t half,
+                             uint32_t walker0, uint8_t* accepted, uint64_t* naccepted, const uint64_t* peer_ptrs,
+                             int npeers, uint64_t multicast_ptr, int64_t dst_row0, const double* coef, int ldc,
+                             const double* prior, const double* chi2, const double* part, int nblk, int ldp,
+                             void* stream) {
+  csl_fused_combine fc;
+  fc.p = *p; fc.coef = coef; fc.ldc = ldc; fc.prior = prior; fc.chi2 = chi2; fc.part = part; fc.nblk = nblk;
+  fc.ldp = ldp; fc.lnl_q = lnl_q;
+  k_stretch_accept<true><<<warp_grid(Ns), SAMP_THREADS, 0, (cudaStream_t)stream>>>(
+      Ns, ndim, s, lnl_s, q, lnl_q, zz, nullptr, seed, step, half, walker0, (uint32_t)Nc, accepted,
+      reinterpret_cast<const unsigned long long*>(peer_ptrs), npeers, (unsigned long long)multicast_ptr,
+      (long long)dst_row0, reinterpret_cast<unsigned long long*>(naccepted), fc);
+  return csl_check_launch("k_stretch_accept<fused>");
 }
 
 extern "C" int csl_stretch_accept(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q,
