@@ -330,22 +330,12 @@ k_stretch_propose_prepare(csl_program_t p, int Ns, int Wp, int Nc, const double*
 // position into every rank's replica over NVLink -- peer pointers (st.global on mapped peer memory) or
 // one multimem.st through the NVSwitch multicast address -- so the "all-gather of the complementary
 // half" is fused into the accept step; a device-side barrier follows on the stream.
-// what the fused variant needs to assemble lnl(q) itself
-struct csl_fused_combine {
-  csl_program_t p;
-  const double* coef; int ldc;
-  const double* prior; const double* chi2; const double* part; int nblk, ldp;
-  double* lnl_q;
-};
-
-template <bool FUSED>
 __global__ void __launch_bounds__(SAMP_THREADS)
 k_stretch_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ lnl_s, const double* __restrict__ q,
                  const double* __restrict__ lnl_q, const double* __restrict__ zz, const double* __restrict__ u_acc,
                  uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0, uint32_t Nc,
                  uint8_t* __restrict__ accepted, const unsigned long long* __restrict__ peers, int npeers,
-                 unsigned long long mc_ptr, long long dst_row0, unsigned long long* __restrict__ nacc,
-                 csl_fused_combine fc) {
+                 unsigned long long mc_ptr, long long dst_row0, unsigned long long* __restrict__ nacc) {
   const int k = warp_global(), lane = threadIdx.x & 31;
   if (k >= Ns) {                               // whole warps only; keep them for the block-wide count
     if (nacc) __syncthreads_count(0);
@@ -354,21 +344,7 @@ k_stretch_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ ln
   double ua;
   if (u_acc) ua = u_acc[k];
   else { double uz; int64_t j; philox_stretch(seed, walker0 + (uint32_t)k, half, step, Nc, uz, j, ua); }
-  double lq;
-  if (FUSED) {
-    // the proposal's lnl is assembled here (k_sum_partials + k_combine folded in; same order of additions)
-    double v = 0.0;
-    if (lane == 0) {
-      double chi2 = 0.0;
-      if (fc.part) for (int i = 0; i < fc.nblk; ++i) chi2 += fc.part[(long long)i * fc.ldp + k];
-      else if (fc.chi2) chi2 = fc.chi2[k];
-      v = combine_walker(fc.p, k, fc.coef, fc.ldc, fc.prior[k], fc.part != nullptr || fc.chi2 != nullptr, chi2);
-      fc.lnl_q[k] = v;
-    }
-    lq = shfl_d(v, 0);
-  } else {
-    lq = lnl_q[k];
-  }
+  const double lq = lnl_q[k];
   // lnpdiff = (dim - 1.) * log(zz) + newlnprob - lnprob0 ; accept = lnpdiff > log(u)
   const double newlnp = -lq, lnp0 = -lnl_s[k];
   const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)nd - 1.0, log(zz[k])), newlnp), lnp0);
@@ -422,6 +398,60 @@ __global__ void k_peer_barrier(const unsigned long long* __restrict__ flag_ptrs,
     __nanosleep(40);
   } while (clock64() - t0 < 8000000000ll);
   __threadfence_system();
+}
+
+// Combine + accept (+ publish) of the native step loop: k_sum_partials, k_combine and k_stretch_accept in one
+// launch.  Phase 1, one THREAD per walker: lnl(q) from the chi^2 partial sums (same order of additions as
+// the staged kernels), the accept test, lnl update.  Phase 2, the CTA's 256 rows as one contiguous range:
+// accepted rows are copied q -> s, and every row's final position goes to the replicas of all ranks.
+struct csl_fused_combine {
+  csl_program_t p;
+  const double* coef; int ldc;
+  const double* prior; const double* chi2; const double* part; int nblk, ldp;
+  double* lnl_q;
+};
+#define SAB_THREADS 256
+__global__ void __launch_bounds__(SAB_THREADS)
+k_stretch_combine_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ lnl_s,
+                         const double* __restrict__ q, const double* __restrict__ zz, uint64_t seed, uint32_t step,
+                         uint32_t half, uint32_t walker0, uint32_t Nc, uint8_t* __restrict__ accepted,
+                         const unsigned long long* __restrict__ peers, int npeers, unsigned long long mc_ptr,
+                         long long dst_row0, unsigned long long* __restrict__ nacc, csl_fused_combine fc) {
+  __shared__ unsigned char sacc[SAB_THREADS];
+  const int k0 = blockIdx.x * SAB_THREADS, k = k0 + threadIdx.x;
+  bool acc = false;
+  if (k < Ns) {
+    double uz, ua;
+    int64_t j;
+    philox_stretch(seed, walker0 + (uint32_t)k, half, step, Nc, uz, j, ua);
+    double chi2 = 0.0;
+    if (fc.part) for (int i = 0; i < fc.nblk; ++i) chi2 += fc.part[(long long)i * fc.ldp + k];
+    else if (fc.chi2) chi2 = fc.chi2[k];
+    const double lq = combine_walker(fc.p, k, fc.coef, fc.ldc, fc.prior[k], fc.part != nullptr || fc.chi2 != nullptr, chi2);
+    fc.lnl_q[k] = lq;
+    // lnpdiff = (dim - 1.) * log(zz) + newlnprob - lnprob0 ; accept = lnpdiff > log(u)
+    const double newlnp = -lq, lnp0 = -lnl_s[k];
+    const double lnpdiff = __dsub_rn(__dadd_rn(__dmul_rn((double)nd - 1.0, log(zz[k])), newlnp), lnp0);
+    acc = lnpdiff > log(ua);
+    if (acc) lnl_s[k] = lq;
+    if (accepted) accepted[k] = acc ? 1 : 0;
+  }
+  sacc[threadIdx.x] = acc ? 1 : 0;
+  const int c = __syncthreads_count(acc);
+  if (nacc && threadIdx.x == 0 && c) atomicAdd(nacc, (unsigned long long)c);
+  const int nw = min(SAB_THREADS, Ns - k0);
+  const long long base = (long long)k0 * nd, dbase = (dst_row0 + k0) * nd;
+  for (int idx = threadIdx.x; idx < nw * nd; idx += SAB_THREADS) {
+    const bool a = sacc[idx / nd] != 0;
+    const double v = a ? q[base + idx] : s[base + idx];
+    if (a) s[base + idx] = v;
+    if (mc_ptr) {
+      double* dst = reinterpret_cast<double*>(mc_ptr) + dbase + idx;
+      asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" :: "l"(dst), "d"(v) : "memory");
+    } else {
+      for (int r = 0; r < npeers; ++r) reinterpret_cast<double*>(peers[r])[dbase + idx] = v;
+    }
+  }
 }
 
 // wrapper bookkeeping, samplers/emcee.py:70-88
@@ -578,9 +608,9 @@ static int stretch_accept_impl(int Ns, int Nc, int ndim, double* s, double* lnl_
   CSL_REQUIRE(Ns > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && s && lnl_s && q && lnl_q && zz,
               "csl_stretch_accept: bad argument");
   CSL_REQUIRE(npeers == 0 || peers || mc_ptr, "csl_stretch_accept: peer pointers missing");
-  k_stretch_accept<false><<<warp_grid(Ns), SAMP_THREADS, 0, (cudaStream_t)stream>>>(
+  k_stretch_accept<<<warp_grid(Ns), SAMP_THREADS, 0, (cudaStream_t)stream>>>(
       Ns, ndim, s, lnl_s, q, lnl_q, zz, u_acc, seed, step, half, walker0, (uint32_t)Nc, accepted, peers, npeers, mc_ptr,
-      dst_row0, nacc, csl_fused_combine());
+      dst_row0, nacc);
   return csl_check_launch("k_stretch_accept");
 }
 
@@ -603,11 +633,11 @@ int csl_fused_combine_accept(const csl_program_t* p, int Ns, int Nc, int ndim, d
   csl_fused_combine fc;
   fc.p = *p; fc.coef = coef; fc.ldc = ldc; fc.prior = prior; fc.chi2 = chi2; fc.part = part; fc.nblk = nblk;
   fc.ldp = ldp; fc.lnl_q = lnl_q;
-  k_stretch_accept<true><<<warp_grid(Ns), SAMP_THREADS, 0, (cudaStream_t)stream>>>(
-      Ns, ndim, s, lnl_s, q, lnl_q, zz, nullptr, seed, step, half, walker0, (uint32_t)Nc, accepted,
+  k_stretch_combine_accept<<<(Ns + SAB_THREADS - 1) / SAB_THREADS, SAB_THREADS, 0, (cudaStream_t)stream>>>(
+      Ns, ndim, s, lnl_s, q, zz, seed, step, half, walker0, (uint32_t)Nc, accepted,
       reinterpret_cast<const unsigned long long*>(peer_ptrs), npeers, (unsigned long long)multicast_ptr,
       (long long)dst_row0, reinterpret_cast<unsigned long long*>(naccepted), fc);
-  return csl_check_launch("k_stretch_accept<fused>");
+  return csl_check_launch("k_stretch_combine_accept");
 }
 
 extern "C" int csl_stretch_accept(int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q,
