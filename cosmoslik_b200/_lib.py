@@ -15,7 +15,7 @@ MAX_DIM, MAX_TERMS, MAX_PLAW = 64, 8, 4
 SPEC_STRIDE, TILE_STRIDE, STACK = 64, 32, 16
 OP = dict(PUSHP=0, PUSHC=1, ADD=2, SUB=3, MUL=4, DIV=5, NEG=6, EXP=7, LOG=8, POW=9, SQRT=10, STORE=11, SQR=12)
 S_NLPAD, S_NTERM, S_NPLAW, S_CAL = 0, 1, 2, 3
-S_LTAB, S_CALMODE, S_TERM_COEF, S_PLAW_AMP, S_PLAW_IDX = 4, 5, 8, 24, 28
+S_LTAB, S_CALMODE, S_TERM_COEF, S_PLAW_AMP, S_PLAW_IDX, S_IDXBOUND = 4, 5, 8, 24, 28, 32
 MAX_CLASS = 8
 BIN_STRIDE, SEG_GROUP = 16, 8
 B_ROW, B_SPEC, B_LO, B_HI, B_WINOFF_LO, B_WINOFF_HI, B_TABOFF_LO, B_TABOFF_HI, B_DMAX = 0, 1, 2, 3, 4, 5, 6, 7, 8

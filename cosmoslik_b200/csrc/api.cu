@@ -115,7 +115,7 @@ extern "C" int csl_stretch_run(const csl_program_t* p, csl_ensemble_t* e, int ns
                                         (uint32_t)h, g0, acc, e->naccepted, e->replica ? e->peer_ptrs : nullptr,
                                         e->replica ? e->npeers : 0, e->replica ? e->multicast_ptr : 0, (int64_t)g0,
                                         e->ws_coef, Wp, e->ws_prior, parts ? nullptr : e->ws_chi2,
-                                        parts ? e->ws_part : nullptr, p->n_pad / CSL_BM, Wp, stream);
+                                        parts ? e->ws_part : nullptr, p->n_pad / 32, Wp, stream);
           if (rc) return rc;
           if (e->replica) {
             rc = csl_peer_barrier(e->flag_ptrs, e->rank, e->npeers, ++e->epoch, stream);

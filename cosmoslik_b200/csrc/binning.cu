@@ -185,7 +185,8 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
 // D[l] = logB[l+1] - logB[l] (host, extended precision).  Within a bin the kernel takes one exact exp at
 // the first column (times the amplitude) and advances by a Taylor polynomial in y = idx D: degree 5 when
 // |y| <= 0.0035 (truncation y^6/6! < 3e-18), 6 when |y| <= 0.012 (< 7e-18), 10 when |y| <= 0.1 (< 3e-19),
-// decided per warp from the largest |D| of the group's bins (bin records) -- otherwise exp at every column.
+// decided ONCE per group from the largest |D| of its bins (bin records) times the host's bound on |idx|
+// (spectrum record) -- otherwise, and for walkers outside the bound, exp at every column.
 // A bin that begins at the column where the previous bin of the group ended (top-hat bins) inherits the
 // state instead of taking a new exp.  Rounding grows by ~1 ulp per column (<= 8 bins x a few tens of
 // columns: a few 1e-14 relative at worst), far inside the 1e-10 budget on lnL.
@@ -262,7 +263,8 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
   static_assert(RS % 2 == 0, "staged rows are copied in 16-byte pieces");
   __shared__ __align__(16) double srow[SEG_SMEM_DOUBLES];
   __shared__ int slo[CSL_SEG_GROUP], srw[CSL_SEG_GROUP], spre[CSL_SEG_GROUP + 1];
-  __shared__ float sgmax[CSL_MAX_PLAW];              // max |D_q| over the group's bins
+  __shared__ float sbound[CSL_MAX_PLAW];             // host bound on |idx_q| of this spectrum
+  __shared__ int smode;                              // the group's static Taylor mode
   __shared__ int scont[CSL_SEG_GROUP];               // bin starts at the column where the previous bin ended
   __shared__ double slogb[CSL_SEG_GROUP][NPX];       // logB_q at each bin's first column
   __shared__ long long sbase;
@@ -301,7 +303,13 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
     }
     spre[CSL_SEG_GROUP] = pre;
     sbase = base < 0 ? 0 : base;
-    for (int q = 0; q < CSL_MAX_PLAW; ++q) sgmax[q] = gmax[q];
+    double ym = 0.0;
+    for (int q = 0; q < CSL_MAX_PLAW; ++q) {
+      const float bq = __int_as_float(spec[CSL_S_IDXBOUND + q]);
+      sbound[q] = bq;
+      if (q < NP) ym = fmax(ym, fabs((double)bq) * (double)gmax[q]);
+    }
+    smode = ym <= 0.0035 ? 0 : ym <= 0.012 ? 1 : ym <= 0.1 ? 2 : 3;
   }
   if (NP > 0 && tid < CSL_SEG_GROUP * NP) {                    // independent of tid 0's loop: the records again
     const int b = tid / NPX, q = tid % NPX;
@@ -335,15 +343,27 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
 #pragma unroll
     for (int q = 0; q < NPX; ++q) E[j][q] = 0.0;
   }
-  // Taylor degree of the whole group, from the largest |D| of its bins (warp-uniform)
-  double ymax = 0.0;
+  // Taylor degree: ONE static choice per group, from the largest |D| of its bins and the host's bound on
+  // |idx| (spectrum record: the prior box of the index parameter, else 4) -- the same
+  // for every walker, so a walker's arithmetic never depends on which walkers share its thread, warp or GPU.
+  // A walker whose index lies outside a SOFT bound takes the exact-exp mode instead; outside a hard bound (a
+  // prior box, stored negative) its lnl is +inf whatever this kernel computes, so it needs no special care.
+  int mode[SEG_WPT];
 #pragma unroll
-  for (int j = 0; j < SEG_WPT; ++j)
+  for (int j = 0; j < SEG_WPT; ++j) {
+    bool inside = true;
 #pragma unroll
-    for (int q = 0; q < NP; ++q) ymax = fmax(ymax, fabs(pidx[j][q]) * (double)sgmax[q]);
-  const int mode = __all_sync(0xffffffffu, ymax <= 0.0035) ? 0 : __all_sync(0xffffffffu, ymax <= 0.012) ? 1
-                   : __all_sync(0xffffffffu, ymax <= 0.1) ? 2 : 3;
+    for (int q = 0; q < NP; ++q)     // hard bounds (stored negative) need no check; NaN -> outside
+      inside = inside && (sbound[q] < 0.f || fabs(pidx[j][q]) <= (double)sbound[q]);
+    mode[j] = inside ? smode : 3;
+  }
+  // if any thread of the CTA holds two walkers of different modes, every thread runs the group twice, once
+  // per walker slot at that walker's own mode (only the slot's results are stored): still one code path
+  const int split = __syncthreads_or(mode[0] != mode[1]);
 
+  for (int run = 0; run < (split ? SEG_WPT : 1); ++run) {
+  const int run_mode = split ? mode[run] : mode[0];
+  const unsigned store_mask = split ? (1u << run) : ~0u;
   for (int p0 = 0; p0 < total; p0 += CAP) {
     const int p1 = min(p0 + CAP, total);
     // stage columns p0 .. p1 of the group (weighted rows, contiguous in the host-built table)
@@ -382,14 +402,14 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
 #pragma unroll
           for (int j = 0; j < SEG_WPT; ++j) {
             const double tot = at[j] + ap[j];
-            if (live_w[j])
+            if (live_w[j] && (store_mask >> j & 1u))
               R[(long long)row * ldr + w[j]] = cal_on_model ? __dsub_rn(d, __dmul_rn(tot, cal[j]))
                                                             : __dsub_rn(__dmul_rn(cal[j], d), tot);
           }
         }
       }
     };
-    switch (mode) {
+    switch (run_mode) {
       case 0: run_bins(std::integral_constant<int, 0>{}); break;
       case 1: run_bins(std::integral_constant<int, 1>{}); break;
       case 2: run_bins(std::integral_constant<int, 2>{}); break;
@@ -397,6 +417,7 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
     }
     __syncthreads();
   }
+  }   // run
   // rows whose window is empty (no columns at all) still owe r = cal * d
 #pragma unroll 1
   for (int b = 0; b < CSL_SEG_GROUP; ++b) {

@@ -93,18 +93,23 @@ k_trsm_chi2(csl_program_t p, double* R, int ldr, double* __restrict__ chi2) {
 
 // ---- explicit-inverse mode ---------------------------------------------------------------------------
 // Y = M R with M = L^-1 (lower triangular, inverted once on the host in extended precision and verified
-// against the substitution result before it is used).  Every 64-row block of Y is an independent tile
-// product over K = 64 (i+1) columns, so the grid is (column tiles x row blocks) with no sequential
-// dependency, two CTAs per SM, and the same flop count as the blocked solve (n^2 + 64 n).  Each CTA
-// writes the column sums of squares of its row block to part[i, :]; k_sum_partials adds the row blocks
-// in a fixed order.
-__global__ void __launch_bounds__(CSL_THREADS, 2)
+// against the substitution result before it is used).  Every row block of Y is an independent tile
+// product over the columns up to its diagonal, so the grid is (column tiles x row blocks) with no sequential
+// dependency and the same flop count as the blocked solve (n^2 + 64 n).  Each warp writes the column sums
+// of squares of its 32 rows to part[row / 32, :]; the consumer (k_sum_partials, or the fused accept kernel)
+// adds the n_pad / 32 partials in a fixed order.
+//   ROWS = 64: 8 warps, 2 CTAs per SM -- the bulk shape.
+//   ROWS = 32: 4 warps, 4 CTAs per SM, twice as many (shorter) CTAs -- for launches too small to fill the
+//              GPU with 64-row tiles (a few thousand walkers).  Both shapes run the same DMMA sequence per
+//              32 x 32 warp tile, so chi^2 is bitwise the same whichever is chosen.
+template <int ROWS>
+__global__ void __launch_bounds__(4 * ROWS, 128 / ROWS)
 k_trigemm_chi2(csl_program_t p, const double* __restrict__ R, int ldr, double* __restrict__ part, int grp) {
+  constexpr int THREADS = 4 * ROWS, ASZ = ROWS * CSL_LDA;
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
-  double* Bs = As + 2 * CSL_ASZ;
-  double* red = Bs + 2 * CSL_BSZ;           // [2][128]
-  const int npad = p.n_pad, nblk = npad / CSL_BM;
+  double* Bs = As + 2 * ASZ;
+  const int npad = p.n_pad, nblk = npad / ROWS;
   // CTA order: row block i costs i+1 units, and the hardware hands CTAs out in index order, so the order
   // IS the schedule.  Column tiles are taken in super-groups of `grp` tiles whose R panels fit in L2
   // together; within a super-group all the longest row blocks go first (longest-processing-time order),
@@ -127,10 +132,11 @@ k_trigemm_chi2(csl_program_t p, const double* __restrict__ R, int ldr, double* _
   unsigned mmask = 0;
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi)
-    if (i * CSL_BM + wm0 + mi * 8 < p.n) mmask |= 1u << mi;
-  const int kend = min((i + 1) * CSL_BM, (p.n + CSL_KC - 1) / CSL_KC * CSL_KC);
-  gemm_stream_AB(acc, p.Minv + (long long)i * CSL_BM * npad, npad, R + c0, ldr, kend / CSL_KC, As, Bs, tid, wm0, wn0,
-                 lane, mmask, i * CSL_BM);
+    if (i * ROWS + wm0 + mi * 8 < p.n) mmask |= 1u << mi;
+  const int kend = min((i + 1) * ROWS, (p.n + CSL_KC - 1) / CSL_KC * CSL_KC);
+  gemm_stream_AB<ROWS, THREADS>(acc, p.Minv + (long long)i * ROWS * npad, npad, R + c0, ldr, kend / CSL_KC, As, Bs,
+                                tid, wm0, wn0, lane, mmask, i * ROWS);
+  double* prow = part + (long long)((i * ROWS + wm0) / 32) * ldr + c0 + wn0;
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
@@ -141,10 +147,8 @@ k_trigemm_chi2(csl_program_t p, const double* __restrict__ R, int ldr, double* _
       v += shfl_xor_d(v, 4);
       v += shfl_xor_d(v, 8);
       v += shfl_xor_d(v, 16);
-      if (g == 0) red[(warp >> 2) * CSL_BN + wn0 + ni * 8 + 2 * t + e] = v;
+      if (g == 0) prow[ni * 8 + 2 * t + e] = v;
     }
-  __syncthreads();
-  if (tid < CSL_BN) part[(long long)i * ldr + c0 + tid] = red[tid] + red[CSL_BN + tid];
 }
 
 __global__ void k_sum_partials(int nblk, int W, int ldr, const double* __restrict__ part, double* __restrict__ chi2) {
@@ -170,22 +174,37 @@ int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi
   cudaStream_t s = (cudaStream_t)stream;
   if (p->chi2_mode == 1) {
     CSL_REQUIRE(p->Minv && ws_part, "csl_chi2: explicit-inverse mode needs Minv and the partial-sum workspace");
-    static bool attr1 = false;
-    const size_t smem1 = (size_t)(2 * CSL_ASZ + 2 * CSL_BSZ + 2 * CSL_BN) * sizeof(double);
-    if (!attr1) {
-      cudaError_t e = cudaFuncSetAttribute(k_trigemm_chi2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-      if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-      attr1 = true;
-    }
-    const int nblk = p->n_pad / CSL_BM;
     // super-group: as many column tiles as keep their R panels (n_pad x 128 doubles each) within ~96 MB
     // (measured at n_pad = 640, 256 tiles: tile-major 0.445 ms, 16: 0.45, 64: 0.409, 256: 0.408)
     long long panel = (long long)p->n_pad * CSL_BN * sizeof(double);
     int grp = (int)((96ll << 20) / panel);
     grp = grp < 1 ? 1 : (grp > 256 ? 256 : grp);
     if (const char* e = getenv("CSL_TRIGEMM_GROUP")) grp = atoi(e) > 0 ? atoi(e) : grp;
-    k_trigemm_chi2<<<(W / CSL_BN) * nblk, CSL_THREADS, smem1, s>>>(*p, R, ldr, ws_part, grp);
-    if (sum_partials) k_sum_partials<<<(W + 255) / 256, 256, 0, s>>>(nblk, W, ldr, ws_part, chi2);
+    // tile shape: 64-row CTAs unless they would not even fill the GPU three times over
+    const int nblk64 = p->n_pad / CSL_BM, ntile = W / CSL_BN;
+    int sms = 148;
+    { static int cached = 0; if (!cached) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev); } sms = cached > 0 ? cached : sms; }
+    int rows = (long long)ntile * nblk64 < 6ll * sms ? 32 : 64;
+    if (const char* e = getenv("CSL_TRIGEMM_ROWS")) rows = atoi(e) == 32 ? 32 : 64;
+    static bool attr64 = false, attr32 = false;
+    if (rows == 64) {
+      const size_t smem1 = (size_t)(2 * CSL_ASZ + 2 * CSL_BSZ) * sizeof(double);
+      if (!attr64) {
+        cudaError_t e = cudaFuncSetAttribute(k_trigemm_chi2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+        attr64 = true;
+      }
+      k_trigemm_chi2<64><<<ntile * nblk64, 256, smem1, s>>>(*p, R, ldr, ws_part, grp);
+    } else {
+      const size_t smem1 = (size_t)(2 * 32 * CSL_LDA + 2 * CSL_BSZ) * sizeof(double);
+      if (!attr32) {
+        cudaError_t e = cudaFuncSetAttribute(k_trigemm_chi2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+        attr32 = true;
+      }
+      k_trigemm_chi2<32><<<ntile * nblk64 * 2, 128, smem1, s>>>(*p, R, ldr, ws_part, grp);
+    }
+    if (sum_partials) k_sum_partials<<<(W + 255) / 256, 256, 0, s>>>(2 * nblk64, W, ldr, ws_part, chi2);
     return csl_check_launch("k_trigemm_chi2");
   }
   CSL_REQUIRE(p->Lmat && p->Linv_diag, "csl_chi2: program has no factor");

@@ -95,25 +95,28 @@ __device__ __forceinline__ void warp_mma_chunk(double (&acc)[4][4][2], const dou
   }
 }
 
-// cp.async a [CSL_BM x CSL_KC] tile of a row-major matrix (row stride ld doubles) into As.
+// cp.async a [ROWS x CSL_KC] tile of a row-major matrix (row stride ld doubles) into As, by THREADS threads.
+template <int ROWS = CSL_BM, int THREADS = CSL_THREADS>
 __device__ __forceinline__ void load_A_tile_async(double* As, const double* __restrict__ A, long long ld,
                                                   int tid) {
-  // 64 rows x 8 chunks of 16 bytes = 512 chunks, 2 per thread
+  // ROWS rows x 8 chunks of 16 bytes, 2 per thread for (64, 256) and (32, 128)
+  static_assert((ROWS * CSL_KC / 2) % THREADS == 0, "A tile must divide over the threads");
 #pragma unroll
-  for (int it = 0; it < (CSL_BM * CSL_KC / 2) / CSL_THREADS; ++it) {
-    int c = tid + it * CSL_THREADS;
+  for (int it = 0; it < (ROWS * CSL_KC / 2) / THREADS; ++it) {
+    int c = tid + it * THREADS;
     int r = c >> 3, q = c & 7;
     cp_async16(As + r * CSL_LDA + q * 2, A + (long long)r * ld + q * 2);
   }
 }
 
 // cp.async a [CSL_KC x CSL_BN] tile (row stride ld doubles) into Bs.
+template <int THREADS = CSL_THREADS>
 __device__ __forceinline__ void load_B_tile_async(double* Bs, const double* __restrict__ B, long long ld,
                                                   int tid) {
-  // 16 rows x 64 chunks = 1024 chunks, 4 per thread
+  // 16 rows x 64 chunks = 1024 chunks, 4 (8) per thread
 #pragma unroll
-  for (int it = 0; it < (CSL_KC * CSL_BN / 2) / CSL_THREADS; ++it) {
-    int c = tid + it * CSL_THREADS;
+  for (int it = 0; it < (CSL_KC * CSL_BN / 2) / THREADS; ++it) {
+    int c = tid + it * THREADS;
     int r = c >> 6, q = c & 63;
     cp_async16(Bs + r * CSL_LDB + q * 2, B + (long long)r * ld + q * 2);
   }
@@ -125,25 +128,28 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xo
 #define CSL_ASZ (CSL_BM * CSL_LDA)   // doubles per A stage
 #define CSL_BSZ (CSL_KC * CSL_LDB)   // doubles per B stage
 
-// acc += A[64, 16*nchunk] * B[16*nchunk, 128], both operands streamed from global memory through a
-// two-stage cp.async pipeline.  All threads of the CTA call this; on return the stages are free.
+// acc += A[ROWS, 16*nchunk] * B[16*nchunk, 128], both operands streamed from global memory through a
+// two-stage cp.async pipeline (A stage = ROWS * CSL_LDA doubles).  All threads of the CTA (THREADS = 4 ROWS:
+// one warp per 32 x 32 piece of the tile) call this; on return the stages are free.
+template <int ROWS = CSL_BM, int THREADS = CSL_THREADS>
 __device__ __forceinline__ void gemm_stream_AB(double (&acc)[4][4][2], const double* __restrict__ A,
                                                long long lda, const double* __restrict__ B, long long ldb,
                                                int nchunk, double* As, double* Bs, int tid, int wm0, int wn0,
                                                int lane, unsigned mmask = 0xFu, int tri_row0 = -1) {
   // tri_row0 >= 0: A is lower triangular and this tile's first row is global row tri_row0 (columns start
   // at 0): 8-row groups that lie entirely above the diagonal of a chunk are skipped.
+  constexpr int ASZ = ROWS * CSL_LDA;
   if (nchunk <= 0) return;
-  load_A_tile_async(As, A, lda, tid);
-  load_B_tile_async(Bs, B, ldb, tid);
+  load_A_tile_async<ROWS, THREADS>(As, A, lda, tid);
+  load_B_tile_async<THREADS>(Bs, B, ldb, tid);
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
   for (int c = 0; c < nchunk; ++c) {
     const int cur = c & 1;
     if (c + 1 < nchunk) {
-      load_A_tile_async(As + (cur ^ 1) * CSL_ASZ, A + (long long)(c + 1) * CSL_KC, lda, tid);
-      load_B_tile_async(Bs + (cur ^ 1) * CSL_BSZ, B + (long long)(c + 1) * CSL_KC * ldb, ldb, tid);
+      load_A_tile_async<ROWS, THREADS>(As + (cur ^ 1) * ASZ, A + (long long)(c + 1) * CSL_KC, lda, tid);
+      load_B_tile_async<THREADS>(Bs + (cur ^ 1) * CSL_BSZ, B + (long long)(c + 1) * CSL_KC * ldb, ldb, tid);
       cp_async_commit();
     }
     unsigned m = mmask;
@@ -152,7 +158,7 @@ __device__ __forceinline__ void gemm_stream_AB(double (&acc)[4][4][2], const dou
       for (int mi = 0; mi < 4; ++mi)
         if (tri_row0 + wm0 + mi * 8 + 7 < c * CSL_KC) m &= ~(1u << mi);
     }
-    if (m) warp_mma_chunk(acc, As + cur * CSL_ASZ, Bs + cur * CSL_BSZ, wm0, wn0, lane, m);
+    if (m) warp_mma_chunk(acc, As + cur * ASZ, Bs + cur * CSL_BSZ, wm0, wn0, lane, m);
     cp_async_wait<0>();
     __syncthreads();
   }

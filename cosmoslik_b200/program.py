@@ -235,6 +235,22 @@ class CompiledProgram(object):
         self._dev('Sigma', q.sigma, np.float64)
         self.flops.update(cov_chol=2 * (n * (n + 1) // 2 * K + n ** 3 // 6 + n * n // 2))
 
+    def _index_bound(self, e):
+        """A bound on |idx| for a power-law index expression, the same for every walker: it fixes the Taylor
+        degree of the segmented-sum kernel's recurrence per group of bins (spectrum record CSL_S_IDXBOUND).
+        A parameter with a hard prior box (`min`/`max`/`range`) gives its box -- returned NEGATIVE, meaning
+        "hard": a walker outside it has lnl = +inf whatever chi^2 is, so the kernel need not treat it
+        specially.  Anything else gives 4 ("soft"): walkers outside a soft bound are still evaluated exactly
+        (exp at every column), only slower."""
+        if isinstance(e, Const):
+            return -abs(float(e.v))
+        if isinstance(e, Par):
+            los = [lo for i, lo, hi in self.host.get("box", ()) if i == e.index]
+            his = [hi for i, lo, hi in self.host.get("box", ()) if i == e.index]
+            if los and np.isfinite(max(los)) and np.isfinite(min(his)):
+                return -float(max(abs(max(los)), abs(min(his)), 1e-300))
+        return 4.0
+
     def _build_bandpower(self, P, code, q, factor=True):
         nspec = len(q.blocks)
         spec_tab = np.zeros((nspec, L.SPEC_STRIDE), np.int32)
@@ -294,6 +310,9 @@ class CompiledProgram(object):
                     dl = np.where(np.isfinite(dl), dl, 1e300).astype(np.float64)   # next to a zero base: never "small"
                     ltab[:, NT + 4 * k + 2] = dl
                     rec[L.S_PLAW_AMP + k] = code.coef(amp); rec[L.S_PLAW_IDX + k] = code.coef(idx_e)
+                    bnd = self._index_bound(Expr.wrap(idx_e))      # round the magnitude up, keep the sign flag
+                    bnd = np.copysign(np.nextafter(np.float32(min(abs(bnd), 3e38)), np.float32(np.inf)), np.float32(bnd))
+                    rec[L.S_IDXBOUND + k] = bnd.view(np.int32)
                 else:
                     rec[L.S_PLAW_AMP + k] = rec[L.S_PLAW_IDX + k] = zero_row
             templ.append(ltab.ravel()); toff += ltab.size
@@ -481,7 +500,7 @@ class DeviceProgram(CompiledProgram):
             ws = dict(coef=t.empty((max(self.ncoef, 1), Wp), **kw), prior=t.empty(Wp, **kw),
                       R=t.empty((max(self.n_pad, 1), Wp), **kw) if self.n_pad else None,
                       chi2=t.empty(Wp, **kw) if self.n_pad else None,
-                      part=t.empty((self.n_pad // L.BM, Wp), **kw) if self.n_pad else None,
+                      part=t.empty((self.n_pad // 32, Wp), **kw) if self.n_pad else None,   # one partial per 32 rows
                       x=t.empty((Wp, self.ndim), **kw), lnl=t.empty(Wp, **kw))
             self._ws[Wp] = ws
         return ws

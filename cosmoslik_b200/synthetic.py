@@ -206,6 +206,8 @@ def build_script(ns, prob, sampler=None):
                     kw["min"] = 0
                 if k == "n_cib":
                     kw["range"] = (0.0, 2.0)
+                if k == "n_tilt":
+                    kw["range"] = (-0.5, 0.5)
                 if k in ("y_cal", "cal150", "cal220"):
                     kw["gaussian_prior"] = (1.0, 5 * scales[k])
                 self[k] = ns.param(**kw)

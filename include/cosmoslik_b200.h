@@ -67,7 +67,11 @@ enum {
                         cl[l] = sum_t coef[TERM_COEF[t]] T_t[l]
                               + sum_q coef[PLAW_AMP[q]] M_q[l] exp(coef[PLAW_IDX[q]] logB_q[l])
                         (padding terms point at an all-zero coefficient row / zero columns)  */
-  CSL_S_TERM_COEF = 8, CSL_S_PLAW_AMP = 24, CSL_S_PLAW_IDX = 28
+  CSL_S_TERM_COEF = 8, CSL_S_PLAW_AMP = 24, CSL_S_PLAW_IDX = 28,
+  CSL_S_IDXBOUND = 32 /* [CSL_MAX_PLAW]: float32 bits, a bound on |coef[PLAW_IDX[q]]| the host expects of every walker
+                         (the parameter's prior box, stored NEGATIVE = hard: outside it lnl is +inf anyway;
+                         else +4 = soft: walkers outside it take exp per column): fixes the Taylor degree of
+                         the power-law recurrence per group of bins */
 };
 
 /* tile record, int32 words (table tile_tab[ntile][CSL_TILE_STRIDE]) */
@@ -168,7 +172,7 @@ int csl_direct_residual(const csl_program_t* p, int W, const double* coef, int l
 /* chi2[w] = || L^-1 R[:, w] ||^2 on DMMA (replaces cho_solve + dot, spt_lowl.py:133 / mspec_lnl.py:73).
  *   chi2_mode 0: blocked forward substitution, 64-row blocks, R is overwritten by L^-1 R;
  *   chi2_mode 1: tile products with the host-inverted factor Minv (chosen by the host only when the
- *                inverse reproduces the substitution result to 1e-13); needs ws_part [n_pad/64, ldr]. */
+ *                inverse reproduces the substitution result to 1e-13); needs ws_part [n_pad/32, ldr] (one partial sum per 32 rows). */
 int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part, void* stream);
 
 /* resid_mode 3 (replaces cho_factor(beam_cov + sigma) + cho_solve per call, SPTSZ_lowl.py:66-69):
@@ -182,7 +186,7 @@ int csl_combine(const csl_program_t* p, int W, const double* coef, int ldc, cons
                 const double* chi2, double* lnl, void* stream);
 
 /* The four calls above in sequence.  Workspace (device, caller owned):
- *   coef [ncoef, Wp], prior [Wp], R [n_pad, Wp], chi2 [Wp], part [n_pad/64, Wp]
+ *   coef [ncoef, Wp], prior [Wp], R [n_pad, Wp], chi2 [Wp], part [n_pad/32, Wp]
  *   with Wp = W rounded up to CSL_BN. */
 int csl_lnl(const csl_program_t* p, int W, const double* x, double* lnl,
             double* ws_coef, double* ws_prior, double* ws_R, double* ws_chi2, double* ws_part, void* stream);
