@@ -102,13 +102,16 @@ k_trsm_chi2(csl_program_t p, double* R, int ldr, double* __restrict__ chi2) {
 //   ROWS = 32: 4 warps, 4 CTAs per SM, twice as many (shorter) CTAs -- for launches too small to fill the
 //              GPU with 64-row tiles (a few thousand walkers).  Both shapes run the same DMMA sequence per
 //              32 x 32 warp tile, so chi^2 is bitwise the same whichever is chosen.
+// pipeline depth: 2 stages for the bulk shape (two resident CTAs hide each other's load latency; measured
+// 0.406 vs 0.412 ms with 3), 3 for the small-launch shape (0.066 vs 0.071 ms at 4096 walkers)
+#define CHI2_STAGES(ROWS) ((ROWS) == 32 ? 3 : 2)
 template <int ROWS>
 __global__ void __launch_bounds__(4 * ROWS, 128 / ROWS)
 k_trigemm_chi2(csl_program_t p, const double* __restrict__ R, int ldr, double* __restrict__ part, int grp) {
   constexpr int THREADS = 4 * ROWS, ASZ = ROWS * CSL_LDA;
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
-  double* Bs = As + 2 * ASZ;
+  double* Bs = As + CHI2_STAGES(ROWS) * ASZ;
   const int npad = p.n_pad, nblk = npad / ROWS;
   // CTA order: row block i costs i+1 units, and the hardware hands CTAs out in index order, so the order
   // IS the schedule.  Column tiles are taken in super-groups of `grp` tiles whose R panels fit in L2
@@ -134,8 +137,12 @@ k_trigemm_chi2(csl_program_t p, const double* __restrict__ R, int ldr, double* _
   for (int mi = 0; mi < 4; ++mi)
     if (i * ROWS + wm0 + mi * 8 < p.n) mmask |= 1u << mi;
   const int kend = min((i + 1) * ROWS, (p.n + CSL_KC - 1) / CSL_KC * CSL_KC);
-  gemm_stream_AB<ROWS, THREADS>(acc, p.Minv + (long long)i * ROWS * npad, npad, R + c0, ldr, kend / CSL_KC, As, Bs,
-                                tid, wm0, wn0, lane, mmask, i * ROWS);
+  if (CHI2_STAGES(ROWS) == 3)
+    gemm_stream_AB3<ROWS, THREADS>(acc, p.Minv + (long long)i * ROWS * npad, npad, R + c0, ldr, kend / CSL_KC, As, Bs,
+                                   tid, wm0, wn0, lane, mmask, i * ROWS);
+  else
+    gemm_stream_AB<ROWS, THREADS>(acc, p.Minv + (long long)i * ROWS * npad, npad, R + c0, ldr, kend / CSL_KC, As, Bs,
+                                  tid, wm0, wn0, lane, mmask, i * ROWS);
   double* prow = part + (long long)((i * ROWS + wm0) / 32) * ldr + c0 + wn0;
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni)
@@ -188,7 +195,7 @@ int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi
     if (const char* e = getenv("CSL_TRIGEMM_ROWS")) rows = atoi(e) == 32 ? 32 : 64;
     static bool attr64 = false, attr32 = false;
     if (rows == 64) {
-      const size_t smem1 = (size_t)(2 * CSL_ASZ + 2 * CSL_BSZ) * sizeof(double);
+      const size_t smem1 = (size_t)CHI2_STAGES(64) * (CSL_ASZ + CSL_BSZ) * sizeof(double);
       if (!attr64) {
         cudaError_t e = cudaFuncSetAttribute(k_trigemm_chi2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
@@ -196,7 +203,7 @@ int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi
       }
       k_trigemm_chi2<64><<<ntile * nblk64, 256, smem1, s>>>(*p, R, ldr, ws_part, grp);
     } else {
-      const size_t smem1 = (size_t)(2 * 32 * CSL_LDA + 2 * CSL_BSZ) * sizeof(double);
+      const size_t smem1 = (size_t)CHI2_STAGES(32) * (32 * CSL_LDA + CSL_BSZ) * sizeof(double);
       if (!attr32) {
         cudaError_t e = cudaFuncSetAttribute(k_trigemm_chi2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));

@@ -164,6 +164,43 @@ __device__ __forceinline__ void gemm_stream_AB(double (&acc)[4][4][2], const dou
   }
 }
 
+// The same product through a THREE-stage pipeline: the load of chunk c+2 is issued before chunk c is
+// multiplied, so a chunk has two multiply-times to arrive (one is not enough when a CTA runs alone on its SM,
+// as in launches of a few thousand walkers), still with one CTA barrier per chunk.
+// As / Bs hold 3 stages.
+template <int ROWS = CSL_BM, int THREADS = CSL_THREADS>
+__device__ __forceinline__ void gemm_stream_AB3(double (&acc)[4][4][2], const double* __restrict__ A,
+                                                long long lda, const double* __restrict__ B, long long ldb,
+                                                int nchunk, double* As, double* Bs, int tid, int wm0, int wn0,
+                                                int lane, unsigned mmask, int tri_row0) {
+  constexpr int ASZ = ROWS * CSL_LDA;
+  if (nchunk <= 0) return;
+  auto load = [&](int c) {
+    if (c < nchunk) {
+      const int st = c % 3;
+      load_A_tile_async<ROWS, THREADS>(As + st * ASZ, A + (long long)c * CSL_KC, lda, tid);
+      load_B_tile_async<THREADS>(Bs + st * CSL_BSZ, B + (long long)c * CSL_KC * ldb, ldb, tid);
+    }
+    cp_async_commit();                       // always a group, possibly empty: wait_group counts groups
+  };
+  load(0);
+  load(1);
+  for (int c = 0; c < nchunk; ++c) {
+    cp_async_wait<1>();                      // chunk c has landed (all but the newest group)
+    __syncthreads();                         // ... for every thread; and chunk c-1 is consumed by all
+    load(c + 2);                             // into the stage chunk c-1 occupied
+    unsigned m = mmask;
+    if (tri_row0 >= 0) {
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+        if (tri_row0 + wm0 + mi * 8 + 7 < c * CSL_KC) m &= ~(1u << mi);
+    }
+    const int st = c % 3;
+    if (m) warp_mma_chunk(acc, As + st * ASZ, Bs + st * CSL_BSZ, wm0, wn0, lane, m);
+  }
+  cp_async_wait<0>();
+}
+
 // Same with the B operand already resident in shared memory as [16*nchunk][CSL_LDB].
 __device__ __forceinline__ void gemm_stream_A(double (&acc)[4][4][2], const double* __restrict__ A,
                                               long long lda, const double* Bsm, int nchunk, double* As,
