@@ -6,7 +6,8 @@ chain containers and the ``samplers`` / ``likelihoods`` / ``models`` namespaces.
 """
 from .core import *          # noqa: F401,F403
 from .core import __all__ as _core_all
-from .chains import Chain, Chains, load_chain, get_covariance, combine_covs, gelman_rubin  # noqa: F401
+from .chains import (Chain, Chains, load_chain, load_cosmomc_chain, get_covariance, combine_covs,  # noqa: F401
+                     gelman_rubin)
 from . import samplers, likelihoods, models, dist  # noqa: F401
 
 __all__ = list(_core_all) + ["Chain", "Chains", "load_chain", "get_covariance", "combine_covs", "gelman_rubin",

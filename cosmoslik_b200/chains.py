@@ -8,9 +8,10 @@ records, ``rows`` a structured array with fields f0..fN (lnl, weight, params)
 (metropolis_hastings.py:181-186,211,221,237; emcee.py:40-46,82), which
 ``load_chain`` regroups by chain id (chains.py:930-962).  Files written by this
 package load with the reference's ``load_chain`` and vice versa
-(tests/test_chains_io.py).  Plotting and the CosmoMC text loaders are out of
-scope.
+(tests/test_chains_io.py).  ``load_cosmomc_chain`` reads the text formats
+(chains.py:805-880) that ``Chain.savechain`` writes.  Plotting is out of scope.
 """
+import os
 import pickle
 import re
 from itertools import chain as _iterchain
@@ -18,11 +19,22 @@ from itertools import chain as _iterchain
 import numpy as np
 
 __all__ = ["Chain", "Chains", "get_covariance", "get_correlation", "combine_covs", "load_chain",
-           "ChainWriter", "gelman_rubin", "device_summary"]
+           "load_cosmomc_chain", "ChainWriter", "gelman_rubin", "device_summary"]
 
 
 def _is_listlike(v):
     return not isinstance(v, str) and hasattr(v, "__iter__")
+
+
+class _RowCall(object):
+    """picklable `row -> func(**row)` for pool.map"""
+    def __init__(self, func): self.func = func
+    def __call__(self, row): return self.func(**row)
+
+
+class _Reweight(object):
+    def __init__(self, func): self.func = func
+    def __call__(self, weight, **row): return {"weight": weight * self.func(weight=weight, **row)}
 
 
 class Chain(dict):
@@ -82,6 +94,42 @@ class Chain(dict):
     def skew(self, params=None):
         d = self.matrix(params) - self.mean(params)
         return np.average(d ** 3, axis=0, weights=self["weight"]) / self.std(params) ** 3
+
+    def confbound(self, param, level=0.95, bound=None):
+        """Upper or lower confidence bound from the weighted 1000-bin histogram (chains.py:98-119);
+        bound=None picks 'upper' for positively skewed parameters."""
+        if bound is None:
+            bound = "upper" if self.skew(param) > 0 else "lower"
+        if bound == "lower":
+            level = 1 - level
+        H, x = np.histogram(self[param], weights=self["weight"], bins=1000)
+        xc = (x[1:] + x[:-1]) / 2
+        b = np.interp(level, np.cumsum(H) / float(H.sum()), xc)
+        return (self[param].min(), b) if bound == "upper" else (b, self[param].max())
+
+    def postprocd(self, func, nthreads=1, pool=None):
+        """A new chain with the keys `func(**row)` returns added, row by row (chains.py:133-176); rows for which
+        a key is missing get nan.  `pool` is anything with a `.map`; nthreads > 1 makes a process pool."""
+        own = None
+        if pool is None and nthreads != 1:
+            import multiprocessing
+            own = pool = multiprocessing.Pool(nthreads)
+        try:
+            mapper = map if pool is None else pool.map
+            out = list(mapper(_RowCall(func), self.iterrows()))
+        finally:
+            if own is not None:
+                own.terminate()
+        c = self.copy()
+        keys = []
+        for d in out:
+            keys += [k for k in d if k not in keys]
+        c.update({k: np.array([d.get(k, np.nan) for d in out]) for k in keys})
+        return c
+
+    def reweighted(self, func, nthreads=1, pool=None):
+        """A new chain whose weights are multiplied by `func(**row)` (chains.py:178-203)."""
+        return self.postprocd(_Reweight(func), nthreads=nthreads, pool=pool)
 
     def acceptance(self):
         return 1.0 / np.mean(self["weight"])
@@ -309,9 +357,11 @@ class ChainWriter(object):
             self.f.close()
 
 
-def load_chain(filename):
-    """Load a chain file written by this package or by the reference's samplers;
-    also accepts a file holding one pickled Chain / Chains."""
+def load_chain(filename, repack=False):
+    """Load a chain file written by this package or by the reference's samplers (chains.py:930-962);
+    also accepts a file holding one pickled Chain / Chains.  repack=True rewrites a block-structured file
+    as one pickled Chains object (faster to load next time) unless another process still has it open for
+    writing (chains.py:964-976)."""
     with open(filename, "rb") as f:
         head = pickle.load(f)
         if isinstance(head, (Chain, Chains)):
@@ -334,4 +384,89 @@ def load_chain(filename):
             out.append(Chain({n: np.concatenate([b["f%d" % k] for b in blocks]) for k, n in enumerate(names)}))
         else:
             out.append(Chain(dict(zip(names, np.vstack(blocks).T))))
+    if repack and not _open_for_writing(filename):
+        tmp = filename + ".repack"
+        with open(tmp, "wb") as f:
+            pickle.dump(out, f)
+        os.replace(tmp, filename)
     return out
+
+
+def _open_for_writing(filename):
+    """True if some process holds `filename` open for writing (the chain is still running)."""
+    target = os.path.realpath(filename)
+    try:
+        pids = [p for p in os.listdir("/proc") if p.isdigit()]
+    except OSError:
+        return True                       # cannot tell: do not touch the file
+    for pid in pids:
+        fddir = "/proc/%s/fd" % pid
+        try:
+            fds = os.listdir(fddir)
+        except OSError:
+            continue
+        for fd in fds:
+            try:
+                if os.path.realpath(os.path.join(fddir, fd)) != target:
+                    continue
+                with open("/proc/%s/fdinfo/%s" % (pid, fd)) as g:
+                    flags = [ln for ln in g if ln.startswith("flags:")]
+                if flags and int(flags[0].split()[1], 8) & 3:      # O_WRONLY or O_RDWR
+                    return True
+            except (OSError, ValueError):
+                continue
+    return False
+
+
+def load_cosmomc_chain(path, paramnames=None):
+    """Text chains (chains.py:805-880): a file whose first line is `# name name ...` (what `Chain.savechain`
+    writes), a CosmoMC file with a `<root>.paramnames` beside it (columns weight, lnl, parameters...), a
+    directory with one file per parameter (WMAP style; last column is the value), or a prefix with
+    `<path>_1, <path>_2, ...` -> Chains."""
+
+    def names_from(pn):
+        with open(pn) as f:
+            return ["weight", "lnl"] + [line.split()[0] for line in f if line.strip()]
+
+    def one(fn, names):
+        if os.path.isdir(fn):
+            if names is not None:
+                raise ValueError("Can't specify custom parameter names if loading chain from a directory.")
+            cols = {}
+            for k in sorted(os.listdir(fn)):
+                try:
+                    cols[k] = np.loadtxt(os.path.join(fn, k), usecols=[-1])
+                except Exception:
+                    pass
+            return Chain(cols)
+        if names is None:
+            d, base = os.path.dirname(fn), os.path.basename(fn)
+            pn = [os.path.join(d, f) for f in os.listdir(d)
+                  if f.endswith(".paramnames") and base.startswith(f[:-len(".paramnames")])]
+            if len(pn) > 1:
+                raise ValueError("Found multiple paramnames files for this chain; %s" % pn)
+            if pn:
+                names = names_from(pn[0])
+        elif isinstance(names, str):
+            names = names_from(names)
+        with open(fn) as f:
+            if names is None:
+                line = f.readline()
+                if not line.startswith("#"):
+                    raise ValueError("Couldn't find any paramnames. Specify paramnames=... by hand.")
+                names = line.replace("#", "").split()
+            try:
+                data = np.loadtxt(f, ndmin=2).T
+            except Exception:
+                return None
+        return Chain(zip(names, data))
+
+    path = os.path.abspath(path)
+    d, base = os.path.dirname(path), os.path.basename(path)
+    files = sorted(os.path.join(d, f) for f in os.listdir(d)
+                   if f == base or re.fullmatch(re.escape(base) + r"_[0-9]+(\.txt)?", f))
+    if len(files) == 1:
+        return one(files[0], paramnames)
+    if len(files) > 1:
+        return Chains([c for c in (one(f, paramnames) for f in files) if c is not None])
+    raise IOError("File not found: " + path)

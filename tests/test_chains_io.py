@@ -114,3 +114,91 @@ def test_gelman_rubin_host():
     ref = osamp.gelman_rubin([m[0] for m in mom], [m[1] for m in mom], [m[2] for m in mom])
     np.testing.assert_allclose(got, ref, rtol=1e-13)
     assert set(chains.gelman_rubin()) == {"x", "y"}
+
+
+# ---- text formats and row-wise post-processing -----------------------------
+def _toy_chain(seed=0, n=400):
+    rs = np.random.RandomState(seed)
+    return Chain(lnl=rs.chisquare(3, n), weight=rs.randint(1, 6, n).astype(float), a=rs.standard_normal(n),
+                 b=rs.standard_normal(n) ** 2)
+
+
+def test_savechain_text_round_trip_and_cosmomc_layouts(tmp_path):
+    from cosmoslik_b200 import load_cosmomc_chain
+    c = _toy_chain()
+    p = str(tmp_path / "one.txt")
+    c.savechain(p)
+    back = load_cosmomc_chain(p)
+    assert list(back.keys()) == ["lnl", "weight", "a", "b"]
+    for k in back:
+        np.testing.assert_allclose(back[k], c[k], rtol=1e-15)
+    # CosmoMC layout: root_1.txt, root_2.txt + root.paramnames (columns: weight, lnl, parameters)
+    for i in (1, 2):
+        cc = _toy_chain(i)
+        np.savetxt(str(tmp_path / ("run_%d.txt" % i)), np.column_stack([cc["weight"], cc["lnl"], cc["a"], cc["b"]]))
+    (tmp_path / "run.paramnames").write_text("a   a_{label}\nb   b\n")
+    cs = load_cosmomc_chain(str(tmp_path / "run"))
+    assert isinstance(cs, Chains) and len(cs) == 2
+    np.testing.assert_allclose(cs[0]["a"], _toy_chain(1)["a"], rtol=1e-15)
+    np.testing.assert_allclose(cs[1]["weight"], _toy_chain(2)["weight"])
+    # one file per parameter (WMAP style): the last column is the value
+    d = tmp_path / "wmap"; d.mkdir()
+    np.savetxt(str(d / "omegabh2"), np.column_stack([np.arange(5), np.linspace(0.02, 0.03, 5)]))
+    w = load_cosmomc_chain(str(d))
+    np.testing.assert_allclose(w["omegabh2"], np.linspace(0.02, 0.03, 5))
+    with pytest.raises(IOError):
+        load_cosmomc_chain(str(tmp_path / "nothing_here"))
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted")
+def test_text_chain_written_here_loads_with_the_reference(tmp_path):
+    R = refshim.load()
+    c = _toy_chain(3)
+    p = str(tmp_path / "x.txt")
+    c.savechain(p); c.savecov(str(tmp_path / "x.cov"))
+    import cosmoslik.chains as rch
+    rc = rch.load_cosmomc_chain(p)
+    for k in ("lnl", "weight", "a", "b"):
+        np.testing.assert_allclose(rc[k], c[k], rtol=1e-15)
+    rc2 = rch.Chain(dict(c))
+    np.testing.assert_allclose(np.loadtxt(str(tmp_path / "x.cov")), rc2.cov(["a", "b"]), rtol=1e-12)
+    # the same statistics through both containers
+    np.testing.assert_allclose(c.confbound("b"), rc2.confbound("b"), rtol=1e-12)
+    np.testing.assert_allclose(c.confbound("a", level=0.68, bound="lower"), rc2.confbound("a", level=0.68, bound="lower"),
+                               rtol=1e-12)
+    f = lambda a, **_: np.exp(-a ** 2 / 2)
+    np.testing.assert_allclose(c.reweighted(f)["weight"], rc2.reweighted(f)["weight"], rtol=1e-15)
+    g = lambda a, b, **_: {"s": a + b} if a > 0 else {}
+    np.testing.assert_array_equal(c.postprocd(g)["s"], rc2.postprocd(g)["s"])
+
+
+def test_reweighted_and_postprocd_without_the_reference():
+    c = _toy_chain(4)
+    r = c.reweighted(lambda a, **_: np.exp(-a ** 2 / 2))
+    np.testing.assert_allclose(r["weight"], c["weight"] * np.exp(-c["a"] ** 2 / 2), rtol=1e-15)
+    assert r is not c and np.array_equal(r["a"], c["a"])
+    pp = c.postprocd(lambda a, b, **_: {"s": a + b} if a > 0 else {})
+    assert np.all(np.isnan(pp["s"][c["a"] <= 0])) and np.allclose(pp["s"][c["a"] > 0], (c["a"] + c["b"])[c["a"] > 0])
+    lo, hi = c.confbound("b", level=0.95)
+    assert lo == c["b"].min() and c["b"].min() < hi < c["b"].max()          # positively skewed -> upper bound
+
+
+def test_load_chain_repack(tmp_path):
+    path = str(tmp_path / "blocks.chain")
+    w = ChainWriter(path, ["lnl", "weight", "a"], "ndarray")
+    rs = np.random.RandomState(1)
+    for cid in (0, 1, 0, 1):
+        w.write(cid, rs.standard_normal((5, 3)))
+    # still open for writing: repack must leave the file alone
+    w.flush()
+    before = open(path, "rb").read()
+    c1 = load_chain(path, repack=True)
+    assert open(path, "rb").read() == before
+    w.close()
+    c2 = load_chain(path, repack=True)
+    assert open(path, "rb").read() != before
+    c3 = load_chain(path)                                   # now a single pickled Chains
+    assert isinstance(c3, Chains) and len(c3) == 2
+    for x, y, z in zip(c1, c2, c3):
+        for k in x:
+            np.testing.assert_array_equal(x[k], y[k]); np.testing.assert_array_equal(x[k], z[k])
