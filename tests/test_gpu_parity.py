@@ -149,6 +149,42 @@ def test_both_binning_kernels_match_the_oracle(torch, binning):
     assert relerr(slik.evaluate_batch(X), ref) < RTOL
 
 
+def test_segmented_binning_index_bounds_and_position_independence(torch):
+    """The Taylor degree of the power-law recurrence is fixed per bin group from the host's bound on the
+    index: a prior box is a hard bound, a parameter without one gets the soft bound 4 and walkers beyond it
+    are re-run in the exact-exp mode.  Either way lnl matches the oracle and a walker's value does not depend
+    on its position in the batch (bitwise)."""
+    prob = synthetic.planck_lite_problem(6)
+
+    def unboxed(ns):
+        scr = synthetic.build_script(ns, prob)()
+        for k in ("n_cib", "n_tilt"):
+            scr[k].__dict__.pop("range", None)
+        return scr
+
+    oslik, slik = ort.Slik(unboxed(ORACLE)), Slik(unboxed(PRODUCT))
+    prog = slik.program(binning="segsum")
+    bounds = prog.host["spec_tab"][:, L.S_IDXBOUND:L.S_IDXBOUND + 2].view(np.float32)
+    assert np.all((bounds == 0) | (bounds >= 4.0))                 # soft (positive) bounds only
+    boxed = Slik(synthetic.build_script(PRODUCT, prob)()).program(binning="segsum")
+    hb = boxed.host["spec_tab"][:, L.S_IDXBOUND:L.S_IDXBOUND + 2].view(np.float32)
+    assert np.all(hb <= 0) and np.any(np.isclose(hb, -2.0)) and np.any(np.isclose(hb, -0.5))   # hard = negative
+    names = list(slik.get_sampled())
+    x0 = np.array([prob["truth"][k] for k in names]); sc = np.array([prob["scales"][k] for k in names])
+    rs = np.random.RandomState(12)
+    X = x0 + sc * rs.standard_normal((1024, len(names)))
+    wild = rs.choice(1024, 37, replace=False)                      # indices far outside the soft bound
+    X[wild, names.index("n_cib")] = rs.uniform(4.5, 6.0, wild.size) * rs.choice([-1, 1], wild.size)
+    X[wild[:9], names.index("n_tilt")] = rs.uniform(4.1, 5.0, 9)
+    got = slik.evaluate_batch(X)
+    pick = np.concatenate([wild, rs.choice(1024, 40, replace=False)])
+    ref = np.array([oslik.evaluate(*X[i])[0] for i in pick])
+    assert relerr(got[pick], ref) < RTOL
+    perm = rs.permutation(1024)
+    np.testing.assert_array_equal(slik.evaluate_batch(X[perm]), got[perm])
+    np.testing.assert_array_equal(slik.evaluate_batch(X[:300]), got[:300])        # another tile shape, same bits
+
+
 def test_segmented_binning_with_ragged_walker_counts(torch):
     """walker counts that leave the last 256-walker CTA of k_bin_segsum half empty"""
     prob = synthetic.planck_lite_problem(5)

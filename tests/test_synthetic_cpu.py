@@ -46,3 +46,42 @@ def test_spt_multifreq_shape():
     x0 = np.array([oslik.get_start()[k] for k in cp.names])
     ref = oslik.evaluate(*x0)[0]
     assert abs(TI.lnl(cp, x0) - ref) <= 1e-10 * abs(ref)
+
+
+def test_segmented_sum_tables(planck):
+    """Host tables of k_bin_segsum: the weighted column table is window weight x ell-table row, the bins of a
+    group are contiguous in it, groups are sorted longest first within a class, and index bounds from prior
+    boxes are stored negative (hard)."""
+    from cosmoslik_b200 import _lib as L
+    slik = Slik(synthetic.build_script(PRODUCT, planck)())
+    cp = CompiledProgram(list(slik.get_sampled()), slik.params.priors, slik.trace(), binning="segsum")
+    assert cp.meta["nsegclass"] == 2 and cp.meta["nclass"] == 0
+    bt, st = cp.host["bin_tab"], cp.host["spec_tab"]
+    tpl, win = cp.tables["templates"], cp.tables["windows"]
+    for c in range(cp.meta["nsegclass"]):
+        NT, NP, b0, nb = (int(v) for v in cp.segcls[c])
+        RS, LS = NT + 2 * NP, NT + 4 * NP
+        assert nb % L.SEG_GROUP == 0
+        widths = []
+        for g0 in range(b0, b0 + nb, L.SEG_GROUP):
+            recs = bt[g0:g0 + L.SEG_GROUP]
+            live = [r for r in recs if r[L.B_ROW] >= 0 and r[L.B_HI] > r[L.B_LO]]
+            widths.append(sum(int(r[L.B_HI] - r[L.B_LO]) for r in live))
+            off = None
+            for r in live:
+                t = (int(r[L.B_TABOFF_HI]) << 32) | (int(r[L.B_TABOFF_LO]) & 0xFFFFFFFF)
+                assert off is None or t == off                       # contiguous, in record order
+                lo, hi = int(r[L.B_LO]), int(r[L.B_HI])
+                woff = (int(r[L.B_WINOFF_HI]) << 32) | (int(r[L.B_WINOFF_LO]) & 0xFFFFFFFF)
+                w = win[woff + lo:woff + hi]
+                base = int(st[r[L.B_SPEC]][L.S_LTAB])
+                rows = tpl[base + lo * LS:base + hi * LS].reshape(hi - lo, LS)
+                cols = tpl[t:t + (hi - lo) * RS].reshape(hi - lo, RS)
+                np.testing.assert_array_equal(cols[:, :NT], w[:, None] * rows[:, :NT])
+                np.testing.assert_array_equal(cols[:, NT:NT + NP], w[:, None] * rows[:, NT + 1::4][:, :NP])
+                np.testing.assert_array_equal(cols[:, NT + NP:], rows[:, NT + 2::4][:, :NP])
+                off = t + (hi - lo) * RS
+        assert widths == sorted(widths, reverse=True)
+    hb = st[:, L.S_IDXBOUND:L.S_IDXBOUND + 2].view(np.float32)
+    assert np.all(hb <= 0) and np.any(np.isclose(hb, -2.0)) and np.any(np.isclose(hb, -0.5))
+    assert cp.flops["seg_flops"] > 0
