@@ -66,8 +66,19 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
     constexpr int NCH = CSL_KC * LSTRIDE / 2;
     for (int c = tid; c < NCH; c += CSL_THREADS) cp_async16(L + 2 * c, ltab + (long long)l0 * LSTRIDE + 2 * c);
   };
-  // 8 consecutive columns per thread: one exact exp at the first, Taylor advances after it (warp votes pick
-  // the degree; a column pair with a large log-step falls back to exp)
+  // the host's bound on |idx_q| (spectrum record; negative = hard bound from a prior box): the Taylor degree of
+  // a column is chosen from bound * |D|, the same for every walker, so a walker's value never depends on its
+  // neighbours; a walker outside a soft bound takes exp at every column
+  double bnd[NP > 0 ? NP : 1];
+  bool inside[NP > 0 ? NP : 1];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    const float bq = __int_as_float(spec[CSL_S_IDXBOUND + q]);
+    bnd[q] = fabs((double)bq);
+    inside[q] = bq < 0.f || fabs(pidx[q]) <= bnd[q];
+  }
+  // 8 consecutive columns per thread: one exact exp at the first, Taylor advances after it (a column with a
+  // large log-step falls back to exp)
   auto build_B = [&](double* B, const double* L) {
     const double* row = L + grp * (CSL_KC / 2) * LSTRIDE;     // warp-uniform address -> shared-memory broadcast
     double E[NP > 0 ? NP : 1];
@@ -84,10 +95,10 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
       if (r + 1 < CSL_KC / 2) {
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-          const double y = pidx[q] * row[NT + 4 * q + 2];
-          const double ay = fabs(y);
-          if (__all_sync(0xffffffffu, ay <= 0.012)) E[q] *= exp_taylor<6>(y);
-          else if (__all_sync(0xffffffffu, ay <= 0.1)) E[q] *= exp_taylor<10>(y);
+          const double D = row[NT + 4 * q + 2];
+          const double y = pidx[q] * D, ay = bnd[q] * fabs(D);      // ay: warp-uniform (broadcast row)
+          if (ay <= 0.012 && inside[q]) E[q] *= exp_taylor<6>(y);
+          else if (ay <= 0.1 && inside[q]) E[q] *= exp_taylor<10>(y);
           else E[q] = exp(pidx[q] * row[LSTRIDE + NT + 4 * q]);
         }
       }

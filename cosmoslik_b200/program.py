@@ -514,9 +514,11 @@ class DeviceProgram(CompiledProgram):
                 and x.shape[1] == self.ndim and x.is_contiguous()):
             raise ValueError("x must be a contiguous float64 CUDA tensor [W, %d]" % self.ndim)
         W = x.shape[0]
-        ws = self.workspace(W)
         if out is None:
             out = t.empty(W, dtype=t.float64, device=self.device)
+        if W == 0:                      # an empty batch has an empty answer; nothing is launched
+            return out
+        ws = self.workspace(W)
         st = L.stream_ptr()
         if timers is None:
             L.check(self.lib.csl_lnl(C.byref(self.struct), W, x.data_ptr(), out.data_ptr(), ws["coef"].data_ptr(),
@@ -556,10 +558,14 @@ class DeviceProgram(CompiledProgram):
     def lnl_host(self, x_host, out_host=None):
         """End-to-end evaluation with HOST numpy buffers through csl_lnl_host (H2D, kernels, D2H)."""
         x_host = np.ascontiguousarray(x_host, dtype=np.float64)
+        if x_host.ndim != 2 or x_host.shape[1] != self.ndim:
+            raise ValueError("x must be an array [W, %d]" % self.ndim)
         W = x_host.shape[0]
-        ws = self.workspace(W)
         if out_host is None:
             out_host = np.empty(W)
+        if W == 0:
+            return out_host
+        ws = self.workspace(W)
         L.check(self.lib.csl_lnl_host(C.byref(self.struct), W, x_host.ctypes.data, out_host.ctypes.data,
                                       ws["x"].data_ptr(), ws["lnl"].data_ptr(), ws["coef"].data_ptr(),
                                       ws["prior"].data_ptr(), L.ptr(ws["R"]), L.ptr(ws["chi2"]), L.ptr(ws["part"]),

@@ -264,6 +264,25 @@ def check_rows(rows, g, lnl_exact=False):
     return x
 
 
+def test_empty_batch_and_bad_shapes(torch, spt_data):
+    g = golden("spt_lowl_lnl.npz")
+    slik = Slik(B.spt_script(spt_data, "s12", g["tt"])())
+    nd = len(slik.get_sampled())
+    assert slik.evaluate_batch(np.empty((0, nd))).shape == (0,)
+    assert tuple(slik.evaluate_batch(torch.empty((0, nd), dtype=torch.float64, device="cuda")).shape) == (0,)
+    with pytest.raises(ValueError):
+        slik.evaluate_batch(np.zeros((3, nd + 1)))
+    with pytest.raises(ValueError):
+        slik.evaluate_batch(torch.zeros((3, nd), dtype=torch.float32, device="cuda"))
+    # NaN parameters: a NaN fails every prior box (priors.py:26-28) -> +inf, like the reference
+    x = np.array(g["s12_x"][:4])
+    x[1, 0] = np.nan
+    out = slik.evaluate_batch(x)
+    ref = np.array(g["s12_lnl"][:4])
+    assert np.isfinite(out[[0, 2, 3]]).all() and relerr(out[[0, 2, 3]], ref[[0, 2, 3]]) < RTOL
+    assert np.isinf(out[1]) or np.isnan(out[1])
+
+
 def test_mh_quickstart_matches_the_reference_chain(torch, tmp_path):
     """config 1 script, generic per-step path; z @ F runs on the device so positions agree to
     rounding of a 2-term dot product, decisions and weights exactly"""
