@@ -17,7 +17,8 @@ OP = dict(PUSHP=0, PUSHC=1, ADD=2, SUB=3, MUL=4, DIV=5, NEG=6, EXP=7, LOG=8, POW
 S_NLPAD, S_NTERM, S_NPLAW, S_CAL = 0, 1, 2, 3
 S_LTAB, S_CALMODE, S_TERM_COEF, S_PLAW_AMP, S_PLAW_IDX, S_IDXBOUND = 4, 5, 8, 24, 28, 32
 MAX_CLASS = 8
-BIN_STRIDE, SEG_GROUP = 16, 8
+BIN_STRIDE, SEG_GROUP, GRP_STRIDE = 16, 8, 128
+G_PRE, G_LO, G_ROW, G_CONT, G_MODE, G_BASE_LO, G_BASE_HI, G_SPEC, G_DATA, G_LOGB = 0, 9, 17, 25, 33, 34, 35, 36, 40, 56
 B_ROW, B_SPEC, B_LO, B_HI, B_WINOFF_LO, B_WINOFF_HI, B_TABOFF_LO, B_TABOFF_HI, B_DMAX = 0, 1, 2, 3, 4, 5, 6, 7, 8
 T_ROW0, T_NROWS, T_SPEC, T_LBEGIN, T_LEND, T_WINOFF_LO, T_WINOFF_HI, T_WINLD, T_GLO, T_GHI = 0, 1, 2, 3, 4, 5, 6, 7, 8, 16
 
@@ -35,7 +36,8 @@ class Program(C.Structure):
                   "gauss_idx", "gauss_c", "gauss_w", "scalar_coef", "spec_tab", "tile_tab",
                   "templates", "windows", "data", "direct_coef", "Lmat", "Linv_diag", "Minv")] +
                 [("chi2_mode", C.c_int32), ("nsegclass", C.c_int32), ("segcls", (C.c_int32 * 4) * 8),
-                 ("bin_tab", C.c_void_p), ("Sigma", C.c_void_p), ("n_base", C.c_int32), ("nmode", C.c_int32)])
+                 ("bin_tab", C.c_void_p), ("Sigma", C.c_void_p), ("n_base", C.c_int32), ("nmode", C.c_int32),
+                 ("grp_tab", C.c_void_p)])
 
 
 class Ensemble(C.Structure):

@@ -267,19 +267,12 @@ template <int NT, int NP>
 __global__ void __launch_bounds__(SEG_TPB, SEG_MINB)
 k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restrict__ coef, int ldc,
              double* __restrict__ R, int ldr) {
-  constexpr int LSTRIDE = NT + 4 * NP;
   constexpr int RS = NT + 2 * NP;                    // > 0: the host never emits an empty class
   constexpr int CAP = SEG_SMEM_DOUBLES / (RS > 0 ? RS : 1);
   constexpr int NPX = NP > 0 ? NP : 1, NTX = NT > 0 ? NT : 1;
   static_assert(RS % 2 == 0, "staged rows are copied in 16-byte pieces");
   __shared__ __align__(16) double srow[SEG_SMEM_DOUBLES];
-  __shared__ int slo[CSL_SEG_GROUP], srw[CSL_SEG_GROUP], spre[CSL_SEG_GROUP + 1];
-  __shared__ float sbound[CSL_MAX_PLAW];             // host bound on |idx_q| of this spectrum
-  __shared__ int smode;                              // the group's static Taylor mode
-  __shared__ int scont[CSL_SEG_GROUP];               // bin starts at the column where the previous bin ended
-  __shared__ double slogb[CSL_SEG_GROUP][NPX];       // logB_q at each bin's first column
-  __shared__ long long sbase;
-  __shared__ double sdat[CSL_SEG_GROUP];             // data value of each bin's residual row
+  __shared__ __align__(16) int32_t sg[CSL_GRP_STRIDE];          // the group record (host-built, CSL_G_*)
   const int tid = threadIdx.x;
   int w[SEG_WPT];
   bool live_w[SEG_WPT];
@@ -289,48 +282,30 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
     live_w[j] = w[j] < W;
     if (!live_w[j]) w[j] = W - 1;             // replay a valid walker, never stored
   }
-  const int b_begin = bin0 + blockIdx.y * CSL_SEG_GROUP;
-  const int32_t* first = p.bin_tab + (long long)b_begin * CSL_BIN_STRIDE;
-  const int32_t* spec = p.spec_tab + (long long)first[CSL_B_SPEC] * CSL_SPEC_STRIDE;   // one spectrum per group
+  // bin records come in whole groups and classes start on a group boundary: group = bin0 / 8 + blockIdx.y
+  const int32_t* __restrict__ grec = p.grp_tab + (long long)(bin0 / CSL_SEG_GROUP + blockIdx.y) * CSL_GRP_STRIDE;
+  if (tid < CSL_GRP_STRIDE / 4)
+    reinterpret_cast<int4*>(sg)[tid] = __ldg(reinterpret_cast<const int4*>(grec) + tid);
+  const int32_t* spec = p.spec_tab + (long long)__ldg(grec + CSL_G_SPEC) * CSL_SPEC_STRIDE;   // one spectrum per group
   const double* __restrict__ ltab = p.templates + spec[CSL_S_LTAB];
-  if (tid == 0) {
-    int pre = 0, prev_hi = -1;                                 // columns of the group, back to back
-    long long base = -1;
-    float gmax[CSL_MAX_PLAW] = {0.f, 0.f, 0.f, 0.f};
-    for (int b = 0; b < CSL_SEG_GROUP; ++b) {
-      const int32_t* rec = first + b * CSL_BIN_STRIDE;        // records are padded to whole groups
-      const bool live = (b_begin + b < bin0 + nbins) && rec[CSL_B_ROW] >= 0;
-      const int ncol = live ? max(rec[CSL_B_HI] - rec[CSL_B_LO], 0) : 0;
-      slo[b] = live ? rec[CSL_B_LO] : 0;
-      srw[b] = live ? rec[CSL_B_ROW] : -1;
-      if (ncol > 0 && base < 0) base = ((long long)rec[CSL_B_TABOFF_HI] << 32) | (unsigned)rec[CSL_B_TABOFF_LO];
-      scont[b] = ncol > 0 && rec[CSL_B_LO] == prev_hi;
-      if (ncol > 0) {
-        prev_hi = rec[CSL_B_HI];
-        for (int q = 0; q < CSL_MAX_PLAW; ++q) gmax[q] = fmaxf(gmax[q], __int_as_float(rec[CSL_B_DMAX + q]));
-      }
-      spre[b] = pre;
-      pre += ncol;
-    }
-    spre[CSL_SEG_GROUP] = pre;
-    sbase = base < 0 ? 0 : base;
-    double ym = 0.0;
-    for (int q = 0; q < CSL_MAX_PLAW; ++q) {
-      const float bq = __int_as_float(spec[CSL_S_IDXBOUND + q]);
-      sbound[q] = bq;
-      if (q < NP) ym = fmax(ym, fabs((double)bq) * (double)gmax[q]);
-    }
-    smode = ym <= 0.0035 ? 0 : ym <= 0.012 ? 1 : ym <= 0.1 ? 2 : 3;
-  }
-  if (NP > 0 && tid < CSL_SEG_GROUP * NP) {                    // independent of tid 0's loop: the records again
-    const int b = tid / NPX, q = tid % NPX;
-    const int32_t* rec = first + b * CSL_BIN_STRIDE;
-    slogb[b][q] = __ldg(ltab + (long long)max(rec[CSL_B_LO], 0) * LSTRIDE + NT + 4 * q);
-  }
-  if (tid >= 64 && tid < 64 + CSL_SEG_GROUP) {
-    const int row = first[(tid - 64) * CSL_BIN_STRIDE + CSL_B_ROW];
-    sdat[tid - 64] = row >= 0 ? __ldg(p.data + row) : 0.0;
-  }
+  // columns p0 .. p0+CAP of the group -> shared memory (weighted rows, contiguous in the host-built table).
+  // The first pass is issued here, from the record in global memory, so it flies together with the record
+  // and coefficient loads; one barrier later everything is in place.
+  const int total = __ldg(grec + CSL_G_PRE + CSL_SEG_GROUP);
+  const long long sbase = ((long long)__ldg(grec + CSL_G_BASE_HI) << 32) | (unsigned)__ldg(grec + CSL_G_BASE_LO);
+  auto stage = [&](int p0) {
+    const double* __restrict__ gsrc = p.templates + sbase + (long long)p0 * RS;
+    const int n16 = (min(p0 + CAP, total) - p0) * RS / 2;
+    for (int i = tid; i < n16; i += SEG_TPB) cp_async16(srow + 2 * i, gsrc + 2 * i);
+    cp_async_commit();
+  };
+  stage(0);
+  const int* spre = sg + CSL_G_PRE;
+  const int* slo = sg + CSL_G_LO;
+  const int* srw = sg + CSL_G_ROW;
+  const int* scont = sg + CSL_G_CONT;
+  const double* sdat = reinterpret_cast<const double*>(sg + CSL_G_DATA);
+  const double (*slogb)[CSL_MAX_PLAW] = reinterpret_cast<const double (*)[CSL_MAX_PLAW]>(sg + CSL_G_LOGB);
   double cf[SEG_WPT][NTX], pamp[SEG_WPT][NPX], pidx[SEG_WPT][NPX], cal[SEG_WPT];
   const int calrow = spec[CSL_S_CAL];
   const bool cal_on_model = spec[CSL_S_CALMODE] != 0;      // r = d - cal*b  (SPTSZ_lowl.py:68)
@@ -345,8 +320,8 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
     }
     cal[j] = calrow >= 0 ? coef[(long long)calrow * ldc + w[j]] : 1.0;
   }
+  cp_async_wait<0>();
   __syncthreads();
-  const int total = spre[CSL_SEG_GROUP];
   double E[SEG_WPT][NPX], at[SEG_WPT], ap[SEG_WPT];       // running state of the bin being summed
 #pragma unroll
   for (int j = 0; j < SEG_WPT; ++j) {
@@ -354,18 +329,21 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
 #pragma unroll
     for (int q = 0; q < NPX; ++q) E[j][q] = 0.0;
   }
-  // Taylor degree: ONE static choice per group, from the largest |D| of its bins and the host's bound on
-  // |idx| (spectrum record: the prior box of the index parameter, else 4) -- the same
+  // Taylor degree: ONE static choice per group (group record, computed by the host from the largest |D| of
+  // its bins and its bound on |idx|: the prior box of the index parameter, else 4) -- the same
   // for every walker, so a walker's arithmetic never depends on which walkers share its thread, warp or GPU.
   // A walker whose index lies outside a SOFT bound takes the exact-exp mode instead; outside a hard bound (a
   // prior box, stored negative) its lnl is +inf whatever this kernel computes, so it needs no special care.
+  const int smode = sg[CSL_G_MODE];
   int mode[SEG_WPT];
 #pragma unroll
   for (int j = 0; j < SEG_WPT; ++j) {
     bool inside = true;
 #pragma unroll
-    for (int q = 0; q < NP; ++q)     // hard bounds (stored negative) need no check; NaN -> outside
-      inside = inside && (sbound[q] < 0.f || fabs(pidx[j][q]) <= (double)sbound[q]);
+    for (int q = 0; q < NP; ++q) {   // hard bounds (stored negative) need no check; NaN -> outside
+      const float bq = __int_as_float(spec[CSL_S_IDXBOUND + q]);
+      inside = inside && (bq < 0.f || fabs(pidx[j][q]) <= (double)bq);
+    }
     mode[j] = inside ? smode : 3;
   }
   // if any thread of the CTA holds two walkers of different modes, every thread runs the group twice, once
@@ -377,15 +355,11 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
   const unsigned store_mask = split ? (1u << run) : ~0u;
   for (int p0 = 0; p0 < total; p0 += CAP) {
     const int p1 = min(p0 + CAP, total);
-    // stage columns p0 .. p1 of the group (weighted rows, contiguous in the host-built table)
-    {
-      const double* __restrict__ gsrc = p.templates + sbase + (long long)p0 * RS;
-      const int n16 = (p1 - p0) * RS / 2;
-      for (int i = tid; i < n16; i += SEG_TPB) cp_async16(srow + 2 * i, gsrc + 2 * i);
-      cp_async_commit();
+    if (p0 > 0 || (run > 0 && total > CAP)) {        // the first pass of the first run is already staged
+      stage(p0);
       cp_async_wait<0>();
+      __syncthreads();
     }
-    __syncthreads();
     auto run_bins = [&](auto tag) {
       constexpr int MODE = decltype(tag)::value;
 #pragma unroll 1

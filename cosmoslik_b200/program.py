@@ -76,7 +76,7 @@ class CompiledProgram(object):
 
     _PTR_FIELDS = ("code_op", "code_arg", "code_val", "box_idx", "box_lo", "box_hi", "gauss_idx", "gauss_c",
                    "gauss_w", "scalar_coef", "spec_tab", "tile_tab", "templates", "windows", "data",
-                   "direct_coef", "Lmat", "Linv_diag", "Minv", "bin_tab", "Sigma")
+                   "direct_coef", "Lmat", "Linv_diag", "Minv", "bin_tab", "Sigma", "grp_tab")
 
     def __init__(self, names, priors, lnl_expr, chi2_mode="auto", binning="auto"):
         self.chi2_mode = chi2_mode
@@ -255,6 +255,7 @@ class CompiledProgram(object):
         nspec = len(q.blocks)
         spec_tab = np.zeros((nspec, L.SPEC_STRIDE), np.int32)
         tiles, segbins, templ, wins, data = [], [], [], [], []
+        ltabs = []                  # ell-table of each spectrum (for the group records)
         segtabs, segoff = [], 0     # weighted column rows of the segmented-sum bins (appended after the ell-tables)
         toff = 0      # running offset into the ell-table buffer (doubles, kept even)
         woff = 0      # running offset into the window buffer
@@ -316,6 +317,7 @@ class CompiledProgram(object):
                 else:
                     rec[L.S_PLAW_AMP + k] = rec[L.S_PLAW_IDX + k] = zero_row
             templ.append(ltab.ravel()); toff += ltab.size
+            ltabs.append(ltab)
             cal = blk.cal
             if isinstance(cal, Expr) and not (isinstance(cal, Const) and cal.v == 1.0):
                 rec[L.S_CAL] = code.coef(cal)
@@ -456,6 +458,45 @@ class CompiledProgram(object):
         self._dev('spec_tab', spec_tab, np.int32)
         self._dev('tile_tab', tile_arr, np.int32)
         self._dev('bin_tab', bin_arr, np.int32)
+        # group records: what one CTA of k_bin_segsum needs about its SEG_GROUP bins, in one 512-byte load
+        ngrp = len(bin_arr) // L.SEG_GROUP if segbins else 0
+        grp = np.zeros((max(ngrp, 1), L.GRP_STRIDE), np.int32)
+        for g in range(ngrp):
+            recs = bin_arr[g * L.SEG_GROUP:(g + 1) * L.SEG_GROUP]
+            rec_g = grp[g]
+            dbl = rec_g.view(np.float64)                      # same buffer, 8-byte view (word 2 k <-> double k)
+            s_idx = int(recs[0][L.B_SPEC])
+            NTs, NPs = int(spec_tab[s_idx][L.S_NTERM]), int(spec_tab[s_idx][L.S_NPLAW])
+            pre, prev_hi, base = 0, -1, -1
+            gmax = np.zeros(L.MAX_PLAW, np.float32)
+            for b, r in enumerate(recs):
+                live = r[L.B_ROW] >= 0
+                ncol = max(int(r[L.B_HI]) - int(r[L.B_LO]), 0) if live else 0
+                rec_g[L.G_PRE + b] = pre
+                rec_g[L.G_LO + b] = int(r[L.B_LO]) if live else 0
+                rec_g[L.G_ROW + b] = int(r[L.B_ROW]) if live else -1
+                rec_g[L.G_CONT + b] = 1 if (ncol > 0 and int(r[L.B_LO]) == prev_hi) else 0
+                if ncol > 0:
+                    if base < 0:
+                        base = (int(r[L.B_TABOFF_HI]) << 32) | (int(r[L.B_TABOFF_LO]) & 0xFFFFFFFF)
+                    prev_hi = int(r[L.B_HI])
+                    gmax = np.maximum(gmax, r[L.B_DMAX:L.B_DMAX + L.MAX_PLAW].view(np.float32))
+                dbl[L.G_DATA // 2 + b] = d[int(r[L.B_ROW])] if live else 0.0
+                lo_b = max(int(r[L.B_LO]), 0) if live else 0
+                for k in range(NPs):
+                    dbl[L.G_LOGB // 2 + b * L.MAX_PLAW + k] = ltabs[s_idx][lo_b, NTs + 4 * k]
+                pre += ncol
+            rec_g[L.G_PRE + L.SEG_GROUP] = pre
+            bounds = np.abs(spec_tab[s_idx][L.S_IDXBOUND:L.S_IDXBOUND + L.MAX_PLAW].view(np.float32)).astype(np.float64)
+            ym = float(np.max(bounds[:NPs] * gmax[:NPs].astype(np.float64))) if NPs else 0.0
+            rec_g[L.G_MODE] = 0 if ym <= 0.0035 else 1 if ym <= 0.012 else 2 if ym <= 0.1 else 3
+            base = max(base, 0)
+            lo32 = base & 0xFFFFFFFF
+            rec_g[L.G_BASE_LO] = lo32 - (1 << 32) if lo32 >= (1 << 31) else lo32
+            rec_g[L.G_BASE_HI] = base >> 32
+            rec_g[L.G_SPEC] = s_idx
+        self._dev('grp_tab', grp, np.int32)
+        self.host["grp_tab"] = grp
         self._dev('templates', np.concatenate(templ), np.float64)
         self._dev('windows', np.concatenate(wins), np.float64)
         self._dev('data', d, np.float64)

@@ -47,6 +47,7 @@ extern "C" {
 #define CSL_MAX_CLASS  8   /* distinct (NT, NP) spectrum classes per program */
 #define CSL_BIN_STRIDE 16  /* int32 words per bin record (segmented-sum binning) */
 #define CSL_SEG_GROUP  8   /* bins per CTA row of the segmented-sum kernel    */
+#define CSL_GRP_STRIDE 128 /* int32 words per group record (segmented-sum binning) */
 
 /* coefficient bytecode (one flat program; STORE pops into coef row `arg`) */
 enum {
@@ -101,6 +102,21 @@ enum {
   CSL_B_DMAX = 8     /* [CSL_MAX_PLAW]: float32 bits, max |D_q[l]| over [lo, hi) (see k_bin_segsum) */
 };
 
+/* group record, int32 words (table grp_tab[nsegbin / CSL_SEG_GROUP][CSL_GRP_STRIDE]): everything one CTA of
+ * k_bin_segsum needs about its CSL_SEG_GROUP bins, precomputed by the host from the bin records so that the
+ * kernel's prologue is one 512-byte load (record g describes bin records 8 g .. 8 g + 7) */
+enum {
+  CSL_G_PRE = 0,     /* [9]: columns of the group's bins laid back to back: bin b owns [PRE[b], PRE[b+1])   */
+  CSL_G_LO = 9,      /* [8]: first ell column of each bin                                                   */
+  CSL_G_ROW = 17,    /* [8]: residual row of each bin, -1 = padding                                         */
+  CSL_G_CONT = 25,   /* [8]: 1 if the bin starts at the column where the previous bin of the group ended    */
+  CSL_G_MODE = 33,   /* Taylor mode of the group: 0/1/2 = degree 5/6/10, 3 = exp at every column            */
+  CSL_G_BASE_LO = 34, CSL_G_BASE_HI = 35,   /* offset (doubles, in `templates`) of the group's weighted columns */
+  CSL_G_SPEC = 36,
+  CSL_G_DATA = 40,   /* [8] doubles: data value of each bin's residual row                                  */
+  CSL_G_LOGB = 56    /* [8][CSL_MAX_PLAW] doubles: logB_q at each bin's first column                        */
+};
+
 /*
  * A compiled posterior ("device program").  Built on the host from the plugin
  * tree; the struct itself lives in host memory, its pointers are device
@@ -140,6 +156,7 @@ typedef struct csl_program {
    * per-walker Cholesky factorisation (csl_cov_chi2). */
   const double* Sigma;      /* [n_base, n_base] row-major */
   int32_t n_base, nmode;
+  const int32_t* grp_tab;   /* group records of the segmented-sum bins (CSL_G_*), one per CSL_SEG_GROUP bin records */
 } csl_program_t;
 
 int csl_abi_version(void);

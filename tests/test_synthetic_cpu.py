@@ -85,3 +85,23 @@ def test_segmented_sum_tables(planck):
     hb = st[:, L.S_IDXBOUND:L.S_IDXBOUND + 2].view(np.float32)
     assert np.all(hb <= 0) and np.any(np.isclose(hb, -2.0)) and np.any(np.isclose(hb, -0.5))
     assert cp.flops["seg_flops"] > 0
+    # group records (one 512-byte load per CTA) restate the bin records of their group
+    gt = cp.host["grp_tab"]
+    assert gt.shape == (len(bt) // L.SEG_GROUP, L.GRP_STRIDE)
+    d = cp.tables["data"]
+    for g, rec in enumerate(gt):
+        recs = bt[g * L.SEG_GROUP:(g + 1) * L.SEG_GROUP]
+        dbl = rec.view(np.float64)
+        pre = 0
+        for b, r in enumerate(recs):
+            live = r[L.B_ROW] >= 0
+            ncol = max(int(r[L.B_HI] - r[L.B_LO]), 0) if live else 0
+            assert rec[L.G_PRE + b] == pre and rec[L.G_ROW + b] == (r[L.B_ROW] if live else -1)
+            if live:
+                assert rec[L.G_LO + b] == r[L.B_LO] and dbl[L.G_DATA // 2 + b] == d[r[L.B_ROW]]
+            pre += ncol
+        assert rec[L.G_PRE + L.SEG_GROUP] == pre and rec[L.G_SPEC] == recs[0][L.B_SPEC]
+        assert 0 <= rec[L.G_MODE] <= 3
+    # plik-lite bins are contiguous: every bin but the first of a group continues the previous one
+    full = [rec for rec in gt if rec[L.G_PRE + L.SEG_GROUP] > 0 and np.all(rec[L.G_ROW:L.G_ROW + 8] >= 0)]
+    assert full and all(list(rec[L.G_CONT:L.G_CONT + 8]) == [0] + [1] * 7 for rec in full)
