@@ -498,6 +498,12 @@ def main():
     try:
         return _main(args)
     finally:
+        if args.impl == "b200":
+            try:
+                from cosmoslik_b200 import dist
+                dist.shutdown()
+            except Exception:
+                pass
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         os.close(real_stdout)

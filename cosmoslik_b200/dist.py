@@ -51,6 +51,16 @@ def init_from_env(backend=None):
     return d.get_rank(), d.get_world_size()
 
 
+def shutdown():
+    """Tear the process group down (torchrun scripts call this last)."""
+    try:
+        import torch.distributed as d
+        if d.is_available() and d.is_initialized():
+            d.destroy_process_group()
+    except Exception:
+        pass
+
+
 def shard_bounds(n, rank=None, size=None):
     """[lo, hi) of the contiguous slice of n items owned by `rank` (equal shares; the first
     n % size ranks take one more)."""
