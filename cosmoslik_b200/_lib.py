@@ -76,6 +76,7 @@ SIGNATURES = {
                                 _u64, _u32, _u32, _dbl, _dbl, _vp, _vp, _int, _vp]),
     "csl_mh_moments": (_int, [_int, _int, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
     "csl_rows_moments": (_int, [_int, _int, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp]),
+    "csl_rows_gauss_prior": (_int, [_int, _int, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp]),
     "csl_stretch_propose": (_int, [_int, _int, _int, _vp, _vp, _dbl, _vp, _vp, _u64, _u32, _u32, _u32,
                                    _vp, _vp, _vp]),
     "csl_stretch_accept": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _u32,

@@ -19,7 +19,7 @@ from itertools import chain as _iterchain
 import numpy as np
 
 __all__ = ["Chain", "Chains", "get_covariance", "get_correlation", "combine_covs", "load_chain",
-           "load_cosmomc_chain", "ChainWriter", "gelman_rubin", "device_summary"]
+           "load_cosmomc_chain", "ChainWriter", "gelman_rubin", "device_summary", "device_add_gauss_prior"]
 
 
 def _is_listlike(v):
@@ -298,11 +298,41 @@ def rhat_from_moments(n, mu, var):
     return np.sqrt(((nbar - 1) / nbar * W + B_over_n) / W)
 
 
+def device_add_gauss_prior(stats, params, mean, covstd, names):
+    """``Chain.add_gauss_prior`` (chains.py:206-233) applied to EVERY chain of a finished sampler run, in
+    place on the device row buffer: weight *= exp(-dlnl), lnl += dlnl with
+    dlnl = (x - mean)^T cov^-1 (x - mean) / 2 over `params` (a name with its standard deviation, or a list
+    of names with their covariance).  `names` = the sampled parameter names in column order."""
+    import torch
+    from . import _lib as L
+    rows, nrows = stats["rows"], stats["nrows"]
+    W, cap, rl = rows.shape
+    names = list(names)
+    if _is_listlike(params):
+        idx = [names.index(p) for p in params]
+        cinv = np.linalg.inv(np.atleast_2d(np.asarray(covstd, dtype=float)))
+        mu = np.asarray(mean, dtype=float).ravel()
+    else:
+        idx = [names.index(params)]
+        cinv = np.array([[1.0 / float(covstd) ** 2]])
+        mu = np.array([float(mean)])
+    if cinv.shape != (len(idx), len(idx)) or mu.shape != (len(idx),):
+        raise ValueError("add_gauss_prior: mean / covariance do not match the parameter list")
+    dev = rows.device
+    d_idx = torch.tensor(idx, dtype=torch.int32, device=dev)
+    d_mu = torch.from_numpy(mu).to(dev)
+    d_ci = torch.from_numpy(np.ascontiguousarray(cinv)).to(dev)
+    L.check(L.lib().csl_rows_gauss_prior(W, rl - 2, rows.data_ptr(), nrows.data_ptr(), cap, len(idx), d_idx.data_ptr(),
+                                         d_mu.data_ptr(), d_ci.data_ptr(), L.stream_ptr()), "csl_rows_gauss_prior")
+    return stats
+
+
 def device_summary(stats, burn_rows=0):
-    """Weighted mean and covariance of ALL chains / walkers of a finished sampler run, reduced on the
-    device from its row buffer (`stats` = what ``sampler.run`` returned) -- the numbers
-    ``Chains.join().mean()`` / ``.cov()`` give (chains.py:78-96, 345-355; covariance denominator
-    sum(w) - 1), without copying the rows to the host.  With several GPUs the sums are all-reduced."""
+    """Weighted mean, standard deviation and covariance of ALL chains / walkers of a finished sampler run,
+    reduced on the device from its row buffer (`stats` = what ``sampler.run`` returned) -- the numbers
+    ``Chains.join().mean()`` / ``.std()`` / ``.cov()`` give (chains.py:78-96, 345-355; covariance
+    denominator sum(w) - 1, std with denominator sum(w) like numpy.average), without copying the rows to the
+    host.  With several GPUs the sums are all-reduced."""
     import torch
     from . import _lib as L
     from . import dist
@@ -321,7 +351,8 @@ def device_summary(stats, burn_rows=0):
                                  part.data_ptr(), out.data_ptr(), st), "csl_rows_moments")
     dist.all_reduce_sum(out[1 + nd:])
     h = out.cpu().numpy()
-    return dict(weight=h[0], mean=h[1:1 + nd] / h[0], cov=h[1 + nd:].reshape(nd, nd) / (h[0] - 1))
+    c2 = h[1 + nd:].reshape(nd, nd)
+    return dict(weight=h[0], mean=h[1:1 + nd] / h[0], cov=c2 / (h[0] - 1), std=np.sqrt(np.diag(c2) / h[0]))
 
 
 # --------------------------------------------------------------------------

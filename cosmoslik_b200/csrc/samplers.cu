@@ -454,6 +454,30 @@ k_stretch_combine_accept(int Ns, int nd, double* __restrict__ s, double* __restr
   }
 }
 
+// Chain.add_gauss_prior on the device (chains.py:206-233): every stored row of every chain gets
+//   dlnl = (x_P - mean)^T Cinv (x_P - mean) / 2 ,  weight *= exp(-dlnl) ,  lnl += dlnl
+// for the np parameters listed in pidx (Cinv [np, np] row-major; a single parameter: Cinv = 1 / std^2).
+// One thread per row slot; rows are (lnl, weight, x...) records of 2 + nd doubles.
+__global__ void __launch_bounds__(256)
+k_rows_gauss_prior(int W, int nd, double* __restrict__ rows, const int32_t* __restrict__ nrows, int cap, int np,
+                   const int32_t* __restrict__ pidx, const double* __restrict__ mean, const double* __restrict__ cinv) {
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= (long long)W * cap) return;
+  const int w = (int)(slot / cap), r = (int)(slot - (long long)w * cap);
+  if (r >= min(nrows[w], cap)) return;
+  double* row = rows + slot * (2 + nd);
+  double q = 0.0;
+  for (int i = 0; i < np; ++i) {
+    const double di = row[2 + pidx[i]] - mean[i];
+    double t = 0.0;
+    for (int k = 0; k < np; ++k) t = fma(cinv[i * np + k], row[2 + pidx[k]] - mean[k], t);
+    q = fma(di, t, q);
+  }
+  const double dlnl = 0.5 * q;
+  row[1] *= exp(-dlnl);
+  row[0] += dlnl;
+}
+
 // wrapper bookkeeping, samplers/emcee.py:70-88
 __global__ void __launch_bounds__(SAMP_THREADS)
 k_emcee_rows(int W, int nd, double* __restrict__ pos_old, const double* __restrict__ pos_new,
@@ -588,6 +612,16 @@ extern "C" int csl_rows_moments(int W, int ndim, const double* rows, const int32
                                 const double* mean, double* partial, double* out, void* stream) {
   CSL_REQUIRE(burn_rows >= 0, "csl_rows_moments: burn_rows must be >= 0");
   return moments_impl(W, ndim, rows, nrows, cap, mean, partial, out, burn_rows, stream);
+}
+
+extern "C" int csl_rows_gauss_prior(int W, int ndim, double* rows, const int32_t* nrows, int cap, int np,
+                                    const int32_t* pidx, const double* mean, const double* cinv, void* stream) {
+  CSL_REQUIRE(W > 0 && cap > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && rows && nrows, "csl_rows_gauss_prior: bad argument");
+  CSL_REQUIRE(np >= 1 && np <= ndim && pidx && mean && cinv, "csl_rows_gauss_prior: parameter list");
+  const long long slots = (long long)W * cap;
+  k_rows_gauss_prior<<<(unsigned)((slots + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, ndim, rows, nrows, cap, np,
+                                                                                       pidx, mean, cinv);
+  return csl_check_launch("k_rows_gauss_prior");
 }
 
 extern "C" int csl_stretch_propose(int Ns, int Nc, int ndim, const double* s, const double* comp, double a,

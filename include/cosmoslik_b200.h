@@ -260,6 +260,12 @@ int csl_mh_moments(int W, int ndim, const double* rows, const int32_t* nrows, in
 int csl_rows_moments(int W, int ndim, const double* rows, const int32_t* nrows, int cap, int burn_rows,
                      const double* mean, double* partial, double* out, void* stream);
 
+/* Chain.add_gauss_prior on the device rows (chains.py:206-233): for the np parameters pidx [np] (device int32),
+ * mean [np], Cinv [np, np] (device; one parameter: 1 / std^2), every stored row gets
+ *   dlnl = (x_P - mean)^T Cinv (x_P - mean) / 2,  weight *= exp(-dlnl),  lnl += dlnl.   In place. */
+int csl_rows_gauss_prior(int W, int ndim, double* rows, const int32_t* nrows, int cap, int np,
+                         const int32_t* pidx, const double* mean, const double* cinv, void* stream);
+
 /* ---- affine-invariant ensemble sampler (samplers/emcee.py + emcee 2.x stretch move) ------- */
 
 /* proposals for the Ns active walkers s [Ns, ndim] against the complementary half comp [Nc, ndim]:

@@ -462,6 +462,23 @@ def test_device_summary_matches_chain_statistics(torch):
     np.testing.assert_allclose(got["mean"], joined.mean(names), rtol=1e-12)
     np.testing.assert_allclose(got["cov"], joined.cov(names), rtol=1e-10)
     assert got["weight"] == joined["weight"].sum()
+    np.testing.assert_allclose(got["std"], joined.std(names), rtol=1e-10)
+    # Chain.add_gauss_prior on the device rows: one parameter with a standard deviation, then two with a covariance
+    from cosmoslik_b200.chains import device_add_gauss_prior
+    full = Chains([Chain(dict(zip(["lnl", "weight"] + names, rows[c, :nrows[c]].T))) for c in range(nch)])
+    Cp = np.array([[0.5, 0.1], [0.1, 0.8]])
+    want = Chains([c.add_gauss_prior(names[1], 0.2, 0.7).add_gauss_prior([names[0], names[3]], [0.1, -0.3], Cp)
+                   for c in full])
+    device_add_gauss_prior(st, names[1], 0.2, 0.7, names)
+    device_add_gauss_prior(st, [names[0], names[3]], [0.1, -0.3], Cp, names)
+    rows2 = st["rows"].cpu().numpy()
+    for c in range(nch):
+        np.testing.assert_allclose(rows2[c, :nrows[c], 0], want[c]["lnl"], rtol=1e-13)
+        np.testing.assert_allclose(rows2[c, :nrows[c], 1], want[c]["weight"], rtol=1e-12)
+        np.testing.assert_array_equal(rows2[c, :nrows[c], 2:], rows[c, :nrows[c], 2:])
+    got2 = device_summary(st, burn_rows=0)
+    np.testing.assert_allclose(got2["mean"], want.join().mean(names), rtol=1e-11)
+    np.testing.assert_allclose(got2["cov"], want.join().cov(names), rtol=1e-9)
 
 
 # ---------------------------------------------------------------- stretch move
