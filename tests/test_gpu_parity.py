@@ -149,6 +149,29 @@ def test_both_binning_kernels_match_the_oracle(torch, binning):
     assert relerr(slik.evaluate_batch(X), ref) < RTOL
 
 
+def test_tile_shapes_give_the_same_bits(torch, monkeypatch):
+    """The chi^2 tile product has a 64-row bulk shape and a 32-row shape for small launches, picked by launch
+    size: forcing either must not change a single bit (so neither does the number of GPUs a batch is sharded
+    over), and both match the oracle."""
+    prob = synthetic.spt_multifreq_problem(2, nbins=40, lmax=1201)       # dense windows, 240 rows, tiles of 40
+    oslik = ort.Slik(synthetic.build_script(ORACLE, prob)())
+    slik = Slik(synthetic.build_script(PRODUCT, prob)())
+    prog = slik.program(chi2_mode="inverse")
+    assert prog.meta["nclass"] > 0 and prog.meta["chi2_mode"] == 1
+    names = list(slik.get_sampled())
+    x0 = np.array([prob["truth"][k] for k in names]); sc = np.array([prob["scales"][k] for k in names])
+    X = x0 + sc * np.random.RandomState(13).standard_normal((700, len(names))) * 2
+    out = {}
+    for rows in ("64", "32"):
+        monkeypatch.setenv("CSL_TRIGEMM_ROWS", rows)
+        out[rows] = slik.evaluate_batch(X)
+    np.testing.assert_array_equal(out["64"], out["32"])
+    monkeypatch.delenv("CSL_TRIGEMM_ROWS")
+    np.testing.assert_array_equal(slik.evaluate_batch(X), out["64"])       # whatever the heuristic picks
+    ref = np.array([oslik.evaluate(*x)[0] for x in X[:60]])
+    assert relerr(out["32"][:60], ref) < RTOL
+
+
 def test_segmented_binning_index_bounds_and_position_independence(torch):
     """The Taylor degree of the power-law recurrence is fixed per bin group from the host's bound on the
     index: a prior box is a hard bound, a parameter without one gets the soft bound 4 and walkers beyond it
