@@ -218,6 +218,11 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
 #define SEG_UNROLL 2
 #endif
 
+// staged-row stride: NT real template terms + NP (w M_q) + NP D_q, padded to a whole number of 16-byte pieces
+__host__ __device__ constexpr int seg_row_stride(int nt, int np) { return (nt + 2 * np + 1) & ~1; }
+// the padded template-term class {0, 2, 4, 8} the ell-tables are laid out for (k_bin_residual's classes)
+__host__ __device__ constexpr int seg_pad_terms(int nt) { return nt <= 0 ? 0 : nt <= 2 ? 2 : nt <= 4 ? 4 : 8; }
+
 // ncol staged columns starting at `row`, for the SEG_WPT walkers of a thread.
 // MODE 0 / 1 / 2: Taylor degree 5 / 6 / 10 in y = idx D;  MODE 3: exact exp at every column (ltab, l = ell
 // index of the first column, give the next column's logB; lend = one past the bin's last column).
@@ -228,7 +233,8 @@ __device__ __forceinline__ void seg_cols(const double* __restrict__ row, int nco
                                          const double (&pidx)[SEG_WPT][NP > 0 ? NP : 1],
                                          double (&E)[SEG_WPT][NP > 0 ? NP : 1], double (&at)[SEG_WPT],
                                          double (&ap)[SEG_WPT], const double* __restrict__ ltab, int l, int lend) {
-  constexpr int RS = NT + 2 * NP, LSTRIDE = NT + 4 * NP;
+  // NT is the spectrum's REAL number of template terms; its ell-table rows are laid out for the padded class
+  constexpr int RS = seg_row_stride(NT, NP), NTP = seg_pad_terms(NT), LSTRIDE = NTP + 4 * NP;
   auto column = [&](const double* __restrict__ r, int lcur) {
     double T[NT > 0 ? NT : 1], M[NP > 0 ? NP : 1], D[NP > 0 ? NP : 1];
 #pragma unroll
@@ -250,7 +256,7 @@ __device__ __forceinline__ void seg_cols(const double* __restrict__ row, int nco
         else if (MODE == 1) E[j][q] *= exp_taylor<6>(pidx[j][q] * D[q]);
         else if (MODE == 2) E[j][q] *= exp_taylor<10>(pidx[j][q] * D[q]);
         else if (lcur + 1 < lend)
-          E[j][q] = pamp[j][q] * exp(pidx[j][q] * __ldg(ltab + (long long)(lcur + 1) * LSTRIDE + NT + 4 * q));
+          E[j][q] = pamp[j][q] * exp(pidx[j][q] * __ldg(ltab + (long long)(lcur + 1) * LSTRIDE + NTP + 4 * q));
       }
     }
   };
@@ -267,10 +273,9 @@ template <int NT, int NP>
 __global__ void __launch_bounds__(SEG_TPB, SEG_MINB)
 k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restrict__ coef, int ldc,
              double* __restrict__ R, int ldr) {
-  constexpr int RS = NT + 2 * NP;                    // > 0: the host never emits an empty class
+  constexpr int RS = seg_row_stride(NT, NP);         // > 0: the host never emits an empty class
   constexpr int CAP = SEG_SMEM_DOUBLES / (RS > 0 ? RS : 1);
   constexpr int NPX = NP > 0 ? NP : 1, NTX = NT > 0 ? NT : 1;
-  static_assert(RS % 2 == 0, "staged rows are copied in 16-byte pieces");
   __shared__ __align__(16) double srow[SEG_SMEM_DOUBLES];
   __shared__ __align__(16) int32_t sg[CSL_GRP_STRIDE];          // the group record (host-built, CSL_G_*)
   const int tid = threadIdx.x;
@@ -434,12 +439,17 @@ static int launch_seg(const csl_program_t* p, int bin0, int nbins, int W, const 
 
 static int dispatch_seg(int nt, int np, const csl_program_t* p, int b0, int nb, int W, const double* coef, int ldc,
                         double* R, int ldr, cudaStream_t s) {
-  switch (nt) {
+  switch (nt) {           // the REAL number of template terms: no FMA is spent on padding terms
     case 0: CSL_DISPATCH_SEG_NP(0)
+    case 1: CSL_DISPATCH_SEG_NP(1)
     case 2: CSL_DISPATCH_SEG_NP(2)
+    case 3: CSL_DISPATCH_SEG_NP(3)
     case 4: CSL_DISPATCH_SEG_NP(4)
+    case 5: CSL_DISPATCH_SEG_NP(5)
+    case 6: CSL_DISPATCH_SEG_NP(6)
+    case 7: CSL_DISPATCH_SEG_NP(7)
     case 8: CSL_DISPATCH_SEG_NP(8)
-    default: return csl_fail(CSL_E_BADARG, "csl_bin_residual: template class must be 0, 2, 4 or 8");
+    default: return csl_fail(CSL_E_BADARG, "csl_bin_residual: template terms must be 0..8");
   }
 }
 
@@ -498,7 +508,7 @@ extern "C" int csl_bin_residual(const csl_program_t* p, int W, const double* coe
   }
   for (int c = 0; c < p->nsegclass; ++c) {
     const int32_t* k = p->segcls[c];
-    CSL_REQUIRE(k[0] + 2 * k[1] > 0 && p->bin_tab, "csl_bin_residual: empty segmented class");
+    CSL_REQUIRE(k[0] + 2 * k[1] > 0 && p->bin_tab && p->grp_tab, "csl_bin_residual: empty segmented class");
     int rc = dispatch_seg(k[0], k[1], p, k[2], k[3], W, coef, ldc, R, ldr, s);
     if (rc) return rc;
   }

@@ -333,6 +333,7 @@ class CompiledProgram(object):
             # per-row segmented sum does the minimum work; dense windows go to the DMMA tile product
             seg = self.binning == "segsum" or (self.binning == "auto" and covered <= 2 * nl)
             per_elem = len(terms) + 20 * len(m.plaws)
+            NTr = len(terms) if len(terms) + NP > 0 else NT      # segmented-sum class: real term count
             if seg:
                 for b in range(_rup(nb, L.SEG_GROUP)):
                     rec_b = np.zeros(L.BIN_STRIDE, np.int32)
@@ -345,11 +346,12 @@ class CompiledProgram(object):
                         rec_b[L.B_WINOFF_HI] = off >> 32
                         lo_b, hi_b = supports[b]
                         # the bin's columns as the kernel consumes them: [w T_t.., w M_q.., D_q..] per column
+                        # (REAL template terms only: the segmented-sum classes are keyed by len(terms))
                         wrow = wp[b, lo_b:hi_b, None]
-                        cols = np.empty((hi_b - lo_b, NT + 2 * NP))
-                        cols[:, :NT] = wrow * ltab[lo_b:hi_b, :NT]
-                        cols[:, NT:NT + NP] = wrow * ltab[lo_b:hi_b, NT + 1::4][:, :NP]
-                        cols[:, NT + NP:] = ltab[lo_b:hi_b, NT + 2::4][:, :NP]
+                        cols = np.zeros((hi_b - lo_b, (NTr + 2 * NP + 1) // 2 * 2))     # stride padded to 16 bytes
+                        cols[:, :NTr] = wrow * ltab[lo_b:hi_b, :NTr]
+                        cols[:, NTr:NTr + NP] = wrow * ltab[lo_b:hi_b, NT + 1::4][:, :NP]
+                        cols[:, NTr + NP:NTr + 2 * NP] = ltab[lo_b:hi_b, NT + 2::4][:, :NP]
                         rec_b[L.B_TABOFF_LO], rec_b[L.B_TABOFF_HI] = segoff, 0      # relative; rebased below
                         segtabs.append(cols.ravel()); segoff += cols.size
                         for k in range(len(m.plaws)):
@@ -359,13 +361,13 @@ class CompiledProgram(object):
                             rec_b[L.B_DMAX + k] = dmax.view(np.int32)
                     else:
                         rec_b[L.B_ROW], rec_b[L.B_SPEC] = -1, s     # group padding: skipped by the kernel
-                    segbins.append(((NT, NP), rec_b))
+                    segbins.append(((NTr, NP), rec_b))
                 flops_exec += 2 * covered
                 builds += covered * per_elem
                 # FP64 instructions k_bin_segsum issues per column and walker: NT template FMAs, and per power
                 # law 1 FMA + the advance (y = idx D, degree-6 Horner, E *= P: 8; degree 5 / 10 when |y| allows /
                 # demands); the window weight is folded into the host-built column table
-                seg_ops += covered * (NT + 9 * NP)
+                seg_ops += covered * (NTr + 9 * NP)
             for t0 in (range(0, nb, L.BM) if not seg else ()):
                 nr = min(L.BM, nb - t0)
                 lo, hi = _support(wp[t0:t0 + nr])

@@ -59,8 +59,8 @@ def test_segmented_sum_tables(planck):
     bt, st = cp.host["bin_tab"], cp.host["spec_tab"]
     tpl, win = cp.tables["templates"], cp.tables["windows"]
     for c in range(cp.meta["nsegclass"]):
-        NT, NP, b0, nb = (int(v) for v in cp.segcls[c])
-        RS, LS = NT + 2 * NP, NT + 4 * NP
+        NT, NP, b0, nb = (int(v) for v in cp.segcls[c])          # NT: REAL template terms of the class
+        RS = (NT + 2 * NP + 1) // 2 * 2                            # staged-row stride, padded to 16 bytes
         assert nb % L.SEG_GROUP == 0
         widths = []
         for g0 in range(b0, b0 + nb, L.SEG_GROUP):
@@ -75,11 +75,13 @@ def test_segmented_sum_tables(planck):
                 woff = (int(r[L.B_WINOFF_HI]) << 32) | (int(r[L.B_WINOFF_LO]) & 0xFFFFFFFF)
                 w = win[woff + lo:woff + hi]
                 base = int(st[r[L.B_SPEC]][L.S_LTAB])
+                NTP = int(st[r[L.B_SPEC]][L.S_NTERM]); LS = NTP + 4 * NP       # ell-table layout: padded class
+                assert NTP >= NT
                 rows = tpl[base + lo * LS:base + hi * LS].reshape(hi - lo, LS)
                 cols = tpl[t:t + (hi - lo) * RS].reshape(hi - lo, RS)
                 np.testing.assert_array_equal(cols[:, :NT], w[:, None] * rows[:, :NT])
-                np.testing.assert_array_equal(cols[:, NT:NT + NP], w[:, None] * rows[:, NT + 1::4][:, :NP])
-                np.testing.assert_array_equal(cols[:, NT + NP:], rows[:, NT + 2::4][:, :NP])
+                np.testing.assert_array_equal(cols[:, NT:NT + NP], w[:, None] * rows[:, NTP + 1::4][:, :NP])
+                np.testing.assert_array_equal(cols[:, NT + NP:NT + 2 * NP], rows[:, NTP + 2::4][:, :NP])
                 off = t + (hi - lo) * RS
         assert widths == sorted(widths, reverse=True)
     hb = st[:, L.S_IDXBOUND:L.S_IDXBOUND + 2].view(np.float32)
