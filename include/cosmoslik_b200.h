@@ -97,8 +97,9 @@ enum {
   CSL_B_HI = 3,      /* one past the last non-zero column                       */
   CSL_B_WINOFF_LO = 4, CSL_B_WINOFF_HI = 5,  /* offset (doubles) of the window row */
   CSL_B_TABOFF_LO = 6, CSL_B_TABOFF_HI = 7,  /* offset (doubles, in `templates`) of the bin's weighted column rows
-                                                [w T_0..w T_{NT-1}, w M_q.., D_q..] for l in [lo, hi); the bins of a
-                                                group are contiguous there, in record order */
+                                                [w T_0..w T_{NT-1}, w M_q.., D_q.., pad to an even count] for l in
+                                                [lo, hi), NT = real template terms; the bins of a group are contiguous
+                                                there, in record order */
   CSL_B_DMAX = 8     /* [CSL_MAX_PLAW]: float32 bits, max |D_q[l]| over [lo, hi) (see k_bin_segsum) */
 };
 
@@ -149,7 +150,8 @@ typedef struct csl_program {
   const double* Minv;       /* [n_pad, n_pad] row-major L^-1 (lower), or NULL                     */
   int32_t chi2_mode;        /* 0: blocked forward substitution; 1: explicit-inverse tile product  */
   int32_t nsegclass;        /* segmented-sum classes (spectra with block-sparse windows)          */
-  int32_t segcls[CSL_MAX_CLASS][4];  /* per class: NT, NP, first bin record, number of bin records */
+  int32_t segcls[CSL_MAX_CLASS][4];  /* per class: NT (the spectra's REAL number of template terms, 0..8), NP (padded:
+                                        0/1/2/4), first bin record, number of bin records (a multiple of CSL_SEG_GROUP) */
   const int32_t* bin_tab;
   /* resid_mode 3: model-dependent covariance C = Sigma + V V^T (SPTSZ_lowl.py:62-81).  The residual
    * vector stacks r (n_base rows) and the nmode columns of V (n_base rows each); chi^2 = r^T C^-1 r by a
