@@ -567,6 +567,29 @@ def test_stretch_device_streams_and_sampling(torch):
 
 
 # ---------------------------------------------------------------- full BASELINE sizes (properties)
+def test_spt_multifreq_full_size_properties(torch):
+    """BASELINE configs[2] at its full size (6 cross-spectra x 50 bins, ell 50..3300, dense windows, 16 384
+    walkers) through the DMMA binning kernel: a random sample of walkers against the oracle, invariance under
+    walker permutation (bitwise), and lnl = prior alone on noise-free data at the truth."""
+    prob = synthetic.spt_multifreq_problem(0)
+    slik = Slik(synthetic.build_script(PRODUCT, prob)())
+    oslik = ort.Slik(synthetic.build_script(ORACLE, prob)())
+    prog = slik.program()
+    assert prog.meta["nclass"] > 0 and prog.meta["nsegclass"] == 0 and prog.meta["n"] == 300
+    names = list(slik.get_sampled())
+    x0 = np.array([prob["truth"][k] for k in names]); sc = np.array([prob["scales"][k] for k in names])
+    rs = np.random.RandomState(3)
+    W = 16384
+    X = x0 + sc * rs.standard_normal((W, len(names)))
+    got = slik.evaluate_batch(torch.from_numpy(X).cuda()).cpu().numpy()
+    pick = rs.choice(W, 24, replace=False)
+    ref = np.array([oslik.evaluate(*X[i])[0] for i in pick])
+    assert relerr(got[pick], ref) < RTOL
+    perm = rs.permutation(W)
+    np.testing.assert_array_equal(slik.evaluate_batch(torch.from_numpy(X[perm]).cuda()).cpu().numpy(), got[perm])
+    np.testing.assert_array_equal(slik.evaluate_batch(X[:1000]), got[:1000])          # a smaller launch, same bits
+
+
 def test_planck_lite_full_size_properties(torch):
     """config 4 at 65 536 walkers: a random sample of walkers against the oracle, quadratic scaling
     of chi^2 along a ray from the best fit, and invariance under walker permutation."""
