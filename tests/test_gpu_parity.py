@@ -208,6 +208,30 @@ def test_segmented_binning_index_bounds_and_position_independence(torch):
     np.testing.assert_array_equal(slik.evaluate_batch(X[:300]), got[:300])        # another tile shape, same bits
 
 
+def test_segmented_binning_wide_windows_take_several_staging_passes(torch):
+    """Numerically dense windows forced through the segmented sum: a group of 8 bins has ~6000 columns, far
+    more than one staging pass holds, so bins are cut by pass boundaries and keep their running sums and
+    power-law state in registers across passes; the bins all start at column 0, so none inherits the state."""
+    prob = synthetic.spt_multifreq_problem(1, nbins=12, lmax=801)
+    oslik = ort.Slik(synthetic.build_script(ORACLE, prob)())
+    slik = Slik(synthetic.build_script(PRODUCT, prob)())
+    prog = slik.program(binning="segsum")
+    assert prog.meta["nsegclass"] > 0 and prog.meta["nclass"] == 0
+    gt = prog.host["grp_tab"]
+    assert gt[:, L.G_PRE + L.SEG_GROUP].max() > 3072 // 4            # more columns than any pass can stage
+    assert not gt[:, L.G_CONT:L.G_CONT + L.SEG_GROUP].any()
+    names = list(slik.get_sampled())
+    x0 = np.array([prob["truth"][k] for k in names]); sc = np.array([prob["scales"][k] for k in names])
+    X = x0 + sc * np.random.RandomState(14).standard_normal((300, len(names))) * 2
+    ref = np.array([oslik.evaluate(*x)[0] for x in X[:50]])
+    got = slik.evaluate_batch(X)
+    assert relerr(got[:50], ref) < RTOL
+    # and the DMMA tile product on the same windows agrees with it to rounding
+    dm = Slik(synthetic.build_script(PRODUCT, prob)())
+    dm.program(binning="dmma")
+    assert relerr(dm.evaluate_batch(X), got) < 1e-12
+
+
 def test_segmented_binning_with_ragged_walker_counts(torch):
     """walker counts that leave the last 256-walker CTA of k_bin_segsum half empty"""
     prob = synthetic.planck_lite_problem(5)
