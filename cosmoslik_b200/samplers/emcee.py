@@ -178,7 +178,7 @@ class emcee(SlikSampler):
         def to_dev(arr, dtype):
             return torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(dev)
 
-        # Fast path: whole steps are enqueued from C (csl_stretch_run) -- no Python between the ~17 kernel
+        # Fast path: whole steps are enqueued from C (csl_stretch_run) -- no Python between the ~11 kernel
         # launches of a step.  Needs device streams and either one GPU or the symmetric-memory replica.
         native = self.streams is None and timers is None and (size == 1 or replica is not None) \
             and not getattr(self, "python_loop", False)
