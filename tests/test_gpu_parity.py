@@ -590,6 +590,48 @@ def test_stretch_device_streams_and_sampling(torch):
     assert 0.3 < st["accepted"] / st["evals"] < 0.9
 
 
+@pytest.mark.parametrize("chi2_mode,k", [("inverse", 300), ("trsm", 256)])
+def test_native_fused_step_loop_matches_the_oracle_and_the_staged_kernels(torch, monkeypatch, chi2_mode, k):
+    """csl_stretch_run (fused propose+prepare and combine+accept kernels, device Philox streams) on a binned
+    bandpower likelihood: positions bit-exact against the oracle driven by oracle/philox.py's streams, and
+    bitwise equal to the per-stage Python loop and to the unfused C loop (CSL_NO_FUSE=1); a walker count that
+    leaves the 128-walker tiles ragged; both chi^2 kernels."""
+    prob = synthetic.planck_lite_problem(7)
+    nsteps, seed = 3, 99
+
+    def run(python_loop=False):
+        sl = Slik(synthetic.build_script(PRODUCT, prob, sampler=lambda s: samplers.emcee(
+            s, num_samples=k * nsteps, nwalkers=k, seed=seed))())
+        sl.program(chi2_mode=chi2_mode)
+        sl.sampler.init_pos = pos0
+        if python_loop:
+            sl.sampler.python_loop = True
+        st = sl.sampler.run(sl.evaluate)
+        return st["pos"].cpu().numpy(), st["lnl"].cpu().numpy(), st["rows"].cpu().numpy(), st["nrows"].cpu().numpy()
+
+    names = sorted(prob["truth"])
+    x0 = np.array([prob["truth"][n] for n in names]); sc = np.array([prob["scales"][n] for n in names])
+    pos0 = x0 + sc * np.random.RandomState(5).standard_normal((k, len(names)))
+    native = run()
+    staged = run(python_loop=True)
+    monkeypatch.setenv("CSL_NO_FUSE", "1")
+    unfused = run()
+    monkeypatch.delenv("CSL_NO_FUSE")
+    for a, b, c in zip(native, staged, unfused):
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, c)
+    oslik = ort.Slik(synthetic.build_script(ORACLE, prob)())
+    lnprob = lambda q: np.array([-oslik.evaluate(*x)[0] for x in np.atleast_2d(q)])
+
+    def streams(i):
+        a = [ophilox.stretch_streams(seed, i, h, np.arange(k // 2) + h * (k // 2), k // 2) for h in (0, 1)]
+        return (np.array([a[0][0], a[1][0]]), np.array([a[0][1], a[1][1]]), np.array([a[0][2], a[1][2]]))
+
+    _, opos, olnp = osamp.emcee_wrapper_rows(pos0, lnprob, nsteps, streams)
+    np.testing.assert_array_equal(native[0], opos)
+    assert relerr(native[1], -olnp) < RTOL
+
+
 # ---------------------------------------------------------------- full BASELINE sizes (properties)
 def test_spt_multifreq_full_size_properties(torch):
     """BASELINE configs[2] at its full size (6 cross-spectra x 50 bins, ell 50..3300, dense windows, 16 384
