@@ -245,6 +245,12 @@ class Slik(object):
     # -- tracing / compilation ------------------------------------------------
     def trace(self):
         """Run the script's __call__ once with symbolic parameters."""
+        return self._trace()[1]
+
+    def _trace(self):
+        """(tree after the symbolic call, traced result): the tree is what the reference hands back
+        as the second element of ``Slik.evaluate`` (cosmoslik.py:141) -- whatever the script stored
+        on itself during ``__call__`` is there as an expression of the sampled parameters."""
         tree = self.params.deepcopy()
         for i, name in enumerate(self._sampled):
             tree[name] = sym.Par(i, name)
@@ -256,7 +262,36 @@ class Slik(object):
             out = sym.Const(float(out))
         if not isinstance(out, (sym.Expr, sym.LnlTerm)):
             raise TypeError("script __call__ returned %r; expected a likelihood term or parameter expression" % type(out))
+        return tree, out
+
+    def extra_exprs(self, keys):
+        """The derived quantities ``params[k]`` a sampler's ``output_extra_params`` names
+        (metropolis_hastings.py:228: ``s.extra[k]`` with ``extra`` the evaluated tree), as scalar
+        expressions of the sampled parameters.  KeyError for a name the script never sets, as the
+        reference's lookup; TypeError for a value that is not a scalar function of the parameters."""
+        tree = self._trace()[0]
+        out = []
+        for k in keys:
+            try:
+                v = tree[k]
+            except (KeyError, AttributeError):
+                raise KeyError("output_extra_params: the script has no '%s' after __call__" % (k,)) from None
+            try:
+                out.append(sym.Expr.wrap(v))
+            except TypeError:
+                raise TypeError("output_extra_params: '%s' is %r, not a scalar function of the sampled "
+                                "parameters" % (k, type(v))) from None
         return out
+
+    def extras_program(self, keys):
+        """Device program evaluating ``output_extra_params`` for a batch of points (cached per key list)."""
+        keys = tuple(keys)
+        cached = getattr(self, "_extras", None)
+        if cached is None or cached[0] != keys:
+            from .program import ExtrasProgram
+            cached = (keys, ExtrasProgram(list(self._sampled), self.extra_exprs(keys)))
+            self._extras = cached
+        return cached[1]
 
     def program(self, **options):
         """The compiled device program (cached).  Options (see program.CompiledProgram):

@@ -614,3 +614,48 @@ class DeviceProgram(CompiledProgram):
                                       ws["prior"].data_ptr(), L.ptr(ws["R"]), L.ptr(ws["chi2"]), L.ptr(ws["part"]),
                                       L.stream_ptr()), "csl_lnl_host")
         return out_host
+
+
+class _NoPriors(object):
+    """prior tables of a program that only evaluates parameter expressions"""
+    uniform_priors = ()
+    gaussian_priors = ()
+
+
+def compile_extras(names, exprs):
+    """Host-side tables of the derived-quantity program (no CUDA needed): every expression becomes
+    one coefficient row of the bytecode; returns (CompiledProgram, coefficient row of each expression)."""
+    cp = CompiledProgram(list(names), _NoPriors, LnlSum([Expr.wrap(e) for e in exprs]))
+    return cp, [int(i) for i in cp.tables["scalar_coef"][:len(exprs)]]
+
+
+class ExtrasProgram(DeviceProgram):
+    """``output_extra_params`` on the device: the derived quantities a script stores on itself during
+    ``__call__`` (the reference writes ``s.extra[k]`` next to every sample, metropolis_hastings.py:228)
+    are scalar expressions of the sampled parameters; they are compiled to the same coefficient
+    bytecode as a likelihood's amplitudes and evaluated for any batch of points by the priors +
+    bytecode kernel (csl_eval_prepare) -- no per-point Python."""
+
+    def __init__(self, names, exprs, device=None):
+        super().__init__(list(names), _NoPriors, LnlSum([Expr.wrap(e) for e in exprs]), device=device)
+        self.rows = [int(i) for i in self.tables["scalar_coef"][:len(exprs)]]
+
+    def values(self, x):
+        """device tensor x [N, ndim] -> device tensor [N, nextra]"""
+        t = self.torch
+        if not (isinstance(x, t.Tensor) and x.is_cuda and x.dtype == t.float64 and x.dim() == 2
+                and x.shape[1] == self.ndim and x.is_contiguous()):
+            raise ValueError("x must be a contiguous float64 CUDA tensor [N, %d]" % self.ndim)
+        N = x.shape[0]
+        if N == 0 or not self.rows:
+            return t.empty((N, len(self.rows)), dtype=t.float64, device=self.device)
+        ws = self.workspace(N)
+        Wp = _rup(N, L.BN)
+        L.check(self.lib.csl_eval_prepare(C.byref(self.struct), N, x.data_ptr(), ws["coef"].data_ptr(), Wp,
+                                          ws["prior"].data_ptr(), L.stream_ptr()), "csl_eval_prepare")
+        return ws["coef"][self.rows, :N].t().contiguous()
+
+    def values_host(self, X):
+        """numpy [N, ndim] -> numpy [N, nextra]"""
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, self.ndim)
+        return self.values(self.torch.from_numpy(X).to(self.device)).cpu().numpy()

@@ -40,7 +40,7 @@ from .. import _lib as L
 from .. import dist
 from ..chains import ChainWriter
 from ..core import SlikSampler, arguments, sample
-from .utils import initialize_covariance, program_of
+from .utils import append_extras_of_next, extras_of, initialize_covariance, program_of
 
 
 class emcee(SlikSampler):
@@ -51,9 +51,13 @@ class emcee(SlikSampler):
         if output_extra_params is None:
             output_extra_params = []
         super().__init__(**arguments(exclude=["params"]))
-        if self.output_extra_params:
-            raise NotImplementedError("output_extra_params needs per-point Python evaluation")
-        self.output_extra_params = OrderedDict()
+        # name -> dtype name (emcee.py:28); float columns only, evaluated on the device (Slik.extras_program)
+        self.output_extra_params = OrderedDict(k if isinstance(k, tuple) else (k, np.dtype("float").name)
+                                               for k in self.output_extra_params)
+        for k_, dt in self.output_extra_params.items():
+            if np.dtype(dt) != np.dtype("float"):
+                raise NotImplementedError("output_extra_params: column '%s' has dtype %s; the batched sampler "
+                                          "writes float64 columns only" % (k_, dt))
         self.sampled = params.find_sampled()
         self.x0 = [params[k].start for k in self.sampled]
         self.cov_est = initialize_covariance(self.sampled, self.cov_est)
@@ -67,7 +71,7 @@ class emcee(SlikSampler):
         return rs.multivariate_normal([v.start for v in self.sampled.values()], self.cov_est, size=int(self.nwalkers))
 
     def sample(self, lnl):
-        for blocks in self._run(program_of(lnl), emit=True):
+        for blocks in self._run(program_of(lnl), emit=True, extras=self._file_extras(lnl)):
             for wid, rows in blocks:
                 for r in rows:
                     s = sample(r[2:].copy(), r[0], r[1], None)
@@ -87,12 +91,25 @@ class emcee(SlikSampler):
         """Batched entry point: advance the ensemble `nsteps` steps and return the state dict.
         ``resume=True`` continues from the state the previous call left (positions, lnl, weights)
         without re-evaluating the start positions."""
-        prog = lnl_or_program if hasattr(lnl_or_program, "struct") else program_of(lnl_or_program)
-        for _ in self._run(prog, emit=False, nsteps=nsteps, resume=resume):
+        if hasattr(lnl_or_program, "struct"):
+            prog, extras = lnl_or_program, None
+            if self.output_extra_params and self.output_file is not None:
+                raise ValueError("output_extra_params: pass the bound Slik.evaluate, not the program, so that "
+                                 "the derived quantities can be compiled")
+        else:
+            prog, extras = program_of(lnl_or_program), self._file_extras(lnl_or_program)
+        for _ in self._run(prog, emit=False, nsteps=nsteps, resume=resume, extras=extras):
             pass
         return self.stats
 
-    def _run(self, prog, emit, nsteps=None, resume=False):
+    def _file_extras(self, lnl):
+        """The reference's wrapper puts extra columns in the chain FILE only (emcee.py:74 yields
+        ``sample(-l, x, weight)`` without them, :78 writes them)."""
+        if self.output_file is None:
+            return None
+        return extras_of(lnl, list(self.output_extra_params))
+
+    def _run(self, prog, emit, nsteps=None, resume=False, extras=None):
         torch, lib = prog.torch, prog.lib
         dev = prog.device
         nd = len(self.x0)
@@ -150,7 +167,7 @@ class emcee(SlikSampler):
         writer = None
         if self.output_file is not None:
             path = self.output_file if rank == 0 else "%s.rank%d" % (self.output_file, rank)
-            writer = ChainWriter(path, ["lnl", "weight"] + list(self.sampled), "list")
+            writer = ChainWriter(path, ["lnl", "weight"] + list(self.sampled) + list(self.output_extra_params), "list")
         prev_n = np.zeros(W, dtype=np.int64)
         st = L.stream_ptr()
         timers = getattr(self, "timers", None)     # bench.py: CUDA-event pairs per stage
@@ -177,6 +194,12 @@ class emcee(SlikSampler):
 
         def to_dev(arr, dtype):
             return torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(dev)
+
+        def file_rows(blocks):
+            """rows as the chain file holds them: with the extra columns, if any, appended"""
+            if extras is None:
+                return blocks
+            return append_extras_of_next(blocks, pos.cpu().numpy(), extras, nd)
 
         # Fast path: whole steps are enqueued from C (csl_stretch_run) -- no Python between the ~11 kernel
         # launches of a step.  Needs device streams and either one GPU or the symmetric-memory replica.
@@ -210,7 +233,7 @@ class emcee(SlikSampler):
                 if (emit or writer is not None) and (i % F == 0 or i == nsteps):
                     blocks, prev_n = self._collect_rows(rows, nrows, prev_n, gid, rl)
                     if writer is not None:
-                        for wid, r in blocks:
+                        for wid, r in file_rows(blocks):
                             for c0 in range(0, len(r), F):
                                 writer.write(wid, r[c0:c0 + F])
                         writer.flush()
@@ -267,7 +290,7 @@ class emcee(SlikSampler):
                 if (emit or writer is not None) and ((i + 1) % F == 0 or i == nsteps - 1):
                     blocks, prev_n = self._collect_rows(rows, nrows, prev_n, gid, rl)
                     if writer is not None:
-                        for wid, r in blocks:
+                        for wid, r in file_rows(blocks):
                             for c0 in range(0, len(r), F):      # records of at most output_freq rows (emcee.py:80-84)
                                 writer.write(wid, r[c0:c0 + F])
                         writer.flush()

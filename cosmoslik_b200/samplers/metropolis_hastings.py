@@ -29,7 +29,7 @@ from .. import _lib as L
 from .. import dist
 from ..chains import ChainWriter
 from ..core import SlikSampler, arguments, sample
-from .utils import initialize_covariance, program_of, proposal_factor
+from .utils import append_extras, extras_of, initialize_covariance, program_of, proposal_factor
 
 
 class metropolis_hastings(SlikSampler):
@@ -41,12 +41,16 @@ class metropolis_hastings(SlikSampler):
         if output_extra_params is None:
             output_extra_params = []
         super().__init__(**arguments(exclude=["params"]))
-        if self.output_extra_params:
-            raise NotImplementedError("output_extra_params needs per-point Python evaluation, which the "
-                                      "batched sampler does not do")
         if yield_rejected:
             raise NotImplementedError("yield_rejected is not supported by the batched sampler")
-        self.output_extra_params = OrderedDict()
+        # name -> dtype name, as the reference (:103); the values are scalar expressions of the sampled
+        # parameters evaluated on the device (Slik.extras_program), so only float columns exist
+        self.output_extra_params = OrderedDict(k if isinstance(k, tuple) else (k, np.dtype("float").name)
+                                               for k in self.output_extra_params)
+        for k, dt in self.output_extra_params.items():
+            if np.dtype(dt) != np.dtype("float"):
+                raise NotImplementedError("output_extra_params: column '%s' has dtype %s; the batched sampler "
+                                          "writes float64 columns only" % (k, dt))
         self.sampled = params.find_sampled()
         self.x0 = [params[k].start for k in self.sampled]
         self.cov_est = initialize_covariance(self.sampled, self.cov_est)
@@ -57,10 +61,11 @@ class metropolis_hastings(SlikSampler):
     def sample(self, lnl):
         """Generator of ``sample(x, lnl, weight)`` objects (attribute ``chain`` = chain id),
         chain by chain within each block of ``mpi_comm_freq`` steps."""
-        for blocks in self._run(program_of(lnl), emit=True):
+        nd, extra_names = len(self.x0), list(self.output_extra_params)
+        for blocks in self._run(program_of(lnl), emit=True, extras=extras_of(lnl, extra_names)):
             for cid, rows in blocks:
                 for r in rows:
-                    s = sample(r[2:].copy(), r[0], r[1], None)
+                    s = sample(r[2:2 + nd].copy(), r[0], r[1], dict(zip(extra_names, r[2 + nd:])) if extra_names else None)
                     s.chain = cid
                     yield s
 
@@ -68,8 +73,14 @@ class metropolis_hastings(SlikSampler):
         """Batched entry point: run to completion and return a dict with the final state
         (device tensors) and, if ``keep_rows``, the device row buffer
         ``rows [nchains_local, cap, 2+ndim]`` with per-chain counts ``nrows``."""
-        prog = lnl_or_program if hasattr(lnl_or_program, "struct") else program_of(lnl_or_program)
-        for _ in self._run(prog, emit=False):
+        if hasattr(lnl_or_program, "struct"):
+            prog, extras = lnl_or_program, None
+            if self.output_extra_params:
+                raise ValueError("output_extra_params: pass the bound Slik.evaluate, not the program, so that "
+                                 "the derived quantities can be compiled")
+        else:
+            prog, extras = program_of(lnl_or_program), extras_of(lnl_or_program, list(self.output_extra_params))
+        for _ in self._run(prog, emit=False, extras=extras):
             pass
         return self.stats
 
@@ -94,7 +105,7 @@ class metropolis_hastings(SlikSampler):
         return rhat_from_moments(allm[:, 0], allm[:, 1:1 + nd], allm[:, 1 + nd:])
 
     # ------------------------------------------------------------------
-    def _run(self, prog, emit):
+    def _run(self, prog, emit, extras=None):
         torch, lib = prog.torch, prog.lib
         dev = prog.device
         nd = len(self.x0)
@@ -133,7 +144,8 @@ class metropolis_hastings(SlikSampler):
         writer = None
         if self.output_file is not None:
             path = self.output_file if rank == 0 else "%s.rank%d" % (self.output_file, rank)
-            writer = _FileBlocks(path, ["lnl", "weight"] + list(self.sampled), S, single=(ntot == 1))
+            writer = _FileBlocks(path, ["lnl", "weight"] + list(self.sampled) + list(self.output_extra_params), S,
+                                 single=(ntot == 1))
         if dist.is_master() and self.print_level >= 1 and self.output_file:
             print("Starting MCMC chain (%s)..." % self.output_file)
         prev_n = np.zeros(W, dtype=np.int64)
@@ -195,6 +207,8 @@ class metropolis_hastings(SlikSampler):
                     slab = rows[:, a:b].cpu().numpy() if b > a else np.zeros((W, 0, rl))
                     blocks = [(lo + c, slab[c, prev_n[c] - a:n_now[c] - a]) for c in range(W)]
                     prev_n = n_now
+                    if extras is not None:
+                        blocks = append_extras(blocks, extras, nd)
                     if writer is not None:
                         for cid, r in blocks:
                             writer.add(cid, r)

@@ -11,7 +11,7 @@ import numpy as np
 from ..core import sample
 from ..likelihoods.priors import priors as likelihoods_priors
 from .metropolis_hastings import metropolis_hastings
-from .utils import program_of
+from .utils import extras_of, program_of
 
 
 class priors(metropolis_hastings):
@@ -36,12 +36,15 @@ class priors(metropolis_hastings):
 
     def sample(self, lnl):
         prog = program_of(lnl)
+        names = list(self.output_extra_params)
+        extras = extras_of(lnl, names)
         n = int(self.num_samples / float(max(1, int(self.nchains))))
         block = 65536
         for i0 in range(0, n, block):
             X = self.draw_x(min(block, n - i0))
             vals = prog.lnl_host(X)
-            for x, v in zip(X, vals):
-                s = sample(x.copy(), v, 1, None)
+            E = extras.values_host(X) if extras is not None else None
+            for i, (x, v) in enumerate(zip(X, vals)):
+                s = sample(x.copy(), v, 1, dict(zip(names, E[i])) if E is not None else None)
                 s.chain = 0
                 yield s

@@ -228,7 +228,7 @@ def ensemble_step(p, lnprob, lnprob_fn, u_z, j, u_acc, a=2.0):
     return p, lnprob, nacc
 
 
-def emcee_wrapper_rows(pos0, lnprob_fn, nsteps, streams, a=2.0):
+def emcee_wrapper_rows(pos0, lnprob_fn, nsteps, streams, a=2.0, blob_fn=None):
     """samplers/emcee.py:66-88: the reference's bookkeeping around
     ``run_mcmc(pos, 1)``.
 
@@ -237,6 +237,9 @@ def emcee_wrapper_rows(pos0, lnprob_fn, nsteps, streams, a=2.0):
     weight, x_old) is emitted -- the lnl written beside the OLD position is
     that of the NEXT position (:68, :74, :78) -- and the weight resets to 1.
     ``streams(i) -> (u_z, j, u_acc)`` supplies step i's numbers.
+    ``blob_fn(x)``, if given, stands for the ``params`` blob emcee returns with ``posnext``; like the
+    lnl, the extras the reference writes beside the old position are those of the next one (:68, :78),
+    and the row tuples get them as a fourth element.
     Returns (rows_per_walker, final_pos, final_lnprob)."""
     pos = np.array(pos0, dtype=float)
     k = pos.shape[0]
@@ -250,7 +253,8 @@ def emcee_wrapper_rows(pos0, lnprob_fn, nsteps, streams, a=2.0):
             if (pos[w] == posnext[w]).all() and i != nsteps - 1:
                 weight[w] += 1
             else:
-                rows[w].append((-lnprob[w], weight[w], pos[w].copy()))
+                row = (-lnprob[w], weight[w], pos[w].copy())
+                rows[w].append(row if blob_fn is None else row + (blob_fn(posnext[w]),))
                 weight[w] = 1
         pos = posnext
     return rows, pos, lnprob

@@ -55,3 +55,22 @@ def gauss_script(cov, sampler=None, start=0.0):
             return self.like([self["p%02d" % i] for i in range(ndim)])
 
     return gauss
+
+
+def derived_script(sampler=None):
+    """two parameters plus derived quantities stored on the script in __call__ (the script of
+    oracle/make_golden_extras.py, for ``output_extra_params``)"""
+    class derived(SlikPlugin):
+        def __init__(self):
+            super().__init__()
+            self.a = param(start=0, scale=1)
+            self.b = param(start=0.5, scale=1, min=-4)
+            self.sampler = sampler(self) if sampler else None
+
+        def __call__(self):
+            self.r2 = self.a ** 2 + self.b ** 2
+            self.ratio = (self.a - 1.5) / (2 + self.b ** 2)
+            self.fixed = 3.25
+            return self.r2 / 2
+
+    return derived

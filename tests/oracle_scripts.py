@@ -43,6 +43,23 @@ def quick_script():
     return quick
 
 
+def derived_script():
+    """the script of oracle/make_golden_extras.py (derived quantities stored in __call__)"""
+    class derived(runtime.Plugin):
+        def __init__(self):
+            super().__init__()
+            self.a = runtime.Param(start=0, scale=1)
+            self.b = runtime.Param(start=0.5, scale=1, min=-4)
+
+        def __call__(self):
+            self.r2 = self.a ** 2 + self.b ** 2
+            self.ratio = (self.a - 1.5) / (2 + self.b ** 2)
+            self.fixed = 3.25
+            return self.r2 / 2
+
+    return derived
+
+
 def gauss_script(cov):
     ndim = cov.shape[0]
     cinv = np.linalg.inv(cov)

@@ -1,0 +1,91 @@
+"""``output_extra_params`` on the GPU: derived quantities a script stores on itself in ``__call__`` are
+compiled to the coefficient bytecode and evaluated by the priors/bytecode kernel for every emitted row
+(reference: metropolis_hastings.py:103, 183-186, 221, 228).  Checked against a run of the UNMODIFIED
+reference with the same injected streams (tests/golden/mh_extras.npz, oracle/make_golden_extras.py)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+import b200_scripts as B
+from cosmoslik_b200 import Slik, load_chain, samplers
+
+pytestmark = pytest.mark.gpu
+
+
+def test_mh_extra_columns_match_the_reference(tmp_path):
+    g = golden("mh_extras.npz")
+    names = [str(k) for k in g["extra_names"]]
+    n = len(g["u"])
+    out = str(tmp_path / "extras.chain")
+    streams = dict(z=g["z"][:, None, :], u=g["u"][:, None])
+    slik = Slik(B.derived_script(lambda s: samplers.metropolis_hastings(
+        s, num_samples=n, streams=streams, output_file=out, output_extra_params=names, mpi_comm_freq=50,
+        max_weight=5))())
+    rows = list(slik.sample())
+    assert len(rows) == len(g["weight"]), "different number of emitted rows: a decision flipped"
+    np.testing.assert_array_equal([s.weight for s in rows], g["weight"])
+    np.testing.assert_allclose([s.x for s in rows], g["x"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose([s.lnl for s in rows], g["lnl"], rtol=1e-10, atol=1e-13)
+    got = np.array([[s.extra[k] for k in names] for s in rows])
+    np.testing.assert_allclose(got, g["extras"], rtol=1e-12, atol=1e-12)
+    assert np.all(got[:, names.index("fixed")] == 3.25)
+    # the chain file: header carries the extra names, every record the extra columns, and the
+    # single-process block structure (last row of each block dropped) is the reference's
+    c = load_chain(out)[0]
+    assert list(c.keys()) == ["lnl", "weight", "a", "b", "r2", "ratio", "fixed"]
+    assert len(c["lnl"]) == len(g["file_lnl"])
+    np.testing.assert_array_equal(c["weight"], g["file_weight"])
+    for k in ("a", "b", "r2", "ratio", "fixed"):
+        np.testing.assert_allclose(c[k], g["file_" + k], rtol=1e-12, atol=1e-12)
+
+
+def test_extras_program_on_a_batch():
+    """Slik.extras_program evaluates the derived quantities for any batch of points (ragged sizes,
+    the empty batch) and the priors sampler attaches them to its samples"""
+    slik = Slik(B.derived_script(lambda s: samplers.metropolis_hastings(s, num_samples=10))())
+    ex = slik.extras_program(["ratio", "r2"])
+    X = np.random.RandomState(3).standard_normal((333, 2))
+    got = ex.values_host(X)
+    ref = np.stack([(X[:, 0] - 1.5) / (2 + X[:, 1] ** 2), X[:, 0] ** 2 + X[:, 1] ** 2], axis=1)
+    np.testing.assert_allclose(got, ref, rtol=1e-14, atol=0)
+    assert ex.values_host(np.empty((0, 2))).shape == (0, 2)
+    assert slik.extras_program(["ratio", "r2"]) is ex
+    with pytest.raises(KeyError):
+        slik.extras_program(["nope"])
+
+
+def test_emcee_file_extras_are_those_of_the_next_position(tmp_path):
+    """the emcee wrapper writes extras to the chain FILE only, and -- like the lnl -- those of the
+    position the walker moved to (emcee.py:66-78)"""
+    import oracle_scripts as S
+    from oracle import runtime as ort, samplers as osamp
+    k, nsteps, names = 24, 13, ["ratio", "r2"]
+    rs = np.random.RandomState(11)
+    streams = [(rs.uniform(size=(2, k // 2)), rs.randint(k // 2, size=(2, k // 2)), rs.uniform(size=(2, k // 2)))
+               for _ in range(nsteps)]
+    out = str(tmp_path / "emcee_extras.chain")
+    slik = Slik(B.derived_script(lambda s: samplers.emcee(
+        s, num_samples=k * nsteps, nwalkers=k, streams=lambda i: streams[i], seed=3, output_file=out,
+        output_freq=4, output_extra_params=names))())
+    pos0 = slik.sampler.initial_positions()
+    slik.sampler.init_pos = pos0
+    yielded = list(slik.sample())
+    assert all(s.extra is None for s in yielded)                 # emcee.py:74: no extras on the samples
+    oslik = ort.Slik(S.derived_script()())
+
+    def lnprob(q):
+        return np.array([-oslik.evaluate(*x)[0] for x in np.atleast_2d(q)])
+
+    def blob(x):
+        p = oslik.evaluate(*x)[1]
+        return [p[n] for n in names]
+
+    rows, opos, _ = osamp.emcee_wrapper_rows(pos0, lnprob, nsteps, lambda i: streams[i], blob_fn=blob)
+    np.testing.assert_array_equal(slik.sampler.stats["pos"].cpu().numpy(), opos)
+    chains = load_chain(out)
+    assert len(chains) == k and list(chains[0].keys()) == ["lnl", "weight", "a", "b", "ratio", "r2"]
+    for w in range(k):
+        np.testing.assert_array_equal(chains[w]["weight"], [r[1] for r in rows[w]])
+        np.testing.assert_array_equal(chains[w]["a"], [r[2][0] for r in rows[w]])
+        for i, n in enumerate(names):
+            np.testing.assert_allclose(chains[w][n], [r[3][i] for r in rows[w]], rtol=1e-13, atol=0)

@@ -208,3 +208,43 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_output_extra_params_compile_to_bytecode():
+    """derived quantities (metropolis_hastings.py:228, ``s.extra[k]``) are read off the traced tree and
+    compiled to coefficient rows; the bytecode reproduces the reference's values at its own samples"""
+    from cosmoslik_b200.program import compile_extras
+    g = golden("mh_extras.npz")
+    names = [str(k) for k in g["extra_names"]]
+    slik = Slik(B.derived_script()())
+    cp, rows = compile_extras(list(slik.get_sampled()), slik.extra_exprs(names))
+    assert cp.meta["nbox"] == 0 and cp.meta["ngauss"] == 0 and cp.meta["resid_mode"] == 0
+    assert len(rows) == len(names) == 4
+    for x, ref in zip(g["x"][:200], g["extras"][:200]):
+        coef = TI.run_bytecode(cp, x)
+        np.testing.assert_allclose([coef[r] for r in rows], ref, rtol=4e-16, atol=0)
+    with pytest.raises(KeyError):
+        slik.extra_exprs(["nonexistent"])
+
+    class vec(SlikPlugin):
+        def __init__(self):
+            super().__init__()
+            self.a = param(start=0, scale=1)
+            self.sampler = None
+
+        def __call__(self):
+            self.v = np.arange(3.0)
+            return self.a ** 2 / 2
+
+    with pytest.raises(TypeError):
+        Slik(vec()).extra_exprs(["v"])
+
+
+def test_sampler_extra_params_bookkeeping():
+    """constructor side of output_extra_params: name -> dtype map like the reference (:103); non-float
+    columns are refused"""
+    from cosmoslik_b200 import samplers
+    s = B.derived_script(lambda p: samplers.metropolis_hastings(p, num_samples=10, output_extra_params=["r2", ("ratio", "float64")]))()
+    assert list(s.sampler.output_extra_params.items()) == [("r2", "float64"), ("ratio", "float64")]
+    with pytest.raises(NotImplementedError):
+        B.derived_script(lambda p: samplers.metropolis_hastings(p, num_samples=10, output_extra_params=[("n", "int64")]))()
