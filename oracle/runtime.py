@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE ONLY -- imported by ``tests/``, ``__graft_entry__.smoke()``
 and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs, never by the
 product package ``cosmoslik_b200``.
 
-Parity status: PINNED.  ``tests/test_oracle_vs_reference.py`` runs this file
+Parity status: PINNED.  ``tests/test_oracle_golden.py`` runs this file
 side by side with the unmodified reference (via ``oracle/refshim.py``) when
 ``/root/reference`` is mounted, and ``tests/test_oracle_golden.py`` checks it
 against the committed outputs of the reference in ``tests/golden/`` everywhere
@@ -266,7 +266,7 @@ def proposal_factor(cov_est, ndim, proposal_scale):
     (metropolis_hastings.py:141-142).  numpy's legacy generator factors the
     covariance by SVD, ``(u, s, v) = svd(cov)``, and returns
     ``mean + standard_normal(ndim) @ (sqrt(s)[:, None] * v)``; checked bitwise
-    against numpy in tests/test_oracle_vs_reference.py."""
+    against numpy in tests/test_oracle_golden.py."""
     cov = np.asarray(cov_est, dtype=float) / ndim * proposal_scale ** 2
     _, s, v = np.linalg.svd(cov)
     return np.sqrt(s)[:, None] * v

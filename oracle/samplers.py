@@ -5,7 +5,7 @@ TEST INFRASTRUCTURE ONLY (see oracle/runtime.py for the rules).
 Parity status:
   * ``mh_mcmc`` / ``mh_single_process_blocks`` / ``pooled_new_cov``: PINNED
     against the unmodified reference run with the same injected streams
-    (tests/golden/mh_*.npz, tests/test_oracle_vs_reference.py).
+    (tests/golden/mh_*.npz, tests/test_oracle_golden.py).
   * ``stretch_half`` / ``ensemble_step``: the reference delegates the stretch
     move to the third-party package ``emcee`` (samplers/emcee.py:63-68; not in
     requirements.txt or setup.py, version unpinned; the 4-tuple returned by
