@@ -1,0 +1,175 @@
+"""The CPU oracle side by side with the UNMODIFIED reference, live, on inputs the committed golden
+vectors do not contain (fresh seeds, other sampler options).  Runs only where the reference tree is
+mounted (the build container); skipped on the GPU box, where tests/test_oracle_golden.py checks the
+oracle against the committed outputs of the same reference code instead."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import likes, refshim, runtime, samplers
+import oracle_scripts as S
+
+pytestmark = pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def R():
+    return refshim.load()
+
+
+def _ref_spt_script(R, which, tt):
+    core = R.core
+
+    class script(core.SlikPlugin):
+        def __init__(self):
+            super().__init__()
+            self.spt = R.spt_lowl.spt_lowl(which)
+            self.cmb = {"TT": tt}
+            self.sampler = None
+
+        def __call__(self):
+            return self.spt(self.cmb)
+
+    return script
+
+
+@pytest.mark.parametrize("which", ["s12", "k11"])
+def test_spt_lowl_lnl_at_fresh_points(R, spt_data, which):
+    tt = S.synthetic_tt() * 1.03 + 7.0                      # not the golden spectrum
+    ref = R.core.Slik(_ref_spt_script(R, which, tt)())
+    ora = runtime.Slik(S.spt_script(spt_data, which, tt)())
+    names = list(ref.get_sampled().keys())
+    assert [str(n) for n in names] == list(ora.get_sampled())
+    start = np.array([ref.get_start()[k] for k in names], dtype=float)
+    scale = np.array([ref.get_sampled()[k].scale for k in names], dtype=float)
+    X = start + 2.0 * scale * np.random.RandomState(777).standard_normal((40, len(names)))
+    X[3, -1] = -0.5                                          # an amplitude below its min -> hard prior
+    n_inf = 0
+    for x in X:
+        a, b = ref.evaluate(*x)[0], ora.evaluate(*x)[0]
+        if np.isinf(a):
+            assert np.isinf(b)
+            n_inf += 1
+        else:
+            assert abs(a - b) <= 1e-13 * abs(a)
+    assert n_inf >= 1
+
+
+def test_clust_poisson_egfs_at_fresh_parameters(R):
+    ref, ora = R.clust_poisson_egfs.clust_poisson_egfs(), likes.ClustPoissonEgfs()
+    for Aps, Acib, ncib in np.random.RandomState(5).uniform([0.1, 0.1, 0.1], [50, 30, 2.0], size=(10, 3)):
+        np.testing.assert_array_equal(ora(Aps=Aps, Acib=Acib, ncib=ncib)(spectra="cl_TT", lmax=2000),
+                                      ref(Aps=Aps, Acib=Acib, ncib=ncib)(spectra="cl_TT", lmax=2000))
+
+
+def test_priors_plugin_on_random_trees(R):
+    """likelihoods/priors.py:6-30 on trees mixing every way of declaring a prior"""
+    rs = np.random.RandomState(9)
+    decls = [dict(start=0, scale=1), dict(start=0, min=-1), dict(start=0, max=2), dict(start=0, min=-1, max=1),
+             dict(start=0, range=(-3, 3)), dict(start=0, uniform_prior=(-2, 2), gaussian_prior=(0.3, 1.5)),
+             dict(start=0, gaussian_prior=(-1.0, 0.25))]
+    core = R.core
+    for _ in range(20):
+        pick = [decls[i] for i in rs.randint(len(decls), size=5)]
+        rt = core.SlikDict(**{"p%d" % i: core.param(**d) for i, d in enumerate(pick)})
+        ot = runtime.Tree(**{"p%d" % i: runtime.Param(**d) for i, d in enumerate(pick)})
+        rp, op = R.priors.priors(rt), runtime.Priors(ot)
+        assert [tuple(u) for u in rp.uniform_priors] == [tuple(u) for u in op.uniform_priors]
+        assert [tuple(g) for g in rp.gaussian_priors] == [tuple(g) for g in op.gaussian_priors]
+        for _ in range(8):
+            vals = rs.uniform(-3.5, 3.5, size=5)
+            r2, o2 = rt.deepcopy(), ot.clone()
+            for i, v in enumerate(vals):
+                r2["p%d" % i] = v
+                o2["p%d" % i] = v
+            a, b = rp(r2), op(o2)
+            assert (np.isinf(a) and np.isinf(b)) or a == b
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(max_weight=3), dict(temp=2.5), dict(proposal_scale=1.1, max_weight=25)])
+def test_mh_rows_with_fresh_streams_and_options(R, opts):
+    """metropolis_hastings._mcmc (:144-164) with injected streams: rows bit for bit"""
+    from oracle.make_golden import run_injected_mh
+    core = R.core
+
+    class quick(core.SlikPlugin):
+        def __init__(self):
+            super().__init__()
+            self.a = core.param(start=0.3, scale=0.7, min=-2.5)
+            self.b = core.param(start=-0.2, scale=1.3, gaussian_prior=(0.0, 2.0))
+
+        def __call__(self):
+            return (self.a ** 2 + self.b ** 2 + self.a * self.b) / 2
+
+    class oquick(runtime.Plugin):
+        def __init__(self):
+            super().__init__()
+            self.a = runtime.Param(start=0.3, scale=0.7, min=-2.5)
+            self.b = runtime.Param(start=-0.2, scale=1.3, gaussian_prior=(0.0, 2.0))
+
+        def __call__(self):
+            return (self.a ** 2 + self.b ** 2 + self.a * self.b) / 2
+
+    rs = np.random.RandomState(31337)
+    n = 1500
+    z, u = rs.standard_normal((n, 2)), rs.uniform(size=n)
+    names, rrows, _ = run_injected_mh(R, quick, n, z, u, **opts)
+    oslik = runtime.Slik(oquick())
+    x0 = [oslik.get_sampled()[k].start for k in oslik.get_sampled()]
+    F = runtime.proposal_factor(runtime.initialize_covariance(oslik.get_sampled()), 2, opts.get("proposal_scale", 2.4))
+    zs, us = iter(z), iter(u)
+    kw = {k: v for k, v in opts.items() if k in ("max_weight", "temp")}
+    orows = list(samplers.mh_mcmc(oslik.evaluate, x0, n, lambda cx: np.asarray(cx) + np.dot(next(zs), F),
+                                  lambda: next(us), **kw))
+    assert [str(k) for k in names] == list(oslik.get_sampled())
+    assert len(orows) == len(rrows) > 50
+    np.testing.assert_array_equal([r.weight for r in orows], [r[1] for r in rrows])
+    np.testing.assert_array_equal([r.x for r in orows], [r[2] for r in rrows])
+    np.testing.assert_array_equal([r.lnl for r in orows], [r[0] for r in rrows])
+
+
+def test_covariance_sources(R, tmp_path):
+    """samplers/utils.py:4-23 + chains.py:891-927: dict of scales, (names, array), covariance file,
+    later sources overriding earlier ones"""
+    core = R.core
+    covfile = str(tmp_path / "prop.covmat")
+    with open(covfile, "w") as f:
+        f.write("# b c\n1.5 0.2\n0.2 0.8\n")
+    decl = dict(a=dict(start=0, scale=2.0), b=dict(start=1, scale=0.5), c=dict(start=1), d=dict(start=0, scale=0.1))
+    rs_ = core.SlikDict(**{k: core.param(**v) for k, v in decl.items()}).find_sampled()
+    os_ = runtime.Tree(**{k: runtime.Param(**v) for k, v in decl.items()}).find_sampled()
+    sources = [(["c", "a"], np.array([[4.0, 0.3], [0.3, 9.0]])), covfile]
+    np.testing.assert_array_equal(R.sutils.initialize_covariance(rs_, sources), runtime.initialize_covariance(os_, sources))
+    np.testing.assert_array_equal(R.sutils.initialize_covariance(rs_, covfile), runtime.initialize_covariance(os_, covfile))
+    dat = np.random.RandomState(2).standard_normal((300, 4)) @ np.random.RandomState(3).standard_normal((4, 4))
+    w = np.random.RandomState(4).randint(0, 9, size=300).astype(float)
+    np.testing.assert_allclose(runtime.get_covariance(dat, w), R.chains.get_covariance(dat, w), rtol=1e-14)
+
+
+def test_product_chain_statistics_against_the_reference_container(R):
+    """the host container the samplers fill (cosmoslik_b200.chains.Chain) against cosmoslik.chains.Chain
+    on the same weighted samples"""
+    from cosmoslik_b200 import Chain
+    rs = np.random.RandomState(12)
+    n = 500
+    d = {"weight": rs.randint(1, 7, size=n).astype(float), "lnl": rs.uniform(0, 9, size=n),
+         "a": rs.standard_normal(n), "b": rs.gamma(2.0, size=n), "c.d": rs.standard_normal(n) * 3 + 1}
+    mine, ref = Chain(d), R.chains.Chain(d)
+    ps = ["a", "b", "c.d"]
+    np.testing.assert_allclose(mine.mean(ps), ref.mean(ps), rtol=1e-14)
+    np.testing.assert_allclose(mine.std(ps), ref.std(ps), rtol=1e-13)
+    np.testing.assert_allclose(mine.cov(ps), ref.cov(ps), rtol=1e-13)
+    np.testing.assert_allclose(mine.corr(ps), ref.corr(ps), rtol=1e-13)
+    assert mine.acceptance() == ref.acceptance() and mine.length() == ref.length()
+    assert mine.length(unique=False) == ref.length(unique=False)
+    for k in ps:
+        np.testing.assert_array_equal(mine.burnin(120)[k], ref.burnin(120)[k])
+        np.testing.assert_array_equal(mine.thin(7)[k], ref.thin(7)[k])
+        np.testing.assert_array_equal(mine.thin(7)["weight"], ref.thin(7)["weight"])
+    bm, br = mine.best_fit(), ref.best_fit()
+    assert {k: bm[k] for k in ps} == {k: br[k] for k in ps}
+    g_m = mine.add_gauss_prior(["a", "b"], [0.1, 2.0], np.array([[1.0, 0.2], [0.2, 2.0]]))
+    g_r = ref.add_gauss_prior(["a", "b"], [0.1, 2.0], np.array([[1.0, 0.2], [0.2, 2.0]]))
+    np.testing.assert_allclose(g_m["weight"], g_r["weight"], rtol=1e-13)
