@@ -323,7 +323,32 @@ class Slik(object):
         for k, v in bound.items():
             params[k] = v
         x = np.array([[float(bound[k]) for k in self._sampled]])
-        return float(self.program().lnl_host(x)[0]), params
+        lnl = float(self.program().lnl_host(x)[0])
+        # the reference hands back the EVALUATED tree (cosmoslik.py:141): scalar quantities the script stored
+        # on itself during __call__ are filled in from the trace (none after a hard-prior hit, :135-137)
+        derived = self.derived_names()
+        if derived and lnl != np.inf:
+            for k, v in zip(derived, self.extras_program(derived).values_host(x)[0]):
+                params[k] = float(v)
+        return lnl, params
+
+    def derived_names(self):
+        """Dotted names of the scalar quantities the script's __call__ stores on the tree as functions of
+        the sampled parameters (found once, from the symbolic trace)."""
+        names = getattr(self, "_derived_names", None)
+        if names is None:
+            names = []
+
+            def walk(node, prefix):
+                for k, v in dict.items(node):
+                    if isinstance(v, SlikDict):
+                        walk(v, prefix + (k,))
+                    elif isinstance(v, sym.Expr) and not isinstance(v, (sym.Par, sym.Const)):
+                        names.append(".".join(prefix + (k,)))
+
+            walk(self._trace()[0], ())
+            self._derived_names = names = sorted(names)
+        return names
 
     def evaluate_batch(self, X):
         """lnl for every row of X [W, ndim].  numpy in -> numpy out (host buffers,

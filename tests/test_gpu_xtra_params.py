@@ -89,3 +89,14 @@ def test_emcee_file_extras_are_those_of_the_next_position(tmp_path):
         np.testing.assert_array_equal(chains[w]["a"], [r[2][0] for r in rows[w]])
         for i, n in enumerate(names):
             np.testing.assert_allclose(chains[w][n], [r[3][i] for r in rows[w]], rtol=1e-13, atol=0)
+
+
+def test_evaluate_returns_the_evaluated_tree():
+    """cosmoslik.py:141: the second element of Slik.evaluate carries what the script stored on itself"""
+    slik = Slik(B.derived_script(lambda s: samplers.metropolis_hastings(s, num_samples=10))())
+    assert slik.derived_names() == ["r2", "ratio"]
+    lnl, p = slik.evaluate(0.3, -0.4)
+    assert abs(lnl - 0.125) < 1e-15 and p["a"] == 0.3 and p["b"] == -0.4
+    assert abs(p["r2"] - 0.25) < 1e-15 and abs(p["ratio"] - (0.3 - 1.5) / (2 + 0.16)) < 1e-15
+    lnl, p = slik.evaluate(a=0.3, b=-5.0)                    # below b's min: the script is not called (:135-137)
+    assert lnl == np.inf and "r2" not in p

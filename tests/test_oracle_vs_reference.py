@@ -2,12 +2,9 @@
 vectors do not contain (fresh seeds, other sampler options).  Runs only where the reference tree is
 mounted (the build container); skipped on the GPU box, where tests/test_oracle_golden.py checks the
 oracle against the committed outputs of the same reference code instead."""
-import os
-
 import numpy as np
 import pytest
 
-from conftest import golden
 from oracle import likes, refshim, runtime, samplers
 import oracle_scripts as S
 
