@@ -65,3 +65,34 @@ def test_emcee_file_rows_get_the_extras_of_the_next_position():
     assert sum(len(d) for d in direct) > k
     for w in range(k):
         np.testing.assert_array_equal(np.array(got[w]), np.array(direct[w]))
+
+
+def test_polychord_prior_transform_and_constructor():
+    """samplers/polychord.py:43-52: the unit cube maps onto min/max (or range) boxes; a parameter without
+    a box is refused; without PyPolyChord ``sample`` raises ImportError instead of falling back"""
+    import pytest
+    from cosmoslik_b200 import SlikPlugin, param, samplers
+
+    class script(SlikPlugin):
+        def __init__(self, bad=False):
+            super().__init__()
+            self.a = param(start=0, scale=1, min=-2, max=3)
+            self.b = param(start=1, scale=1, range=(0.5, 1.5))
+            if bad:
+                self.c = param(start=0, scale=1, min=0)
+
+        def __call__(self):
+            return (self.a ** 2 + self.b ** 2) / 2
+
+    s = script()
+    pc = samplers.polychord(s, output_file="chains/pc", nlive=50)
+    assert pc.nlive == 50 and pc.num_repeats is None and list(pc.sampled) == ["a", "b"]
+    cube = np.array([[0.0, 0.0], [1.0, 1.0], [0.25, 0.5]])
+    np.testing.assert_array_equal(pc.prior_transform(cube), [[-2, 0.5], [3, 1.5], [-0.75, 1.0]])
+    np.testing.assert_array_equal(pc.prior_transform(cube[2]), [-0.75, 1.0])
+    with pytest.raises(ValueError):
+        pc.prior_transform(np.zeros((2, 3)))
+    with pytest.raises(Exception, match="min/max"):
+        samplers.polychord(script(bad=True), output_file="chains/pc")
+    with pytest.raises(ImportError):
+        pc.sample(lambda *x: None)

@@ -100,3 +100,27 @@ def test_evaluate_returns_the_evaluated_tree():
     assert abs(p["r2"] - 0.25) < 1e-15 and abs(p["ratio"] - (0.3 - 1.5) / (2 + 0.16)) < 1e-15
     lnl, p = slik.evaluate(a=0.3, b=-5.0)                    # below b's min: the script is not called (:135-137)
     assert lnl == np.inf and "r2" not in p
+
+
+def test_polychord_callbacks_on_a_batch():
+    """samplers/polychord.py:38-52 batched: cube -> parameters -> (-lnl, extras) for all live points at once"""
+    from cosmoslik_b200 import SlikPlugin, param
+
+    class script(SlikPlugin):
+        def __init__(self):
+            super().__init__()
+            self.a = param(start=0, scale=1, min=-2, max=3)
+            self.b = param(start=1, scale=1, range=(0.5, 1.5))
+            self.sampler = samplers.polychord(self, output_file="chains/pc", output_extra_params=["s"])
+
+        def __call__(self):
+            self.s = self.a + 2 * self.b
+            return (self.a ** 2 + self.b ** 2) / 2
+
+    slik = Slik(script())
+    cube = np.random.RandomState(8).uniform(size=(257, 2))
+    theta = slik.sampler.prior_transform(cube)
+    assert theta[:, 0].min() >= -2 and theta[:, 0].max() <= 3 and theta[:, 1].min() >= 0.5 and theta[:, 1].max() <= 1.5
+    logl, ex = slik.sampler.loglikelihood(slik.evaluate, theta)
+    np.testing.assert_allclose(logl, -(theta[:, 0] ** 2 + theta[:, 1] ** 2) / 2, rtol=1e-14, atol=1e-16)
+    np.testing.assert_allclose(ex[:, 0], theta[:, 0] + 2 * theta[:, 1], rtol=1e-15, atol=0)
