@@ -202,3 +202,34 @@ def test_load_chain_repack(tmp_path):
     for x, y, z in zip(c1, c2, c3):
         for k in x:
             np.testing.assert_array_equal(x[k], y[k]); np.testing.assert_array_equal(x[k], z[k])
+
+
+@pytest.mark.parametrize("nrows", [0, 1, 49, 50, 51, 99, 100, 150, 237])
+def test_single_process_blocks_for_every_row_count(tmp_path, nrows):
+    """metropolis_hastings.py:219-244 at the boundaries: an exact multiple of mpi_comm_freq ends with an
+    empty record, every record drops its last row; rows reach the writer in arbitrary pieces"""
+    freq, nd = 50, 3
+    rs = np.random.RandomState(nrows)
+    rows = rs.standard_normal((nrows, 2 + nd))
+    orows = [osamp.Row(r[2:], r[0], r[1]) for r in rows]
+    _, blocks = osamp.mh_single_process_blocks(orows, nd, freq)
+    path = str(tmp_path / "b.chain")
+    fb = _FileBlocks(path, ["lnl", "weight", "a", "b", "c"], freq, single=True)
+    at = 0
+    while at < nrows:
+        m = int(rs.randint(1, 70))
+        fb.add(0, rows[at:at + m])
+        at += m
+    fb.finish()
+    recs = []
+    with open(path, "rb") as f:
+        pickle.load(f)
+        while True:
+            try:
+                recs.append(pickle.load(f))
+            except EOFError:
+                break
+    assert len(recs) == len(blocks)
+    for (cid, rec), blk in zip(recs, blocks):
+        assert cid == 0
+        np.testing.assert_array_equal(rec.view(float).reshape(-1, 2 + nd), blk)

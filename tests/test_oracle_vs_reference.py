@@ -170,3 +170,48 @@ def test_product_chain_statistics_against_the_reference_container(R):
     g_m = mine.add_gauss_prior(["a", "b"], [0.1, 2.0], np.array([[1.0, 0.2], [0.2, 2.0]]))
     g_r = ref.add_gauss_prior(["a", "b"], [0.1, 2.0], np.array([[1.0, 0.2], [0.2, 2.0]]))
     np.testing.assert_allclose(g_m["weight"], g_r["weight"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("freq,n", [(50, 1200), (37, 900), (100, 400)])
+def test_chain_file_block_structure_live(R, tmp_path, freq, n):
+    """the product's file writer (samplers.metropolis_hastings._FileBlocks, single-process branch) fed with
+    the rows the reference yields must reproduce, record by record, the file the reference wrote in the
+    same run (metropolis_hastings.py:219-244), for several mpi_comm_freq"""
+    import pickle
+    from oracle.make_golden import run_injected_mh
+    from cosmoslik_b200.samplers.metropolis_hastings import _FileBlocks
+    core = R.core
+
+    class quick(core.SlikPlugin):
+        def __init__(self):
+            super().__init__()
+            self.a = core.param(start=0, scale=1)
+            self.b = core.param(start=0, scale=1)
+
+        def __call__(self):
+            return (self.a ** 2 + self.b ** 2) / 2
+
+    rs = np.random.RandomState(freq)
+    ref_file, my_file = str(tmp_path / "ref.chain"), str(tmp_path / "mine.chain")
+    names, rows, _ = run_injected_mh(R, quick, n, rs.standard_normal((n, 2)), rs.uniform(size=n), tmpfile=ref_file,
+                                     mpi_comm_freq=freq)
+    fb = _FileBlocks(my_file, ["lnl", "weight"] + [str(k) for k in names], freq, single=True)
+    arr = np.array([np.hstack([r[0], r[1], r[2]]) for r in rows])
+    for i in range(0, len(arr), 41):
+        fb.add(0, arr[i:i + 41])
+    fb.finish()
+
+    def records(path):
+        out = []
+        with open(path, "rb") as f:
+            while True:
+                try:
+                    out.append(pickle.load(f))
+                except EOFError:
+                    return out
+
+    mine, ref = records(my_file), records(ref_file)
+    assert list(mine[0]) == list(ref[0]) and len(mine) == len(ref)
+    for (i1, r1), (i2, r2) in zip(mine[1:], ref[1:]):
+        assert i1 == i2 and r1.dtype == r2.dtype and len(r1) == len(r2)
+        np.testing.assert_array_equal(r1.view(float), r2.view(float))
