@@ -215,3 +215,30 @@ def test_chain_file_block_structure_live(R, tmp_path, freq, n):
     for (i1, r1), (i2, r2) in zip(mine[1:], ref[1:]):
         assert i1 == i2 and r1.dtype == r2.dtype and len(r1) == len(r2)
         np.testing.assert_array_equal(r1.view(float), r2.view(float))
+
+
+def test_product_covariance_sources_against_the_reference(R, tmp_path):
+    """the product's host helpers (samplers.initialize_covariance, chains.combine_covs) on every source
+    format the reference accepts (samplers/utils.py:4-23; chains.py:891-927): scales, (names, array),
+    covariance file, a Chain, and lists of them with later entries overriding earlier ones"""
+    import cosmoslik_b200 as cb
+    core = R.core
+    covfile = str(tmp_path / "prop.covmat")
+    with open(covfile, "w") as f:
+        f.write("# b c\n1.5 0.2\n0.2 0.8\n")
+    rs = np.random.RandomState(21)
+    cd = {"weight": rs.randint(1, 5, size=80).astype(float), "lnl": rs.uniform(size=80),
+          "a": rs.standard_normal(80), "d": rs.standard_normal(80) * 0.3}
+    decl = dict(a=dict(start=0, scale=2.0), b=dict(start=1, scale=0.5), c=dict(start=1), d=dict(start=0, scale=0.1))
+    r_s = core.SlikDict(**{k: core.param(**v) for k, v in decl.items()}).find_sampled()
+    b_s = cb.SlikDict(**{k: cb.param(**v) for k, v in decl.items()}).find_sampled()
+    assert list(r_s.keys()) == list(b_s.keys())
+    tup = (["c", "a"], np.array([[4.0, 0.3], [0.3, 9.0]]))
+    for r_src, b_src in ((covfile, covfile), ([tup, covfile], [tup, covfile]), ([covfile, tup], [covfile, tup]),
+                         ([covfile, R.chains.Chain(cd)], [covfile, cb.Chain(cd)])):
+        np.testing.assert_allclose(cb.samplers.initialize_covariance(b_s, b_src),
+                                   R.sutils.initialize_covariance(r_s, r_src), rtol=1e-14, atol=0)
+    with pytest.raises(ValueError):
+        cb.samplers.initialize_covariance(b_s)                 # 'c' has neither a scale nor a covariance
+    with pytest.raises(ValueError):
+        R.sutils.initialize_covariance(r_s)
