@@ -1,3 +1,4 @@
+import numpy as np
 from numpy import ix_
 
 from ..chains import combine_covs
@@ -23,7 +24,6 @@ def proposal_factor(cov_est, ndim, proposal_scale):
     ``multivariate_normal(cur_x, cov_est/ndim*scale**2)`` builds from an SVD
     (metropolis_hastings.py:141-142), so that injected normal streams reproduce the
     reference's proposals."""
-    import numpy as np
     cov = np.asarray(cov_est, dtype=float) / ndim * proposal_scale ** 2
     _, s, v = np.linalg.svd(cov)
     return np.sqrt(s)[:, None] * v
@@ -54,7 +54,6 @@ def extras_of(lnl, names):
 def append_extras(blocks, extras, ndim):
     """[(chain id, rows [m, 2+ndim])] -> the same with the derived-quantity columns appended
     (rows [m, 2+ndim+nextra]); every new row of the block is evaluated in one device batch."""
-    import numpy as np
     counts = [len(r) for _, r in blocks]
     if sum(counts) == 0:
         nx = len(extras.rows)
@@ -75,7 +74,6 @@ def append_extras_of_next(blocks, pos_now, extras, ndim):
     the last step), so the position a row moved to is the x of that walker's next row, and for its
     newest row the walker's current position ``pos_now[c]`` (it has not moved since).
     ``blocks[c] = (walker id, rows [m, 2+ndim])`` for local walker c, ``pos_now [W, ndim]``."""
-    import numpy as np
     nxt = [np.vstack([r[1:, 2:2 + ndim], pos_now[c][None, :]]) for c, (_, r) in enumerate(blocks) if len(r)]
     nx = len(extras.rows)
     if not nxt:
