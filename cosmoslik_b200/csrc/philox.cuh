@@ -24,7 +24,8 @@ __device__ __forceinline__ philox_out philox4x32_10(uint32_t c0, uint32_t c1, ui
   return o;
 }
 
-// two words -> double in the open interval (0,1)
+// two words -> double in (0, 1]: never 0 (log is taken of it); for m >= 2^52 the +0.5 is absorbed by rounding,
+// and the single value m = 2^53 - 1 (probability 2^-53) gives exactly 1.0
 __device__ __forceinline__ double philox_u01(uint32_t hi, uint32_t lo) {
   uint64_t m = ((uint64_t)(hi >> 5) << 26) + (uint64_t)(lo >> 6);
   return ((double)m + 0.5) * (1.0 / 9007199254740992.0);

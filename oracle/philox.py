@@ -53,8 +53,9 @@ def philox4x32(counter, key, rounds=10):
 
 
 def u01(hi, lo):
-    """Two 32-bit words -> double in the OPEN interval (0, 1):
-    ((hi >> 5) * 2^26 + (lo >> 6) + 0.5) * 2^-53."""
+    """Two 32-bit words -> double in (0, 1]:
+    ((hi >> 5) * 2^26 + (lo >> 6) + 0.5) * 2^-53.  Never 0 (the samplers take its log); for
+    m >= 2^52 the +0.5 is absorbed by rounding and m = 2^53 - 1 gives exactly 1.0."""
     hi = np.asarray(hi, dtype=np.uint64)
     lo = np.asarray(lo, dtype=np.uint64)
     m = (hi >> np.uint64(5)) * np.uint64(1 << 26) + (lo >> np.uint64(6))
