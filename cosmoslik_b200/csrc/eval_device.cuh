@@ -2,7 +2,9 @@
 // kernels (samplers.cu): priors + coefficient bytecode on one parameter row, and the final lnl combine.
 //   reference: cosmoslik_plugins/likelihoods/priors.py:24-30 ; cosmoslik/cosmoslik.py:135-141
 #pragma once
+#ifndef CSL_HOST_TWIN      // tests/host_twin/eval_twin.cpp compiles this header with g++ and supplies the few names it needs
 #include "common.cuh"
+#endif
 
 // xr: the walker's parameter row (any address space); w: its column; columns w >= W are tile padding
 // (their coefficients are written, their prior is not).
