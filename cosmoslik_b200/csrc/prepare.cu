@@ -55,6 +55,14 @@ extern "C" int csl_eval_prepare(const csl_program_t* p, int W, const double* x, 
   const int Wp = (p->ncoef > 0) ? ldc : W;   // coefficient columns W..ldc-1 replay walker W-1
   int grid = (Wp + PREP_THREADS - 1) / PREP_THREADS;
   size_t smem = (size_t)PREP_THREADS * (p->ndim + 1) * sizeof(double);
+  // the x tile of 128 walkers passes the 48 KB default limit of dynamic shared memory from ndim = 48 on
+  // (66.5 KB at CSL_MAX_DIM = 64): opt in to what this program needs, once per size
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+    configured = smem;
+  }
   k_prepare<<<grid, PREP_THREADS, smem, (cudaStream_t)stream>>>(*p, W, Wp, x, coef, ldc, prior);
   return csl_check_launch("k_prepare");
 }

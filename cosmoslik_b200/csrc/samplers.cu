@@ -653,6 +653,12 @@ int csl_fused_propose_prepare(const csl_program_t* p, int Ns, int Wp, int Nc, co
                               double a, uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0, double* q,
                               double* zz, double* coef, int ldc, double* prior, void* stream) {
   const size_t smem = (size_t)SPP_THREADS * (p->ndim + 1) * sizeof(double);
+  static size_t configured = 48 * 1024;      // as in csl_eval_prepare: above 48 KB from ndim = 48 on
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_stretch_propose_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+    configured = smem;
+  }
   k_stretch_propose_prepare<<<(Wp + SPP_THREADS - 1) / SPP_THREADS, SPP_THREADS, smem, (cudaStream_t)stream>>>(
       *p, Ns, Wp, Nc, s, comp, a, seed, step, half, walker0, q, zz, coef, ldc, prior);
   return csl_check_launch("k_stretch_propose_prepare");
