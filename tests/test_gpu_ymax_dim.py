@@ -78,3 +78,28 @@ def test_one_parameter_too_many_is_refused():
     slik = Slik(B.gauss_script(Cv, lambda s: samplers.metropolis_hastings(s, num_samples=10))())
     with pytest.raises(ValueError, match="1..%d" % ND):
         slik.program()
+
+
+def test_adaptive_mh_at_the_maximum_dimension():
+    """pooled proposal update at 64 parameters: the device moments kernel (1 + 64 + 64^2 sums) and the host
+    SVD factor against oracle.mh_lockstep"""
+    Cv = _cov()
+    rs = np.random.RandomState(5)
+    nch, nsteps = 16, 300
+    z, u = rs.standard_normal((nsteps, nch, ND)), rs.uniform(size=(nsteps, nch))
+    slik = Slik(B.gauss_script(Cv, lambda s: samplers.metropolis_hastings(
+        s, num_samples=nsteps * nch, nchains=nch, streams=dict(z=z, u=u), proposal_update_start=100,
+        mpi_comm_freq=100))())
+    got = {}
+    for s in slik.sample():
+        got.setdefault(s.chain, []).append((s.lnl, s.weight, s.x))
+    oslik = ort.Slik(S.gauss_script(Cv)())
+    lnl_batch = lambda X: np.array([oslik.evaluate(*x)[0] for x in X])
+    rows, _, adapt = osamp.mh_lockstep(lnl_batch, np.zeros((nch, ND)), nsteps, np.eye(ND), z=z, u=u,
+                                       proposal_update_start=100, exchange=100)
+    assert len(adapt) == len(slik.sampler.adaptations) == 1 and adapt[0][0] == slik.sampler.adaptations[0][0] == 200
+    np.testing.assert_allclose(slik.sampler.adaptations[0][1], adapt[0][1], rtol=1e-9, atol=1e-12)
+    for c in range(nch):
+        assert len(got.get(c, [])) == len(rows[c]), "chain %d: a decision flipped" % c
+        np.testing.assert_array_equal([r[1] for r in got[c]], [r[1] for r in rows[c]])
+        np.testing.assert_allclose([r[2] for r in got[c]], [r[2] for r in rows[c]], rtol=0, atol=1e-9)
