@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from conftest import ROOT
 from cosmoslik_b200 import _lib
 
@@ -64,3 +66,25 @@ def test_integration_md_struct_matches_the_binding():
     exec(code, ns)
     assert ctypes.sizeof(ns["csl_program_t"]) == ctypes.sizeof(_lib.Program)
     assert [f[0] for f in ns["csl_program_t"]._fields_] == [f[0] for f in _lib.Program._fields_]
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: include/cosmoslik_b200.h must compile as C99 and as C++ on its own (no CUDA,
+    no torch types), and a C program can take the address of every declared entry point"""
+    import shutil
+    import subprocess
+    gcc, gxx = shutil.which("gcc"), shutil.which("g++")
+    if gcc is None or gxx is None:
+        pytest.skip("no gcc / g++")
+    header = os.path.join(ROOT, "include", "cosmoslik_b200.h")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", header])
+    subprocess.check_call([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", header])
+    names = sorted(set(re.findall(r"\b(csl_[a-z0-9_]+)\s*\(", open(header).read())))
+    assert len(names) >= 20
+    src = tmp_path / "use.c"
+    src.write_text('#include "cosmoslik_b200.h"\nvoid* table[] = {%s};\nint main(void) { return table[0] == 0; }\n'
+                   % ", ".join("(void*)%s" % n for n in names))
+    exe = str(tmp_path / "use")
+    subprocess.check_call([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
+                           "-L", os.path.join(ROOT, "cosmoslik_b200"), "-lcosmoslik_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "cosmoslik_b200")])
