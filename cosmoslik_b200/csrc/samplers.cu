@@ -557,6 +557,7 @@ extern "C" int csl_mh_propose(int W, int ndim, const double* cur_x, double* test
   CSL_REQUIRE(mode >= 0 && mode <= 2, "csl_mh_propose: mode must be 0, 1 or 2");
   CSL_REQUIRE(mode == 2 || inj, "csl_mh_propose: injected stream missing");
   CSL_REQUIRE(mode == 0 || F, "csl_mh_propose: proposal factor missing");
+  static_assert((size_t)CSL_MAX_DIM * CSL_MAX_DIM * sizeof(double) <= 48 * 1024, "proposal factor must fit the default dynamic shared memory");
   size_t smem = mode ? (size_t)ndim * ndim * sizeof(double) : 0;
   k_mh_propose<<<warp_grid(W), SAMP_THREADS, smem, (cudaStream_t)stream>>>(W, ndim, cur_x, test_x, mode, inj, F,
                                                                            seed, step, chain0);
@@ -595,6 +596,7 @@ extern "C" int csl_mh_gauss_run(const csl_program_t* p, int W, int nsteps, const
 static int moments_impl(int W, int ndim, const double* rows, const int32_t* nrows, int cap, const double* mean,
                         double* partial, double* out, int burn, void* stream) {
   CSL_REQUIRE(W > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && rows && nrows && partial && out, "csl_mh_moments: bad argument");
+  static_assert((size_t)MOM_TILE * (2 + CSL_MAX_DIM) * sizeof(double) <= 48 * 1024, "row tile must fit the default dynamic shared memory");
   const int m = 1 + ndim + ndim * ndim;
   cudaStream_t s = (cudaStream_t)stream;
   k_mh_moments<<<MOM_BLOCKS, SAMP_THREADS, (size_t)MOM_TILE * (2 + ndim) * sizeof(double), s>>>(W, ndim, rows, nrows, cap, mean, partial, burn);
