@@ -586,6 +586,7 @@ extern "C" int csl_mh_gauss_run(const csl_program_t* p, int W, int nsteps, const
               "csl_mh_gauss_run: null argument");
   CSL_REQUIRE(p->ndim >= 1 && p->ndim <= 32 && p->n >= 1 && p->n <= 32, "csl_mh_gauss_run: ndim and n must be <= 32");
   CSL_REQUIRE((z && z_is_delta) || F, "csl_mh_gauss_run: proposal factor missing");
+  static_assert((size_t)(32 * 32 + 32 * 32 + 32) * sizeof(double) <= 48 * 1024, "factors of the 32-parameter limit above fit the default dynamic shared memory");
   size_t smem = (size_t)(p->ndim * p->ndim + p->n * p->n + p->n) * sizeof(double);
   k_mh_gauss_run<<<warp_grid(W), SAMP_THREADS, smem, (cudaStream_t)stream>>>(
       *p, W, nsteps, Lfac, mean, perm, cur_x, cur_lnl, cur_weight, z, z_is_delta, u, F, seed, step0, chain0, temp,

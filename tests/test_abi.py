@@ -88,3 +88,27 @@ def test_header_is_plain_c(tmp_path):
     subprocess.check_call([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
                            "-L", os.path.join(ROOT, "cosmoslik_b200"), "-lcosmoslik_b200",
                            "-Wl,-rpath," + os.path.join(ROOT, "cosmoslik_b200")])
+
+
+def test_every_dynamic_shared_memory_launch_is_bounded_or_opts_in():
+    """a launch whose dynamic shared memory grows with the problem must either opt in to the size
+    (cudaFuncSetAttribute) or prove at compile time that it stays under the 48 KB default (static_assert):
+    k_prepare missed both and refused to launch from 48 parameters on until the ndim = 64 tests found it"""
+    csrc = os.path.join(ROOT, "cosmoslik_b200", "csrc")
+    checked = 0
+    for fn in sorted(os.listdir(csrc)):
+        if not fn.endswith(".cu"):
+            continue
+        src = open(os.path.join(csrc, fn)).read()
+        for m in re.finditer(r"<<<(.*?)>>>", src, flags=re.S):
+            args = [a.strip() for a in re.split(r",(?![^()]*\))", m.group(1))]
+            if len(args) < 3 or args[2] == "0":
+                continue
+            # the enclosing function: from the previous line starting in column 0 with a letter up to the launch
+            start = max(src.rfind("\nstatic ", 0, m.start()), src.rfind("\nextern ", 0, m.start()),
+                        src.rfind("\nint ", 0, m.start()), src.rfind("\ntemplate ", 0, m.start()))
+            body = src[start:m.start()]
+            assert "cudaFuncSetAttribute" in body or "static_assert" in body, \
+                "%s: launch with dynamic shared memory %r neither opts in nor bounds it" % (fn, args[2])
+            checked += 1
+    assert checked >= 8
