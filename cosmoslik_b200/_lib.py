@@ -48,7 +48,18 @@ class Ensemble(C.Structure):
                 [(n, C.c_void_p) for n in ("pos", "lnl", "q", "lnl_q", "zz", "weight", "pos_old", "rows", "nrows",
                                            "accepted", "naccepted", "ws_coef", "ws_prior", "ws_R", "ws_chi2",
                                            "ws_part", "replica", "peer_ptrs", "flag_ptrs")] +
-                [("multicast_ptr", C.c_uint64), ("epoch", C.c_uint64), ("npeers", C.c_int32), ("rank", C.c_int32)])
+                [("multicast_ptr", C.c_uint64), ("epoch", C.c_uint64), ("npeers", C.c_int32), ("rank", C.c_int32),
+                 ("sync", C.c_void_p)])
+
+
+class MHState(C.Structure):
+    """csl_mh_t"""
+    _fields_ = ([(n, C.c_int32) for n in ("ndim", "W", "cap")] +
+                [("chain0", C.c_uint32), ("seed", C.c_uint64), ("temp", C.c_double), ("max_weight", C.c_double),
+                 ("yield_rejected", C.c_int32), ("inj_is_delta", C.c_int32)] +
+                [(n, C.c_void_p) for n in ("cur_x", "cur_lnl", "cur_weight", "test_x", "test_lnl", "rows", "nrows",
+                                           "accepted", "margin", "naccepted", "F", "step", "inj_z", "inj_u",
+                                           "ws_coef", "ws_prior", "ws_R", "ws_chi2", "ws_part")])
 
 
 _P = C.POINTER(Program)
@@ -83,7 +94,16 @@ SIGNATURES = {
                                   _vp, _vp, _vp]),
     "csl_stretch_accept_publish": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _u32,
                                           _vp, _vp, _vp, _int, _u64, C.c_int64, _vp]),
-    "csl_peer_barrier": (_int, [_vp, _int, _int, _u64, _vp]),
+    "csl_peer_barrier": (_int, [_vp, _int, _int, _u64, _vp, _vp]),
+    "csl_peer_wait": (_int, [_vp, _int, _int, _u64, _vp, _vp]),
+    "csl_sizeof_mh": (_int, []),
+    "csl_mh_run": (_int, [_P, C.POINTER(MHState), _int, _vp]),
+    "csl_mh_graph_create": (_int, [_P, C.POINTER(MHState), _int, C.POINTER(C.c_void_p)]),
+    "csl_graph_launch": (_int, [_vp, _vp]),
+    "csl_graph_nodes": (_int, [_vp]),
+    "csl_graph_destroy": (_int, [_vp]),
+    "csl_mh_moments_fused": (_int, [_int, _int, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
+    "csl_mh_adapt_factor": (_int, [_int, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),
     "csl_stretch_run": (_int, [_P, C.POINTER(Ensemble), _int, _u32, C.c_int64, _vp]),
     "csl_emcee_rows": (_int, [_int, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _vp]),
     "csl_chain_moments": (_int, [_int, _int, _vp, _vp, _int, _int, _vp, _vp]),
@@ -112,7 +132,8 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             f = getattr(L, name)
             f.restype, f.argtypes = res, args
-        if L.csl_sizeof_program() != C.sizeof(Program) or L.csl_sizeof_ensemble() != C.sizeof(Ensemble):
+        if (L.csl_sizeof_program() != C.sizeof(Program) or L.csl_sizeof_ensemble() != C.sizeof(Ensemble)
+                or L.csl_sizeof_mh() != C.sizeof(MHState)):
             raise ImportError("cosmoslik_b200: struct layout mismatch between header and binding")
         _lib = L
     return _lib

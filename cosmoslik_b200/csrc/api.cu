@@ -38,6 +38,25 @@ extern "C" int csl_device_info(int device, int32_t* out) {
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// SM count of the CURRENT device, cached per device (launch-shape decisions)
+int csl_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+
+// integer environment override (sweeps / debugging); callers cache the result in a function-local static
+int csl_env_int(const char* name, int fallback) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : fallback;
+}
+
 extern "C" int csl_lnl(const csl_program_t* p, int W, const double* x, double* lnl, double* ws_coef,
                        double* ws_prior, double* ws_R, double* ws_chi2, double* ws_part, void* stream) {
   CSL_REQUIRE(p && x && lnl && ws_prior && W > 0, "csl_lnl: null argument");
@@ -81,11 +100,12 @@ extern "C" int csl_stretch_run(const csl_program_t* p, csl_ensemble_t* e, int ns
   CSL_REQUIRE(e->ndim == p->ndim && e->n0 >= 0 && e->n1 >= 0 && e->h0 > 0 && e->h1 > 0, "csl_stretch_run: bad ensemble");
   CSL_REQUIRE(e->pos && e->lnl && e->q && e->lnl_q && e->zz && e->weight && e->pos_old && e->rows && e->nrows,
               "csl_stretch_run: ensemble buffer missing");
-  CSL_REQUIRE(e->replica == nullptr || (e->peer_ptrs && e->flag_ptrs && e->npeers > 0),
-              "csl_stretch_run: replica given without peer / flag pointers");
+  CSL_REQUIRE(e->replica == nullptr || (e->peer_ptrs && e->flag_ptrs && e->npeers > 0 && e->sync),
+              "csl_stretch_run: replica given without peer / flag pointers / sync words");
   const int nd = e->ndim, W = e->n0 + e->n1;
   // binned bandpower likelihoods take the fused stages; everything else the staged ones
-  const bool fused = p->resid_mode == 1 && e->ws_coef && e->ws_R && e->ws_chi2 && getenv("CSL_NO_FUSE") == nullptr;
+  static const bool no_fuse = csl_env_int("CSL_NO_FUSE", 0) != 0;
+  const bool fused = p->resid_mode == 1 && e->ws_coef && e->ws_R && e->ws_chi2 && !no_fuse;
   for (int i = 0; i < nsteps; ++i) {
     const uint32_t step = step0 + (uint32_t)i;
     for (int h = 0; h < 2; ++h) {
@@ -101,26 +121,29 @@ extern "C" int csl_stretch_run(const csl_program_t* p, csl_ensemble_t* e, int ns
         double* q = e->q + (long long)r0 * nd;
         uint8_t* acc = e->accepted ? e->accepted + r0 : nullptr;
         if (fused) {
-          // propose+prepare | residual | chi^2 (partials) | combine+accept(+publish): 2 + nclass launches per half
+          // propose+prepare | residual | chi^2 (partials) | combine+accept(+publish+signal): 2 + nclass launches
+          // per half.  Sharded: the proposal kernel WAITS for every peer's previous half-step (epoch), the accept
+          // kernel's last CTA SIGNALS this one (epoch + 1): no separate barrier launch.
           const int Wp = round_up(ns, CSL_BN);
+          csl_peer_args pa;
+          pa.flag_ptrs = e->flag_ptrs; pa.sync = e->sync; pa.epoch = e->epoch; pa.rank = e->rank; pa.world = e->npeers;
           rc = csl_fused_propose_prepare(p, ns, Wp, csize, s, comp, e->a, e->seed, step, (uint32_t)h, g0, q,
-                                         e->zz + r0, e->ws_coef, Wp, e->ws_prior, stream);
+                                         e->zz + r0, e->ws_coef, Wp, e->ws_prior, e->replica ? &pa : nullptr, stream);
           if (rc) return rc;
           rc = csl_bin_residual(p, Wp, e->ws_coef, Wp, e->ws_R, Wp, stream);
           if (rc) return rc;
           rc = csl_chi2_impl(p, Wp, e->ws_R, Wp, e->ws_chi2, e->ws_part, false, stream);
           if (rc) return rc;
           const bool parts = p->chi2_mode == 1;
+          pa.epoch = e->epoch + 1;
           rc = csl_fused_combine_accept(p, ns, csize, nd, s, e->lnl + r0, q, e->lnl_q, e->zz + r0, e->seed, step,
                                         (uint32_t)h, g0, acc, e->naccepted, e->replica ? e->peer_ptrs : nullptr,
                                         e->replica ? e->npeers : 0, e->replica ? e->multicast_ptr : 0, (int64_t)g0,
                                         e->ws_coef, Wp, e->ws_prior, parts ? nullptr : e->ws_chi2,
-                                        parts ? e->ws_part : nullptr, p->n_pad / 32, Wp, stream);
+                                        parts ? e->ws_part : nullptr, p->n_pad / 32, Wp, e->replica ? &pa : nullptr,
+                                        stream);
           if (rc) return rc;
-          if (e->replica) {
-            rc = csl_peer_barrier(e->flag_ptrs, e->rank, e->npeers, ++e->epoch, stream);
-            if (rc) return rc;
-          }
+          if (e->replica) ++e->epoch;
           continue;
         }
         rc = csl_stretch_propose(ns, csize, nd, s, comp, e->a, nullptr, nullptr, e->seed, step, (uint32_t)h, g0, q,
@@ -136,14 +159,26 @@ extern "C" int csl_stretch_run(const csl_program_t* p, csl_ensemble_t* e, int ns
           rc = csl_stretch_accept(ns, csize, nd, s, e->lnl + r0, q, e->lnl_q, e->zz + r0, nullptr, e->seed, step,
                                   (uint32_t)h, g0, acc, e->naccepted, stream);
         if (rc) return rc;
+        if (e->replica) {
+          rc = csl_peer_barrier(e->flag_ptrs, e->rank, e->npeers, ++e->epoch, e->sync, stream);
+          if (rc) return rc;
+        }
+        continue;
       }
-      if (e->replica) {
-        rc = csl_peer_barrier(e->flag_ptrs, e->rank, e->npeers, ++e->epoch, stream);
+      if (e->replica) {       // no walker of this colour here: the peers still wait for this rank's signal
+        if (fused) rc = csl_peer_signal(e->flag_ptrs, e->rank, e->npeers, ++e->epoch, stream);
+        else rc = csl_peer_barrier(e->flag_ptrs, e->rank, e->npeers, ++e->epoch, e->sync, stream);
         if (rc) return rc;
       }
     }
     int rc = csl_emcee_rows(W, nd, e->pos_old, e->pos, e->lnl, e->weight, (int64_t)step == last_step ? 1 : 0, e->rows,
                             e->nrows, e->cap, stream);
+    if (rc) return rc;
+  }
+  // fused + sharded: the last half-step has been signalled but not waited for -- whoever reads the replica next
+  // (a per-stage step, the host) must see every peer's stores
+  if (e->replica && fused && nsteps > 0) {
+    int rc = csl_peer_wait(e->flag_ptrs, e->rank, e->npeers, e->epoch, e->sync, stream);
     if (rc) return rc;
   }
   return 0;

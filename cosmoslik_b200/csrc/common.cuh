@@ -15,17 +15,29 @@ int csl_fail(int code, const char* msg);
 int csl_check_launch(const char* what);
 
 // internal (C++ linkage, not in the C ABI): fused stages of csl_stretch_run and the chi^2 partial sums
+struct csl_peer_args {            // exchange ordering of a sharded ensemble folded into a fused stage (samplers.cu)
+  const uint64_t* flag_ptrs;      // device array [world] of every rank's flag array
+  uint32_t* sync;                 // device uint32[2]: sticky status word, ticket counter
+  uint64_t epoch;                 // wait: epoch every peer must have reached; signal: epoch announced
+  int rank, world;
+};
+long long csl_barrier_timeout_cycles();
+int csl_peer_signal(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, void* stream);
 int csl_fused_propose_prepare(const csl_program_t* p, int Ns, int Wp, int Nc, const double* s, const double* comp,
                               double a, uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0, double* q,
-                              double* zz, double* coef, int ldc, double* prior, void* stream);
+                              double* zz, double* coef, int ldc, double* prior, const csl_peer_args* wait,
+                              void* stream);
 int csl_fused_combine_accept(const csl_program_t* p, int Ns, int Nc, int ndim, double* s, double* lnl_s, const double* q,
                              double* lnl_q, const double* zz, uint64_t seed, uint32_t step, uint32_t half,
                              uint32_t walker0, uint8_t* accepted, uint64_t* naccepted, const uint64_t* peer_ptrs,
                              int npeers, uint64_t multicast_ptr, int64_t dst_row0, const double* coef, int ldc,
                              const double* prior, const double* chi2, const double* part, int nblk, int ldp,
-                             void* stream);
+                             const csl_peer_args* signal, void* stream);
 int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part, bool sum_partials,
                   void* stream);
+// device / environment facts read once per process (api.cu)
+int csl_sm_count();
+int csl_env_int(const char* name, int fallback);
 
 #define CSL_REQUIRE(cond, msg) do { if (!(cond)) return csl_fail(CSL_E_BADARG, msg); } while (0)
 

@@ -6,6 +6,7 @@
 // walker per step.
 #include "eval_device.cuh"
 #include "philox.cuh"
+#include <stdlib.h>
 
 #define SAMP_THREADS 256
 #define SAMP_WARPS (SAMP_THREADS / 32)
@@ -297,12 +298,77 @@ k_stretch_propose(int Ns, int Nc, int nd, const double* __restrict__ s, const do
 // thread per walker computes its proposal row (same arithmetic as k_stretch_propose), keeps it in shared
 // memory and runs prepare_walker on it.  Columns Ns..Wp-1 of the coefficient tile replay walker Ns-1.
 #define SPP_THREADS 128
+
+// ---- device-side exchange ordering of the sharded ensemble (replaces a separate barrier launch) -----------
+// Every rank owns uint64 flags[world] in symmetric memory; flags[r] on rank k = the last half-step epoch whose
+// position stores rank r has finished publishing into rank k's replica.
+//   signal: the LAST CTA of the publishing kernel (ticket counter) stores the epoch into its slot on every
+//           peer with a system-scope release (cumulative over the CTAs' stores, each followed by a
+//           system fence before its ticket).
+//   wait:   the first thing the next proposal kernel does -- thread r of every CTA spins on flags[r] with
+//           acquire loads until it reaches the epoch, then the CTA proceeds to read the complementary half.
+// A rank can therefore run ahead of a slow peer by at most one half-step, and the write-after-read hazard on the
+// replica is excluded by the same chain (a peer's stores for half-step e+1 come after its wait for e, which
+// comes after this rank's signal for e, which comes after this rank's reads for e).
+// sync[0] = sticky status word (bit 0: a wait timed out -- the host raises), sync[1] = ticket counter.
+__device__ __forceinline__ bool peer_wait_flag(const unsigned long long* mine, unsigned long long epoch,
+                                               unsigned int* sync, long long timeout_cycles) {
+  unsigned long long seen = 0;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+    if (seen >= epoch) return true;
+    if (sync && *reinterpret_cast<volatile unsigned int*>(sync) != 0u) return false;   // already failed: do not spin again
+    if (clock64() - t0 > timeout_cycles) {
+      if (sync) atomicOr(sync, 1u);
+      else __trap();                       // no status word to report through: fail loudly
+      return false;
+    }
+    __nanosleep(32);
+  }
+}
+
+// all CTAs call this after their last peer store; the last one to arrive signals every peer
+__device__ __forceinline__ void peer_signal_last_cta(const unsigned long long* __restrict__ flag_ptrs, int rank, int world,
+                                                     unsigned long long epoch, unsigned int* sync) {
+  __shared__ unsigned int s_last;
+  __syncthreads();                                  // this CTA's stores are all issued
+  if (threadIdx.x == 0) {
+    __threadfence_system();                         // ... and ordered before the ticket
+    const unsigned int t = atomicAdd(sync + 1, 1u);
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    if ((int)threadIdx.x < world) {
+      __threadfence_system();
+      unsigned long long* theirs = reinterpret_cast<unsigned long long*>(flag_ptrs[threadIdx.x]) + rank;
+      asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(theirs), "l"(epoch) : "memory");
+    }
+    if (threadIdx.x == 0) sync[1] = 0u;             // ready for the next publishing launch (stream ordered)
+  }
+}
+
+struct csl_peer_sync {
+  const unsigned long long* flag_ptrs;   // device array [world] of every rank's flag array, or nullptr (one GPU)
+  unsigned int* sync;                    // [2]: status, ticket
+  unsigned long long epoch;              // wait: the epoch every peer must have reached; signal: the epoch announced
+  long long timeout_cycles;
+  int rank, world;
+};
+
 __global__ void __launch_bounds__(SPP_THREADS)
 k_stretch_propose_prepare(csl_program_t p, int Ns, int Wp, int Nc, const double* __restrict__ s,
-                          const double* __restrict__ comp, double a, uint64_t seed, uint32_t step, uint32_t half,
+                          const double* comp, double a, uint64_t seed, uint32_t step, uint32_t half,
                           uint32_t walker0, double* __restrict__ q, double* __restrict__ zz,
-                          double* __restrict__ coef, int ldc, double* __restrict__ prior) {
+                          double* __restrict__ coef, int ldc, double* __restrict__ prior, csl_peer_sync ps) {
   extern __shared__ double sq[];
+  if (ps.flag_ptrs) {                    // sharded: the peers' stores of the previous half-step must have landed
+    if ((int)threadIdx.x < ps.world)
+      peer_wait_flag(reinterpret_cast<const unsigned long long*>(ps.flag_ptrs[ps.rank]) + threadIdx.x, ps.epoch,
+                     ps.sync, ps.timeout_cycles);
+    __syncthreads();
+  }
   const int nd = p.ndim, lds = nd + 1;
   const int w = blockIdx.x * SPP_THREADS + threadIdx.x;
   if (w >= Wp) return;
@@ -316,7 +382,7 @@ k_stretch_propose_prepare(csl_program_t p, int Ns, int Wp, int Nc, const double*
   const long long sb = (long long)k * nd, cb = (long long)j * nd;
   double* qr = sq + threadIdx.x * lds;
   for (int i = 0; i < nd; ++i) {
-    const double c = comp[cb + i];
+    const double c = __ldcg(comp + cb + i);            // L2 is the point of coherence for the peers' stores
     const double v = __dsub_rn(c, __dmul_rn(z, __dsub_rn(c, s[sb + i])));     // q = c - zz * (c - s)
     qr[i] = v;
     if (w < Ns) q[sb + i] = v;
@@ -378,25 +444,22 @@ k_stretch_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ ln
 }
 
 // Device-side barrier across the ranks of one NVLink domain, launched on the compute stream right after
-// the publishing accept kernel.  flags[r] (one per rank, symmetric memory, uint64[world]) holds the last
-// epoch each peer has reached.  Thread r signals peer r with a system-scope release store (cumulative:
-// the previous kernel's peer stores are ordered before it) and spins on its own slot r with acquire
-// loads.  The host never blocks.  A bounded spin (~4 s) guards against a dead peer.
+// the publishing accept kernel of the STAGED (per-stage) path; the native step loop folds the same signal /
+// wait into its accept and proposal kernels instead.  Thread r signals peer r with a system-scope release store
+// (cumulative: the previous kernel's peer stores are ordered before it) and spins on its own slot r with
+// acquire loads.  The host never blocks.  A wait that exceeds the timeout sets the sticky status word (the host
+// checks it and raises) -- or traps when no status word was given; it never passes silently.
+// signal = 0: wait only (end of csl_stretch_run: the caller may read the replica afterwards).
 __global__ void k_peer_barrier(const unsigned long long* __restrict__ flag_ptrs, int rank, int world,
-                               unsigned long long epoch) {
+                               unsigned long long epoch, int signal, unsigned int* sync, long long timeout_cycles) {
   const int r = threadIdx.x;
   if (r >= world) return;
-  __threadfence_system();
-  unsigned long long* theirs = reinterpret_cast<unsigned long long*>(flag_ptrs[r]) + rank;
-  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(theirs), "l"(epoch) : "memory");
-  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(flag_ptrs[rank]) + r;
-  unsigned long long seen = 0;
-  const long long t0 = clock64();
-  do {
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-    if (seen >= epoch) break;
-    __nanosleep(40);
-  } while (clock64() - t0 < 8000000000ll);
+  if (signal) {
+    __threadfence_system();
+    unsigned long long* theirs = reinterpret_cast<unsigned long long*>(flag_ptrs[r]) + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(theirs), "l"(epoch) : "memory");
+  }
+  peer_wait_flag(reinterpret_cast<const unsigned long long*>(flag_ptrs[rank]) + r, epoch, sync, timeout_cycles);
   __threadfence_system();
 }
 
@@ -410,15 +473,17 @@ struct csl_fused_combine {
   const double* prior; const double* chi2; const double* part; int nblk, ldp;
   double* lnl_q;
 };
-#define SAB_THREADS 256
+#define SAB_THREADS 256          // largest CTA; launches of a few thousand walkers use smaller ones (more CTAs)
 __global__ void __launch_bounds__(SAB_THREADS)
 k_stretch_combine_accept(int Ns, int nd, double* __restrict__ s, double* __restrict__ lnl_s,
                          const double* __restrict__ q, const double* __restrict__ zz, uint64_t seed, uint32_t step,
                          uint32_t half, uint32_t walker0, uint32_t Nc, uint8_t* __restrict__ accepted,
                          const unsigned long long* __restrict__ peers, int npeers, unsigned long long mc_ptr,
-                         long long dst_row0, unsigned long long* __restrict__ nacc, csl_fused_combine fc) {
+                         long long dst_row0, unsigned long long* __restrict__ nacc, csl_fused_combine fc,
+                         csl_peer_sync ps) {
   __shared__ unsigned char sacc[SAB_THREADS];
-  const int k0 = blockIdx.x * SAB_THREADS, k = k0 + threadIdx.x;
+  const int nthr = blockDim.x;
+  const int k0 = blockIdx.x * nthr, k = k0 + threadIdx.x;
   bool acc = false;
   if (k < Ns) {
     double uz, ua;
@@ -439,9 +504,9 @@ k_stretch_combine_accept(int Ns, int nd, double* __restrict__ s, double* __restr
   sacc[threadIdx.x] = acc ? 1 : 0;
   const int c = __syncthreads_count(acc);
   if (nacc && threadIdx.x == 0 && c) atomicAdd(nacc, (unsigned long long)c);
-  const int nw = min(SAB_THREADS, Ns - k0);
+  const int nw = min(nthr, Ns - k0);
   const long long base = (long long)k0 * nd, dbase = (dst_row0 + k0) * nd;
-  for (int idx = threadIdx.x; idx < nw * nd; idx += SAB_THREADS) {
+  for (int idx = threadIdx.x; idx < nw * nd; idx += nthr) {
     const bool a = sacc[idx / nd] != 0;
     const double v = a ? q[base + idx] : s[base + idx];
     if (a) s[base + idx] = v;
@@ -452,6 +517,8 @@ k_stretch_combine_accept(int Ns, int nd, double* __restrict__ s, double* __restr
       for (int r = 0; r < npeers; ++r) reinterpret_cast<double*>(peers[r])[dbase + idx] = v;
     }
   }
+  // sharded: announce this half-step to every peer once ALL CTAs of this launch have stored
+  if (ps.flag_ptrs) peer_signal_last_cta(ps.flag_ptrs, ps.rank, ps.world, ps.epoch, ps.sync);
 }
 
 // Chain.add_gauss_prior on the device (chains.py:206-233): every stored row of every chain gets
@@ -652,18 +719,40 @@ static int stretch_accept_impl(int Ns, int Nc, int ndim, double* s, double* lnl_
 }
 
 // ---- fused stages of the native step loop (api.cu: csl_stretch_run); not part of the C ABI -----------------
+long long csl_barrier_timeout_cycles() {
+  // CSL_BARRIER_TIMEOUT_S (default 120 s): how long a rank waits for a peer's half-step before it gives up.
+  // Read once; clock64 ticks at the SM clock (<= 2 GHz on B200).
+  static long long cached = 0;
+  if (!cached) {
+    double sec = 120.0;
+    if (const char* e = getenv("CSL_BARRIER_TIMEOUT_S")) { const double v = atof(e); if (v > 0) sec = v; }
+    cached = (long long)(sec * 2.0e9);
+  }
+  return cached;
+}
+
+static csl_peer_sync make_peer_sync(const csl_peer_args* a) {
+  csl_peer_sync ps;
+  ps.flag_ptrs = a ? reinterpret_cast<const unsigned long long*>(a->flag_ptrs) : nullptr;
+  ps.sync = a ? a->sync : nullptr;
+  ps.epoch = a ? (unsigned long long)a->epoch : 0ull;
+  ps.timeout_cycles = csl_barrier_timeout_cycles();
+  ps.rank = a ? a->rank : 0;
+  ps.world = a ? a->world : 0;
+  return ps;
+}
+
 int csl_fused_propose_prepare(const csl_program_t* p, int Ns, int Wp, int Nc, const double* s, const double* comp,
                               double a, uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0, double* q,
-                              double* zz, double* coef, int ldc, double* prior, void* stream) {
+                              double* zz, double* coef, int ldc, double* prior, const csl_peer_args* wait,
+                              void* stream) {
   const size_t smem = (size_t)SPP_THREADS * (p->ndim + 1) * sizeof(double);
-  static size_t configured = 48 * 1024;      // as in csl_eval_prepare: above 48 KB from ndim = 48 on
-  if (smem > configured) {
+  if (smem > 48 * 1024) {                      // above the default from ndim = 48 on; per device, cheap: set every time
     cudaError_t e = cudaFuncSetAttribute(k_stretch_propose_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-    configured = smem;
   }
   k_stretch_propose_prepare<<<(Wp + SPP_THREADS - 1) / SPP_THREADS, SPP_THREADS, smem, (cudaStream_t)stream>>>(
-      *p, Ns, Wp, Nc, s, comp, a, seed, step, half, walker0, q, zz, coef, ldc, prior);
+      *p, Ns, Wp, Nc, s, comp, a, seed, step, half, walker0, q, zz, coef, ldc, prior, make_peer_sync(wait));
   return csl_check_launch("k_stretch_propose_prepare");
 }
 
@@ -672,14 +761,20 @@ int csl_fused_combine_accept(const csl_program_t* p, int Ns, int Nc, int ndim, d
                              uint32_t walker0, uint8_t* accepted, uint64_t* naccepted, const uint64_t* peer_ptrs,
                              int npeers, uint64_t multicast_ptr, int64_t dst_row0, const double* coef, int ldc,
                              const double* prior, const double* chi2, const double* part, int nblk, int ldp,
-                             void* stream) {
+                             const csl_peer_args* signal, void* stream) {
   csl_fused_combine fc;
   fc.p = *p; fc.coef = coef; fc.ldc = ldc; fc.prior = prior; fc.chi2 = chi2; fc.part = part; fc.nblk = nblk;
   fc.ldp = ldp; fc.lnl_q = lnl_q;
-  k_stretch_combine_accept<<<(Ns + SAB_THREADS - 1) / SAB_THREADS, SAB_THREADS, 0, (cudaStream_t)stream>>>(
+  // CTA size: 256 walkers per CTA in bulk; launches of a few thousand walkers take 64 so that the serial
+  // per-walker phase and the peer stores spread over more SMs (CSL_SAB_THREADS overrides, for sweeps)
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("CSL_SAB_THREADS"); forced = e ? atoi(e) : 0; }
+  int nthr = forced > 0 ? forced : (Ns <= 16384 ? 64 : SAB_THREADS);
+  nthr = nthr < 32 ? 32 : (nthr > SAB_THREADS ? SAB_THREADS : nthr / 32 * 32);
+  k_stretch_combine_accept<<<(Ns + nthr - 1) / nthr, nthr, 0, (cudaStream_t)stream>>>(
       Ns, ndim, s, lnl_s, q, zz, seed, step, half, walker0, (uint32_t)Nc, accepted,
       reinterpret_cast<const unsigned long long*>(peer_ptrs), npeers, (unsigned long long)multicast_ptr,
-      (long long)dst_row0, reinterpret_cast<unsigned long long*>(naccepted), fc);
+      (long long)dst_row0, reinterpret_cast<unsigned long long*>(naccepted), fc, make_peer_sync(signal));
   return csl_check_launch("k_stretch_combine_accept");
 }
 
@@ -703,11 +798,40 @@ extern "C" int csl_stretch_accept_publish(int Ns, int Nc, int ndim, double* s, d
                              reinterpret_cast<unsigned long long*>(naccepted), stream);
 }
 
-extern "C" int csl_peer_barrier(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, void* stream) {
+static int peer_barrier_impl(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, int signal,
+                             uint32_t* sync, void* stream) {
   CSL_REQUIRE(flag_ptrs && world > 0 && world <= 32 && rank >= 0 && rank < world, "csl_peer_barrier: bad argument");
   k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(flag_ptrs), rank, world,
-                                                      (unsigned long long)epoch);
+                                                      (unsigned long long)epoch, signal, sync,
+                                                      csl_barrier_timeout_cycles());
   return csl_check_launch("k_peer_barrier");
+}
+
+extern "C" int csl_peer_barrier(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, uint32_t* sync,
+                                void* stream) {
+  return peer_barrier_impl(flag_ptrs, rank, world, epoch, 1, sync, stream);
+}
+
+extern "C" int csl_peer_wait(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, uint32_t* sync,
+                             void* stream) {
+  return peer_barrier_impl(flag_ptrs, rank, world, epoch, 0, sync, stream);
+}
+
+// a rank with no walker in a half still owes its peers the half-step's signal
+__global__ void k_peer_signal(const unsigned long long* __restrict__ flag_ptrs, int rank, int world,
+                              unsigned long long epoch) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  __threadfence_system();
+  unsigned long long* theirs = reinterpret_cast<unsigned long long*>(flag_ptrs[r]) + rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(theirs), "l"(epoch) : "memory");
+}
+
+int csl_peer_signal(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, void* stream) {
+  CSL_REQUIRE(flag_ptrs && world > 0 && world <= 32 && rank >= 0 && rank < world, "csl_peer_signal: bad argument");
+  k_peer_signal<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(flag_ptrs), rank, world,
+                                                     (unsigned long long)epoch);
+  return csl_check_launch("k_peer_signal");
 }
 
 extern "C" int csl_emcee_rows(int W, int ndim, double* pos_old, const double* pos_new, const double* lnl_new,

@@ -40,6 +40,7 @@ from .. import _lib as L
 from .. import dist
 from ..chains import ChainWriter
 from ..core import SlikSampler, arguments, sample
+from .rowstream import RowBlockStream, blocks_of
 from .utils import append_extras_of_next, extras_of, initialize_covariance, program_of
 
 
@@ -63,11 +64,12 @@ class emcee(SlikSampler):
         self.cov_est = initialize_covariance(self.sampled, self.cov_est)
         self.stats = {}
 
-    def initial_positions(self):
+    def initial_positions(self, seed=None):
         """Scatter of the walkers around the start point (emcee.py:49-53)."""
         if self.init_pos is not None:
             return np.ascontiguousarray(self.init_pos, dtype=float)
-        rs = np.random.RandomState(None if self.seed is None else int(self.seed) % (2 ** 32))
+        seed = self.seed if seed is None else seed
+        rs = np.random.RandomState(None if seed is None else int(seed) % (2 ** 32))
         return rs.multivariate_normal([v.start for v in self.sampled.values()], self.cov_est, size=int(self.nwalkers))
 
     def sample(self, lnl):
@@ -77,15 +79,6 @@ class emcee(SlikSampler):
                     s = sample(r[2:].copy(), r[0], r[1], None)
                     s.chain = wid
                     yield s
-
-    @staticmethod
-    def _collect_rows(rows, nrows, prev_n, gid, rl):
-        """device row buffer -> [(global walker id, new rows)] since the previous collection"""
-        W = rows.shape[0]
-        n_now = nrows.cpu().numpy().astype(np.int64)
-        a_, b_ = (int(prev_n.min()), int(n_now.max())) if W else (0, 0)
-        slab = rows[:, a_:b_].cpu().numpy() if b_ > a_ else np.zeros((W, 0, rl))
-        return [(int(gid[c]), slab[c, prev_n[c] - a_:n_now[c] - a_]) for c in range(W)], n_now
 
     def run(self, lnl_or_program, nsteps=None, resume=False):
         """Batched entry point: advance the ensemble `nsteps` steps and return the state dict.
@@ -118,20 +111,37 @@ class emcee(SlikSampler):
             raise ValueError("nwalkers must be even")
         h = k // 2
         rank, size = dist.get_rank(), dist.get_size()
-        lo0, hi0 = dist.shard_bounds(h, rank, size)          # my slice of the first half
-        lo1, hi1 = dist.shard_bounds(k - h, rank, size)      # my slice of the second half
+
+        def local_ids(r):
+            a0, b0 = dist.shard_bounds(h, r, size)               # slice of the first half
+            a1, b1 = dist.shard_bounds(k - h, r, size)           # slice of the second half
+            return a0, b0, a1, b1, np.concatenate([np.arange(a0, b0), h + np.arange(a1, b1)])
+
+        lo0, hi0, lo1, hi1, gid = local_ids(rank)                # global walker ids of the local rows
         n0, n1 = hi0 - lo0, hi1 - lo1
         W = n0 + n1
-        gid = np.concatenate([np.arange(lo0, hi0), h + np.arange(lo1, hi1)])   # global walker ids
         if nsteps is None:
             nsteps = int(ceil(self.num_samples / float(k)))
-        seed = int(self.seed) if self.seed is not None else int(np.random.SeedSequence().entropy & (2 ** 63 - 1))
+        # an unseeded run draws its key on rank 0: every rank must use the same key AND the same start scatter
+        seed = int(self.seed) if self.seed is not None else \
+            dist.broadcast_int(int(np.random.SeedSequence().entropy & (2 ** 63 - 1)))
         kw = dict(dtype=torch.float64, device=dev)
         rl = 2 + nd
-        cap = max(nsteps, int(getattr(self, "row_capacity", 0)), 1)
+        F = max(int(self.output_freq), 1)
+        consume = emit or self.output_file is not None
+        # Rows: with a consumer (generator or chain file) the device holds ONE block of output_freq steps per
+        # walker and hands it to the host asynchronously (rowstream); without one (run(): batched use, tests,
+        # device statistics) the whole history of the call stays on the device.
+        ring = consume
+        cap = F if ring else max(nsteps, int(getattr(self, "row_capacity", 0)), 1)
+        need = W * cap * rl * 8
+        if need > 0.8 * torch.cuda.mem_get_info(dev)[0]:
+            raise MemoryError("row buffer for %d walkers x %d steps needs %.1f GB: run with an output_file / as a "
+                              "generator (rows are then streamed in blocks of output_freq steps), or in shorter calls"
+                              % (W, cap, need / 1e9))
         prev = self.stats if (resume and self.stats and tuple(self.stats["pos"].shape) == (W, nd)) else None
         if prev is None:
-            pos_all = self.initial_positions()
+            pos_all = self.initial_positions(seed)
             if pos_all.shape != (k, nd):
                 raise ValueError("initial positions must be [nwalkers, ndim]")
             pos = torch.from_numpy(pos_all[gid]).to(dev).contiguous()   # local: first-half then second-half slice
@@ -164,15 +174,19 @@ class emcee(SlikSampler):
         nrows = torch.zeros(W, dtype=torch.int32, device=dev)
         accepted = torch.zeros(W, dtype=torch.uint8, device=dev)
         pos_old = pos.clone()                        # refreshed by csl_emcee_rows at the end of every step
+        # ONE chain file for all ranks, written by rank 0 (the reference's master writes one file)
+        file_all = self.output_file is not None and size > 1
         writer = None
-        if self.output_file is not None:
-            path = self.output_file if rank == 0 else "%s.rank%d" % (self.output_file, rank)
-            writer = ChainWriter(path, ["lnl", "weight"] + list(self.sampled) + list(self.output_extra_params), "list")
-        prev_n = np.zeros(W, dtype=np.int64)
+        if self.output_file is not None and rank == 0:
+            writer = ChainWriter(self.output_file, ["lnl", "weight"] + list(self.sampled) + list(self.output_extra_params), "list")
+        all_ids = np.concatenate([local_ids(r)[4] for r in range(size)]) if file_all else gid
+        per_rank = [len(local_ids(r)[4]) for r in range(size)]
+        stream = RowBlockStream(torch, dev, W, cap, rl, all_ranks=file_all, total=k, counts=per_rank) if consume else None
+        local_stream = RowBlockStream(torch, dev, W, cap, rl) if (consume and file_all and emit and rank != 0) else None
+        status = replica.sync if replica is not None else None
         st = L.stream_ptr()
         timers = getattr(self, "timers", None)     # bench.py: CUDA-event pairs per stage
         nacc = torch.zeros((), dtype=torch.int64, device=dev)
-        F = int(self.output_freq)
         t_host0 = time.perf_counter()
         step0 = int(prev["steps_done"]) if prev is not None else 0       # Philox step counter continues on resume
 
@@ -195,13 +209,51 @@ class emcee(SlikSampler):
         def to_dev(arr, dtype):
             return torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(dev)
 
-        def file_rows(blocks):
-            """rows as the chain file holds them: with the extra columns, if any, appended"""
-            if extras is None:
-                return blocks
-            return append_extras_of_next(blocks, pos.cpu().numpy(), extras, nd)
+        pending = [None]
 
-        # Fast path: whole steps are enqueued from C (csl_stretch_run) -- no Python between the ~11 kernel
+        def submit_block():
+            """end of an output block (stream order): hand its rows over, start an empty block"""
+            pos_snap = None
+            if extras is not None:                 # the file's derived columns belong to where a walker moved TO
+                pos_snap = dist.all_gather_rows(pos.clone(), k, per_rank) if file_all else pos.clone()
+            ticket = (stream.submit(rows, nrows, status),
+                      local_stream.submit(rows, nrows) if local_stream is not None else None, pos_snap)
+            nrows.zero_()
+            return ticket
+
+        def hand_over(ticket):
+            """host side of a block: file records on rank 0 (every rank's walkers), local rows to the consumer"""
+            slot, lslot, pos_snap = ticket
+            got = stream.collect(slot)
+            mine = None
+            if got is not None:
+                blocks = blocks_of(got[0], got[1], all_ids)
+                if writer is not None:
+                    recs = blocks if extras is None else append_extras_of_next(blocks, pos_snap.cpu().numpy(), extras, nd)
+                    for wid, r in recs:
+                        for c0 in range(0, len(r), F):      # records of at most output_freq rows (emcee.py:80-84)
+                            writer.write(wid, r[c0:c0 + F])
+                    writer.flush()
+                if file_all:
+                    at = int(sum(per_rank[:rank]))
+                    mine = blocks[at:at + W]
+                else:
+                    mine = blocks
+            if lslot is not None:
+                got = local_stream.collect(lslot)
+                mine = blocks_of(got[0], got[1], gid)
+            return mine
+
+        def end_of_block():
+            """submit this block, then consume the PREVIOUS one on the host while the device runs on"""
+            out = None
+            ticket = submit_block()
+            if pending[0] is not None:
+                out = hand_over(pending[0])
+            pending[0] = ticket
+            return out
+
+        # Fast path: whole steps are enqueued from C (csl_stretch_run) -- no Python between the kernel
         # launches of a step.  Needs device streams and either one GPU or the symmetric-memory replica.
         native = self.streams is None and timers is None and (size == 1 or replica is not None) \
             and not getattr(self, "python_loop", False)
@@ -219,26 +271,22 @@ class emcee(SlikSampler):
                 ens.replica, ens.peer_ptrs = replica.tensor.data_ptr(), replica.peers_dev.data_ptr()
                 ens.flag_ptrs, ens.multicast_ptr = replica.flag_ptrs.data_ptr(), replica.multicast
                 ens.epoch, ens.npeers, ens.rank = replica._epoch, replica.npeers, replica.handle.rank
+                ens.sync = replica.sync.data_ptr()
 
         try:
             i = 0
             while native and i < nsteps:
                 # one call per output block (or for the whole run when nobody consumes rows)
-                nb = min(F - (i % F), nsteps - i) if (emit or writer is not None) else nsteps - i
+                nb = min(F - (i % F), nsteps - i) if consume else nsteps - i
                 L.check(lib.csl_stretch_run(C.byref(prog.struct), C.byref(ens), nb, step0 + i, step0 + nsteps - 1, st),
                         "csl_stretch_run")
                 if replica is not None:
                     replica._epoch = int(ens.epoch)
                 i += nb
-                if (emit or writer is not None) and (i % F == 0 or i == nsteps):
-                    blocks, prev_n = self._collect_rows(rows, nrows, prev_n, gid, rl)
-                    if writer is not None:
-                        for wid, r in file_rows(blocks):
-                            for c0 in range(0, len(r), F):
-                                writer.write(wid, r[c0:c0 + F])
-                        writer.flush()
-                    if emit:
-                        yield blocks
+                if consume and (i % F == 0 or i == nsteps):
+                    out = end_of_block()
+                    if emit and out is not None:
+                        yield out
             for i in (range(nsteps) if not native else ()):
                 step = step0 + i
                 inj = self.streams(step) if self.streams is not None else None
@@ -287,22 +335,27 @@ class emcee(SlikSampler):
                 L.check(lib.csl_emcee_rows(W, nd, pos_old.data_ptr(), pos.data_ptr(), lnl_pos.data_ptr(),
                                            weight.data_ptr(), 1 if i == nsteps - 1 else 0, rows.data_ptr(),
                                            nrows.data_ptr(), cap, st), "csl_emcee_rows")
-                if (emit or writer is not None) and ((i + 1) % F == 0 or i == nsteps - 1):
-                    blocks, prev_n = self._collect_rows(rows, nrows, prev_n, gid, rl)
-                    if writer is not None:
-                        for wid, r in file_rows(blocks):
-                            for c0 in range(0, len(r), F):      # records of at most output_freq rows (emcee.py:80-84)
-                                writer.write(wid, r[c0:c0 + F])
-                        writer.flush()
-                    if emit:
-                        yield blocks
+                if consume and ((i + 1) % F == 0 or i == nsteps - 1):
+                    out = end_of_block()
+                    if emit and out is not None:
+                        yield out
+            if pending[0] is not None:
+                out = hand_over(pending[0])
+                pending[0] = None
+                if emit and out is not None:
+                    yield out
         finally:
             if writer is not None:
                 writer.close()
         host_ms = 1e3 * (time.perf_counter() - t_host0) / max(nsteps, 1)   # CPU time to ENQUEUE one step
         exchange = ("none" if size == 1 else "nccl all_gather" if replica is None else
-                    "accept kernel stores to every rank's replica over NVLink (%s) + device barrier"
+                    "accept kernel stores to every rank's replica over NVLink (%s); release signal in its last CTA, "
+                    "acquire wait at the head of the next proposal kernel"
                     % ("multimem.st multicast" if replica.multicast else "peer pointers"))
-        self.stats = dict(exchange=exchange, host_ms_per_step=host_ms, pos=pos, lnl=lnl_pos, weight=weight, rows=rows,
-                          nrows=nrows, nsteps=nsteps, steps_done=step0 + nsteps, walker_ids=gid, seed=seed,
-                          accepted=int(nacc.item()), evals=nsteps * W)
+        n_acc = int(nacc.item())                  # synchronises: the status word below is final
+        if replica is not None:
+            replica.check()
+        self.stats = dict(exchange=exchange, host_ms_per_step=host_ms, pos=pos, lnl=lnl_pos, weight=weight,
+                          rows=None if ring else rows, nrows=None if ring else nrows, nsteps=nsteps,
+                          steps_done=step0 + nsteps, walker_ids=gid, seed=seed, accepted=n_acc, evals=nsteps * W,
+                          row_storage_bytes=int(rows.numel() * 8 + (stream.W * stream.width * 16 if stream else 0)))

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSL_ABI_VERSION 1
+#define CSL_ABI_VERSION 2
 
 /* error codes (negative; positive values are cudaError_t) */
 #define CSL_E_BADARG   (-1)
@@ -249,6 +249,60 @@ int csl_mh_gauss_run(const csl_program_t* p, int W, int nsteps, const double* Lf
                      uint64_t seed, uint32_t step0, uint32_t chain0, double temp, double max_weight,
                      double* rows, int32_t* nrows, int cap, void* stream);
 
+/* State of one rank's share of a batch of MH chains, for csl_mh_run (all pointers device pointers, caller owned). */
+typedef struct csl_mh {
+  int32_t ndim, W, cap;          /* parameters, chains on this GPU, row-buffer capacity per chain              */
+  uint32_t chain0;               /* global id of local chain 0 (Philox key)                                   */
+  uint64_t seed;
+  double temp, max_weight;       /* metropolis_hastings.py:43, :41                                            */
+  int32_t yield_rejected;        /* :160 -- a rejected proposal is emitted as a weight-0 row                   */
+  int32_t inj_is_delta;          /* inj_z holds offsets (exact add) instead of standard normals               */
+  double *cur_x, *cur_lnl, *cur_weight, *test_x, *test_lnl;
+  double* rows;                  /* [W, cap, 2 + ndim]: (lnl, weight, x...) at slot nrows[w]++                */
+  int32_t* nrows;
+  uint8_t* accepted;             /* [W] last decision, or NULL                                                */
+  double* margin;                /* [W] log(u) - temp (cur - test) of the last step, or NULL                  */
+  uint64_t* naccepted;           /* device counter, or NULL                                                   */
+  const double* F;               /* [ndim, ndim] row-major: test_x = cur_x + z F (rewritten in place by
+                                    csl_mh_adapt_factor between blocks)                                       */
+  uint32_t* step;                /* DEVICE step counter: Philox step number of the next MH step; csl_mh_run
+                                    advances it by nsteps (a block's kernel arguments never change, so one CUDA
+                                    graph serves every block)                                                 */
+  const double* inj_z;           /* injected streams for the steps of ONE call: [nsteps, W, ndim], or NULL     */
+  const double* inj_u;           /* [nsteps, W], or NULL -> Philox                                            */
+  double *ws_coef, *ws_prior, *ws_R, *ws_chi2, *ws_part;   /* csl_lnl workspace for W chains                  */
+} csl_mh_t;
+int csl_sizeof_mh(void);
+
+/* `nsteps` MH steps of every chain (replaces the loop of _mcmc, :150-164, for any compiled posterior): per step
+ * the fused proposal + priors + bytecode kernel, the residual and chi^2 kernels of the program, and the fused
+ * lnl-combine + accept + weight + row-emission kernel, enqueued on `stream` from C.  Chain contents are bit for
+ * bit those of csl_mh_propose / csl_lnl / csl_mh_accept. */
+int csl_mh_run(const csl_program_t* p, const csl_mh_t* m, int nsteps, void* stream);
+
+/* The same block of `nsteps` steps captured ONCE into a CUDA graph (an internal capture stream is used: the
+ * caller's stream may be the legacy default stream, which cannot capture); csl_graph_launch replays it on
+ * `stream` -- one host call per block.  The state's pointers and nsteps are frozen into the graph; the step
+ * counter, the proposal factor and the injected-stream buffers are read through their pointers at run time.
+ * The graph handle is host memory owned by the library until csl_graph_destroy. */
+int csl_mh_graph_create(const csl_program_t* p, const csl_mh_t* m, int nsteps, void** graph_out);
+int csl_graph_launch(void* graph, void* stream);
+int csl_graph_nodes(void* graph);
+int csl_graph_destroy(void* graph);
+
+/* Proposal adaptation without leaving the device (replaces the master's get_new_cov + the SVD inside draw_x).
+ * csl_mh_moments_fused: ONE pass over the last half of every chain's rows,
+ *   out = [sum w, sum w (x - ref), sum w (x - ref)(x - ref)^T]   (1 + ndim + ndim^2 doubles; partial [592, that]);
+ *   `ref` [ndim] is a fixed point (the start point), identical on every rank, so ONE all-reduce of `out` pools
+ *   the ranks.
+ * csl_mh_adapt_factor: from the (all-reduced) sums, cov_out = pooled covariance (denominator sum w - 1,
+ *   chains.py:507-512), F_out = factor with F^T F = cov / ndim * proposal_scale^2 (Cholesky; a direction nobody
+ *   moved in gives a zero column), mean_out (may be NULL) = pooled mean. */
+int csl_mh_moments_fused(int W, int ndim, const double* rows, const int32_t* nrows, int cap, const double* ref,
+                         double* partial, double* out, void* stream);
+int csl_mh_adapt_factor(int ndim, const double* mom, double proposal_scale, const double* ref, double* cov_out,
+                        double* F_out, double* mean_out, void* stream);
+
 /* get_new_cov (:249-253) sufficient statistics over the last half of every chain's rows:
  * pass 1 (mean == NULL): out[0] = sum w, out[1..ndim] = sum w x.
  * pass 2 (mean given):   out[1+ndim ..] = sum w (x-mean)(x-mean)^T  [ndim*ndim].
@@ -299,8 +353,15 @@ int csl_stretch_accept_publish(int Ns, int Nc, int ndim, double* s, double* lnl_
 
 /* Device-side barrier over the ranks of one NVLink domain, on `stream` (the host does not block).
  * flag_ptrs[world]: device addresses of every rank's uint64[world] flag array (symmetric memory, zeroed
- * once); epoch must increase by one per call.  Orders the peer stores of the preceding kernel. */
-int csl_peer_barrier(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, void* stream);
+ * once); epoch must increase by one per call.  Orders the peer stores of the preceding kernel.
+ * sync: device uint32[2] owned by the caller, zeroed once -- sync[0] is a STICKY status word: a wait that
+ * exceeds CSL_BARRIER_TIMEOUT_S (environment, default 120 s) sets bit 0 and every later wait returns at once, so
+ * the host must read it before trusting results (samplers.emcee does, per output block); sync == NULL makes a
+ * timed-out wait trap instead.  A timed-out barrier never passes silently.
+ * Used by the per-stage path; csl_stretch_run folds the same signal / wait into its accept / proposal kernels. */
+int csl_peer_barrier(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, uint32_t* sync, void* stream);
+/* wait only: returns (stream ordered) once every peer has announced `epoch` */
+int csl_peer_wait(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, uint32_t* sync, void* stream);
 
 /* wrapper bookkeeping of samplers/emcee.py:70-88 after a full step: a walker that did not move
  * gains weight; one that moved (or any walker on the last step) emits (lnl_next, weight, x_old) and its
@@ -329,6 +390,9 @@ typedef struct csl_ensemble {
   uint64_t multicast_ptr;        /* NVSwitch multicast address of the replica, or 0                     */
   uint64_t epoch;                /* barrier epoch, advanced by csl_stretch_run                          */
   int32_t npeers, rank;
+  uint32_t* sync;                /* device uint32[2], zeroed once: [0] sticky status (bit 0 = a peer wait timed out:
+                                    the results of the run are void), [1] ticket counter of the publishing kernel;
+                                    required when replica != NULL                                         */
 } csl_ensemble_t;
 
 /* `nsteps` full stretch-move steps (both half-updates: propose, priors, foregrounds, binning, chi^2,

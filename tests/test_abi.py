@@ -44,8 +44,10 @@ def test_constants_match_header():
 
 def test_library_loads_and_struct_layout_agrees():
     lib = _lib.lib()
-    assert lib.csl_abi_version() == 1
+    assert lib.csl_abi_version() == 2
     assert lib.csl_sizeof_program() == ctypes.sizeof(_lib.Program)
+    assert lib.csl_sizeof_ensemble() == ctypes.sizeof(_lib.Ensemble)
+    assert lib.csl_sizeof_mh() == ctypes.sizeof(_lib.MHState)
 
 
 def test_argument_validation_without_a_gpu():
