@@ -57,24 +57,49 @@ int csl_env_int(const char* name, int fallback) {
   return (e && *e) ? atoi(e) : fallback;
 }
 
-extern "C" int csl_lnl(const csl_program_t* p, int W, const double* x, double* lnl, double* ws_coef,
-                       double* ws_prior, double* ws_R, double* ws_chi2, double* ws_part, void* stream) {
-  CSL_REQUIRE(p && x && lnl && ws_prior && W > 0, "csl_lnl: null argument");
+// the four stages on W walkers whose workspace columns start at the given pointers and have stride ld
+static int lnl_ld(const csl_program_t* p, int W, const double* x, double* lnl, double* ws_coef, double* ws_prior,
+                  double* ws_R, double* ws_chi2, double* ws_part, int ld, void* stream) {
   const int Wp = round_up(W, CSL_BN);
-  int rc = csl_eval_prepare(p, W, x, ws_coef, Wp, ws_prior, stream);
+  int rc = csl_eval_prepare_ld(p, W, p->ncoef > 0 ? Wp : W, x, ws_coef, ld, ws_prior, stream);
   if (rc) return rc;
   const double* chi2 = nullptr;
   if (p->resid_mode != 0) {
     CSL_REQUIRE(ws_R && ws_chi2 && ws_coef, "csl_lnl: workspace missing for the quadratic form");
-    if (p->resid_mode == 1 || p->resid_mode == 3) rc = csl_bin_residual(p, Wp, ws_coef, Wp, ws_R, Wp, stream);
-    else rc = csl_direct_residual(p, W, ws_coef, Wp, ws_R, Wp, stream);
+    if (p->resid_mode == 1 || p->resid_mode == 3) rc = csl_bin_residual(p, Wp, ws_coef, ld, ws_R, ld, stream);
+    else rc = csl_direct_residual_ld(p, W, Wp, ws_coef, ld, ws_R, ld, stream);
     if (rc) return rc;
-    if (p->resid_mode == 3) rc = csl_cov_chi2(p, W, ws_R, Wp, ws_chi2, stream);
-    else rc = csl_chi2(p, Wp, ws_R, Wp, ws_chi2, ws_part, stream);
+    if (p->resid_mode == 3) rc = csl_cov_chi2(p, W, ws_R, ld, ws_chi2, stream);
+    else rc = csl_chi2(p, Wp, ws_R, ld, ws_chi2, ws_part, stream);
     if (rc) return rc;
     chi2 = ws_chi2;
   }
-  return csl_combine(p, W, ws_coef, Wp, ws_prior, chi2, lnl, stream);
+  return csl_combine(p, W, ws_coef, ld, ws_prior, chi2, lnl, stream);
+}
+
+extern "C" int csl_lnl(const csl_program_t* p, int W, const double* x, double* lnl, double* ws_coef,
+                       double* ws_prior, double* ws_R, double* ws_chi2, double* ws_part, void* stream) {
+  CSL_REQUIRE(p && x && lnl && ws_prior && W > 0, "csl_lnl: null argument");
+  return lnl_ld(p, W, x, lnl, ws_coef, ws_prior, ws_R, ws_chi2, ws_part, round_up(W, CSL_BN), stream);
+}
+
+// two library-owned side streams + events per device for the end-to-end call: the second half-batch's H2D copy
+// and the first half-batch's D2H copy run under the other half's kernels
+struct csl_side { cudaStream_t st[2]; cudaEvent_t fork, join[2]; bool ok; };
+static csl_side* side_streams() {
+  static csl_side sides[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  csl_side* sd = &sides[dev];
+  if (!sd->ok) {
+    for (int i = 0; i < 2; ++i) {
+      if (cudaStreamCreateWithFlags(&sd->st[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&sd->join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&sd->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    sd->ok = true;
+  }
+  return sd;
 }
 
 extern "C" int csl_lnl_host(const csl_program_t* p, int W, const double* x_host, double* lnl_host, double* x_dev,
@@ -82,14 +107,38 @@ extern "C" int csl_lnl_host(const csl_program_t* p, int W, const double* x_host,
                             double* ws_part, void* stream) {
   CSL_REQUIRE(p && x_host && lnl_host && x_dev && lnl_dev && W > 0, "csl_lnl_host: null argument");
   cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e = cudaMemcpyAsync(x_dev, x_host, (size_t)W * p->ndim * sizeof(double), cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-  int rc = csl_lnl(p, W, x_dev, lnl_dev, ws_coef, ws_prior, ws_R, ws_chi2, ws_part, stream);
-  if (rc) return rc;
-  e = cudaMemcpyAsync(lnl_host, lnl_dev, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s);
-  if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-  e = cudaStreamSynchronize(s);
-  if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+  const int ld = round_up(W, CSL_BN), nd = p->ndim;
+  static const int single = csl_env_int("CSL_E2E_SINGLE", 0);
+  csl_side* sd = (W >= 4 * CSL_BN && !single) ? side_streams() : nullptr;
+  cudaError_t e;
+#define CSL_CUDA(call) do { e = (call); if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e)); } while (0)
+  if (!sd) {
+    CSL_CUDA(cudaMemcpyAsync(x_dev, x_host, (size_t)W * nd * sizeof(double), cudaMemcpyHostToDevice, s));
+    int rc = lnl_ld(p, W, x_dev, lnl_dev, ws_coef, ws_prior, ws_R, ws_chi2, ws_part, ld, stream);
+    if (rc) return rc;
+    CSL_CUDA(cudaMemcpyAsync(lnl_host, lnl_dev, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CSL_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  }
+  // halves are whole 128-walker tiles, so every walker's arithmetic is what the single batch does
+  const int w_half = round_up((W + 1) / 2, CSL_BN);
+  CSL_CUDA(cudaEventRecord(sd->fork, s));
+  for (int c = 0; c < 2; ++c) {
+    const int w0 = c * w_half, wc = c == 0 ? w_half : W - w_half;
+    if (wc <= 0) continue;
+    cudaStream_t sc = sd->st[c];
+    CSL_CUDA(cudaStreamWaitEvent(sc, sd->fork, 0));
+    CSL_CUDA(cudaMemcpyAsync(x_dev + (size_t)w0 * nd, x_host + (size_t)w0 * nd, (size_t)wc * nd * sizeof(double),
+                             cudaMemcpyHostToDevice, sc));
+    int rc = lnl_ld(p, wc, x_dev + (size_t)w0 * nd, lnl_dev + w0, ws_coef ? ws_coef + w0 : nullptr, ws_prior + w0,
+                    ws_R ? ws_R + w0 : nullptr, ws_chi2 ? ws_chi2 + w0 : nullptr, ws_part ? ws_part + w0 : nullptr, ld, sc);
+    if (rc) return rc;
+    CSL_CUDA(cudaMemcpyAsync(lnl_host + w0, lnl_dev + w0, (size_t)wc * sizeof(double), cudaMemcpyDeviceToHost, sc));
+    CSL_CUDA(cudaEventRecord(sd->join[c], sc));
+    CSL_CUDA(cudaStreamWaitEvent(s, sd->join[c], 0));
+  }
+  CSL_CUDA(cudaStreamSynchronize(s));
+#undef CSL_CUDA
   return 0;
 }
 

@@ -35,6 +35,11 @@ int csl_fused_combine_accept(const csl_program_t* p, int Ns, int Nc, int ndim, d
                              const csl_peer_args* signal, void* stream);
 int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part, bool sum_partials,
                   void* stream);
+// stage variants with the padded walker count (columns written) separate from the workspace stride (prepare.cu)
+int csl_eval_prepare_ld(const csl_program_t* p, int W, int Wp, const double* x, double* coef, int ldc, double* prior,
+                        void* stream);
+int csl_direct_residual_ld(const csl_program_t* p, int W, int Wp, const double* coef, int ldc, double* R, int ldr,
+                           void* stream);
 // device / environment facts read once per process (api.cu)
 int csl_sm_count();
 int csl_env_int(const char* name, int fallback);

@@ -36,35 +36,39 @@ __global__ void k_combine(csl_program_t p, int W, const double* __restrict__ coe
   lnl[w] = combine_walker(p, w, coef, ldc, prior[w], chi2 != nullptr, chi2 != nullptr ? chi2[w] : 0.0);
 }
 
-// resid_mode 2: R[i, w] = coef[direct_coef[i], w] - data[i]; rows n..n_pad are zero
-__global__ void k_direct_residual(csl_program_t p, int W, const double* __restrict__ coef, int ldc,
+// resid_mode 2: R[i, w] = coef[direct_coef[i], w] - data[i]; rows n..n_pad and columns W..Wp are zero
+__global__ void k_direct_residual(csl_program_t p, int W, int Wp, const double* __restrict__ coef, int ldc,
                                   double* __restrict__ R, int ldr) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   int i = blockIdx.y;
-  if (w >= ldr) return;
+  if (w >= Wp) return;
   double v = 0.0;
   if (i < p.n && w < W) v = __dsub_rn(coef[(long long)p.direct_coef[i] * ldc + w], p.data[i]);
   R[(long long)i * ldr + w] = v;
 }
 
-extern "C" int csl_eval_prepare(const csl_program_t* p, int W, const double* x, double* coef, int ldc,
-                                double* prior, void* stream) {
+// W walkers are evaluated; coefficient columns W..Wp-1 (tile padding) replay walker W-1; ldc is the stride
+int csl_eval_prepare_ld(const csl_program_t* p, int W, int Wp, const double* x, double* coef, int ldc, double* prior,
+                        void* stream) {
   CSL_REQUIRE(p && x && prior && W > 0, "csl_eval_prepare: null argument or W <= 0");
   CSL_REQUIRE(p->ndim >= 1 && p->ndim <= CSL_MAX_DIM, "csl_eval_prepare: ndim out of range");
-  CSL_REQUIRE(p->ncoef == 0 || (coef && ldc >= W), "csl_eval_prepare: coef buffer / ldc");
-  const int Wp = (p->ncoef > 0) ? ldc : W;   // coefficient columns W..ldc-1 replay walker W-1
+  CSL_REQUIRE(p->ncoef == 0 || (coef && ldc >= Wp && Wp >= W), "csl_eval_prepare: coef buffer / ldc");
   int grid = (Wp + PREP_THREADS - 1) / PREP_THREADS;
   size_t smem = (size_t)PREP_THREADS * (p->ndim + 1) * sizeof(double);
   // the x tile of 128 walkers passes the 48 KB default limit of dynamic shared memory from ndim = 48 on
-  // (66.5 KB at CSL_MAX_DIM = 64): opt in to what this program needs, once per size
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
+  // (66.5 KB at CSL_MAX_DIM = 64): opt in to what this program needs (per device; cheap, so every time)
+  if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-    configured = smem;
   }
   k_prepare<<<grid, PREP_THREADS, smem, (cudaStream_t)stream>>>(*p, W, Wp, x, coef, ldc, prior);
   return csl_check_launch("k_prepare");
+}
+
+extern "C" int csl_eval_prepare(const csl_program_t* p, int W, const double* x, double* coef, int ldc,
+                                double* prior, void* stream) {
+  CSL_REQUIRE(p && (p->ncoef == 0 || ldc >= W), "csl_eval_prepare: coef buffer / ldc");
+  return csl_eval_prepare_ld(p, W, (p->ncoef > 0) ? ldc : W, x, coef, ldc, prior, stream);   // columns W..ldc-1 replay walker W-1
 }
 
 extern "C" int csl_combine(const csl_program_t* p, int W, const double* coef, int ldc, const double* prior,
@@ -74,11 +78,16 @@ extern "C" int csl_combine(const csl_program_t* p, int W, const double* coef, in
   return csl_check_launch("k_combine");
 }
 
+int csl_direct_residual_ld(const csl_program_t* p, int W, int Wp, const double* coef, int ldc, double* R, int ldr,
+                           void* stream) {
+  CSL_REQUIRE(p && coef && R && W > 0 && ldr >= Wp && Wp >= W, "csl_direct_residual: bad argument");
+  CSL_REQUIRE(p->resid_mode == 2, "csl_direct_residual: program has no direct residual");
+  dim3 grid((Wp + 255) / 256, p->n_pad);
+  k_direct_residual<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, W, Wp, coef, ldc, R, ldr);
+  return csl_check_launch("k_direct_residual");
+}
+
 extern "C" int csl_direct_residual(const csl_program_t* p, int W, const double* coef, int ldc, double* R,
                                    int ldr, void* stream) {
-  CSL_REQUIRE(p && coef && R && W > 0 && ldr >= W, "csl_direct_residual: bad argument");
-  CSL_REQUIRE(p->resid_mode == 2, "csl_direct_residual: program has no direct residual");
-  dim3 grid((ldr + 255) / 256, p->n_pad);
-  k_direct_residual<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, W, coef, ldc, R, ldr);
-  return csl_check_launch("k_direct_residual");
+  return csl_direct_residual_ld(p, W, ldr, coef, ldc, R, ldr, stream);
 }

@@ -307,6 +307,7 @@ class metropolis_hastings(SlikSampler):
             if int(nrows.max().item()) > cap:
                 raise RuntimeError("row buffer overflow")
         finally:
+            graph_nodes = int(lib.csl_graph_nodes(graph)) if graph else 0
             if graph:
                 lib.csl_graph_destroy(graph)
             if writer is not None:
@@ -316,7 +317,7 @@ class metropolis_hastings(SlikSampler):
         self.stats = dict(cur_x=cur_x, cur_lnl=cur_lnl, cur_weight=cur_w, rows=rows, nrows=nrows, steps=steps,
                           chains=(lo, hi), seed=seed, last_margin=margin, last_accepted=accepted,
                           accepted=int(nacc.item()) if not gauss else None,
-                          host_ms_per_step=1e3 * t_host / max(steps, 1),
+                          host_ms_per_step=1e3 * t_host / max(steps, 1), graph_nodes=graph_nodes,
                           loop="csl_mh_gauss_run (one launch per block)" if gauss else
                                ("CUDA graph per block (csl_mh_graph_create)" if use_graph else "csl_mh_run"))
 

@@ -64,6 +64,28 @@ def mh(out):
              nrows=st["nrows"].cpu().numpy(), cov=slik.sampler.cov_est, nadapt=len(slik.sampler.adaptations))
 
 
+def stretch_file(out):
+    """both ranks run with the SAME output_file: rank 0 must write every rank's walkers into it"""
+    from namespaces import PRODUCT
+    from cosmoslik_b200 import Slik, samplers, synthetic
+    prob = synthetic.spt_multifreq_problem(1, nbins=12, lmax=801)
+    k, nsteps = 194, 9                      # 97 walkers per half: ragged shares over 2 ranks
+    slik = Slik(synthetic.build_script(PRODUCT, prob, sampler=lambda s: samplers.emcee(
+        s, num_samples=k * nsteps, nwalkers=k, seed=11, output_file=out, output_freq=4))())
+    n = sum(1 for _ in slik.sample())       # the generator yields this rank's walkers only
+    np.savez(out + ".rank%d.npz" % dist.get_rank(), n=n, ids=slik.sampler.stats["walker_ids"])
+
+
+def mh_file(out):
+    import b200_scripts as B
+    from cosmoslik_b200 import Slik, samplers
+    nd, nch, nsteps = 4, 11, 230
+    Cv = np.eye(nd) + 0.25
+    slik = Slik(B.gauss_script(Cv, lambda s: samplers.metropolis_hastings(
+        s, num_samples=nsteps * nch, nchains=nch, seed=6, proposal_update=False, mpi_comm_freq=50, output_file=out))())
+    slik.sampler.run(slik.evaluate)
+
+
 if __name__ == "__main__":
     mode = sys.argv[1]
     d.init_process_group("gloo")
@@ -71,5 +93,5 @@ if __name__ == "__main__":
         helpers()
     else:
         torch.cuda.set_device(0)
-        {"stretch": stretch, "mh": mh}[mode](sys.argv[2])
+        {"stretch": stretch, "mh": mh, "stretch_file": stretch_file, "mh_file": mh_file}[mode](sys.argv[2])
     d.destroy_process_group()

@@ -71,3 +71,45 @@ def test_sharded_adaptive_mh_matches_the_single_process_run(tmp_path):
         # the pooled covariance is summed in a different order across ranks: equal to rounding
         np.testing.assert_allclose(z["cov"], slik.sampler.cov_est, rtol=1e-9)
         np.testing.assert_allclose(z["cur_x"], x[int(z["lo"]):int(z["hi"])], rtol=0, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_all_ranks_write_one_chain_file(tmp_path):
+    """metropolis_hastings.py:181-186, 209-212 ("everything still gets dumped into one file"): with two ranks,
+    load_chain(output_file) must return ALL walkers / chains, with the rows of the single-process run"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import b200_scripts as B
+    from namespaces import PRODUCT
+    from cosmoslik_b200 import Slik, load_chain, samplers, synthetic
+    # ---- stretch move
+    out = str(tmp_path / "ens.chain")
+    launch("stretch_file", out, port=29745)
+    prob = synthetic.spt_multifreq_problem(1, nbins=12, lmax=801)
+    k, nsteps = 194, 9
+    single = str(tmp_path / "ens1.chain")
+    slik = Slik(synthetic.build_script(PRODUCT, prob, sampler=lambda s: samplers.emcee(
+        s, num_samples=k * nsteps, nwalkers=k, seed=11, output_file=single, output_freq=4))())
+    slik.sampler.run(slik.evaluate)
+    got, want = load_chain(out), load_chain(single)
+    assert len(got) == len(want) == k
+    for a, b in zip(got, want):
+        assert list(a.keys()) == list(b.keys())
+        for key in a:
+            np.testing.assert_array_equal(a[key], b[key])
+    yielded = [int(np.load(out + ".rank%d.npz" % r)["n"]) for r in range(2)]
+    assert sum(yielded) == sum(c.length() for c in want) and min(yielded) > 0
+    assert not os.path.exists(out + ".rank1")
+    # ---- Metropolis-Hastings
+    out = str(tmp_path / "mh.chain")
+    launch("mh_file", out, port=29746)
+    nd, nch, nsteps = 4, 11, 230
+    Cv = np.eye(nd) + 0.25
+    single = str(tmp_path / "mh1.chain")
+    slik = Slik(B.gauss_script(Cv, lambda s: samplers.metropolis_hastings(
+        s, num_samples=nsteps * nch, nchains=nch, seed=6, proposal_update=False, mpi_comm_freq=50, output_file=single))())
+    slik.sampler.run(slik.evaluate)
+    got, want = load_chain(out), load_chain(single)
+    assert len(got) == len(want) == nch
+    for a, b in zip(got, want):
+        for key in a:
+            np.testing.assert_array_equal(a[key], b[key])
