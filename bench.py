@@ -170,7 +170,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    """SM clock and throttle reasons DURING the timed region (NVML, 4 ms period; nvidia-smi fallback).
+    """SM clock and throttle reasons DURING the timed region (NVML, 8 ms period (CSL_CLOCK_PERIOD_MS); nvidia-smi fallback).
     Construct it BEFORE the barrier that opens the timed region: nvmlInit is slow and contended when several
     ranks start at once."""
     REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
@@ -179,6 +179,7 @@ class ClockSampler(object):
 
     def __init__(self, index):
         self.index, self.samples, self.stop = index, [], False
+        self.period = float(os.environ.get("CSL_CLOCK_PERIOD_MS", "8")) * 1e-3
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.max_mhz, self.nv, self.h = None, None, None
         try:
@@ -206,7 +207,7 @@ class ClockSampler(object):
                     self.samples.append((mhz, mask))
                 except Exception:
                     pass
-                time.sleep(0.004)
+                time.sleep(self.period)
             return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
         while not self.stop:
@@ -346,13 +347,14 @@ def measure_stretch(args, prob, k_total, instrument=True, e2e=True):
     x0 = np.array([prob["truth"][k] for k in names]); sc = np.array([prob["scales"][k] for k in names])
     smp.init_pos = x0 + sc * np.random.RandomState(99).standard_normal((k_total, len(names)))
 
+    clk = ClockSampler(dev)                         # NVML initialised BEFORE the warm-up: the GPU does not idle (and
+                                                    # no rank is late) between the warm-up and the timed region
     smp.row_capacity = args.steps            # same row buffer for the warm-up and the timed run
-    smp.run(prog, nsteps=max(args.warmup, 3))      # warm-up: start positions evaluated, replica built
     if instrument:
-        smp.python_loop = True                      # ... and the instrumented Python loop's code paths
-        smp.run(prog, nsteps=3, resume=True)
+        smp.python_loop = True                      # the instrumented Python loop's code paths ...
+        smp.run(prog, nsteps=3)
         del smp["python_loop"]
-    clk = ClockSampler(dev)                         # NVML initialised BEFORE the barrier: not in the timed region
+    smp.run(prog, nsteps=max(args.warmup, 3), resume=instrument)   # warm-up of the native loop, right before the timed run
     replica = smp["_replica"][1] if "_replica" in smp and smp["_replica"] is not None else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier(); torch.cuda.synchronize()

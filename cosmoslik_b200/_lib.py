@@ -21,6 +21,8 @@ BIN_STRIDE, SEG_GROUP, GRP_STRIDE = 16, 8, 128
 G_PRE, G_LO, G_ROW, G_CONT, G_MODE, G_BASE_LO, G_BASE_HI, G_SPEC, G_DATA, G_LOGB = 0, 9, 17, 25, 33, 34, 35, 36, 40, 56
 B_ROW, B_SPEC, B_LO, B_HI, B_WINOFF_LO, B_WINOFF_HI, B_TABOFF_LO, B_TABOFF_HI, B_DMAX = 0, 1, 2, 3, 4, 5, 6, 7, 8
 T_ROW0, T_NROWS, T_SPEC, T_LBEGIN, T_LEND, T_WINOFF_LO, T_WINOFF_HI, T_WINLD, T_GLO, T_GHI = 0, 1, 2, 3, 4, 5, 6, 7, 8, 16
+T_WINT_LO, T_WINT_HI = 24, 25
+ATILE = 64 * 20      # doubles of one tile-major A tile
 
 _i32p, _f64p, _vp = C.c_void_p, C.c_void_p, C.c_void_p
 
@@ -37,7 +39,8 @@ class Program(C.Structure):
                   "templates", "windows", "data", "direct_coef", "Lmat", "Linv_diag", "Minv")] +
                 [("chi2_mode", C.c_int32), ("nsegclass", C.c_int32), ("segcls", (C.c_int32 * 4) * 8),
                  ("bin_tab", C.c_void_p), ("Sigma", C.c_void_p), ("n_base", C.c_int32), ("nmode", C.c_int32),
-                 ("grp_tab", C.c_void_p)])
+                 ("grp_tab", C.c_void_p), ("MinvT", C.c_void_p), ("LmatT", C.c_void_p), ("LinvT", C.c_void_p),
+                 ("winT", C.c_void_p), ("bin_split", C.c_int32), ("reserved0", C.c_int32)])
 
 
 class Ensemble(C.Structure):
@@ -88,6 +91,7 @@ SIGNATURES = {
     "csl_mh_moments": (_int, [_int, _int, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
     "csl_rows_moments": (_int, [_int, _int, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp]),
     "csl_rows_gauss_prior": (_int, [_int, _int, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp]),
+    "csl_rows_thin": (_int, [_int, _int, _vp, _vp, _int, _dbl, _vp]),
     "csl_stretch_propose": (_int, [_int, _int, _int, _vp, _vp, _dbl, _vp, _vp, _u64, _u32, _u32, _u32,
                                    _vp, _vp, _vp]),
     "csl_stretch_accept": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _u32,
@@ -110,6 +114,9 @@ SIGNATURES = {
     "csl_philox_mh": (_int, [_int, _int, _u64, _u32, _u32, _vp, _vp, _vp]),
     "csl_philox_stretch": (_int, [_int, _int, _u64, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "csl_dgemm_dmma": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp]),
+    "csl_set_option": (_int, [C.c_char_p, _int]),
+    "csl_debug_counters": (_int, [_vp, _int]),
+    "csl_get_option": (_int, [C.c_char_p]),
 }
 
 _lib = None

@@ -19,7 +19,8 @@ from itertools import chain as _iterchain
 import numpy as np
 
 __all__ = ["Chain", "Chains", "get_covariance", "get_correlation", "combine_covs", "load_chain",
-           "load_cosmomc_chain", "ChainWriter", "gelman_rubin", "device_summary", "device_add_gauss_prior"]
+           "load_cosmomc_chain", "ChainWriter", "gelman_rubin", "device_summary", "device_add_gauss_prior", "device_thin",
+           "device_reweighted"]
 
 
 def _is_listlike(v):
@@ -143,27 +144,32 @@ class Chain(dict):
         return self.sample(slice(first, None))
 
     def thin(self, delta):
-        """Keep one row per `delta` units of weight (chains.py:235-243)."""
-        c = np.ceil(np.cumsum(np.append(0, self["weight"])) / float(delta))
-        ids = np.where(c[1:] > c[:-1])[0]
-        w = np.diff(c[[0] + list(ids + 1)])
-        t = self.sample(ids)
-        t["weight"] = w
-        return t
+        """Keep one row per `delta` units of weight (chains.py:235-243).  With S_k = ceil(cumulative weight
+        through row k / delta), row k survives iff it opens a new slot (S_k > S_{k-1}) and its new weight is the
+        number of slots it opens."""
+        slots = np.ceil(np.cumsum(self["weight"]) / float(delta))
+        opened = np.diff(slots, prepend=0.0)
+        keep = np.flatnonzero(opened > 0)
+        out = self.sample(keep)
+        out["weight"] = opened[keep]
+        return out
 
     def thinto(self, num):
         return self.thin(self.length(unique=False) // num)
 
     def add_gauss_prior(self, params, mean, covstd):
-        c = self.copy()
-        dx = self.matrix(params) - mean
+        """Importance-reweight the chain by a Gaussian prior on one parameter (mean, standard deviation) or on
+        several (mean vector, covariance matrix): weight *= exp(-penalty), lnl += penalty (chains.py:206-233)."""
+        x = self.matrix(params)
         if _is_listlike(params):
-            dlnl = np.sum(np.dot(dx, np.linalg.inv(covstd)) * dx, axis=1) / 2
+            resid = x - np.asarray(mean, dtype=float)
+            penalty = np.einsum("ri,ri->r", resid @ np.linalg.inv(covstd), resid) / 2
         else:
-            dlnl = dx ** 2 / 2 / covstd ** 2
-        c["weight"] = c["weight"] * np.exp(-dlnl)
-        c["lnl"] = c["lnl"] + dlnl
-        return c
+            penalty = (x - mean) ** 2 / 2 / covstd ** 2
+        out = self.copy()
+        out["weight"] = out["weight"] * np.exp(-penalty)
+        out["lnl"] = out["lnl"] + penalty
+        return out
 
     def best_fit(self):
         i = int(np.argmin(self["lnl"]))
@@ -324,6 +330,40 @@ def device_add_gauss_prior(stats, params, mean, covstd, names):
     d_ci = torch.from_numpy(np.ascontiguousarray(cinv)).to(dev)
     L.check(L.lib().csl_rows_gauss_prior(W, rl - 2, rows.data_ptr(), nrows.data_ptr(), cap, len(idx), d_idx.data_ptr(),
                                          d_mu.data_ptr(), d_ci.data_ptr(), L.stream_ptr()), "csl_rows_gauss_prior")
+    return stats
+
+
+def device_thin(stats, delta):
+    """``Chain.thin(delta)`` (chains.py:235-243) applied to EVERY chain of a finished sampler run, in place on the
+    device row buffer (``csl_rows_thin``: one warp per chain walks its rows, keeps the rows that open a new slot of
+    `delta` units of cumulative weight and gives them the number of slots they open); ``nrows`` is updated."""
+    from . import _lib as L
+    rows, nrows = stats["rows"], stats["nrows"]
+    W, cap, rl = rows.shape
+    L.check(L.lib().csl_rows_thin(W, rl - 2, rows.data_ptr(), nrows.data_ptr(), cap, float(delta), L.stream_ptr()),
+            "csl_rows_thin")
+    return stats
+
+
+def device_reweighted(stats, names, func):
+    """``Chain.reweighted(func)`` (chains.py:178-203) on the device: `func(**params)` is called ONCE with symbolic
+    parameters (like a script's ``__call__``) and must return a scalar expression of them; it is compiled to the
+    coefficient bytecode and evaluated for every stored row of every chain, whose weight it multiplies.
+    `names` = the sampled parameter names in column order."""
+    import torch
+    from . import symbolic as sym
+    from .program import ExtrasProgram
+    rows, nrows = stats["rows"], stats["nrows"]
+    W, cap, rl = rows.shape
+    names = list(names)
+    expr = func(**{n: sym.Par(i, n) for i, n in enumerate(names)})
+    prog = ExtrasProgram(names, [expr], device=rows.device)
+    live = torch.arange(cap, device=rows.device)[None, :] < nrows.clamp(max=cap)[:, None]
+    x = rows[:, :, 2:][live].contiguous()
+    if x.shape[0]:
+        factor = prog.values(x)[:, 0]
+        w = rows[:, :, 1]
+        w[live] = w[live] * factor
     return stats
 
 

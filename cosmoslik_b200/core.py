@@ -299,7 +299,9 @@ class Slik(object):
         if self._program is None or (options and options != self._program_options):
             from .program import DeviceProgram
             self._program_options = dict(options)
-            self._program = DeviceProgram(list(self._sampled), self.params.priors, self.trace(), **options)
+            tree, out = self._trace()
+            self._program = DeviceProgram(list(self._sampled), self.params.priors, out, derived=_tree_lookup(tree),
+                                          **options)
         return self._program
 
     # -- evaluation -----------------------------------------------------------
@@ -360,6 +362,17 @@ class Slik(object):
 
     def sample(self):
         return self.sampler.sample(self.evaluate)
+
+
+def _tree_lookup(tree):
+    """name -> what the script left under that dotted name after its symbolic __call__, or None"""
+    def look(name):
+        try:
+            v = tree[name]
+        except (AttributeError, KeyError, ValueError):
+            return None
+        return None if isinstance(v, param) else v
+    return look
 
 
 def run_chain(main, nchains=1, pool=None, args=None, kwargs=None):

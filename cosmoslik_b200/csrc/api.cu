@@ -51,11 +51,45 @@ int csl_sm_count() {
   return cached[dev];
 }
 
-// integer environment override (sweeps / debugging); callers cache the result in a function-local static
+// integer environment override; callers cache the result in a function-local static
 int csl_env_int(const char* name, int fallback) {
   const char* e = getenv(name);
   return (e && *e) ? atoi(e) : fallback;
 }
+
+// ---- tuning options (sweeps, A/B tests): process-wide integers, initialised from the environment variable
+// CSL_<NAME IN CAPITALS> on first use; -1 = "let the launcher decide"
+struct csl_option { const char* name; const char* env; int value; bool init; };
+static csl_option g_options[] = {
+    {"pipe", "CSL_PIPE", -1, false},                    // tile movement of the DMMA kernels: 0 cp.async, 1 bulk copies + mbarrier
+    {"trigemm_rows", "CSL_TRIGEMM_ROWS", -1, false},    // 32 / 64: CTA shape of k_trigemm_chi2
+    {"trigemm_group", "CSL_TRIGEMM_GROUP", -1, false},  // column tiles per super-group of k_trigemm_chi2
+    {"trigemm_stages", "CSL_TRIGEMM_STAGES", -1, false},
+    {"trsm_shape", "CSL_TRSM_SHAPE", -1, false},        // k_trsm_chi2 variant
+    {"bin_split", "CSL_BIN_SPLIT", -1, false},          // ell splits of k_bin_residual (0 = by launch size)
+    {"bin_variant", "CSL_BIN_VARIANT", -1, false},      // k_bin_residual variant
+    {"sab_threads", "CSL_SAB_THREADS", -1, false},      // CTA size of k_stretch_combine_accept
+    {"seg_small", "CSL_SEG_SMALL", -1, false},          // k_bin_segsum: 1 walker per thread below this many walkers
+};
+static csl_option* find_option(const char* name) {
+  for (csl_option& o : g_options)
+    if (name && strcmp(o.name, name) == 0) {
+      if (!o.init) { o.value = csl_env_int(o.env, -1); o.init = true; }
+      return &o;
+    }
+  return nullptr;
+}
+int csl_option_value(const char* name) {
+  csl_option* o = find_option(name);
+  return o ? o->value : -1;
+}
+extern "C" int csl_set_option(const char* name, int value) {
+  csl_option* o = find_option(name);
+  if (!o) return csl_fail(CSL_E_BADARG, "csl_set_option: unknown option");
+  o->value = value;
+  return 0;
+}
+extern "C" int csl_get_option(const char* name) { return csl_option_value(name); }
 
 // the four stages on W walkers whose workspace columns start at the given pointers and have stride ld
 static int lnl_ld(const csl_program_t* p, int W, const double* x, double* lnl, double* ws_coef, double* ws_prior,

@@ -29,22 +29,45 @@ __device__ __forceinline__ double exp_taylor(double y) {
   return p;
 }
 
+#define BW_XLD (CSL_BN + 2)       // row stride of a parked partial tile (doubles)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem(const double* local_smem, uint32_t rank) {
+  uint32_t remote;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem)), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+
 template <int NT, int NP>
 __global__ void __launch_bounds__(CSL_THREADS, 2)
-k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coef, int ldc,
+k_bin_residual(csl_program_t p, int tile0, int W, int nsplit, const double* __restrict__ coef, int ldc,
                double* __restrict__ R, int ldr) {
+  // nsplit > 1: launched as thread-block clusters of nsplit CTAs along x; CTA r of a cluster takes the r-th part
+  // of the tile's ell chunks and the partial tiles are summed in rank order through distributed shared memory
+  // (see k_bin_residual_ws below for the full story; nsplit is a property of the PROGRAM, csl_program_t::bin_split)
   constexpr int LSTRIDE = NT + 4 * NP;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   double* As = smem;                       // [2][CSL_ASZ]
   double* Bs = smem + 2 * CSL_ASZ;         // [2][CSL_BSZ]
   double* Ls = Bs + 2 * CSL_BSZ;           // [2][CSL_KC * LSTRIDE]
-  const int32_t* tile = p.tile_tab + (long long)(tile0 + blockIdx.x) * CSL_TILE_STRIDE;
+  const int split = (int)(blockIdx.x % (unsigned)nsplit);
+  const int32_t* tile = p.tile_tab + (long long)(tile0 + blockIdx.x / nsplit) * CSL_TILE_STRIDE;
   const int32_t* spec = p.spec_tab + (long long)tile[CSL_T_SPEC] * CSL_SPEC_STRIDE;
   const int c0 = blockIdx.y * CSL_BN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 32;
 
-  const int l_begin = tile[CSL_T_LBEGIN], l_end = tile[CSL_T_LEND];
+  int l_begin = tile[CSL_T_LBEGIN], l_end = tile[CSL_T_LEND];
+  if (nsplit > 1) {      // this CTA's contiguous share of the chunks; the first (n % nsplit) shares are one longer
+    const int nall = (l_end - l_begin) / CSL_KC, cb = nall / nsplit, ce = nall % nsplit;
+    l_begin += (split * cb + min(split, ce)) * CSL_KC;
+    l_end = l_begin + (cb + (split < ce ? 1 : 0)) * CSL_KC;
+  }
   const long long win_off = ((long long)tile[CSL_T_WINOFF_HI] << 32) | (unsigned)tile[CSL_T_WINOFF_LO];
   const long long win_ld = tile[CSL_T_WINLD];
   const double* __restrict__ Wnd = p.windows + win_off;
@@ -156,6 +179,37 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
   const int row0 = tile[CSL_T_ROW0], nrows = tile[CSL_T_NROWS];
   const int calrow = spec[CSL_S_CAL];
   const bool cal_on_model = spec[CSL_S_CALMODE] != 0;      // r = d - cal*b  (SPTSZ_lowl.py:68)
+  if (nsplit > 1) {
+    // park the partial tile over the (now idle) stages, meet the cluster's other parts in DSMEM: CTA r sums rows
+    // [64 r / nsplit, 64 (r + 1) / nsplit) of all parts in rank order and writes their residuals
+    double* X = smem;                                       // [64][BW_XLD]
+    __syncthreads();                                        // every warp has left the stages
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        double2 v;
+        v.x = acc[mi][ni][0];
+        v.y = acc[mi][ni][1];
+        *reinterpret_cast<double2*>(X + (wm0 + mi * 8 + g) * BW_XLD + wn0 + ni * 8 + 2 * t) = v;
+      }
+    cluster_sync_all();
+    const int rows_per = CSL_BM / nsplit, r_lo = split * rows_per;
+    for (int e = tid; e < rows_per * CSL_BN; e += CSL_THREADS) {
+      const int rl = r_lo + e / CSL_BN, cl = e % CSL_BN;
+      const double* src = X + rl * BW_XLD + cl;
+      double b = ld_dsmem(src, 0);
+      for (int q = 1; q < nsplit; ++q) b += ld_dsmem(src, (uint32_t)q);      // rank order: fixed
+      if (rl < nrows) {
+        const int col = c0 + cl;
+        const double cal = calrow >= 0 ? coef[(long long)calrow * ldc + col] : 1.0;
+        const double d = p.data[row0 + rl];
+        R[(long long)(row0 + rl) * ldr + col] = cal_on_model ? __dsub_rn(d, __dmul_rn(b, cal)) : __dsub_rn(__dmul_rn(cal, d), b);
+      }
+    }
+    cluster_sync_all();                                     // nobody leaves while a peer still reads its tile
+    return;
+  }
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) {
     const int col = c0 + wn0 + ni * 8 + 2 * t;
@@ -180,6 +234,286 @@ k_bin_residual(csl_program_t p, int tile0, int W, const double* __restrict__ coe
         *reinterpret_cast<double2*>(R + (long long)(row0 + rl) * ldr + col) = out;
       }
     }
+  }
+}
+
+// ---- the DMMA binning kernel, warp specialised, with Blackwell tile movement and split-ell clusters ------
+// Roles inside one CTA (13 warps, one CTA per SM):
+//   warps 0..7   MMA consumers: the 64 x 128 tile product, 32 x 32 per warp -- DMMA and shared-memory loads only
+//   warps 8..11  BUILDERS: thread = walker; build the [16 ell x 128 walker] Cl chunk from the staged ell-table rows
+//                (two independent 8-column recurrences per thread, the arithmetic of k_bin_residual bit for bit)
+//   warp 12      PRODUCER: per chunk ONE bulk copy of the tile-major window tile and ONE of the 16 ell-table rows
+// Three rings of stages joined by mbarriers (window tiles: producer -> MMA; ell-table rows: producer -> builders;
+// Cl chunks: builders -> MMA).  The builders' dependent DFMA / exp chains overlap the MMA warps' DMMA stream by
+// construction instead of alternating with it between CTA barriers, and no warp waits for all the others.
+//
+// Split-ell: a thread-block CLUSTER of S CTAs shares one (window tile, walker tile); CTA r of the cluster takes
+// the r-th part of the tile's ell chunks.  The S partial tiles meet in DISTRIBUTED SHARED MEMORY: every CTA parks
+// its accumulators in its own shared memory, and CTA r sums rows [64 r / S, 64 (r + 1) / S) of all S partials in
+// RANK ORDER (fixed order: bitwise reproducible) and writes their residuals.  S is a property of the PROGRAM (host:
+// from the number of chunks per tile), never of the launch size, so a walker's bits do not depend on the batch it
+// is evaluated in.  Small launches (47 SPT bandpowers x 4096 chains = 32 tiles) thus fill 4 x as many SMs, and
+// 1.3-wave launches become 5-wave launches.
+#define BW_MMA_WARPS 8
+#define BW_BUILD_WARPS 4
+#define BW_THREADS ((BW_MMA_WARPS + BW_BUILD_WARPS + 1) * 32)
+#define BW_SA 3
+#define BW_SB 3
+#define BW_SL 3
+
+template <int NT, int NP>
+__global__ void __launch_bounds__(BW_THREADS, 1)
+k_bin_residual_ws(csl_program_t p, int tile0, int W, int nsplit, const double* __restrict__ coef, int ldc,
+                  double* __restrict__ R, int ldr) {
+  constexpr int LSTRIDE = NT + 4 * NP;
+  constexpr int LROWS = CSL_KC * LSTRIDE;                    // doubles of one chunk's ell-table rows
+  extern __shared__ __align__(128) double smem[];
+  double* As = smem;                                         // [BW_SA][CSL_ASZ]
+  double* Bs = As + BW_SA * CSL_ASZ;                         // [BW_SB][CSL_BSZ]
+  double* Ls = Bs + BW_SB * CSL_BSZ;                         // [BW_SL][LROWS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ls + BW_SL * LROWS);
+  uint64_t *fullA = bars, *emptyA = fullA + BW_SA, *fullB = emptyA + BW_SA, *emptyB = fullB + BW_SB,
+           *fullL = emptyB + BW_SB, *emptyL = fullL + BW_SL;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = (int)(blockIdx.x % (unsigned)nsplit);    // == %cluster_ctarank (cluster dims (nsplit, 1, 1))
+  const int32_t* tile = p.tile_tab + (long long)(tile0 + blockIdx.x / nsplit) * CSL_TILE_STRIDE;
+  const int32_t* spec = p.spec_tab + (long long)tile[CSL_T_SPEC] * CSL_SPEC_STRIDE;
+  const int c0 = blockIdx.y * CSL_BN;
+  const int l_begin = tile[CSL_T_LBEGIN], l_end = tile[CSL_T_LEND];
+  const int nchunk_all = (l_end - l_begin) / CSL_KC;
+  // this CTA's share of the chunks: contiguous, the first (nchunk_all % nsplit) shares one longer
+  const int cbase = nchunk_all / nsplit, cextra = nchunk_all % nsplit;
+  const int cfirst = split * cbase + min(split, cextra);
+  const int nchunk = cbase + (split < cextra ? 1 : 0);
+  const int lfirst = l_begin + cfirst * CSL_KC;
+  if (tid == 0) {
+    for (int s = 0; s < BW_SA; ++s) { mbar_init(fullA + s, 1); mbar_init(emptyA + s, BW_MMA_WARPS); }
+    for (int s = 0; s < BW_SB; ++s) { mbar_init(fullB + s, BW_BUILD_WARPS); mbar_init(emptyB + s, BW_MMA_WARPS); }
+    for (int s = 0; s < BW_SL; ++s) { mbar_init(fullL + s, 1); mbar_init(emptyL + s, BW_BUILD_WARPS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  double acc[4][4][2];
+  const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 32;        // meaningful for the MMA warps only
+  if (warp == BW_MMA_WARPS + BW_BUILD_WARPS) {
+    // ---------------------------------------------------------------- producer
+    const long long wt_off = ((long long)tile[CSL_T_WINT_HI] << 32) | (unsigned)tile[CSL_T_WINT_LO];
+    const double* __restrict__ At = p.winT + wt_off + (long long)(lfirst / CSL_KC) * CSL_ATILE;
+    const double* __restrict__ Lt = p.templates + spec[CSL_S_LTAB] + (long long)lfirst * LSTRIDE;
+    for (int c = 0; c < nchunk; ++c) {
+      if (lane == 0) {
+        const int sa = c % BW_SA, sl = c % BW_SL;
+        if (c >= BW_SL) mbar_wait(emptyL + sl, ((c / BW_SL) - 1) & 1);
+        mbar_arrive_expect_tx(fullL + sl, LROWS * sizeof(double));
+        bulk_g2s(Ls + sl * LROWS, Lt + (long long)c * LROWS, LROWS * sizeof(double), fullL + sl);
+        if (c >= BW_SA) mbar_wait(emptyA + sa, ((c / BW_SA) - 1) & 1);
+        mbar_arrive_expect_tx(fullA + sa, CSL_ASZ * sizeof(double));
+        bulk_g2s(As + sa * CSL_ASZ, At + (long long)c * CSL_ATILE, CSL_ASZ * sizeof(double), fullA + sa);
+      }
+    }
+  } else if (warp >= BW_MMA_WARPS) {
+    // ---------------------------------------------------------------- builders: thread = walker
+    const int wl = tid - BW_MMA_WARPS * 32;
+    double cf[NT > 0 ? NT : 1], pamp[NP > 0 ? NP : 1], pidx[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) cf[t] = coef[(long long)spec[CSL_S_TERM_COEF + t] * ldc + c0 + wl];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      pamp[q] = coef[(long long)spec[CSL_S_PLAW_AMP + q] * ldc + c0 + wl];
+      pidx[q] = coef[(long long)spec[CSL_S_PLAW_IDX + q] * ldc + c0 + wl];
+    }
+    double bnd[NP > 0 ? NP : 1];
+    bool inside[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      const float bq = __int_as_float(spec[CSL_S_IDXBOUND + q]);
+      bnd[q] = fabs((double)bq);
+      inside[q] = bq < 0.f || fabs(pidx[q]) <= bnd[q];
+    }
+    for (int c = 0; c < nchunk; ++c) {
+      const int sl = c % BW_SL, sb = c % BW_SB;
+      mbar_wait(fullL + sl, (c / BW_SL) & 1);
+      if (c >= BW_SB) mbar_wait(emptyB + sb, ((c / BW_SB) - 1) & 1);
+      const double* L = Ls + sl * LROWS;
+      double* B = Bs + sb * CSL_BSZ;
+      // two independent 8-column recurrences (columns 0..7 and 8..15), interleaved for instruction-level
+      // parallelism: per column exactly the arithmetic of k_bin_residual's build_B
+      const double* row0 = L;
+      const double* row1 = L + (CSL_KC / 2) * LSTRIDE;
+      double E0[NP > 0 ? NP : 1], E1[NP > 0 ? NP : 1];
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        E0[q] = exp(pidx[q] * row0[NT + 4 * q]);
+        E1[q] = exp(pidx[q] * row1[NT + 4 * q]);
+      }
+#pragma unroll 2
+      for (int r = 0; r < CSL_KC / 2; ++r, row0 += LSTRIDE, row1 += LSTRIDE) {
+        double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { v0 = fma(cf[t], row0[t], v0); v1 = fma(cf[t], row1[t], v1); }
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          v0 = fma(pamp[q] * row0[NT + 4 * q + 1], E0[q], v0);
+          v1 = fma(pamp[q] * row1[NT + 4 * q + 1], E1[q], v1);
+        }
+        B[r * CSL_LDB + wl] = v0;
+        B[(CSL_KC / 2 + r) * CSL_LDB + wl] = v1;
+        if (r + 1 < CSL_KC / 2) {
+#pragma unroll
+          for (int q = 0; q < NP; ++q) {
+            const double D0 = row0[NT + 4 * q + 2], D1 = row1[NT + 4 * q + 2];
+            const double y0 = pidx[q] * D0, ay0 = bnd[q] * fabs(D0);      // ay: warp-uniform (broadcast row)
+            if (ay0 <= 0.012 && inside[q]) E0[q] *= exp_taylor<6>(y0);
+            else if (ay0 <= 0.1 && inside[q]) E0[q] *= exp_taylor<10>(y0);
+            else E0[q] = exp(pidx[q] * row0[LSTRIDE + NT + 4 * q]);
+            const double y1 = pidx[q] * D1, ay1 = bnd[q] * fabs(D1);
+            if (ay1 <= 0.012 && inside[q]) E1[q] *= exp_taylor<6>(y1);
+            else if (ay1 <= 0.1 && inside[q]) E1[q] *= exp_taylor<10>(y1);
+            else E1[q] = exp(pidx[q] * row1[LSTRIDE + NT + 4 * q]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(fullB + sb); mbar_arrive(emptyL + sl); }
+    }
+  } else {
+    // ---------------------------------------------------------------- MMA consumers
+    int glo[4], ghi[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      glo[mi] = tile[CSL_T_GLO + (wm0 >> 3) + mi];
+      ghi[mi] = tile[CSL_T_GHI + (wm0 >> 3) + mi];
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+      const int sa = c % BW_SA, sb = c % BW_SB;
+      const int l0 = lfirst + c * CSL_KC;
+      unsigned mmask = 0;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+        if (l0 + CSL_KC > glo[mi] && l0 < ghi[mi]) mmask |= 1u << mi;
+      mbar_wait(fullA + sa, (c / BW_SA) & 1);
+      mbar_wait(fullB + sb, (c / BW_SB) & 1);
+      if (mmask) warp_mma_chunk(acc, As + sa * CSL_ASZ, Bs + sb * CSL_BSZ, wm0, wn0, lane, mmask);
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(emptyA + sa); mbar_arrive(emptyB + sb); }
+    }
+  }
+
+  const int g = lane >> 2, t = lane & 3;
+  const int row0 = tile[CSL_T_ROW0], nrows = tile[CSL_T_NROWS];
+  const int calrow = spec[CSL_S_CAL];
+  const bool cal_on_model = spec[CSL_S_CALMODE] != 0;      // r = d - cal*b  (SPTSZ_lowl.py:68)
+  if (nsplit == 1) {
+    if (warp >= BW_MMA_WARPS) return;
+    // epilogue: r = cal * d - b   (spt_lowl.py:132), straight from the accumulators
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int col = c0 + wn0 + ni * 8 + 2 * t;
+      double cal0 = 1.0, cal1 = 1.0;
+      if (calrow >= 0) {
+        cal0 = coef[(long long)calrow * ldc + col];
+        cal1 = coef[(long long)calrow * ldc + col + 1];
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int rl = wm0 + mi * 8 + g;
+        if (rl < nrows) {
+          const double d = p.data[row0 + rl];
+          double2 out;
+          if (cal_on_model) {
+            out.x = __dsub_rn(d, __dmul_rn(acc[mi][ni][0], cal0));
+            out.y = __dsub_rn(d, __dmul_rn(acc[mi][ni][1], cal1));
+          } else {
+            out.x = __dsub_rn(__dmul_rn(cal0, d), acc[mi][ni][0]);
+            out.y = __dsub_rn(__dmul_rn(cal1, d), acc[mi][ni][1]);
+          }
+          *reinterpret_cast<double2*>(R + (long long)(row0 + rl) * ldr + col) = out;
+        }
+      }
+    }
+    return;
+  }
+  // ---- split-ell: park the partial tile in shared memory (the rings are idle now), meet in DSMEM
+  double* X = smem;                                         // [64][BW_XLD], over the A / B rings
+  if (warp < BW_MMA_WARPS) {
+    asm volatile("bar.sync 1, %0;" :: "n"(BW_MMA_WARPS * 32) : "memory");     // every MMA warp has left the rings
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        double2 v;
+        v.x = acc[mi][ni][0];
+        v.y = acc[mi][ni][1];
+        *reinterpret_cast<double2*>(X + (wm0 + mi * 8 + g) * BW_XLD + wn0 + ni * 8 + 2 * t) = v;
+      }
+  }
+  cluster_sync_all();                                       // all threads of all CTAs of the cluster
+  if (warp < BW_MMA_WARPS) {
+    const int rows_per = CSL_BM / nsplit;                   // nsplit in {2, 4}
+    const int r_lo = split * rows_per;
+    for (int e = tid; e < rows_per * CSL_BN; e += BW_MMA_WARPS * 32) {
+      const int rl = r_lo + e / CSL_BN, cl = e % CSL_BN;
+      const double* src = X + rl * BW_XLD + cl;
+      double b = ld_dsmem(src, 0);
+      for (int q = 1; q < nsplit; ++q) b += ld_dsmem(src, (uint32_t)q);      // rank order: fixed
+      if (rl < nrows) {
+        const int col = c0 + cl;
+        const double cal = calrow >= 0 ? coef[(long long)calrow * ldc + col] : 1.0;
+        const double d = p.data[row0 + rl];
+        R[(long long)(row0 + rl) * ldr + col] = cal_on_model ? __dsub_rn(d, __dmul_rn(b, cal)) : __dsub_rn(__dmul_rn(cal, d), b);
+      }
+    }
+  }
+  cluster_sync_all();                                       // nobody leaves while a peer still reads its tile
+}
+
+template <int NT, int NP>
+static int launch_class_ws(const csl_program_t* p, int tile0, int ntile, int nsplit, int W, const double* coef, int ldc,
+                           double* R, int ldr, cudaStream_t s) {
+  const size_t smem = (size_t)(BW_SA * CSL_ASZ + BW_SB * CSL_BSZ + BW_SL * CSL_KC * (NT + 4 * NP)) * sizeof(double) +
+                      2 * (BW_SA + BW_SB + BW_SL) * sizeof(uint64_t);
+  static_assert(BW_SA * CSL_ASZ + BW_SB * CSL_BSZ >= CSL_BM * BW_XLD, "the rings must hold the parked partial tile");
+  cudaError_t e = cudaFuncSetAttribute(k_bin_residual_ws<NT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ntile * nsplit, W / CSL_BN, 1);
+  cfg.blockDim = dim3(BW_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = nsplit;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, k_bin_residual_ws<NT, NP>, *p, tile0, W, nsplit, coef, ldc, R, ldr);
+  if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+  return 0;
+}
+
+#define CSL_DISPATCH_WS_NP(NTV)                                                                                  \
+  switch (np) {                                                                                                  \
+    case 0: return launch_class_ws<NTV, 0>(p, tile0, ntile, nsplit, W, coef, ldc, R, ldr, s);                    \
+    case 1: return launch_class_ws<NTV, 1>(p, tile0, ntile, nsplit, W, coef, ldc, R, ldr, s);                    \
+    case 2: return launch_class_ws<NTV, 2>(p, tile0, ntile, nsplit, W, coef, ldc, R, ldr, s);                    \
+    case 4: return launch_class_ws<NTV, 4>(p, tile0, ntile, nsplit, W, coef, ldc, R, ldr, s);                    \
+    default: return csl_fail(CSL_E_BADARG, "csl_bin_residual: power-law class must be 0, 1, 2 or 4");            \
+  }
+
+static int dispatch_class_ws(int nt, int np, const csl_program_t* p, int tile0, int ntile, int nsplit, int W,
+                             const double* coef, int ldc, double* R, int ldr, cudaStream_t s) {
+  switch (nt) {
+    case 0: CSL_DISPATCH_WS_NP(0)
+    case 2: CSL_DISPATCH_WS_NP(2)
+    case 4: CSL_DISPATCH_WS_NP(4)
+    case 8: CSL_DISPATCH_WS_NP(8)
+    default: return csl_fail(CSL_E_BADARG, "csl_bin_residual: template class must be 0, 2, 4 or 8");
   }
 }
 
@@ -454,31 +788,47 @@ static int dispatch_seg(int nt, int np, const csl_program_t* p, int b0, int nb, 
 }
 
 template <int NT, int NP>
-static int launch_class(const csl_program_t* p, int tile0, int ntile, int W, const double* coef, int ldc,
+static int launch_class(const csl_program_t* p, int tile0, int ntile, int nsplit, int W, const double* coef, int ldc,
                         double* R, int ldr, cudaStream_t s) {
-  static bool attr_set = false;
-  const size_t smem = (size_t)(2 * CSL_ASZ + 2 * CSL_BSZ + 2 * CSL_KC * (NT + 4 * NP)) * sizeof(double);
-  if (!attr_set) {
+  size_t smem = (size_t)(2 * CSL_ASZ + 2 * CSL_BSZ + 2 * CSL_KC * (NT + 4 * NP)) * sizeof(double);
+  if (nsplit > 1 && smem < (size_t)CSL_BM * BW_XLD * sizeof(double)) smem = (size_t)CSL_BM * BW_XLD * sizeof(double);
+  {
     cudaError_t e = cudaFuncSetAttribute(k_bin_residual<NT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-    attr_set = true;
   }
-  dim3 grid(ntile, W / CSL_BN);
-  k_bin_residual<NT, NP><<<grid, CSL_THREADS, smem, s>>>(*p, tile0, W, coef, ldc, R, ldr);
+  if (nsplit <= 1) {
+    dim3 grid(ntile, W / CSL_BN);
+    k_bin_residual<NT, NP><<<grid, CSL_THREADS, smem, s>>>(*p, tile0, W, 1, coef, ldc, R, ldr);
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ntile * nsplit, W / CSL_BN, 1);
+  cfg.blockDim = dim3(CSL_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = nsplit;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_bin_residual<NT, NP>, *p, tile0, W, nsplit, coef, ldc, R, ldr);
+  if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
   return 0;
 }
 
 #define CSL_DISPATCH_NP(NTV)                                                                          \
   switch (np) {                                                                                        \
-    case 0: return launch_class<NTV, 0>(p, tile0, ntile, W, coef, ldc, R, ldr, s);                     \
-    case 1: return launch_class<NTV, 1>(p, tile0, ntile, W, coef, ldc, R, ldr, s);                     \
-    case 2: return launch_class<NTV, 2>(p, tile0, ntile, W, coef, ldc, R, ldr, s);                     \
-    case 4: return launch_class<NTV, 4>(p, tile0, ntile, W, coef, ldc, R, ldr, s);                     \
+    case 0: return launch_class<NTV, 0>(p, tile0, ntile, nsplit, W, coef, ldc, R, ldr, s);             \
+    case 1: return launch_class<NTV, 1>(p, tile0, ntile, nsplit, W, coef, ldc, R, ldr, s);             \
+    case 2: return launch_class<NTV, 2>(p, tile0, ntile, nsplit, W, coef, ldc, R, ldr, s);             \
+    case 4: return launch_class<NTV, 4>(p, tile0, ntile, nsplit, W, coef, ldc, R, ldr, s);             \
     default: return csl_fail(CSL_E_BADARG, "csl_bin_residual: power-law class must be 0, 1, 2 or 4");  \
   }
 
-static int dispatch_class(int nt, int np, const csl_program_t* p, int tile0, int ntile, int W, const double* coef,
-                          int ldc, double* R, int ldr, cudaStream_t s) {
+static int dispatch_class(int nt, int np, const csl_program_t* p, int tile0, int ntile, int nsplit, int W,
+                          const double* coef, int ldc, double* R, int ldr, cudaStream_t s) {
   switch (nt) {
     case 0: CSL_DISPATCH_NP(0)
     case 2: CSL_DISPATCH_NP(2)
@@ -503,7 +853,17 @@ extern "C" int csl_bin_residual(const csl_program_t* p, int W, const double* coe
   for (int c = 0; c < p->nclass; ++c) {
     const int32_t* k = p->cls[c];
     CSL_REQUIRE(k[0] + 2 * k[1] > 0, "csl_bin_residual: empty spectrum class");
-    int rc = dispatch_class(k[0], k[1], p, k[2], k[3], W, coef, ldc, R, ldr, s);
+    // The program's ell split (csl_program_t::bin_split, a property of the program, never of the launch) becomes
+    // the cluster size.  bin_variant 2 selects the warp-specialised bulk-copy kernel (measured SLOWER than the
+    // all-warps-build-then-multiply kernel at every size but tiny launches: DESIGN.md); both give the same bits.
+    int nsplit = p->bin_split;
+    if (csl_option_value("bin_split") > 0) nsplit = csl_option_value("bin_split");       // sweeps only: changes the bits
+    if (nsplit != 2 && nsplit != 4) nsplit = 1;
+    int rc;
+    if (p->winT && csl_option_value("bin_variant") == 2)
+      rc = dispatch_class_ws(k[0], k[1], p, k[2], k[3], nsplit, W, coef, ldc, R, ldr, s);
+    else
+      rc = dispatch_class(k[0], k[1], p, k[2], k[3], nsplit, W, coef, ldc, R, ldr, s);
     if (rc) return rc;
   }
   for (int c = 0; c < p->nsegclass; ++c) {

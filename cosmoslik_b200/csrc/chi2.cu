@@ -12,7 +12,7 @@
 
 __global__ void __launch_bounds__(CSL_THREADS, 1)
 k_trsm_chi2(csl_program_t p, double* R, int ldr, double* __restrict__ chi2) {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   double* As = smem;
   double* Bs = As + 2 * CSL_ASZ;
   double* Ts = Bs + 2 * CSL_BSZ;            // [64][CSL_LDB]: T_i as the B operand of the diagonal solve
@@ -91,6 +91,161 @@ k_trsm_chi2(csl_program_t p, double* R, int ldr, double* __restrict__ chi2) {
   if (tid < CSL_BN) chi2[c0 + tid] = red[tid] + red[CSL_BN + tid];
 }
 
+// ---- the blocked solve with Blackwell tile movement and two CTAs per SM ---------------------------------
+// Same arithmetic as k_trsm_chi2 (bitwise), restructured so that nothing but the ring of bulk-copy stages lives in
+// shared memory: T_i = R_i - sum_{j<i} L_ij Y_j is written straight back to R_i in global memory (L2 resident) and
+// the diagonal solve Y_i = inv(L_ii) T_i is just four more chunks of the SAME streamed tile product, with
+// A = the tile-major inverse of the diagonal block and B = the rows of T_i read back by the producer.  That removes
+// the 67 KB T tile (and its bank-conflicting stores), so two CTAs fit on an SM and the 202-register / 1-CTA shape
+// is gone.  A producer warp issues the bulk copies (one per L tile, 16 per R chunk); consumers hand finished rows
+// to it through the `ready` mbarrier after a global fence and a generic -> async proxy fence.  The producer runs
+// ahead on every chunk that does not depend on the rows being finished (chunks of Y_j, j < i - 1).
+#define TRSM_STAGES 4
+__device__ unsigned long long g_trsm_dbg[4];        // debugging counters (flags & 256): stale bulk reads seen
+__global__ void __launch_bounds__(CSL_THREADS + 32, 2)
+k_trsm_chi2_bulk(csl_program_t p, double* R, int ldr, double* __restrict__ chi2, int flags) {
+  constexpr int NCW = CSL_THREADS / 32, STAGE = CSL_ASZ + CSL_BSZ;
+  constexpr uint32_t TX_BYTES = (uint32_t)(CSL_ASZ + CSL_KC * CSL_BN) * sizeof(double);
+  extern __shared__ __align__(128) double smem[];
+  double* red = smem + TRSM_STAGES * STAGE;                  // [2][128]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * CSL_BN);
+  uint64_t* empty = full + TRSM_STAGES;
+  uint64_t* ready = empty + TRSM_STAGES;
+  const int c0 = blockIdx.x * CSL_BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int npad = p.n_pad, nblk = npad / CSL_BM, nct = npad / CSL_KC;
+  constexpr int CPB = CSL_BM / CSL_KC;                       // chunks per 64-row block
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TRSM_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCW); }
+    mbar_init(ready, NCW);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (warp == NCW) {
+    // ---------------- producer: the chunk stream of all row blocks, in order
+    int q = 0;                 // running chunk number (stage = q % STAGES)
+    int nready = 0;            // completions of `ready` waited for so far
+    auto issue = [&](const double* At, const double* Bg) {
+      const int s = q % TRSM_STAGES, use = q / TRSM_STAGES;
+      if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
+      double* As = smem + s * STAGE;
+      double* Bs = As + CSL_ASZ;
+      if (lane == 0) mbar_arrive_expect_tx(full + s, TX_BYTES);
+      __syncwarp();
+      if (lane < CSL_KC) bulk_g2s(Bs + lane * CSL_LDB, Bg + (long long)lane * ldr, CSL_BN * sizeof(double), full + s);
+      else if (lane == CSL_KC) bulk_g2s(As, At, CSL_ASZ * sizeof(double), full + s);
+      ++q;
+    };
+    for (int i = 0; i < nblk; ++i) {
+      const double* Lrow = p.LmatT + (long long)i * nct * CSL_ATILE;
+      for (int c = 0; c < i * CPB; ++c) {
+        // rows of Y_{i-1} are the last thing the consumers finished: wait for them once, before their first chunk
+        if (c == (i - 1) * CPB) {
+          mbar_wait(ready, nready & 1); ++nready;
+          if (flags & 2) { __threadfence(); asm volatile("fence.proxy.async;" ::: "memory"); }
+          if (flags & 64) __nanosleep(3000);
+        }
+        issue(Lrow + (long long)c * CSL_ATILE, R + (long long)c * CSL_KC * ldr + c0);
+      }
+      mbar_wait(ready, nready & 1); ++nready;                // T_i is in R_i
+      if (flags & 2) { __threadfence(); asm volatile("fence.proxy.async;" ::: "memory"); }
+      if (flags & 64) __nanosleep(3000);
+      const double* Dinv = p.LinvT + (long long)i * CPB * CSL_ATILE;
+      for (int c = 0; c < CPB; ++c)
+        issue(Dinv + (long long)c * CSL_ATILE, R + (long long)(i * CSL_BM + c * CSL_KC) * ldr + c0);
+    }
+    return;
+  }
+  // ---------------- consumers
+  const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 32;
+  const int g = lane >> 2, t = lane & 3;
+  double colsq[4][2];
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni) colsq[ni][0] = colsq[ni][1] = 0.0;
+  int q = 0;
+  auto consume = [&](double (&acc)[4][4][2], int nchunk, long long brow0, int which) {
+    for (int c = 0; c < nchunk; ++c, ++q) {
+      const int s = q % TRSM_STAGES;
+      mbar_wait(full + s, (q / TRSM_STAGES) & 1);
+      const double* As = smem + s * STAGE;
+      if (flags & 256) {     // debugging: does the staged B chunk equal what global memory holds now?
+        const double* Bsd = As + CSL_ASZ;
+        const int k = lane & 15, col = wn0 + (lane >> 4) * 16 + (warp >> 2) * 8;
+        for (int j = 0; j < 8; ++j) {
+          const double a = Bsd[k * CSL_LDB + col + j];
+          const double b = __ldcg(R + (brow0 + (long long)c * CSL_KC + k) * ldr + c0 + col + j);
+          if (a != b) atomicAdd(&g_trsm_dbg[which], 1ull);
+        }
+        atomicAdd(&g_trsm_dbg[2], 8ull);
+      }
+      warp_mma_chunk_m<0xF>(acc, As, As + CSL_ASZ, wm0, wn0, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+  };
+  auto publish_rows = [&]() {
+    // this warp's stores to R_i -> visible to the producer's bulk copies (async proxy), then tell it
+    if (flags & 4) __threadfence_system(); else __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ready);
+  };
+  for (int i = 0; i < nblk; ++i) {
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    consume(acc, i * CPB, 0, 0);                             // acc = sum_{j<i} L_ij Y_j
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {                         // T_i = R_i - acc, in place
+      const int rl = wm0 + mi * 8 + g;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        double2* ptr = reinterpret_cast<double2*>(R + (long long)(i * CSL_BM + rl) * ldr + c0 + wn0 + ni * 8 + 2 * t);
+        double2 r = (flags & 16) ? __ldcg(ptr) : *ptr;
+        r.x = r.x - acc[mi][ni][0];
+        r.y = r.y - acc[mi][ni][1];
+        if (flags & 16) __stcg(ptr, r); else *ptr = r;
+        acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      }
+    }
+    publish_rows();
+    consume(acc, CPB, (long long)i * CSL_BM, 1);
+    if (flags & 256) asm volatile("bar.sync 1, %0;" :: "n"(CSL_THREADS) : "memory");   // nobody overwrites T_i while it is being checked
+             // Y_i = inv(L_ii) T_i
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int rl = wm0 + mi * 8 + g;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        double2 y;
+        y.x = acc[mi][ni][0];
+        y.y = acc[mi][ni][1];
+        double2* yp = reinterpret_cast<double2*>(R + (long long)(i * CSL_BM + rl) * ldr + c0 + wn0 + ni * 8 + 2 * t);
+        if (flags & 16) __stcg(yp, y); else *yp = y;
+        colsq[ni][0] = fma(y.x, y.x, colsq[ni][0]);
+        colsq[ni][1] = fma(y.y, y.y, colsq[ni][1]);
+      }
+    }
+    if (i + 1 < nblk) publish_rows();
+  }
+  // reduce over the 8 row groups of the warp (lane bits 2..4), then over the two warp rows
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double v = colsq[ni][e];
+      v += shfl_xor_d(v, 4);
+      v += shfl_xor_d(v, 8);
+      v += shfl_xor_d(v, 16);
+      if (g == 0) red[(warp >> 2) * CSL_BN + wn0 + ni * 8 + 2 * t + e] = v;
+    }
+  asm volatile("bar.sync 1, %0;" :: "n"(CSL_THREADS) : "memory");      // consumers only (the producer has left)
+  if (tid < CSL_BN) chi2[c0 + tid] = red[tid] + red[CSL_BN + tid];
+}
+
 // ---- explicit-inverse mode ---------------------------------------------------------------------------
 // Y = M R with M = L^-1 (lower triangular, inverted once on the host in extended precision and verified
 // against the substitution result before it is used).  Every row block of Y is an independent tile
@@ -109,7 +264,7 @@ template <int ROWS>
 __global__ void __launch_bounds__(4 * ROWS, 128 / ROWS)
 k_trigemm_chi2(csl_program_t p, const double* __restrict__ R, int ldr, double* __restrict__ part, int grp) {
   constexpr int THREADS = 4 * ROWS, ASZ = ROWS * CSL_LDA;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   double* As = smem;
   double* Bs = As + CHI2_STAGES(ROWS) * ASZ;
   const int npad = p.n_pad, nblk = npad / ROWS;
@@ -158,12 +313,123 @@ k_trigemm_chi2(csl_program_t p, const double* __restrict__ R, int ldr, double* _
     }
 }
 
+// ---- the same tile product with Blackwell tile movement ------------------------------------------------
+// One PRODUCER warp feeds a ring of STAGES stages with bulk asynchronous copies (cp.async.bulk, the TMA unit):
+// per k-chunk ONE copy of the tile-major M tile (ROWS x 20 doubles, contiguous in MinvT) and 16 copies of
+// 1 KB R rows into the padded B stage, all completing on the stage's `full` mbarrier (expect_tx).  The
+// CONSUMER warps wait on `full`, run the DMMA chunk, and arrive on `empty`; they never compute a global address,
+// issue a load or meet a CTA-wide barrier inside the loop, and a warp may run up to STAGES chunks ahead of its
+// neighbours.  Per 32 x 32 warp tile the DMMA sequence is the one of k_trigemm_chi2, so chi^2 is bitwise the same.
+template <int ROWS, int STAGES>
+__global__ void __launch_bounds__(4 * ROWS + 32, ROWS == 64 ? 2 : 3)
+k_trigemm_chi2_bulk(csl_program_t p, const double* __restrict__ R, int ldr, double* __restrict__ part, int grp) {
+  constexpr int NCW = ROWS / 8;                          // consumer warps (each 32 x 32 of the ROWS x 128 tile)
+  constexpr int ASZ = ROWS * CSL_LDA, STAGE = ASZ + CSL_BSZ;
+  constexpr uint32_t TX_BYTES = (uint32_t)(ASZ + CSL_KC * CSL_BN) * sizeof(double);
+  extern __shared__ __align__(128) double smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+  uint64_t* empty = full + STAGES;
+  const int npad = p.n_pad, nblk = npad / ROWS;
+  const int ntile = gridDim.x / nblk;
+  const int per = grp * nblk;
+  const int sg = blockIdx.x / per, rem = blockIdx.x - sg * per;
+  const int gcur = min(grp, ntile - sg * grp);
+  const int i = nblk - 1 - rem / gcur, ct = sg * grp + rem % gcur;
+  const int c0 = ct * CSL_BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kend = min((i + 1) * ROWS, (p.n + CSL_KC - 1) / CSL_KC * CSL_KC);
+  const int nchunk = kend / CSL_KC;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCW); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (warp == NCW) {
+    // ---------------- producer
+    const int nct = npad / CSL_KC;
+    const double* __restrict__ At = p.MinvT + ((long long)((i * ROWS) / CSL_BM) * nct) * CSL_ATILE + ((i * ROWS) % CSL_BM) * CSL_LDA;
+    const double* __restrict__ Bg = R + c0;
+    for (int c = 0; c < nchunk; ++c) {
+      const int s = c % STAGES, use = c / STAGES;
+      if (use > 0) mbar_wait(empty + s, (use - 1) & 1);          // the consumers have left this stage
+      double* As = smem + s * STAGE;
+      double* Bs = As + ASZ;
+      if (lane == 0) mbar_arrive_expect_tx(full + s, TX_BYTES);
+      __syncwarp();
+      if (lane < CSL_KC)
+        bulk_g2s(Bs + lane * CSL_LDB, Bg + (long long)(c * CSL_KC + lane) * ldr, CSL_BN * sizeof(double), full + s);
+      else if (lane == CSL_KC)
+        bulk_g2s(As, At + (long long)c * CSL_ATILE, ASZ * sizeof(double), full + s);
+    }
+    return;
+  }
+  // ---------------- consumers
+  const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 32;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  // rows >= n of M are identity rows acting on zero rows of R: skip their 8-row groups altogether
+  unsigned mmask = 0;
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+    if (i * ROWS + wm0 + mi * 8 < p.n) mmask |= 1u << mi;
+  for (int c = 0; c < nchunk; ++c) {
+    const int s = c % STAGES;
+    unsigned m = mmask;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+      if (i * ROWS + wm0 + mi * 8 + 7 < c * CSL_KC) m &= ~(1u << mi);      // 8-row group entirely above the diagonal
+    mbar_wait(full + s, (c / STAGES) & 1);
+    const double* As = smem + s * STAGE;
+    if (m) warp_mma_chunk(acc, As, As + ASZ, wm0, wn0, lane, m);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+  }
+  double* prow = part + (long long)((i * ROWS + wm0) / 32) * ldr + c0 + wn0;
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double v = 0.0;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) v = fma(acc[mi][ni][e], acc[mi][ni][e], v);
+      v += shfl_xor_d(v, 4);
+      v += shfl_xor_d(v, 8);
+      v += shfl_xor_d(v, 16);
+      if (g == 0) prow[ni * 8 + 2 * t + e] = v;
+    }
+}
+
+template <int ROWS, int STAGES>
+static int launch_trigemm_bulk(const csl_program_t* p, int nctas, const double* R, int ldr, double* part, int grp,
+                               cudaStream_t s) {
+  const size_t smem = (size_t)STAGES * (ROWS * CSL_LDA + CSL_BSZ) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+  cudaError_t e = cudaFuncSetAttribute(k_trigemm_chi2_bulk<ROWS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+  k_trigemm_chi2_bulk<ROWS, STAGES><<<nctas, 4 * ROWS + 32, smem, s>>>(*p, R, ldr, part, grp);
+  return 0;
+}
+
 __global__ void k_sum_partials(int nblk, int W, int ldr, const double* __restrict__ part, double* __restrict__ chi2) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
   double s = 0.0;
   for (int i = 0; i < nblk; ++i) s += part[(long long)i * ldr + w];
   chi2[w] = s;
+}
+
+extern "C" int csl_debug_counters(unsigned long long* out4_host, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out4_host, g_trsm_dbg, sizeof(g_trsm_dbg));
+  if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+  if (reset) {
+    unsigned long long z[4] = {0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_trsm_dbg, z, sizeof(z));
+  }
+  return 0;
 }
 
 extern "C" int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part,
@@ -186,41 +452,54 @@ int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi
     long long panel = (long long)p->n_pad * CSL_BN * sizeof(double);
     int grp = (int)((96ll << 20) / panel);
     grp = grp < 1 ? 1 : (grp > 256 ? 256 : grp);
-    if (const char* e = getenv("CSL_TRIGEMM_GROUP")) grp = atoi(e) > 0 ? atoi(e) : grp;
-    // tile shape: 64-row CTAs unless they would not even fill the GPU three times over
+    if (csl_option_value("trigemm_group") > 0) grp = csl_option_value("trigemm_group");
+    // tile shape: 64-row CTAs (2 per SM) unless the launch would leave SMs idle -- then 32-row CTAs: twice as
+    // many, half as long, so the last wave is shorter.  Work of a launch in 64-row-block units: every column
+    // tile carries nblk (nblk + 1) / 2 of them.
     const int nblk64 = p->n_pad / CSL_BM, ntile = W / CSL_BN;
-    int sms = 148;
-    { static int cached = 0; if (!cached) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev); } sms = cached > 0 ? cached : sms; }
+    const int sms = csl_sm_count();
     int rows = (long long)ntile * nblk64 < 6ll * sms ? 32 : 64;
-    if (const char* e = getenv("CSL_TRIGEMM_ROWS")) rows = atoi(e) == 32 ? 32 : 64;
-    static bool attr64 = false, attr32 = false;
-    if (rows == 64) {
+    if (csl_option_value("trigemm_rows") == 32 || csl_option_value("trigemm_rows") == 64) rows = csl_option_value("trigemm_rows");
+    const int pipe = csl_option_value("pipe");
+    const bool bulk = p->MinvT != nullptr && pipe != 0;
+    int rc = 0;
+    if (bulk) {
+      const int st = csl_option_value("trigemm_stages");
+      if (rows == 64) rc = st == 3 ? launch_trigemm_bulk<64, 3>(p, ntile * nblk64, R, ldr, ws_part, grp, s)
+                                   : launch_trigemm_bulk<64, 4>(p, ntile * nblk64, R, ldr, ws_part, grp, s);
+      else rc = st == 4 ? launch_trigemm_bulk<32, 4>(p, ntile * nblk64 * 2, R, ldr, ws_part, grp, s)     // 2 CTAs / SM
+                        : launch_trigemm_bulk<32, 3>(p, ntile * nblk64 * 2, R, ldr, ws_part, grp, s);    // 3 CTAs / SM
+      if (rc) return rc;
+    } else if (rows == 64) {
       const size_t smem1 = (size_t)CHI2_STAGES(64) * (CSL_ASZ + CSL_BSZ) * sizeof(double);
-      if (!attr64) {
-        cudaError_t e = cudaFuncSetAttribute(k_trigemm_chi2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-        if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-        attr64 = true;
-      }
+      cudaError_t e = cudaFuncSetAttribute(k_trigemm_chi2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+      if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
       k_trigemm_chi2<64><<<ntile * nblk64, 256, smem1, s>>>(*p, R, ldr, ws_part, grp);
     } else {
       const size_t smem1 = (size_t)CHI2_STAGES(32) * (32 * CSL_LDA + CSL_BSZ) * sizeof(double);
-      if (!attr32) {
-        cudaError_t e = cudaFuncSetAttribute(k_trigemm_chi2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-        if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-        attr32 = true;
-      }
+      cudaError_t e = cudaFuncSetAttribute(k_trigemm_chi2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+      if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
       k_trigemm_chi2<32><<<ntile * nblk64 * 2, 128, smem1, s>>>(*p, R, ldr, ws_part, grp);
     }
     if (sum_partials) k_sum_partials<<<(W + 255) / 256, 256, 0, s>>>(2 * nblk64, W, ldr, ws_part, chi2);
     return csl_check_launch("k_trigemm_chi2");
   }
   CSL_REQUIRE(p->Lmat && p->Linv_diag, "csl_chi2: program has no factor");
-  static bool attr_set = false;
+  const int shape = csl_option_value("trsm_shape");
+  if (p->LmatT && p->LinvT && shape != 0 && csl_option_value("pipe") != 0) {
+    const int flags = shape > 0 ? shape : 1;
+    size_t smem = (size_t)(TRSM_STAGES * (CSL_ASZ + CSL_BSZ) + 2 * CSL_BN) * sizeof(double) +
+                  (2 * TRSM_STAGES + 1) * sizeof(uint64_t);
+    if (flags & 8) smem = 120 * 1024;                       // debugging: one CTA per SM
+    cudaError_t e = cudaFuncSetAttribute(k_trsm_chi2_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+    k_trsm_chi2_bulk<<<W / CSL_BN, CSL_THREADS + 32, smem, s>>>(*p, R, ldr, chi2, flags);
+    return csl_check_launch("k_trsm_chi2_bulk");
+  }
   const size_t smem = (size_t)CHI2_SMEM_DOUBLES * sizeof(double);
-  if (!attr_set) {
+  {
     cudaError_t e = cudaFuncSetAttribute(k_trsm_chi2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-    attr_set = true;
   }
   k_trsm_chi2<<<W / CSL_BN, CSL_THREADS, smem, s>>>(*p, R, ldr, chi2);
   return csl_check_launch("k_trsm_chi2");
@@ -229,7 +508,7 @@ int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi
 // ---- plain FP64 DMMA GEMM on the same tile core (peak / unit tests) ----------------------------------
 __global__ void __launch_bounds__(CSL_THREADS, 2)
 k_dgemm(int M, int N, int K, const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C) {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   double* As = smem;
   double* Bs = As + 2 * CSL_ASZ;
   const int m0 = blockIdx.x * CSL_BM, c0 = blockIdx.y * CSL_BN;
@@ -257,12 +536,10 @@ extern "C" int csl_dgemm_dmma(int M, int N, int K, const double* A, const double
   CSL_REQUIRE(A && B && C, "csl_dgemm_dmma: null argument");
   CSL_REQUIRE(M > 0 && N > 0 && K > 0 && M % CSL_BM == 0 && N % CSL_BN == 0 && K % CSL_KC == 0,
               "csl_dgemm_dmma: M%64, N%128, K%16 must be 0");
-  static bool attr_set = false;
   const size_t smem = (size_t)(2 * CSL_ASZ + 2 * CSL_BSZ) * sizeof(double);
-  if (!attr_set) {
+  {
     cudaError_t e = cudaFuncSetAttribute(k_dgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-    attr_set = true;
   }
   dim3 grid(M / CSL_BM, N / CSL_BN);
   k_dgemm<<<grid, CSL_THREADS, smem, (cudaStream_t)stream>>>(M, N, K, A, B, C);

@@ -43,6 +43,7 @@ int csl_direct_residual_ld(const csl_program_t* p, int W, int Wp, const double* 
 // device / environment facts read once per process (api.cu)
 int csl_sm_count();
 int csl_env_int(const char* name, int fallback);
+int csl_option_value(const char* name);     // tuning option (csl_set_option / environment), -1 = unset
 
 #define CSL_REQUIRE(cond, msg) do { if (!(cond)) return csl_fail(CSL_E_BADARG, msg); } while (0)
 
@@ -61,6 +62,40 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+
+// ---- Blackwell tile movement: bulk asynchronous copies (the TMA unit; SASS UBLKCP) completing on an mbarrier
+// (SASS SYNCS).  One elected lane issues a copy of a whole contiguous tile -- the A operands are stored TILE-MAJOR
+// by the host for exactly this: a [64 x 16] tile with its 4-double row padding is 10 240 contiguous bytes -- the
+// consumers wait on the stage's "full" barrier, and release the stage by arriving on its "empty" barrier.  No
+// thread of a consumer warp computes an address, issues a load or takes part in a CTA-wide barrier in the main loop.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16; both addresses 16-byte aligned), completing on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+#define CSL_ATILE (CSL_BM * CSL_LDA)     // doubles of one tile-major A tile: 64 rows x (16 + 4 padding)
 
 // One k-chunk (CSL_KC columns) of the CTA tile product on a warp tile of 32 x 32:
 // acc[mi][ni][2] += A[wm0 + 8 mi .., :] * B[:, wn0 + 8 ni ..]

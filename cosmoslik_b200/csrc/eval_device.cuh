@@ -10,21 +10,7 @@
 // (their coefficients are written, their prior is not).
 __device__ __forceinline__ void prepare_walker(const csl_program_t& p, const double* xr, int w, int W,
                                                double* __restrict__ coef, int ldc, double* __restrict__ prior) {
-  // priors.py:26-28: first box that fails `lo <= x <= hi` (NaN fails) gives +inf
-  bool out = false;
-  for (int b = 0; b < p.nbox; ++b) {
-    double v = xr[p.box_idx[b]];
-    if (!(p.box_lo[b] <= v && v <= p.box_hi[b])) out = true;
-  }
-  // priors.py:30: sum((x-c)**2./2/w**2), python sum from 0 in list order
-  double pr = 0.0;
-  for (int k = 0; k < p.ngauss; ++k) {
-    double d = __dsub_rn(xr[p.gauss_idx[k]], p.gauss_c[k]);
-    double wv = p.gauss_w[k];
-    pr = __dadd_rn(pr, __ddiv_rn(__ddiv_rn(__dmul_rn(d, d), 2.0), __dmul_rn(wv, wv)));
-  }
-  if (w < W) prior[w] = out ? CUDART_INF : pr;
-
+  // coefficient bytecode first: priors may refer to derived quantities (coefficient rows)
   double st[CSL_STACK];
   int sp = 0;
   for (int pc = 0; pc < p.ncode; ++pc) {
@@ -46,6 +32,25 @@ __device__ __forceinline__ void prepare_walker(const csl_program_t& p, const dou
       default: break;
     }
   }
+  // A prior's subject is a sampled parameter (index >= 0) or a DERIVED quantity the script sets in __call__
+  // (index < 0: coefficient row -index - 1; the reference evaluates priors again after the call for exactly
+  // these, cosmoslik.py:139-141).  This thread wrote that coefficient a few lines above.
+  // priors.py:26-28: first box that fails `lo <= x <= hi` (NaN fails) gives +inf
+  bool out = false;
+  for (int b = 0; b < p.nbox; ++b) {
+    const int ix = p.box_idx[b];
+    double v = ix >= 0 ? xr[ix] : coef[(long long)(-ix - 1) * ldc + w];
+    if (!(p.box_lo[b] <= v && v <= p.box_hi[b])) out = true;
+  }
+  // priors.py:30: sum((x-c)**2./2/w**2), python sum from 0 in list order
+  double pr = 0.0;
+  for (int k = 0; k < p.ngauss; ++k) {
+    const int ix = p.gauss_idx[k];
+    double d = __dsub_rn(ix >= 0 ? xr[ix] : coef[(long long)(-ix - 1) * ldc + w], p.gauss_c[k]);
+    double wv = p.gauss_w[k];
+    pr = __dadd_rn(pr, __ddiv_rn(__ddiv_rn(__dmul_rn(d, d), 2.0), __dmul_rn(wv, wv)));
+  }
+  if (w < W) prior[w] = out ? CUDART_INF : pr;
 }
 
 // lnl = like + prior with like = sum scalar coefs (+ chi2/2), cosmoslik.py:141; +inf on a hard prior (:135-137)

@@ -270,7 +270,7 @@ k_mh_adapt_factor(int nd, const double* __restrict__ mom, double scale2_over_nd,
   // right-looking Cholesky in shared memory (lower triangle)
   double dmax = 0.0;
   for (int i = 0; i < nd; ++i) dmax = fmax(dmax, A[i * ld + i]);
-  const double tiny = dmax * 1e-14;
+  const double tiny = dmax * 1e-12;
   for (int j = 0; j < nd; ++j) {
     const double piv = A[j * ld + j];
     const bool ok = piv > tiny;

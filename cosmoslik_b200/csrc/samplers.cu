@@ -545,6 +545,39 @@ k_rows_gauss_prior(int W, int nd, double* __restrict__ rows, const int32_t* __re
   row[0] += dlnl;
 }
 
+// Chain.thin on the device (chains.py:235-243): one warp per chain walks its rows in order; with
+// S_k = ceil(cumulative weight through row k / delta), row k is kept iff S_k > S_{k-1} and gets weight S_k - S_{k-1}.
+// Kept rows are compacted to the front of the chain's buffer in place (the write index never passes the read index).
+__global__ void __launch_bounds__(SAMP_THREADS)
+k_rows_thin(int W, int nd, double* __restrict__ rows, int32_t* __restrict__ nrows, int cap, double delta) {
+  const int w = warp_global(), lane = threadIdx.x & 31;
+  if (w >= W) return;
+  const int rl = 2 + nd, nr = min(nrows[w], cap);
+  double* base = rows + (long long)w * cap * rl;
+  double cum = 0.0, prev = 0.0;
+  int out = 0;
+  for (int r = 0; r < nr; ++r) {
+    const double* src = base + (long long)r * rl;
+    cum += src[1];
+    const double slot = ceil(cum / delta);
+    if (slot > prev) {                           // warp-uniform
+      double* dst = base + (long long)out * rl;
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+      if (lane < rl) v0 = src[lane];
+      if (lane + 32 < rl) v1 = src[lane + 32];
+      if (lane + 64 < rl) v2 = src[lane + 64];
+      __syncwarp();
+      if (lane < rl) dst[lane] = (lane == 1) ? slot - prev : v0;
+      if (lane + 32 < rl) dst[lane + 32] = v1;
+      if (lane + 64 < rl) dst[lane + 64] = v2;
+      __syncwarp();
+      ++out;
+      prev = slot;
+    }
+  }
+  if (lane == 0) nrows[w] = out;
+}
+
 // wrapper bookkeeping, samplers/emcee.py:70-88
 __global__ void __launch_bounds__(SAMP_THREADS)
 k_emcee_rows(int W, int nd, double* __restrict__ pos_old, const double* __restrict__ pos_new,
@@ -694,6 +727,12 @@ extern "C" int csl_rows_gauss_prior(int W, int ndim, double* rows, const int32_t
   return csl_check_launch("k_rows_gauss_prior");
 }
 
+extern "C" int csl_rows_thin(int W, int ndim, double* rows, int32_t* nrows, int cap, double delta, void* stream) {
+  CSL_REQUIRE(W > 0 && cap > 0 && ndim >= 1 && ndim <= CSL_MAX_DIM && rows && nrows && delta > 0, "csl_rows_thin: bad argument");
+  k_rows_thin<<<warp_grid(W), SAMP_THREADS, 0, (cudaStream_t)stream>>>(W, ndim, rows, nrows, cap, delta);
+  return csl_check_launch("k_rows_thin");
+}
+
 extern "C" int csl_stretch_propose(int Ns, int Nc, int ndim, const double* s, const double* comp, double a,
                                    const double* u_z, const int64_t* j, uint64_t seed, uint32_t step, uint32_t half,
                                    uint32_t walker0, double* q, double* zz, void* stream) {
@@ -767,8 +806,7 @@ int csl_fused_combine_accept(const csl_program_t* p, int Ns, int Nc, int ndim, d
   fc.ldp = ldp; fc.lnl_q = lnl_q;
   // CTA size: 256 walkers per CTA in bulk; launches of a few thousand walkers take 64 so that the serial
   // per-walker phase and the peer stores spread over more SMs (CSL_SAB_THREADS overrides, for sweeps)
-  static int forced = -1;
-  if (forced < 0) { const char* e = getenv("CSL_SAB_THREADS"); forced = e ? atoi(e) : 0; }
+  const int forced = csl_option_value("sab_threads");
   int nthr = forced > 0 ? forced : (Ns <= 16384 ? 64 : SAB_THREADS);
   nthr = nthr < 32 ? 32 : (nthr > SAB_THREADS ? SAB_THREADS : nthr / 32 * 32);
   k_stretch_combine_accept<<<(Ns + nthr - 1) / nthr, nthr, 0, (cudaStream_t)stream>>>(

@@ -62,6 +62,19 @@ class _Code(object):
         return k
 
 
+def tile_major(M):
+    """Tile-major copy of a row-major matrix [64 a, 16 b] for the bulk-copy (TMA) pipelines: tile (rb, c) = rows
+    64 rb .., columns 16 c .. as 64 rows of 16 + 4 (padding) doubles, tiles ordered rb-major.  One tile is
+    10 240 contiguous bytes -- one cp.async.bulk -- and lands in shared memory in the conflict-free row stride
+    of 20 doubles the DMMA fragment loads want (include/cosmoslik_b200.h, csl_program_t::MinvT)."""
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    nr, nc = M.shape
+    assert nr % L.BM == 0 and nc % L.KC == 0
+    T = np.zeros((nr // L.BM, nc // L.KC, L.BM, L.KC + 4))
+    T[:, :, :, :L.KC] = M.reshape(nr // L.BM, L.BM, nc // L.KC, L.KC).transpose(0, 2, 1, 3)
+    return T.reshape(-1)
+
+
 def _support(rows):
     """[first, last+1) of the non-zero columns of a block of window rows"""
     nz = np.flatnonzero(np.any(rows != 0.0, axis=0))
@@ -76,18 +89,21 @@ class CompiledProgram(object):
 
     _PTR_FIELDS = ("code_op", "code_arg", "code_val", "box_idx", "box_lo", "box_hi", "gauss_idx", "gauss_c",
                    "gauss_w", "scalar_coef", "spec_tab", "tile_tab", "templates", "windows", "data",
-                   "direct_coef", "Lmat", "Linv_diag", "Minv", "bin_tab", "Sigma", "grp_tab")
+                   "direct_coef", "Lmat", "Linv_diag", "Minv", "bin_tab", "Sigma", "grp_tab", "MinvT", "LmatT", "LinvT",
+                   "winT")
 
-    def __init__(self, names, priors, lnl_expr, chi2_mode="auto", binning="auto"):
+    def __init__(self, names, priors, lnl_expr, chi2_mode="auto", binning="auto", binning_split=None, derived=None):
+        self.derived = derived          # name -> value the script's __call__ left on the tree (priors on derived quantities)
         self.chi2_mode = chi2_mode
         self.binning = binning      # 'auto' | 'dmma' | 'segsum' (see _build_bandpower)
+        self.binning_split = binning_split     # None (by tile length) | 1 | 2 | 4: ell split of the DMMA binning tiles
         self.names = list(names)
         self.ndim = len(self.names)
         if not (1 <= self.ndim <= L.MAX_DIM):
             raise ValueError("number of sampled parameters must be in 1..%d" % L.MAX_DIM)
         self.tables = {}
         self.meta = dict(ndim=self.ndim, ncoef=0, ncode=0, nbox=0, ngauss=0, nscalar=0, nspec=0, ntile=0,
-                         n=0, n_pad=0, resid_mode=0, nclass=0, nsegclass=0, n_base=0, nmode=0)
+                         n=0, n_pad=0, resid_mode=0, nclass=0, nsegclass=0, n_base=0, nmode=0, bin_split=1)
         self.cls = np.zeros((L.MAX_CLASS, 4), np.int32)
         self.segcls = np.zeros((L.MAX_CLASS, 4), np.int32)
         self.host = {}
@@ -116,10 +132,34 @@ class CompiledProgram(object):
             raise NotImplementedError("one quadratic-form likelihood per script in this version "
                                       "(sum them into one covariance, as mspec_lnl does)")
         P = self.meta
-        # ---- priors (likelihoods/priors.py:6-30)
+        # ---- priors (likelihoods/priors.py:6-30).  A prior may name a sampled parameter or any quantity the script
+        # sets on itself in __call__ (the reference evaluates priors again after the call, cosmoslik.py:139-141;
+        # `param_ok`, priors.py:25): those are compiled as coefficient rows and referred to by negative indices.
+        # A name that is neither is skipped, as the reference skips it -- but not silently.
         idx = {n: i for i, n in enumerate(self.names)}
-        box = [(idx[n], lo, hi) for n, lo, hi in priors.uniform_priors if n in idx]
-        gau = [(idx[n], c, w) for n, c, w in priors.gaussian_priors if n in idx]
+        self.derived_priors = 0
+
+        def subject(n):
+            if n in idx:
+                return idx[n]
+            v = self.derived(n) if self.derived is not None else None
+            if v is None:
+                import warnings
+                warnings.warn("prior on '%s' ignored: it is neither a sampled parameter nor set by the script "
+                              "(likelihoods/priors.py:25 skips it the same way)" % (n,))
+                return None
+            try:
+                e = Expr.wrap(v)
+            except TypeError:
+                raise TypeError("prior on '%s': the script sets it to %r, not a scalar function of the sampled "
+                                "parameters" % (n, type(v))) from None
+            self.derived_priors += 1
+            return -code.coef(e) - 1
+
+        box = [(subject(n), lo, hi) for n, lo, hi in priors.uniform_priors]
+        box = [b for b in box if b[0] is not None]
+        gau = [(subject(n), c, w) for n, c, w in priors.gaussian_priors]
+        gau = [g for g in gau if g[0] is not None]
         P['nbox'], P['ngauss'] = len(box), len(gau)
         self._dev('box_idx', [b[0] for b in box], np.int32)
         self._dev('box_lo', [b[1] for b in box], np.float64)
@@ -166,6 +206,8 @@ class CompiledProgram(object):
         self.host["L"] = Lf[:n, :n]
         self._dev('Lmat', Lf, np.float64)
         self._dev('Linv_diag', inv, np.float64)
+        self._dev('LmatT', tile_major(Lf), np.float64)
+        self._dev('LinvT', tile_major(inv.reshape(nblk * L.BM, L.BM)), np.float64)
         # explicit inverse of the whole factor (chi2_mode 1): double-precision triangular solve, one step
         # of Newton refinement with the residual in extended precision, and a check against forward
         # substitution; used only if it reproduces the substitution chi^2 to 1e-13
@@ -184,6 +226,7 @@ class CompiledProgram(object):
             if err < 1e-13 or self.chi2_mode == "inverse":
                 Mp = np.eye(npad); Mp[:n, :n] = M
                 self._dev('Minv', Mp, np.float64)
+                self._dev('MinvT', tile_major(Mp), np.float64)
                 self.meta['chi2_mode'] = 1
 
     def _chi2_executed_flops(self):
@@ -210,7 +253,7 @@ class CompiledProgram(object):
         P['resid_mode'] = 2
         self._dev('direct_coef', rows, np.int32)
         self._dev('data', d, np.float64)
-        if all(isinstance(v, Par) for v in q.values) and n <= 32 and self.ndim <= 32:
+        if all(isinstance(v, Par) for v in q.values) and n <= 32 and self.ndim <= 32 and not self.derived_priors:
             # whole-run fused kernel is available (csl_mh_gauss_run)
             self.gauss_direct = dict(perm=np.array([v.index for v in q.values], np.int32),
                                      L=np.ascontiguousarray(self.host["L"]), mean=np.ascontiguousarray(q.mean))
@@ -255,6 +298,7 @@ class CompiledProgram(object):
         nspec = len(q.blocks)
         spec_tab = np.zeros((nspec, L.SPEC_STRIDE), np.int32)
         tiles, segbins, templ, wins, data = [], [], [], [], []
+        wint, wint_off, max_tile_chunks = [], 0, 0   # tile-major window tiles of the DMMA-binned spectra (bulk-copy kernel)
         ltabs = []                  # ell-table of each spectrum (for the group records)
         segtabs, segoff = [], 0     # weighted column rows of the segmented-sum bins (appended after the ell-tables)
         toff = 0      # running offset into the ell-table buffer (doubles, kept even)
@@ -380,6 +424,13 @@ class CompiledProgram(object):
                 rec_t[L.T_WINOFF_LO] = lo32 - (1 << 32) if lo32 >= (1 << 31) else lo32
                 rec_t[L.T_WINOFF_HI] = off >> 32
                 rec_t[L.T_WINLD] = nlp
+                # the same 64 rows tile-major: chunk c (columns 16 c ..) is 1280 contiguous doubles at + c * 1280
+                lo32 = wint_off & 0xFFFFFFFF
+                rec_t[L.T_WINT_LO] = lo32 - (1 << 32) if lo32 >= (1 << 31) else lo32
+                rec_t[L.T_WINT_HI] = wint_off >> 32
+                wt = tile_major(wp[t0:t0 + L.BM])
+                wint.append(wt); wint_off += wt.size
+                max_tile_chunks = max(max_tile_chunks, (hi - lo) // L.KC)
                 for g8 in range(L.BM // 8):
                     glo, ghi = _support(wp[t0 + 8 * g8: t0 + 8 * g8 + 8])
                     rec_t[L.T_GLO + g8], rec_t[L.T_GHI + g8] = glo, ghi
@@ -501,6 +552,16 @@ class CompiledProgram(object):
         self.host["grp_tab"] = grp
         self._dev('templates', np.concatenate(templ), np.float64)
         self._dev('windows', np.concatenate(wins), np.float64)
+        if wint:
+            self._dev('winT', np.concatenate(wint), np.float64)
+        # ell split of the DMMA binning tiles (cluster size of k_bin_residual_ws): from the longest tile's chunk
+        # count only -- a property of the program, so results never depend on the launch size
+        # (long tiles only: >= 96 chunks; programs with one or two window tiles -- the 47 SPT bandpowers -- take 4
+        # parts, because their launches are the ones that cannot fill the GPU otherwise)
+        ndmma = len([1 for _, r in tiles if r[L.T_LEND] > r[L.T_LBEGIN]])
+        self.meta['bin_split'] = (4 if ndmma <= 2 else 2) if max_tile_chunks >= 96 else 1
+        if self.binning_split is not None:
+            self.meta['bin_split'] = int(self.binning_split)
         self._dev('data', d, np.float64)
         self.host["spec_tab"], self.host["tile_tab"], self.host["bin_tab"] = spec_tab, tile_arr, bin_arr
         # work per evaluation: dense windows, non-zero window entries, DMMA blocks that
@@ -512,12 +573,14 @@ class CompiledProgram(object):
 class DeviceProgram(CompiledProgram):
     """A compiled posterior resident on one CUDA device."""
 
-    def __init__(self, names, priors, lnl_expr, device=None, chi2_mode="auto", binning="auto"):
+    def __init__(self, names, priors, lnl_expr, device=None, chi2_mode="auto", binning="auto", binning_split=None,
+                 derived=None):
         torch = L.require_cuda()
         self.lib = L.lib()
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        super().__init__(names, priors, lnl_expr, chi2_mode=chi2_mode, binning=binning)
+        super().__init__(names, priors, lnl_expr, chi2_mode=chi2_mode, binning=binning, binning_split=binning_split,
+                         derived=derived)
         self._ws = {}
         self.dev = {k: torch.from_numpy(v).to(self.device) for k, v in self.tables.items()}
         P = L.Program()

@@ -85,7 +85,8 @@ enum {
   CSL_T_WINOFF_LO = 5, CSL_T_WINOFF_HI = 6, /* offset (doubles) of the tile's first window row   */
   CSL_T_WINLD = 7,   /* window row stride in doubles                            */
   CSL_T_GLO = 8,     /* [8]: per 8-row group, first non-zero column chunk start */
-  CSL_T_GHI = 16     /* [8]: per 8-row group, one past last non-zero column     */
+  CSL_T_GHI = 16,    /* [8]: per 8-row group, one past last non-zero column     */
+  CSL_T_WINT_LO = 24, CSL_T_WINT_HI = 25  /* offset (doubles) of the tile's tile-major windows in winT (chunk 0) */
 };
 
 /* bin record, int32 words (table bin_tab[nsegbin][CSL_BIN_STRIDE]): one window row handled by the
@@ -124,7 +125,9 @@ enum {
  * pointers.  It states, for W walkers at once, what Slik.evaluate computes
  * for one (cosmoslik/cosmoslik.py:109-141):
  *
- *   prior  = likelihoods/priors.py:24-30   (box -> +inf, Gaussian penalties)
+ *   prior  = likelihoods/priors.py:24-30   (box -> +inf, Gaussian penalties); box_idx / gauss_idx >= 0 name a
+ *            sampled parameter, < 0 a DERIVED quantity: coefficient row -idx - 1 (cosmoslik.py:139-141: priors
+ *            are evaluated again after the script's __call__ so that they can depend on what it sets)
  *   coef   = scalar functions of the parameters (bytecode)
  *   lnl    = prior + sum_k coef[scalar_coef[k]] + 1/2 || L^-1 r ||^2
  *   r      = cal * d - W . cl        (resid_mode 1; spt_lowl.py:132,171-182;
@@ -159,6 +162,20 @@ typedef struct csl_program {
   const double* Sigma;      /* [n_base, n_base] row-major */
   int32_t n_base, nmode;
   const int32_t* grp_tab;   /* group records of the segmented-sum bins (CSL_G_*), one per CSL_SEG_GROUP bin records */
+  /* TILE-MAJOR copies of the A operands for the bulk-copy (TMA) pipelines: tile (rb, c) = rows 64 rb .. 64 rb + 63,
+   * columns 16 c .. 16 c + 15 of the matrix, stored as 64 rows of 16 + 4 (padding) doubles = 1280 contiguous
+   * doubles at offset (rb * (ncols / 16) + c) * 1280, so that ONE cp.async.bulk moves a tile into its
+   * conflict-free shared-memory layout.  NULL: the kernels fall back to the row-major tables and cp.async. */
+  const double* MinvT;      /* of Minv      [n_pad, n_pad]                                            */
+  const double* LmatT;      /* of Lmat      [n_pad, n_pad]                                            */
+  const double* LinvT;      /* of Linv_diag [n_pad/64][64, 64]: tile (b, c), c < 4                    */
+  const double* winT;       /* of windows: per tile record, CSL_T_WINT_LO/HI = offset (doubles) of the tile's
+                               chunk 0; chunk c of the tile follows at + c * 1280                      */
+  int32_t bin_split;        /* 1, 2 or 4: ell split of the DMMA binning tiles (thread-block cluster size; the partial
+                               sums are added in rank order).  Fixed per PROGRAM by the host from the chunks per
+                               tile -- never from the launch size -- so that a walker's result does not depend on
+                               the batch it is evaluated in.                                            */
+  int32_t reserved0;
 } csl_program_t;
 
 int csl_abi_version(void);
@@ -322,6 +339,11 @@ int csl_rows_moments(int W, int ndim, const double* rows, const int32_t* nrows, 
 int csl_rows_gauss_prior(int W, int ndim, double* rows, const int32_t* nrows, int cap, int np,
                          const int32_t* pidx, const double* mean, const double* cinv, void* stream);
 
+/* Chain.thin(delta) on the device rows (chains.py:235-243): per chain, with S_k = ceil(cumulative weight through
+ * row k / delta), row k is kept iff S_k > S_{k-1} and gets weight S_k - S_{k-1}; kept rows are compacted in place
+ * and nrows updated. */
+int csl_rows_thin(int W, int ndim, double* rows, int32_t* nrows, int cap, double delta, void* stream);
+
 /* ---- affine-invariant ensemble sampler (samplers/emcee.py + emcee 2.x stretch move) ------- */
 
 /* proposals for the Ns active walkers s [Ns, ndim] against the complementary half comp [Nc, ndim]:
@@ -409,7 +431,15 @@ int csl_stretch_run(const csl_program_t* p, csl_ensemble_t* e, int nsteps, uint3
 int csl_chain_moments(int W, int ndim, const double* rows, const int32_t* nrows, int cap, int burn_rows,
                       double* stats, void* stream);
 
-/* ---- test hooks --------------------------------------------------------------------------- */
+/* ---- tuning / test hooks ------------------------------------------------------------------ */
+/* Process-wide integer options for sweeps and A/B tests (-1 = let the launcher decide; each is initialised from
+ * the environment variable CSL_<NAME>): "pipe" (0 = cp.async pipelines, 1 = bulk copies + mbarrier),
+ * "trigemm_rows", "trigemm_group", "trigemm_stages", "trsm_shape", "bin_split", "bin_variant", "sab_threads",
+ * "seg_small".  Results never depend on them bit-wise unless stated in DESIGN.md. */
+int csl_set_option(const char* name, int value);
+int csl_debug_counters(unsigned long long* out4_host, int reset);   /* kernel self-check counters (debug builds of the sweeps) */
+int csl_get_option(const char* name);
+
 int csl_philox_mh(int W, int ndim, uint64_t seed, uint32_t step, uint32_t chain0, double* z, double* u,
                   void* stream);
 int csl_philox_stretch(int Ns, int Nc, uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0,

@@ -149,14 +149,26 @@ class MspecLike(Plugin):
     Cholesky factor, ``cholesky(cov)`` then ``cho_solve((U, False), d)``
     (mspec_lnl.py:31, 73)."""
 
-    def __init__(self, use, windows, signal, cov, cal=None, egfs_kwargs=None):
+    def __init__(self, use, windows, signal, cov, cal=None, egfs_kwargs=None, resgal=None, cleaning=None):
         super().__init__()
         self.use = OrderedDict(sorted(use.items()))
         self.windows = windows
-        self.signal = signal
         self.cal = cal
         self.egfs_kwargs = egfs_kwargs or {}
-        self.cov = np.asarray(cov)
+        # mspec_lnl.py:27-30, 35-42: cleaning (lincombo of maps, data AND covariance), then resgal, then `use`
+        sig = {k: np.asarray(v, dtype=float) for k, v in signal.items()}
+        cov = np.asarray(cov, dtype=float)
+        if cleaning:
+            sig, cov = lincombo_maps(sig, cov, cleaning)
+        if resgal:
+            sig = {k: v - np.asarray(resgal[k if k in resgal else k[::-1]], dtype=float) for k, v in sig.items()}
+        keys = sorted(sig)
+        rows, at = {}, 0
+        for k in keys:
+            rows[k] = np.arange(at, at + len(sig[k])); at += len(sig[k])
+        pick = np.concatenate([rows[k if k in rows else k[::-1]] for k in self.use])
+        self.signal = {k: sig[k if k in sig else k[::-1]] for k in self.use}
+        self.cov = cov[np.ix_(pick, pick)]
         self.cho_cov = (cholesky(self.cov), False)
 
     def process_signal(self):
@@ -181,6 +193,32 @@ class MspecLike(Plugin):
     def __call__(self, cmb, egfs):
         dcl = self.get_cl_model(cmb, egfs) - self.process_signal()
         return np.dot(dcl, cho_solve(self.cho_cov, dcl)) / 2
+
+
+def lincombo_maps(signal, cov, new_maps, normalize=True):
+    """``mspec.PowerSpectra.lincombo`` restated for dicts (the package is absent; PARITY UNPINNED): maps are replaced
+    by linear combinations ``new = sum_old w old`` (weights normalised to sum 1 unless told otherwise, as the
+    reference's calibration call at mspec_lnl.py:44-45 turns off); every spectrum of two new maps is the bilinear
+    form of the old spectra, written here as explicit loops over the bins, and the covariance follows by the same
+    linear map.  Deliberately a different formulation from the product's (which builds one matrix with kron)."""
+    old = sorted(signal)
+    nb = len(signal[old[0]])
+    w = {A: {a: v / (sum(m.values()) if normalize else 1.0) for a, v in m.items()} for A, m in new_maps.items()}
+    names = sorted(w)
+    new = [(A, B) for i, A in enumerate(names) for B in names[i:]]
+    pos = {k: i for i, k in enumerate(old)}
+    J = np.zeros((len(new) * nb, len(old) * nb))
+    out = {}
+    for r, (A, B) in enumerate(new):
+        acc = np.zeros(nb)
+        for a, wa in w[A].items():
+            for b, wb in w[B].items():
+                k = (a, b) if (a, b) in signal else (b, a)
+                acc = acc + wa * wb * np.asarray(signal[k], dtype=float)
+                for i in range(nb):
+                    J[r * nb + i, pos[k] * nb + i] += wa * wb
+        out[(A, B)] = acc
+    return out, J @ np.asarray(cov, dtype=float) @ J.T
 
 
 class GaussLike(Plugin):

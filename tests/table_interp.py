@@ -33,15 +33,19 @@ def run_bytecode(cp, x):
     return coef
 
 
-def prior(cp, x):
+def prior(cp, x, coef=None):
+    """box / Gaussian priors; negative indices name derived quantities (coefficient row -idx - 1)"""
     t, m = cp.tables, cp.meta
+    if coef is None and (np.any(t["box_idx"][:m["nbox"]] < 0) or np.any(t["gauss_idx"][:m["ngauss"]] < 0)):
+        coef = run_bytecode(cp, x)
+    val = lambda ix: x[ix] if ix >= 0 else coef[-ix - 1]
     for b in range(m["nbox"]):
-        v = x[t["box_idx"][b]]
+        v = val(int(t["box_idx"][b]))
         if not (t["box_lo"][b] <= v <= t["box_hi"][b]):
             return np.inf
     s = 0.0
     for k in range(m["ngauss"]):
-        d = x[t["gauss_idx"][k]] - t["gauss_c"][k]
+        d = val(int(t["gauss_idx"][k])) - t["gauss_c"][k]
         s = s + d * d / 2 / (t["gauss_w"][k] * t["gauss_w"][k])
     return s
 

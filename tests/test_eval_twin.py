@@ -59,8 +59,10 @@ def run(twin, cp, X, chi2=None):
 
 
 def compiled(script_cls):
+    from cosmoslik_b200.core import _tree_lookup
     slik = Slik(script_cls())
-    return CompiledProgram(list(slik.get_sampled()), slik.params.priors, slik.trace())
+    tree, out = slik._trace()
+    return CompiledProgram(list(slik.get_sampled()), slik.params.priors, out, derived=_tree_lookup(tree))
 
 
 def test_quickstart_lnl_through_the_device_source(twin):
@@ -126,3 +128,62 @@ def test_derived_quantities_through_the_device_source(twin):
     cp, rows = compile_extras(list(slik.get_sampled()), slik.extra_exprs(names))
     coef, _, _ = run(twin, cp, g["x"])
     np.testing.assert_allclose(coef[rows, :len(g["x"])].T, g["extras"], rtol=4e-16, atol=0)
+
+
+def test_priors_on_derived_quantities_match_the_live_reference(twin):
+    """cosmoslik.py:139-141: priors are evaluated again after the script's __call__, so add_gaussian_prior /
+    add_uniform_prior may name quantities the script derives there.  The device source (negative prior indices ->
+    coefficient rows) against the unmodified reference on the same script, when /root/reference is mounted, and
+    against the numpy table interpreter always."""
+    from cosmoslik_b200 import SlikPlugin, param
+
+    def build(ns_plugin, ns_param):
+        class derived(ns_plugin):
+            def __init__(self):
+                super().__init__()
+                self.a = ns_param(start=0.3, scale=1)
+                self.b = ns_param(start=0.5, scale=1, min=-4)
+                self.sampler = None
+
+            def __call__(self):
+                self.r2 = self.a ** 2 + self.b ** 2
+                self.ratio = (self.a - 1.5) / (2 + self.b ** 2)
+                self.fixed = 3.25
+                return self.r2 / 2
+        return derived
+
+    def with_priors(script, priors_cls):
+        script.priors = priors_cls(script)
+        script.priors.add_gaussian_prior("r2", 1.0, 0.7)
+        script.priors.add_uniform_prior("ratio", -0.6, 0.1)
+        script.priors.add_gaussian_prior("a", 0.1, 2.0)
+        script.priors.add_gaussian_prior("fixed", 3.0, 0.5)
+        script.priors.add_gaussian_prior("never_set", 0.0, 1.0)     # skipped by the reference (param_ok), and here
+        return script
+
+    from cosmoslik_b200.likelihoods.priors import priors as my_priors
+    from cosmoslik_b200.core import _tree_lookup
+    slik = Slik(with_priors(build(SlikPlugin, param)(), my_priors))
+    tree, out = slik._trace()
+    with pytest.warns(UserWarning, match="never_set"):
+        cp = CompiledProgram(list(slik.get_sampled()), slik.params.priors, out, derived=_tree_lookup(tree))
+    assert cp.derived_priors == 3 and (cp.tables["gauss_idx"][:cp.meta["ngauss"]] < 0).sum() == 2
+    rs = np.random.RandomState(4)
+    X = rs.uniform(-2, 2, (200, 2))
+    X[7] = [0.5, -5.0]                   # the box of a sampled parameter
+    coef, prior, lnl = run(twin, cp, X)
+    want = np.array([TI.lnl(cp, x) for x in X])
+    np.testing.assert_array_equal(np.isinf(lnl), np.isinf(want))
+    f = np.isfinite(want)
+    np.testing.assert_allclose(lnl[f], want[f], rtol=1e-14)
+    assert np.isinf(lnl).sum() > 20 and f.sum() > 20
+    if os.path.isdir("/root/reference"):
+        from oracle import refshim
+        R = refshim.load()
+        script = build(R.core.SlikPlugin, R.core.param)()
+        script.sampler = R.mh.metropolis_hastings(script, num_samples=1)
+        rslik = R.core.Slik(with_priors(script, R.priors.priors if hasattr(R, "priors") else
+                                        __import__("cosmoslik_plugins.likelihoods.priors", fromlist=["priors"]).priors))
+        ref = np.array([rslik.evaluate(*x)[0] for x in X])
+        np.testing.assert_array_equal(np.isinf(lnl), np.isinf(ref))
+        np.testing.assert_allclose(lnl[f], ref[f], rtol=1e-13)

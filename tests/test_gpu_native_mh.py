@@ -141,7 +141,7 @@ def test_device_adaptation_matches_the_host_path(torch):
                                      mom.data_ptr(), st))
     L.check(lib.csl_mh_adapt_factor(nd, mom.data_ptr(), 2.4, ref.data_ptr(), cov.data_ptr(), F.data_ptr(), None, st))
     Fh = F.cpu().numpy()
-    assert np.isfinite(Fh).all() and np.abs(Fh[:, 3]).max() < 1e-6
+    assert np.isfinite(Fh).all() and np.abs(Fh[:, 3]).max() < 1e-4 * np.abs(Fh).max()
 
 
 def test_adaptive_run_on_the_device_recovers_the_target(torch):
@@ -215,3 +215,39 @@ def test_lnl_host_two_streams_equals_the_single_batch(torch, spt_data):
     np.testing.assert_array_equal(a, b)
     c = np.concatenate([slik.evaluate_batch(X[:100]), slik.evaluate_batch(X[100:])])    # 100 < 4 tiles: single stream
     np.testing.assert_array_equal(a, c)
+
+
+def test_device_thin_and_reweighted_match_the_chain_methods(torch):
+    """chains.py:235-243 (thin) and :178-203 (reweighted) applied to every chain's rows on the device"""
+    from cosmoslik_b200 import Chain, Chains
+    from cosmoslik_b200.chains import device_reweighted, device_thin
+    from cosmoslik_b200.symbolic import exp
+    nd, nch, nsteps = 3, 37, 600
+    Cv = np.eye(nd) + 0.3
+    slik = Slik(B.gauss_script(Cv, lambda s: samplers.metropolis_hastings(
+        s, num_samples=nsteps * nch, nchains=nch, seed=12, proposal_update=False))())
+    st = slik.sampler.run(slik.evaluate)
+    names = list(slik.get_sampled())
+    rows, nrows = st["rows"].cpu().numpy(), st["nrows"].cpu().numpy()
+    full = Chains([Chain(dict(zip(["lnl", "weight"] + names, rows[c, :nrows[c]].T))) for c in range(nch)])
+    # reweighted by a function of the parameters (traced once, evaluated by the bytecode kernel)
+    f_host = lambda **p: np.exp(-(p[names[0]] - 0.3) ** 2 / 2 / 0.5 ** 2)
+    f_sym = lambda **p: exp(-(p[names[0]] - 0.3) ** 2 / 2 / 0.5 ** 2)
+    want = Chains([c.reweighted(lambda weight, lnl, **p: f_host(**p)) for c in full])
+    device_reweighted(st, names, f_sym)
+    r2 = st["rows"].cpu().numpy()
+    for c in range(nch):
+        np.testing.assert_allclose(r2[c, :nrows[c], 1], want[c]["weight"], rtol=1e-13)
+        np.testing.assert_array_equal(r2[c, :nrows[c], 2:], rows[c, :nrows[c], 2:])
+    # thin: integer weights again (the MH weights), every chain on its own
+    st["rows"].copy_(torch.from_numpy(rows).cuda())
+    for delta in (3, 7.5):
+        st["rows"].copy_(torch.from_numpy(rows).cuda()); st["nrows"].copy_(torch.from_numpy(nrows).cuda())
+        device_thin(st, delta)
+        r3, n3 = st["rows"].cpu().numpy(), st["nrows"].cpu().numpy()
+        for c in range(nch):
+            t = full[c].thin(delta)
+            assert n3[c] == t.length()
+            np.testing.assert_array_equal(r3[c, :n3[c], 1], t["weight"])
+            np.testing.assert_array_equal(r3[c, :n3[c], 0], t["lnl"])
+            np.testing.assert_array_equal(r3[c, :n3[c], 2], t[names[0]])

@@ -248,3 +248,59 @@ def test_sampler_extra_params_bookkeeping():
     assert list(s.sampler.output_extra_params.items()) == [("r2", "float64"), ("ratio", "float64")]
     with pytest.raises(NotImplementedError):
         B.derived_script(lambda p: samplers.metropolis_hastings(p, num_samples=10, output_extra_params=[("n", "int64")]))()
+
+
+def test_mspec_cleaning_and_resgal():
+    """mspec_lnl.py:38-42: `cleaning` (linear combinations of the maps applied to the data AND their covariance)
+    and `resgal` (residual Galactic power subtracted from the data).  Product (host preprocessing -> device tables,
+    interpreted in numpy) against the oracle's separately written restatement; plus the identities that pin the
+    semantics: the identity combination changes nothing, and a one-map combination with normalize=False IS the
+    calibration the reference applies with the same call (:44-45)."""
+    from cosmoslik_b200.likelihoods.bandpower import lincombo
+    base = make_mspec_problem(None, nbins=12)
+    rs = np.random.RandomState(11)
+    cleaning = {"Tclean": {"T150": 1.0, "T220": -0.25}, "T090": {"T090": 1.0}}
+    new_keys = [("T090", "T090"), ("T090", "Tclean"), ("Tclean", "Tclean")]
+    resgal = {k: 2.0 + rs.uniform(0, 1, 12) for k in new_keys}
+    w = base["windows"][("T090", "T090")]
+    prob = dict(base, use={k: (50, 700) for k in new_keys}, windows={k: w for k in new_keys})
+
+    def scripts(extra):
+        def build(ns_param, ns_Plugin, like_cls, egfs_cls):
+            class script(ns_Plugin):
+                def __init__(self):
+                    super().__init__()
+                    self.Aps = ns_param(start=12.0, scale=2, min=0)
+                    self.Acib = ns_param(start=6.0, scale=1, min=0)
+                    self.ncib = ns_param(start=0.8, scale=0.1, range=(0.1, 2.5))
+                    self.calc = ns_param(start=1.0, scale=0.01, gaussian_prior=(1, 0.02))
+                    self.egfs = egfs_cls()
+                    self.like = like_cls(prob["use"], prob["windows"], base["signal"], base["cov"], **extra)
+                    self.sampler = None
+
+                def __call__(self):
+                    self.like.cal = {"Tclean": self.calc}
+                    return self.like({"cl_TT": prob["cmb"]["cl_TT"]}, self.egfs(Aps=self.Aps, Acib=self.Acib, ncib=self.ncib))
+            return script
+        return (build(ort.Param, ort.Plugin, olikes.MspecLike, olikes.ClustPoissonEgfs),
+                build(param, SlikPlugin, likelihoods.mspec_lnl, models.clust_poisson_egfs))
+
+    for extra in (dict(cleaning=cleaning), dict(cleaning=cleaning, resgal=resgal)):
+        o_cls, b_cls = scripts(extra)
+        oslik = ort.Slik(o_cls())
+        slik, cp = compiled(b_cls)
+        assert cp.meta["n"] == 36
+        x0 = np.array([oslik.get_start()[k] for k in cp.names])
+        vals = []
+        for i in range(6):
+            x = x0 * (1 + 0.05 * rs.standard_normal(len(x0)))
+            ref = oslik.evaluate(*x)[0]
+            assert abs(TI.lnl(cp, x) - ref) <= 1e-10 * abs(ref)
+            vals.append(ref)
+    # identities
+    same, cov_same = lincombo(base["signal"], base["cov"], {m: {m: 1.0} for m in base["maps"]})
+    assert all(np.array_equal(same[k], base["signal"][k]) for k in base["keys"]) and np.allclose(cov_same, base["cov"], rtol=1e-14)
+    cal = {"T090": 1.0, "T150": 1.013, "T220": 0.96}
+    scaled, _ = lincombo(base["signal"], None, {m: {m: cal[m]} for m in base["maps"]}, normalize=False)
+    for (a, b) in base["keys"]:
+        np.testing.assert_allclose(scaled[(a, b)], base["signal"][(a, b)] * cal[a] * cal[b], rtol=1e-15)

@@ -242,3 +242,28 @@ def test_product_covariance_sources_against_the_reference(R, tmp_path):
         cb.samplers.initialize_covariance(b_s)                 # 'c' has neither a scale nor a covariance
     with pytest.raises(ValueError):
         R.sutils.initialize_covariance(r_s)
+
+
+def test_spt_lowl_loader_and_trimming_match_the_live_reference():
+    """likelihoods.spt_lowl(datadir=...): read_newdat on the reference's own tarballs and the lmin / lmax / drop
+    trimming (spt_lowl.py:65-96) against the unmodified plugin, for both data sets and several cuts"""
+    import os
+    from cosmoslik_b200 import likelihoods
+    R = refshim.load()
+    datadir = os.path.join(os.path.dirname(R.spt_lowl.__file__), "data")
+    for which in ("s12", "k11"):
+        for kw in (dict(), dict(lmin=650), dict(lmax=2000), dict(lmin=800, lmax=2500), dict(drop=[0, 5, 46]),
+                   dict(lmin=700, drop=[2, 3])):
+            ref = R.spt_lowl.spt_lowl(which, **kw)
+            mine = likelihoods.spt_lowl(which, datadir=datadir, **kw)
+            np.testing.assert_array_equal(mine.spec, ref.spec)
+            np.testing.assert_array_equal(mine.sigma, ref.sigma)
+            np.testing.assert_array_equal(mine.windows, np.array(ref.windows))
+            assert (mine.windowrange.start, mine.windowrange.stop, mine.lmax) == (ref.windowrange.start, ref.windowrange.stop, ref.lmax)
+            np.testing.assert_allclose(mine.ells, ref.ells, rtol=1e-14)
+    # the default foreground templates read from the same directory
+    ref = R.spt_lowl.spt_lowl("s12")
+    mine = likelihoods.spt_lowl("s12", datadir=datadir)
+    for t in ("template_sz", "template_cl", "template_ps"):
+        n = min(len(getattr(mine.egfs, t)), len(getattr(ref.egfs, t)))
+        np.testing.assert_array_equal(getattr(mine.egfs, t)[:n], getattr(ref.egfs, t)[:n])
