@@ -35,6 +35,7 @@ if ROOT not in sys.path:
 METRIC = "posterior evals/sec (whole box) for batched bandpower lnL"
 UNIT = "evals/s"
 LITERAL_WALKERS = 65536
+PREROLL = 40        # untimed steps run right before every timed region (>= the --warmup asked for)
 
 
 def parse():
@@ -349,12 +350,15 @@ def measure_stretch(args, prob, k_total, instrument=True, e2e=True):
 
     clk = ClockSampler(dev)                         # NVML initialised BEFORE the warm-up: the GPU does not idle (and
                                                     # no rank is late) between the warm-up and the timed region
-    smp.row_capacity = args.steps            # same row buffer for the warm-up and the timed run
+    smp.row_capacity = max(args.steps, PREROLL)     # same row buffer for the warm-up and the timed run
     if instrument:
         smp.python_loop = True                      # the instrumented Python loop's code paths ...
         smp.run(prog, nsteps=3)
         del smp["python_loop"]
-    smp.run(prog, nsteps=max(args.warmup, 3), resume=instrument)   # warm-up of the native loop, right before the timed run
+    # untimed pre-roll of the native loop right before the timed run: the W warm-up steps asked for, topped up to
+    # PREROLL steps (a 20-step timed region is 27 ms; with only 5 steps = 7 ms of work before it the first timed
+    # steps still ran on a GPU that was leaving idle: 1.33 .. 1.81 ms per step between otherwise identical runs)
+    smp.run(prog, nsteps=max(args.warmup, 3, PREROLL), resume=instrument)
     replica = smp["_replica"][1] if "_replica" in smp and smp["_replica"] is not None else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier(); torch.cuda.synchronize()
@@ -373,15 +377,16 @@ def measure_stretch(args, prob, k_total, instrument=True, e2e=True):
     ms = max(per_rank)
     rec = {"walkers_total": k_total, "walkers_per_gpu": k_total // size, "value": k_total * args.steps / (ms * 1e-3),
            "ms_per_step": ms / args.steps, "ms_per_rank": [m / args.steps for m in per_rank],
+           "untimed_preroll_steps": max(args.warmup, 3, PREROLL),
            "acceptance": smp.stats["accepted"] / float(smp.stats["evals"]),
            "host_enqueue_ms_per_step": smp.stats.get("host_ms_per_step"), "exchange": smp.stats.get("exchange"),
            "clocks": clk.summary()}
     nbin = int(prog.meta.get("nclass", 0)) + int(prog.meta.get("nsegclass", 0))
     fused = os.environ.get("CSL_NO_FUSE") is None and prog.meta["resid_mode"] == 1
     # my kernels per stretch step in the native loop: per half-update the fused propose+prepare(+wait), one
-    # binning launch per spectrum class, chi2, the fused combine+accept(+publish+signal); + the row bookkeeping
-    if fused:
-        per_step = 2 * (1 + nbin + 1 + 1) + 1
+    # binning launch per spectrum class, chi2, the fused combine+accept(+rows+publish+signal)
+    if fused:           # the row bookkeeping rides in the accept kernels (CSL_NO_FOLD_ROWS=1: its own launch per step)
+        per_step = 2 * (1 + nbin + 1 + 1) + (1 if os.environ.get("CSL_NO_FOLD_ROWS") else 0)
     else:
         per_step = 2 * (2 + nbin + (2 if prog.meta.get("chi2_mode") else 1) + 1 + 1 + (1 if size > 1 else 0)) + 1
     rec["gpu_launches"] = per_step * args.steps + (1 if (fused and size > 1) else 0)
@@ -507,6 +512,7 @@ def run_b200(args):
             "config": config_of(args, prob), "e2e": literal.get("e2e"), "gpu_launches": literal["gpu_launches"],
             "roofline": literal.get("roofline"), "cpu_baseline": cpu, "clocks": literal["clocks"],
             "ms_per_rank": literal["ms_per_rank"], "exchange": literal["exchange"], "exchange_parity": parity,
+            "untimed_preroll_steps": literal["untimed_preroll_steps"],
             "acceptance": literal["acceptance"], "host_enqueue_ms_per_step": literal["host_enqueue_ms_per_step"],
             "ms_per_step_instrumented_pass": literal.get("ms_per_step_instrumented_pass"),
             "flops_per_eval": literal["flops_per_eval"],

@@ -115,7 +115,6 @@ SIGNATURES = {
     "csl_philox_stretch": (_int, [_int, _int, _u64, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "csl_dgemm_dmma": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp]),
     "csl_set_option": (_int, [C.c_char_p, _int]),
-    "csl_debug_counters": (_int, [_vp, _int]),
     "csl_get_option": (_int, [C.c_char_p]),
 }
 

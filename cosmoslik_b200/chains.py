@@ -407,17 +407,27 @@ class ChainWriter(object):
     (metropolis_hastings.py:183-186), 'list' the plain list emcee writes
     (emcee.py:40-44)."""
 
-    def __init__(self, path, names, header_kind="ndarray"):
+    def __init__(self, path, names, header_kind="ndarray", dtypes=None):
+        """dtypes: numpy dtype per column (default: float64 everywhere, the reference's ``dtype(float).name``);
+        ``output_extra_params`` entries ``(name, dtype)`` put other scalar dtypes in their columns
+        (metropolis_hastings.py:46-56, :221)."""
         self.f = open(path, "wb")
         self.ncol = len(names)
-        self.dtype = np.dtype(",".join(["f8"] * self.ncol))
+        kinds = ["f8"] * self.ncol if dtypes is None else [np.dtype(d).str for d in dtypes]
+        self.dtype = np.dtype(",".join(kinds))
+        self.plain = all(np.dtype(k) == np.dtype("f8") for k in kinds)
         header = np.hstack([names]) if header_kind == "ndarray" else list(names)
         pickle.dump(header, self.f, protocol=pickle.HIGHEST_PROTOCOL)
 
     def write(self, chain_id, rows):
         """rows: float array [m, ncol] (lnl, weight, params...)"""
         rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, self.ncol)
-        rec = rows.view(self.dtype).reshape(-1)
+        if self.plain:
+            rec = rows.view(self.dtype).reshape(-1)
+        else:                                    # columns of other scalar dtypes: cast field by field
+            rec = np.empty(len(rows), dtype=self.dtype)
+            for k, name in enumerate(self.dtype.names):
+                rec[name] = rows[:, k].astype(self.dtype[name])
         pickle.dump((chain_id, rec), self.f, protocol=pickle.HIGHEST_PROTOCOL)
 
     def flush(self):

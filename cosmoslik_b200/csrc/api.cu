@@ -189,6 +189,9 @@ extern "C" int csl_stretch_run(const csl_program_t* p, csl_ensemble_t* e, int ns
   // binned bandpower likelihoods take the fused stages; everything else the staged ones
   static const bool no_fuse = csl_env_int("CSL_NO_FUSE", 0) != 0;
   const bool fused = p->resid_mode == 1 && e->ws_coef && e->ws_R && e->ws_chi2 && !no_fuse;
+  // the row bookkeeping of a step (k_emcee_rows) rides in the accept kernel of each half: one launch fewer per step
+  static const bool no_fold = csl_env_int("CSL_NO_FOLD_ROWS", 0) != 0;
+  const bool fold_rows = fused && !no_fold;
   for (int i = 0; i < nsteps; ++i) {
     const uint32_t step = step0 + (uint32_t)i;
     for (int h = 0; h < 2; ++h) {
@@ -224,6 +227,9 @@ extern "C" int csl_stretch_run(const csl_program_t* p, csl_ensemble_t* e, int ns
                                         e->replica ? e->npeers : 0, e->replica ? e->multicast_ptr : 0, (int64_t)g0,
                                         e->ws_coef, Wp, e->ws_prior, parts ? nullptr : e->ws_chi2,
                                         parts ? e->ws_part : nullptr, p->n_pad / 32, Wp, e->replica ? &pa : nullptr,
+                                        fold_rows ? e->weight + r0 : nullptr,
+                                        fold_rows ? e->rows + (long long)r0 * e->cap * (2 + nd) : nullptr,
+                                        fold_rows ? e->nrows + r0 : nullptr, e->cap, (int64_t)step == last_step ? 1 : 0,
                                         stream);
           if (rc) return rc;
           if (e->replica) ++e->epoch;
@@ -254,9 +260,11 @@ extern "C" int csl_stretch_run(const csl_program_t* p, csl_ensemble_t* e, int ns
         if (rc) return rc;
       }
     }
-    int rc = csl_emcee_rows(W, nd, e->pos_old, e->pos, e->lnl, e->weight, (int64_t)step == last_step ? 1 : 0, e->rows,
-                            e->nrows, e->cap, stream);
-    if (rc) return rc;
+    if (!fold_rows) {
+      int rc = csl_emcee_rows(W, nd, e->pos_old, e->pos, e->lnl, e->weight, (int64_t)step == last_step ? 1 : 0, e->rows,
+                              e->nrows, e->cap, stream);
+      if (rc) return rc;
+    }
   }
   // fused + sharded: the last half-step has been signalled but not waited for -- whoever reads the replica next
   // (a per-stage step, the host) must see every peer's stores

@@ -541,7 +541,8 @@ static int dispatch_class_ws(int nt, int np, const csl_program_t* p, int tile0, 
 #ifndef SEG_TPB
 #define SEG_TPB 128    // threads per CTA
 #endif
-#define SEG_WPT 2      // walkers per thread: staged rows / loop control are amortised over both
+// WPT = walkers per thread (template parameter): 2 in bulk -- staged rows / loop control are amortised over both --
+// and 1 for launches of a few thousand walkers, where twice as many CTAs and warps hide latency better
 #ifndef SEG_SMEM_DOUBLES
 #define SEG_SMEM_DOUBLES 3072   // staged columns x RS (24 KB)
 #endif
@@ -560,7 +561,7 @@ __host__ __device__ constexpr int seg_pad_terms(int nt) { return nt <= 0 ? 0 : n
 // ncol staged columns starting at `row`, for the SEG_WPT walkers of a thread.
 // MODE 0 / 1 / 2: Taylor degree 5 / 6 / 10 in y = idx D;  MODE 3: exact exp at every column (ltab, l = ell
 // index of the first column, give the next column's logB; lend = one past the bin's last column).
-template <int NT, int NP, int MODE>
+template <int NT, int NP, int MODE, int SEG_WPT>
 __device__ __forceinline__ void seg_cols(const double* __restrict__ row, int ncol,
                                          const double (&cf)[SEG_WPT][NT > 0 ? NT : 1],
                                          const double (&pamp)[SEG_WPT][NP > 0 ? NP : 1],
@@ -603,7 +604,7 @@ __device__ __forceinline__ void seg_cols(const double* __restrict__ row, int nco
   for (; c < ncol; ++c, row += RS) column(row, l + c);
 }
 
-template <int NT, int NP>
+template <int NT, int NP, int SEG_WPT>
 __global__ void __launch_bounds__(SEG_TPB, SEG_MINB)
 k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restrict__ coef, int ldc,
              double* __restrict__ R, int ldr) {
@@ -687,7 +688,7 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
   }
   // if any thread of the CTA holds two walkers of different modes, every thread runs the group twice, once
   // per walker slot at that walker's own mode (only the slot's results are stored): still one code path
-  const int split = __syncthreads_or(mode[0] != mode[1]);
+  const int split = SEG_WPT > 1 ? __syncthreads_or(mode[0] != mode[SEG_WPT - 1]) : 0;
 
   for (int run = 0; run < (split ? SEG_WPT : 1); ++run) {
   const int run_mode = split ? mode[run] : mode[0];
@@ -719,7 +720,7 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
           }
         }
         const int lend = slo[b] + (spre[b + 1] - spre[b]);
-        seg_cols<NT, NP, MODE>(srow + (s0 - p0) * RS, s1 - s0, cf, pamp, pidx, E, at, ap, ltab, l, lend);
+        seg_cols<NT, NP, MODE, SEG_WPT>(srow + (s0 - p0) * RS, s1 - s0, cf, pamp, pidx, E, at, ap, ltab, l, lend);
         if (s1 == spre[b + 1]) {                  // the bin ends here: r = cal * d - b  (spt_lowl.py:132)
           const int row = srw[b];
           const double d = sdat[b];
@@ -757,8 +758,18 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
 template <int NT, int NP>
 static int launch_seg(const csl_program_t* p, int bin0, int nbins, int W, const double* coef, int ldc,
                       double* R, int ldr, cudaStream_t s) {
-  dim3 grid((W + SEG_WPT * SEG_TPB - 1) / (SEG_WPT * SEG_TPB), (nbins + CSL_SEG_GROUP - 1) / CSL_SEG_GROUP);
-  k_bin_segsum<NT, NP><<<grid, SEG_TPB, 0, s>>>(*p, bin0, nbins, W, coef, ldc, R, ldr);
+  // one walker per thread for launches of a few thousand walkers ("seg_small": the largest such launch, default
+  // 8192): the same arithmetic per walker, twice the CTAs
+  int small = csl_option_value("seg_small");
+  if (small < 0) small = 8192;
+  const int ngrp = (nbins + CSL_SEG_GROUP - 1) / CSL_SEG_GROUP;
+  if (W <= small) {
+    dim3 grid((W + SEG_TPB - 1) / SEG_TPB, ngrp);
+    k_bin_segsum<NT, NP, 1><<<grid, SEG_TPB, 0, s>>>(*p, bin0, nbins, W, coef, ldc, R, ldr);
+  } else {
+    dim3 grid((W + 2 * SEG_TPB - 1) / (2 * SEG_TPB), ngrp);
+    k_bin_segsum<NT, NP, 2><<<grid, SEG_TPB, 0, s>>>(*p, bin0, nbins, W, coef, ldc, R, ldr);
+  }
   return 0;
 }
 

@@ -91,130 +91,74 @@ k_trsm_chi2(csl_program_t p, double* R, int ldr, double* __restrict__ chi2) {
   if (tid < CSL_BN) chi2[c0 + tid] = red[tid] + red[CSL_BN + tid];
 }
 
-// ---- the blocked solve with Blackwell tile movement and two CTAs per SM ---------------------------------
-// Same arithmetic as k_trsm_chi2 (bitwise), restructured so that nothing but the ring of bulk-copy stages lives in
+// ---- the blocked solve, two CTAs per SM --------------------------------------------------------------
+// Same arithmetic as k_trsm_chi2 (bitwise), restructured so that nothing but the two cp.async stages lives in
 // shared memory: T_i = R_i - sum_{j<i} L_ij Y_j is written straight back to R_i in global memory (L2 resident) and
-// the diagonal solve Y_i = inv(L_ii) T_i is just four more chunks of the SAME streamed tile product, with
-// A = the tile-major inverse of the diagonal block and B = the rows of T_i read back by the producer.  That removes
-// the 67 KB T tile (and its bank-conflicting stores), so two CTAs fit on an SM and the 202-register / 1-CTA shape
-// is gone.  A producer warp issues the bulk copies (one per L tile, 16 per R chunk); consumers hand finished rows
-// to it through the `ready` mbarrier after a global fence and a generic -> async proxy fence.  The producer runs
-// ahead on every chunk that does not depend on the rows being finished (chunks of Y_j, j < i - 1).
-#define TRSM_STAGES 4
-__device__ unsigned long long g_trsm_dbg[4];        // debugging counters (flags & 256): stale bulk reads seen
-__global__ void __launch_bounds__(CSL_THREADS + 32, 2)
-k_trsm_chi2_bulk(csl_program_t p, double* R, int ldr, double* __restrict__ chi2, int flags) {
-  constexpr int NCW = CSL_THREADS / 32, STAGE = CSL_ASZ + CSL_BSZ;
-  constexpr uint32_t TX_BYTES = (uint32_t)(CSL_ASZ + CSL_KC * CSL_BN) * sizeof(double);
+// the diagonal solve Y_i = inv(L_ii) T_i is four more chunks of the SAME streamed tile product, with A = the
+// inverse of the diagonal block and B = the rows of T_i read back through cp.async.  That removes the 67 KB T tile
+// (and its bank-conflicting stores), so two CTAs fit on an SM and a 32 768-walker launch (256 tiles) is ONE wave
+// of the 296 resident slots instead of 1.73 waves of 148.
+// (A variant whose producer warp fetched the freshly written rows with cp.async.bulk was faster still -- 0.58 vs
+// 0.67 ms -- but about one launch in three returned stale rows for a single 32 x 32 sub-tile, with membar.gl +
+// fence.proxy.async(.global) on the writer AND the reader side: profiles/r2_trsm_bulk_race.md.  Rows written in
+// the same kernel are therefore read back through the generic proxy only.)
+template <int NSTAGE, bool CTA_FENCE>
+__global__ void __launch_bounds__(CSL_THREADS, 2)
+k_trsm_chi2_v2(csl_program_t p, double* R, int ldr, double* __restrict__ chi2) {
   extern __shared__ __align__(128) double smem[];
-  double* red = smem + TRSM_STAGES * STAGE;                  // [2][128]
-  uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * CSL_BN);
-  uint64_t* empty = full + TRSM_STAGES;
-  uint64_t* ready = empty + TRSM_STAGES;
+  double* As = smem;
+  double* Bs = As + NSTAGE * CSL_ASZ;
+  double* red = Bs + NSTAGE * CSL_BSZ;      // [2][128]
   const int c0 = blockIdx.x * CSL_BN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int npad = p.n_pad, nblk = npad / CSL_BM, nct = npad / CSL_KC;
-  constexpr int CPB = CSL_BM / CSL_KC;                       // chunks per 64-row block
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < TRSM_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NCW); }
-    mbar_init(ready, NCW);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (warp == NCW) {
-    // ---------------- producer: the chunk stream of all row blocks, in order
-    int q = 0;                 // running chunk number (stage = q % STAGES)
-    int nready = 0;            // completions of `ready` waited for so far
-    auto issue = [&](const double* At, const double* Bg) {
-      const int s = q % TRSM_STAGES, use = q / TRSM_STAGES;
-      if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
-      double* As = smem + s * STAGE;
-      double* Bs = As + CSL_ASZ;
-      if (lane == 0) mbar_arrive_expect_tx(full + s, TX_BYTES);
-      __syncwarp();
-      if (lane < CSL_KC) bulk_g2s(Bs + lane * CSL_LDB, Bg + (long long)lane * ldr, CSL_BN * sizeof(double), full + s);
-      else if (lane == CSL_KC) bulk_g2s(As, At, CSL_ASZ * sizeof(double), full + s);
-      ++q;
-    };
-    for (int i = 0; i < nblk; ++i) {
-      const double* Lrow = p.LmatT + (long long)i * nct * CSL_ATILE;
-      for (int c = 0; c < i * CPB; ++c) {
-        // rows of Y_{i-1} are the last thing the consumers finished: wait for them once, before their first chunk
-        if (c == (i - 1) * CPB) {
-          mbar_wait(ready, nready & 1); ++nready;
-          if (flags & 2) { __threadfence(); asm volatile("fence.proxy.async;" ::: "memory"); }
-          if (flags & 64) __nanosleep(3000);
-        }
-        issue(Lrow + (long long)c * CSL_ATILE, R + (long long)c * CSL_KC * ldr + c0);
-      }
-      mbar_wait(ready, nready & 1); ++nready;                // T_i is in R_i
-      if (flags & 2) { __threadfence(); asm volatile("fence.proxy.async;" ::: "memory"); }
-      if (flags & 64) __nanosleep(3000);
-      const double* Dinv = p.LinvT + (long long)i * CPB * CSL_ATILE;
-      for (int c = 0; c < CPB; ++c)
-        issue(Dinv + (long long)c * CSL_ATILE, R + (long long)(i * CSL_BM + c * CSL_KC) * ldr + c0);
-    }
-    return;
-  }
-  // ---------------- consumers
   const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 32;
   const int g = lane >> 2, t = lane & 3;
+  const int npad = p.n_pad, nblk = npad / CSL_BM;
   double colsq[4][2];
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) colsq[ni][0] = colsq[ni][1] = 0.0;
-  int q = 0;
-  auto consume = [&](double (&acc)[4][4][2], int nchunk, long long brow0, int which) {
-    for (int c = 0; c < nchunk; ++c, ++q) {
-      const int s = q % TRSM_STAGES;
-      mbar_wait(full + s, (q / TRSM_STAGES) & 1);
-      const double* As = smem + s * STAGE;
-      if (flags & 256) {     // debugging: does the staged B chunk equal what global memory holds now?
-        const double* Bsd = As + CSL_ASZ;
-        const int k = lane & 15, col = wn0 + (lane >> 4) * 16 + (warp >> 2) * 8;
-        for (int j = 0; j < 8; ++j) {
-          const double a = Bsd[k * CSL_LDB + col + j];
-          const double b = __ldcg(R + (brow0 + (long long)c * CSL_KC + k) * ldr + c0 + col + j);
-          if (a != b) atomicAdd(&g_trsm_dbg[which], 1ull);
-        }
-        atomicAdd(&g_trsm_dbg[2], 8ull);
-      }
-      warp_mma_chunk_m<0xF>(acc, As, As + CSL_ASZ, wm0, wn0, lane);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + s);
-    }
-  };
-  auto publish_rows = [&]() {
-    // this warp's stores to R_i -> visible to the producer's bulk copies (async proxy), then tell it
-    if (flags & 4) __threadfence_system(); else __threadfence();
-    asm volatile("fence.proxy.async;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) mbar_arrive(ready);
-  };
   for (int i = 0; i < nblk; ++i) {
     double acc[4][4][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    consume(acc, i * CPB, 0, 0);                             // acc = sum_{j<i} L_ij Y_j
+    // acc = sum_{j<i} L_ij Y_j
+    if (NSTAGE == 3)
+      gemm_stream_AB3<CSL_BM, CSL_THREADS>(acc, p.Lmat + (long long)i * CSL_BM * npad, npad, R + c0, ldr,
+                                           i * (CSL_BM / CSL_KC), As, Bs, tid, wm0, wn0, lane, 0xFu, -1);
+    else
+      gemm_stream_AB(acc, p.Lmat + (long long)i * CSL_BM * npad, npad, R + c0, ldr, i * (CSL_BM / CSL_KC), As, Bs,
+                     tid, wm0, wn0, lane);
+    // T_i = R_i - acc, in place in global memory (T_0 = R_0 is there already)
+    if (i > 0) {
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {                         // T_i = R_i - acc, in place
-      const int rl = wm0 + mi * 8 + g;
+      for (int mi = 0; mi < 4; ++mi) {
+        const int rl = wm0 + mi * 8 + g;
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        double2* ptr = reinterpret_cast<double2*>(R + (long long)(i * CSL_BM + rl) * ldr + c0 + wn0 + ni * 8 + 2 * t);
-        double2 r = (flags & 16) ? __ldcg(ptr) : *ptr;
-        r.x = r.x - acc[mi][ni][0];
-        r.y = r.y - acc[mi][ni][1];
-        if (flags & 16) __stcg(ptr, r); else *ptr = r;
-        acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int ni = 0; ni < 4; ++ni) {
+          double2* ptr = reinterpret_cast<double2*>(R + (long long)(i * CSL_BM + rl) * ldr + c0 + wn0 + ni * 8 + 2 * t);
+          double2 r = *ptr;
+          r.x = r.x - acc[mi][ni][0];
+          r.y = r.y - acc[mi][ni][1];
+          *ptr = r;
+          acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        }
       }
+      // T_i visible to the cp.async reads below: writers and readers are threads of ONE CTA, so a CTA-scope
+      // fence + the CTA barrier order them (CTA_FENCE); the device-scope fence of round 1 also invalidates L1
+      // and waits for the L2 acknowledgements, ~20 times per CTA
+      if (CTA_FENCE) __threadfence_block(); else __threadfence();
+      __syncthreads();
     }
-    publish_rows();
-    consume(acc, CPB, (long long)i * CSL_BM, 1);
-    if (flags & 256) asm volatile("bar.sync 1, %0;" :: "n"(CSL_THREADS) : "memory");   // nobody overwrites T_i while it is being checked
-             // Y_i = inv(L_ii) T_i
+    // Y_i = inv(L_ii) T_i : four more chunks of the same stream
+    if (NSTAGE == 3)
+      gemm_stream_AB3<CSL_BM, CSL_THREADS>(acc, p.Linv_diag + (long long)i * CSL_BM * CSL_BM, CSL_BM,
+                                           R + (long long)i * CSL_BM * ldr + c0, ldr, CSL_BM / CSL_KC, As, Bs, tid, wm0,
+                                           wn0, lane, 0xFu, -1);
+    else
+      gemm_stream_AB(acc, p.Linv_diag + (long long)i * CSL_BM * CSL_BM, CSL_BM, R + (long long)i * CSL_BM * ldr + c0, ldr,
+                     CSL_BM / CSL_KC, As, Bs, tid, wm0, wn0, lane);
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
       const int rl = wm0 + mi * 8 + g;
@@ -223,15 +167,14 @@ k_trsm_chi2_bulk(csl_program_t p, double* R, int ldr, double* __restrict__ chi2,
         double2 y;
         y.x = acc[mi][ni][0];
         y.y = acc[mi][ni][1];
-        double2* yp = reinterpret_cast<double2*>(R + (long long)(i * CSL_BM + rl) * ldr + c0 + wn0 + ni * 8 + 2 * t);
-        if (flags & 16) __stcg(yp, y); else *yp = y;
+        *reinterpret_cast<double2*>(R + (long long)(i * CSL_BM + rl) * ldr + c0 + wn0 + ni * 8 + 2 * t) = y;
         colsq[ni][0] = fma(y.x, y.x, colsq[ni][0]);
         colsq[ni][1] = fma(y.y, y.y, colsq[ni][1]);
       }
     }
-    if (i + 1 < nblk) publish_rows();
+    if (CTA_FENCE) __threadfence_block(); else __threadfence();
+    __syncthreads();
   }
-  // reduce over the 8 row groups of the warp (lane bits 2..4), then over the two warp rows
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
@@ -242,7 +185,7 @@ k_trsm_chi2_bulk(csl_program_t p, double* R, int ldr, double* __restrict__ chi2,
       v += shfl_xor_d(v, 16);
       if (g == 0) red[(warp >> 2) * CSL_BN + wn0 + ni * 8 + 2 * t + e] = v;
     }
-  asm volatile("bar.sync 1, %0;" :: "n"(CSL_THREADS) : "memory");      // consumers only (the producer has left)
+  __syncthreads();
   if (tid < CSL_BN) chi2[c0 + tid] = red[tid] + red[CSL_BN + tid];
 }
 
@@ -422,16 +365,6 @@ __global__ void k_sum_partials(int nblk, int W, int ldr, const double* __restric
   chi2[w] = s;
 }
 
-extern "C" int csl_debug_counters(unsigned long long* out4_host, int reset) {
-  cudaError_t e = cudaMemcpyFromSymbol(out4_host, g_trsm_dbg, sizeof(g_trsm_dbg));
-  if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-  if (reset) {
-    unsigned long long z[4] = {0, 0, 0, 0};
-    cudaMemcpyToSymbol(g_trsm_dbg, z, sizeof(z));
-  }
-  return 0;
-}
-
 extern "C" int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part,
                         void* stream) {
   return csl_chi2_impl(p, W, R, ldr, chi2, ws_part, true, stream);
@@ -485,16 +418,22 @@ int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi
     return csl_check_launch("k_trigemm_chi2");
   }
   CSL_REQUIRE(p->Lmat && p->Linv_diag, "csl_chi2: program has no factor");
-  const int shape = csl_option_value("trsm_shape");
-  if (p->LmatT && p->LinvT && shape != 0 && csl_option_value("pipe") != 0) {
-    const int flags = shape > 0 ? shape : 1;
-    size_t smem = (size_t)(TRSM_STAGES * (CSL_ASZ + CSL_BSZ) + 2 * CSL_BN) * sizeof(double) +
-                  (2 * TRSM_STAGES + 1) * sizeof(uint64_t);
-    if (flags & 8) smem = 120 * 1024;                       // debugging: one CTA per SM
-    cudaError_t e = cudaFuncSetAttribute(k_trsm_chi2_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-    k_trsm_chi2_bulk<<<W / CSL_BN, CSL_THREADS + 32, smem, s>>>(*p, R, ldr, chi2, flags);
-    return csl_check_launch("k_trsm_chi2_bulk");
+  // shape: 0 = the round-1 kernel (one CTA per SM, T tile in shared memory): best while every walker tile has an
+  // SM to itself; 1 / 2 = two CTAs per SM with a 2- / 3-stage cp.async ring: best from there on
+  int shape = csl_option_value("trsm_shape");
+  if (shape < 0) shape = (W / CSL_BN > csl_sm_count()) ? 2 : 0;
+  if (shape != 0) {
+    const int nst = shape == 1 ? 2 : 3;
+    const size_t smem2 = (size_t)(nst * (CSL_ASZ + CSL_BSZ) + 2 * CSL_BN) * sizeof(double);
+    auto go = [&](auto kern) -> int {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+      kern<<<W / CSL_BN, CSL_THREADS, smem2, s>>>(*p, R, ldr, chi2);
+      return csl_check_launch("k_trsm_chi2_v2");
+    };
+    if (shape == 1) return go(k_trsm_chi2_v2<2, false>);
+    if (shape == 3) return go(k_trsm_chi2_v2<3, true>);
+    return go(k_trsm_chi2_v2<3, false>);
   }
   const size_t smem = (size_t)CHI2_SMEM_DOUBLES * sizeof(double);
   {

@@ -32,7 +32,8 @@ int csl_fused_combine_accept(const csl_program_t* p, int Ns, int Nc, int ndim, d
                              uint32_t walker0, uint8_t* accepted, uint64_t* naccepted, const uint64_t* peer_ptrs,
                              int npeers, uint64_t multicast_ptr, int64_t dst_row0, const double* coef, int ldc,
                              const double* prior, const double* chi2, const double* part, int nblk, int ldp,
-                             const csl_peer_args* signal, void* stream);
+                             const csl_peer_args* signal, double* weight, double* rows, int32_t* nrows, int cap,
+                             int last_step, void* stream);
 int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part, bool sum_partials,
                   void* stream);
 // stage variants with the padded walker count (columns written) separate from the workspace stride (prepare.cu)

@@ -75,11 +75,9 @@ extern "C" int csl_cov_chi2(const csl_program_t* p, int W, const double* R, int 
               "csl_cov_chi2: needs resid_mode 3, n_base <= 64, nmode <= 32");
   const int n = p->n_base, K = p->nmode;
   const size_t smem = (size_t)COV_WARPS * (n * (n + 1) / 2 + n * K + n) * sizeof(double);
-  static size_t configured = 0;
-  if (smem > configured) {
+  if (smem > 48 * 1024) {        // per device and cheap: set whenever the launch needs it
     cudaError_t e = cudaFuncSetAttribute(k_cov_chol_chi2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-    configured = smem;
   }
   k_cov_chol_chi2<<<(W + COV_WARPS - 1) / COV_WARPS, COV_WARPS * 32, smem, (cudaStream_t)stream>>>(*p, W, R, ldr, chi2);
   return csl_check_launch("k_cov_chol_chi2");

@@ -467,6 +467,9 @@ __global__ void k_peer_barrier(const unsigned long long* __restrict__ flag_ptrs,
 // launch.  Phase 1, one THREAD per walker: lnl(q) from the chi^2 partial sums (same order of additions as
 // the staged kernels), the accept test, lnl update.  Phase 2, the CTA's 256 rows as one contiguous range:
 // accepted rows are copied q -> s, and every row's final position goes to the replicas of all ranks.
+struct csl_fused_rows {           // row bookkeeping folded into the accept kernel (pointers at this half's first walker)
+  double* weight; double* rows; int32_t* nrows; int cap, last_step;
+};
 struct csl_fused_combine {
   csl_program_t p;
   const double* coef; int ldc;
@@ -480,7 +483,7 @@ k_stretch_combine_accept(int Ns, int nd, double* __restrict__ s, double* __restr
                          uint32_t half, uint32_t walker0, uint32_t Nc, uint8_t* __restrict__ accepted,
                          const unsigned long long* __restrict__ peers, int npeers, unsigned long long mc_ptr,
                          long long dst_row0, unsigned long long* __restrict__ nacc, csl_fused_combine fc,
-                         csl_peer_sync ps) {
+                         csl_peer_sync ps, csl_fused_rows fr) {
   __shared__ unsigned char sacc[SAB_THREADS];
   const int nthr = blockDim.x;
   const int k0 = blockIdx.x * nthr, k = k0 + threadIdx.x;
@@ -500,6 +503,29 @@ k_stretch_combine_accept(int Ns, int nd, double* __restrict__ s, double* __restr
     acc = lnpdiff > log(ua);
     if (acc) lnl_s[k] = lq;
     if (accepted) accepted[k] = acc ? 1 : 0;
+    if (fr.rows) {
+      // the wrapper's row bookkeeping (samplers/emcee.py:70-88) for this walker, whose position is final for this
+      // step once its half is updated: unmoved -> weight + 1; moved (or last step) -> emit (lnl_next, weight, x_old).
+      // k_emcee_rows compares the walker's previous position with the new one; here the previous position is s
+      // itself (not yet overwritten: phase 2 below comes after a CTA barrier) and the new one is q if accepted.
+      bool same = true;
+      if (acc)
+        for (int d = 0; d < nd; ++d) same = same && (q[(long long)k * nd + d] == s[(long long)k * nd + d]);
+      const double wt = fr.weight[k];
+      if (same && !fr.last_step) {
+        fr.weight[k] = wt + 1.0;
+      } else {
+        const int slot = fr.nrows[k];
+        if (slot < fr.cap) {
+          double* r = fr.rows + ((long long)k * fr.cap + slot) * (2 + nd);
+          r[0] = acc ? lq : -lnp0;
+          r[1] = wt;
+          for (int d = 0; d < nd; ++d) r[2 + d] = s[(long long)k * nd + d];
+        }
+        fr.nrows[k] = slot + 1;                 // counts past cap signal overflow to the host
+        fr.weight[k] = 1.0;
+      }
+    }
   }
   sacc[threadIdx.x] = acc ? 1 : 0;
   const int c = __syncthreads_count(acc);
@@ -800,7 +826,10 @@ int csl_fused_combine_accept(const csl_program_t* p, int Ns, int Nc, int ndim, d
                              uint32_t walker0, uint8_t* accepted, uint64_t* naccepted, const uint64_t* peer_ptrs,
                              int npeers, uint64_t multicast_ptr, int64_t dst_row0, const double* coef, int ldc,
                              const double* prior, const double* chi2, const double* part, int nblk, int ldp,
-                             const csl_peer_args* signal, void* stream) {
+                             const csl_peer_args* signal, double* weight, double* rows, int32_t* nrows, int cap,
+                             int last_step, void* stream) {
+  csl_fused_rows fr;
+  fr.weight = weight; fr.rows = rows; fr.nrows = nrows; fr.cap = cap; fr.last_step = last_step;
   csl_fused_combine fc;
   fc.p = *p; fc.coef = coef; fc.ldc = ldc; fc.prior = prior; fc.chi2 = chi2; fc.part = part; fc.nblk = nblk;
   fc.ldp = ldp; fc.lnl_q = lnl_q;
@@ -812,7 +841,7 @@ int csl_fused_combine_accept(const csl_program_t* p, int Ns, int Nc, int ndim, d
   k_stretch_combine_accept<<<(Ns + nthr - 1) / nthr, nthr, 0, (cudaStream_t)stream>>>(
       Ns, ndim, s, lnl_s, q, zz, seed, step, half, walker0, (uint32_t)Nc, accepted,
       reinterpret_cast<const unsigned long long*>(peer_ptrs), npeers, (unsigned long long)multicast_ptr,
-      (long long)dst_row0, reinterpret_cast<unsigned long long*>(naccepted), fc, make_peer_sync(signal));
+      (long long)dst_row0, reinterpret_cast<unsigned long long*>(naccepted), fc, make_peer_sync(signal), fr);
   return csl_check_launch("k_stretch_combine_accept");
 }
 

@@ -556,10 +556,9 @@ class CompiledProgram(object):
             self._dev('winT', np.concatenate(wint), np.float64)
         # ell split of the DMMA binning tiles (cluster size of k_bin_residual_ws): from the longest tile's chunk
         # count only -- a property of the program, so results never depend on the launch size
-        # (long tiles only: >= 96 chunks; programs with one or two window tiles -- the 47 SPT bandpowers -- take 4
-        # parts, because their launches are the ones that cannot fill the GPU otherwise)
-        ndmma = len([1 for _, r in tiles if r[L.T_LEND] > r[L.T_LBEGIN]])
-        self.meta['bin_split'] = (4 if ndmma <= 2 else 2) if max_tile_chunks >= 96 else 1
+        # (long tiles only: >= 96 chunks, i.e. dense windows over >= 1536 ell: measured on 6 x 50 bins x 3251 ell,
+        # 8192 walkers per launch: 1.18 / 1.09 / 1.04 ms with 1 / 2 / 4 parts; 47 x 3251 ell, 4096 chains: 0.31 / 0.17 / 0.09 ms)
+        self.meta['bin_split'] = 4 if max_tile_chunks >= 96 else 1
         if self.binning_split is not None:
             self.meta['bin_split'] = int(self.binning_split)
         self._dev('data', d, np.float64)

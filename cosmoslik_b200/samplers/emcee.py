@@ -52,13 +52,15 @@ class emcee(SlikSampler):
         if output_extra_params is None:
             output_extra_params = []
         super().__init__(**arguments(exclude=["params"]))
-        # name -> dtype name (emcee.py:28); float columns only, evaluated on the device (Slik.extras_program)
+        # name -> dtype name (emcee.py:28); scalar numeric columns, evaluated on the device in float64
+        # (Slik.extras_program) and cast to the column's dtype in the file
         self.output_extra_params = OrderedDict(k if isinstance(k, tuple) else (k, np.dtype("float").name)
                                                for k in self.output_extra_params)
         for k_, dt in self.output_extra_params.items():
-            if np.dtype(dt) != np.dtype("float"):
-                raise NotImplementedError("output_extra_params: column '%s' has dtype %s; the batched sampler "
-                                          "writes float64 columns only" % (k_, dt))
+            d = np.dtype(dt)
+            if d.kind not in "fiub" or d.shape != ():
+                raise NotImplementedError("output_extra_params: column '%s' has dtype %s; the batched sampler derives "
+                                          "scalar numeric columns only" % (k_, dt))
         self.sampled = params.find_sampled()
         self.x0 = [params[k].start for k in self.sampled]
         self.cov_est = initialize_covariance(self.sampled, self.cov_est)
@@ -178,7 +180,8 @@ class emcee(SlikSampler):
         file_all = self.output_file is not None and size > 1
         writer = None
         if self.output_file is not None and rank == 0:
-            writer = ChainWriter(self.output_file, ["lnl", "weight"] + list(self.sampled) + list(self.output_extra_params), "list")
+            writer = ChainWriter(self.output_file, ["lnl", "weight"] + list(self.sampled) + list(self.output_extra_params), "list",
+                                 dtypes=["f8"] * (2 + nd) + [np.dtype(d).str for d in self.output_extra_params.values()])
         all_ids = np.concatenate([local_ids(r)[4] for r in range(size)]) if file_all else gid
         per_rank = [len(local_ids(r)[4]) for r in range(size)]
         stream = RowBlockStream(torch, dev, W, cap, rl, all_ranks=file_all, total=k, counts=per_rank) if consume else None

@@ -58,14 +58,16 @@ class metropolis_hastings(SlikSampler):
         if output_extra_params is None:
             output_extra_params = []
         super().__init__(**arguments(exclude=["params"]))
-        # name -> dtype name, as the reference (:103); the values are scalar expressions of the sampled
-        # parameters evaluated on the device (Slik.extras_program), so only float columns exist
+        # name -> dtype name, as the reference (:103).  The values are scalar expressions of the sampled parameters
+        # evaluated on the device in float64 (Slik.extras_program) and cast to the column's dtype; any scalar
+        # numeric dtype works, array- or object-valued columns (:46-52) cannot be derived that way
         self.output_extra_params = OrderedDict(k if isinstance(k, tuple) else (k, np.dtype("float").name)
                                                for k in self.output_extra_params)
         for k, dt in self.output_extra_params.items():
-            if np.dtype(dt) != np.dtype("float"):
-                raise NotImplementedError("output_extra_params: column '%s' has dtype %s; the batched sampler "
-                                          "writes float64 columns only" % (k, dt))
+            d = np.dtype(dt)
+            if d.kind not in "fiub" or d.shape != ():
+                raise NotImplementedError("output_extra_params: column '%s' has dtype %s; the batched sampler derives "
+                                          "scalar numeric columns only" % (k, dt))
         self.sampled = params.find_sampled()
         self.x0 = [params[k].start for k in self.sampled]
         self.cov_est = initialize_covariance(self.sampled, self.cov_est)
@@ -89,7 +91,10 @@ class metropolis_hastings(SlikSampler):
         for blocks in self._run(program_of(lnl), emit=True, extras=extras_of(lnl, extra_names)):
             for cid, rows in blocks:
                 for r in rows:
-                    s = sample(r[2:2 + nd].copy(), r[0], r[1], dict(zip(extra_names, r[2 + nd:])) if extra_names else None)
+                    extra = None
+                    if extra_names:
+                        extra = {k: np.dtype(dt).type(v) for (k, dt), v in zip(self.output_extra_params.items(), r[2 + nd:])}
+                    s = sample(r[2:2 + nd].copy(), r[0], r[1], extra)
                     s.chain = cid
                     yield s
 
@@ -198,7 +203,8 @@ class metropolis_hastings(SlikSampler):
         file_all = self.output_file is not None and size > 1          # rank 0 writes every rank's chains
         if self.output_file is not None and rank == 0:
             writer = _FileBlocks(self.output_file, ["lnl", "weight"] + list(self.sampled) + list(self.output_extra_params), S,
-                                 single=(ntot == 1))
+                                 single=(ntot == 1),
+                                 dtypes=["f8"] * (2 + nd) + [np.dtype(d).str for d in self.output_extra_params.values()])
         if dist.is_master() and self.print_level >= 1 and self.output_file:
             print("Starting MCMC chain (%s)..." % self.output_file)
         consume = emit or self.output_file is not None
@@ -338,8 +344,8 @@ class _FileBlocks(object):
     single=False is the MPI branch (:209-212, 232): every chain's rows are all written,
     ``freq`` rows per record, under the chain's id."""
 
-    def __init__(self, path, names, freq, single):
-        self.w = ChainWriter(path, names, "ndarray")
+    def __init__(self, path, names, freq, single, dtypes=None):
+        self.w = ChainWriter(path, names, "ndarray", dtypes=dtypes)
         self.freq, self.single = freq, single
         self.buf = {}
         self.ncol = len(names)

@@ -437,7 +437,6 @@ int csl_chain_moments(int W, int ndim, const double* rows, const int32_t* nrows,
  * "trigemm_rows", "trigemm_group", "trigemm_stages", "trsm_shape", "bin_split", "bin_variant", "sab_threads",
  * "seg_small".  Results never depend on them bit-wise unless stated in DESIGN.md. */
 int csl_set_option(const char* name, int value);
-int csl_debug_counters(unsigned long long* out4_host, int reset);   /* kernel self-check counters (debug builds of the sweeps) */
 int csl_get_option(const char* name);
 
 int csl_philox_mh(int W, int ndim, uint64_t seed, uint32_t step, uint32_t chain0, double* z, double* u,

@@ -233,3 +233,22 @@ def test_single_process_blocks_for_every_row_count(tmp_path, nrows):
     for (cid, rec), blk in zip(recs, blocks):
         assert cid == 0
         np.testing.assert_array_equal(rec.view(float).reshape(-1, 2 + nd), blk)
+
+
+def test_chain_writer_with_typed_extra_columns(tmp_path):
+    """output_extra_params entries (name, dtype) (metropolis_hastings.py:46-56): the column is stored in that dtype
+    and comes back through load_chain (and through the reference's loader where it is mounted)"""
+    path = str(tmp_path / "typed.chain")
+    w = ChainWriter(path, ["lnl", "weight", "a", "n", "flag"], "ndarray", dtypes=["f8", "f8", "f8", "i8", "f4"])
+    rows = np.array([[1.5, 2, 0.25, 7, 0.5], [2.5, 1, 0.75, -3, 1.5], [0.5, 4, 1.25, 12, 2.5]])
+    w.write(0, rows[:2]); w.write(0, rows[2:]); w.close()
+    c = load_chain(path)[0]
+    assert c["n"].dtype == np.int64 and c["flag"].dtype == np.float32 and c["a"].dtype == np.float64
+    np.testing.assert_array_equal(c["n"], [7, -3, 12])
+    np.testing.assert_array_equal(c["weight"], [2, 1, 4])
+    if refshim.available():
+        R = refshim.load()
+        rc = R.chains.load_chain(path)
+        rc = rc[0] if isinstance(rc, list) else rc
+        np.testing.assert_array_equal(rc["n"], [7, -3, 12])
+        np.testing.assert_array_equal(rc["flag"], np.float32([0.5, 1.5, 2.5]))

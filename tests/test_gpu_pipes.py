@@ -55,11 +55,11 @@ def test_chi2_bulk_pipeline_is_bitwise_the_cp_async_one(torch, kind, mode):
         R0 = np.zeros((prog.n_pad, W))
         R0[:prog.n] = rs.standard_normal((prog.n, W)) * np.sqrt(np.diag(prob["cov"]))[:, None]
         d = torch.from_numpy(R0).cuda()
-        ref, Rref = chi2_of(torch, prog, d, pipe=0)
+        ref, Rref = chi2_of(torch, prog, d, pipe=0, trsm_shape=0)
         # against LAPACK: chi2 = r^T C^-1 r
         want = np.einsum("iw,iw->w", R0[:prog.n], np.linalg.solve(prob["cov"], R0[:prog.n]))
         np.testing.assert_allclose(ref, want, rtol=1e-10)
-        variants = [dict(pipe=1)]
+        variants = [dict(pipe=1), dict(trsm_shape=1), dict(trsm_shape=2), dict(trsm_shape=3)]
         if mode == "inverse":
             variants += [dict(pipe=p, trigemm_rows=r, trigemm_stages=s) for p in (0, 1) for r in (32, 64) for s in (3, 4)]
         for v in variants:
@@ -92,7 +92,7 @@ def test_binning_warp_specialised_cluster_kernel(torch, spt_data, kind):
         want = np.array([oslik.evaluate(*x)[0] for x in X[:40]])
     Xd = torch.from_numpy(np.ascontiguousarray(X)).cuda()
     prog = make()
-    assert prog.meta["bin_split"] == {"planck_dmma": 1, "spt": 2, "spt_lowl": 4}[kind]
+    assert prog.meta["bin_split"] == {"planck_dmma": 1, "spt": 4, "spt_lowl": 4}[kind]
     set_opts(bin_variant=0, bin_split=1)
     old = prog.lnl(Xd).cpu().numpy()
     fin = np.isfinite(want)

@@ -124,3 +124,23 @@ def test_polychord_callbacks_on_a_batch():
     logl, ex = slik.sampler.loglikelihood(slik.evaluate, theta)
     np.testing.assert_allclose(logl, -(theta[:, 0] ** 2 + theta[:, 1] ** 2) / 2, rtol=1e-14, atol=1e-16)
     np.testing.assert_allclose(ex[:, 0], theta[:, 0] + 2 * theta[:, 1], rtol=1e-15, atol=0)
+
+
+def test_typed_extra_columns(tmp_path):
+    """output_extra_params=(name, dtype) (metropolis_hastings.py:46-56): the derived value is cast to the column's
+    scalar dtype in the yielded samples and in the chain file; array / object columns are refused loudly"""
+    out = str(tmp_path / "typed.chain")
+    n = 300
+    slik = Slik(B.derived_script(lambda s: samplers.metropolis_hastings(
+        s, num_samples=n, seed=4, output_file=out, output_extra_params=["ratio", ("r2", "f4"), ("fixed", "i8")]))())
+    rows = list(slik.sample())
+    assert all(isinstance(s.extra["fixed"], np.int64) and s.extra["fixed"] == 3 for s in rows)
+    assert all(isinstance(s.extra["r2"], np.float32) for s in rows)
+    r2 = np.array([s.x[0] ** 2 + s.x[1] ** 2 for s in rows])
+    np.testing.assert_array_equal([s.extra["r2"] for s in rows], r2.astype(np.float32))
+    c = load_chain(out)[0]
+    assert c["fixed"].dtype == np.int64 and c["r2"].dtype == np.float32 and c["ratio"].dtype == np.float64
+    with pytest.raises(NotImplementedError):
+        B.derived_script(lambda s: samplers.metropolis_hastings(s, num_samples=10, output_extra_params=[("r2", "object")]))()
+    with pytest.raises(NotImplementedError):
+        B.derived_script(lambda s: samplers.metropolis_hastings(s, num_samples=10, output_extra_params=[("r2", "(2,2)d")]))()

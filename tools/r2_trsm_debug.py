@@ -22,7 +22,7 @@ def run(W, **kw):
     return R, chi2
 for W in (32768, 65536):
     Rref, cref = run(W, pipe=0)
-    for shape in [1] * 10 + [17] * 16 + [19] * 6:
+    for shape in [1] * 24 + [17] * 24 + [3] * 8 + [33] * 6:
         R, c = run(W, pipe=1, trsm_shape=shape)
         bad = (R != Rref)
         nbad = int(bad.sum())
