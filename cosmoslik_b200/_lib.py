@@ -16,6 +16,7 @@ SPEC_STRIDE, TILE_STRIDE, STACK = 64, 32, 16
 OP = dict(PUSHP=0, PUSHC=1, ADD=2, SUB=3, MUL=4, DIV=5, NEG=6, EXP=7, LOG=8, POW=9, SQRT=10, STORE=11, SQR=12)
 S_NLPAD, S_NTERM, S_NPLAW, S_CAL = 0, 1, 2, 3
 S_LTAB, S_CALMODE, S_TERM_COEF, S_PLAW_AMP, S_PLAW_IDX, S_IDXBOUND = 4, 5, 8, 24, 28, 32
+S_ABERR, S_ABTAB = 6, 7
 MAX_CLASS = 8
 BIN_STRIDE, SEG_GROUP, GRP_STRIDE = 16, 8, 128
 G_PRE, G_LO, G_ROW, G_CONT, G_MODE, G_BASE_LO, G_BASE_HI, G_SPEC, G_DATA, G_LOGB = 0, 9, 17, 25, 33, 34, 35, 36, 40, 56
@@ -40,7 +41,7 @@ class Program(C.Structure):
                 [("chi2_mode", C.c_int32), ("nsegclass", C.c_int32), ("segcls", (C.c_int32 * 4) * 8),
                  ("bin_tab", C.c_void_p), ("Sigma", C.c_void_p), ("n_base", C.c_int32), ("nmode", C.c_int32),
                  ("grp_tab", C.c_void_p), ("MinvT", C.c_void_p), ("LmatT", C.c_void_p), ("LinvT", C.c_void_p),
-                 ("winT", C.c_void_p), ("bin_split", C.c_int32), ("reserved0", C.c_int32)])
+                 ("winT", C.c_void_p), ("bin_split", C.c_int32), ("has_aberr", C.c_int32)])
 
 
 class Ensemble(C.Structure):

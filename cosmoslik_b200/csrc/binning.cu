@@ -102,11 +102,26 @@ k_bin_residual(csl_program_t p, int tile0, int W, int nsplit, const double* __re
   }
   // 8 consecutive columns per thread: one exact exp at the first, Taylor advances after it (a column with a
   // large log-step falls back to exp)
-  auto build_B = [&](double* B, const double* L) {
+  // aberration (SPTSZ_lowl.py:78-79, 84-89): cl[l] *= 1 + G[l] (ln cl[l] - ln cl[l-1]); G = 0 at the first column and
+  // on the padding.  The value of the column before a thread's first one is evaluated from the table in global memory.
+  const bool aberr = spec[CSL_S_ABERR] != 0;
+  const double* __restrict__ gtab = p.templates + spec[CSL_S_ABTAB];
+  auto build_B = [&](double* B, const double* L, int lchunk) {
     const double* row = L + grp * (CSL_KC / 2) * LSTRIDE;     // warp-uniform address -> shared-memory broadcast
     double E[NP > 0 ? NP : 1];
 #pragma unroll
     for (int q = 0; q < NP; ++q) E[q] = exp(pidx[q] * row[NT + 4 * q]);
+    const int lcol = lchunk + grp * (CSL_KC / 2);
+    double lvprev = 0.0;
+    if (aberr && lcol > 0) {
+      const double* rp = ltab + (long long)(lcol - 1) * LSTRIDE;
+      double vp = 0.0;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) vp = fma(cf[t], __ldg(rp + t), vp);
+#pragma unroll
+      for (int q = 0; q < NP; ++q) vp = fma(pamp[q] * __ldg(rp + NT + 4 * q + 1), exp(pidx[q] * __ldg(rp + NT + 4 * q)), vp);
+      lvprev = log(vp);
+    }
 #pragma unroll 2
     for (int r = 0; r < CSL_KC / 2; ++r, row += LSTRIDE) {
       double v = 0.0;
@@ -114,6 +129,11 @@ k_bin_residual(csl_program_t p, int tile0, int W, int nsplit, const double* __re
       for (int t = 0; t < NT; ++t) v = fma(cf[t], row[t], v);
 #pragma unroll
       for (int q = 0; q < NP; ++q) v = fma(pamp[q] * row[NT + 4 * q + 1], E[q], v);
+      if (aberr) {
+        const double gk = __ldg(gtab + lcol + r), lv = log(v);
+        if (gk != 0.0) v = v * (1.0 + gk * (lv - lvprev));
+        lvprev = lv;
+      }
       B[(grp * (CSL_KC / 2) + r) * CSL_LDB + wl] = v;
       if (r + 1 < CSL_KC / 2) {
 #pragma unroll
@@ -152,7 +172,7 @@ k_bin_residual(csl_program_t p, int tile0, int W, int nsplit, const double* __re
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-    build_B(Bs, Ls);
+    build_B(Bs, Ls, l_begin);
     cp_async_wait<0>();
     __syncthreads();
     for (int c = 0; c < nchunk; ++c) {
@@ -163,7 +183,7 @@ k_bin_residual(csl_program_t p, int tile0, int W, int nsplit, const double* __re
       if (c + 1 < nchunk) load_A_tile_async(As + (cur ^ 1) * CSL_ASZ, Wnd + l0 + CSL_KC, win_ld, tid);
       if (c + 2 < nchunk) load_L(Ls + cur * CSL_KC * LSTRIDE, l0 + 2 * CSL_KC);
       cp_async_commit();
-      if (c + 1 < nchunk) build_B(Bs + (cur ^ 1) * CSL_BSZ, Ls + (cur ^ 1) * CSL_KC * LSTRIDE);
+      if (c + 1 < nchunk) build_B(Bs + (cur ^ 1) * CSL_BSZ, Ls + (cur ^ 1) * CSL_KC * LSTRIDE, l0 + CSL_KC);
       unsigned mmask = 0;
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
@@ -871,7 +891,7 @@ extern "C" int csl_bin_residual(const csl_program_t* p, int W, const double* coe
     if (csl_option_value("bin_split") > 0) nsplit = csl_option_value("bin_split");       // sweeps only: changes the bits
     if (nsplit != 2 && nsplit != 4) nsplit = 1;
     int rc;
-    if (p->winT && csl_option_value("bin_variant") == 2)
+    if (p->winT && csl_option_value("bin_variant") == 2 && !p->has_aberr)
       rc = dispatch_class_ws(k[0], k[1], p, k[2], k[3], nsplit, W, coef, ldc, R, ldr, s);
     else
       rc = dispatch_class(k[0], k[1], p, k[2], k[3], nsplit, W, coef, ldc, R, ldr, s);

@@ -11,8 +11,10 @@ beam_cov = V V^T with V_k = W (b_k o dl): the modes become extra window rows of 
 the per-walker factorisation runs in ``csl_cov_chi2``.  Pass either ``beam_modes`` [K, n_ell] or the
 matrix ``beam_corr`` [n_ell, n_ell] (the reference's form; it is factored once into its non-zero eigen
 modes).  The reference plugin cannot run as shipped (bytes/str at :31, cwd-relative window path :35-36,
-``SPTSZ_beam_errors.tar`` missing from the repository) -- the arrays are therefore arguments here, and
-the optional aberration correction (``ab_on``, :78-79, 84-89) is not implemented.
+``SPTSZ_beam_errors.tar`` missing from the repository) -- the arrays are therefore arguments here.
+``ab_on`` applies the aberration correction of :78-79, 84-89 to the model before it is binned:
+dl *= 1 + 0.26 * 1.23e-3 * dln(dl)/dln(l), evaluated per walker in the binning kernel's build stage.
+The arithmetic is pinned by tests/golden/sptsz.npz, produced by the reference's own methods.
 """
 import numpy as np
 
@@ -40,8 +42,7 @@ class SPTSZ_lowl(SlikPlugin):
     def __init__(self, spec, sigma, windows, lmin_window, egfs, beam_modes=None, beam_corr=None, cal=1,
                  ab_on=False, **kwargs):
         super().__init__()
-        if ab_on:
-            raise NotImplementedError("the aberration correction (ab_on) is not implemented")
+        self.ab_on = bool(ab_on)
         if (beam_modes is None) == (beam_corr is None):
             raise ValueError("pass exactly one of beam_modes / beam_corr")
         self.spec = np.asarray(spec, dtype=float)
@@ -60,4 +61,5 @@ class SPTSZ_lowl(SlikPlugin):
             raise ValueError("Need the TT spectrum to at least lmax=%i." % self.lmax)
         dl = tt[:self.lmax] + as_spectrum(self.egfs(lmax=self.lmax), self.lmax)[:self.lmax]
         return LowRankCovBandpowerTerm(dl[self.windowrange], self.windows, self.spec, self.cal, self.sigma,
-                                       self.beam_modes)
+                                       self.beam_modes, aberration=(0.26 * 1.23e-3 if self.ab_on else None),
+                                       ell0=self.windowrange.start)

@@ -103,7 +103,7 @@ class CompiledProgram(object):
             raise ValueError("number of sampled parameters must be in 1..%d" % L.MAX_DIM)
         self.tables = {}
         self.meta = dict(ndim=self.ndim, ncoef=0, ncode=0, nbox=0, ngauss=0, nscalar=0, nspec=0, ntile=0,
-                         n=0, n_pad=0, resid_mode=0, nclass=0, nsegclass=0, n_base=0, nmode=0, bin_split=1)
+                         n=0, n_pad=0, resid_mode=0, nclass=0, nsegclass=0, n_base=0, nmode=0, bin_split=1, has_aberr=0)
         self.cls = np.zeros((L.MAX_CLASS, 4), np.int32)
         self.segcls = np.zeros((L.MAX_CLASS, 4), np.int32)
         self.host = {}
@@ -269,9 +269,10 @@ class CompiledProgram(object):
         if n > 64 or K > 32:
             raise ValueError("low-rank covariance likelihood: at most 64 bandpowers and 32 modes")
         wm = (q.windows[None, :, :] * q.modes[:, None, :]).reshape(K * n, nl)
-        blocks = [SpectrumBlock(q.model, q.windows, q.data, q.cal, cal_on_model=True)]
+        ab = dict(aberration=q.aberration, ell0=q.ell0)
+        blocks = [SpectrumBlock(q.model, q.windows, q.data, q.cal, cal_on_model=True, **ab)]
         if K:
-            blocks.append(SpectrumBlock(q.model, wm, np.zeros(K * n), 1.0))
+            blocks.append(SpectrumBlock(q.model, wm, np.zeros(K * n), 1.0, **ab))
         self._build_bandpower(P, code, BandpowerTerm(blocks, None), factor=False)
         P['resid_mode'] = 3
         P['n_base'], P['nmode'] = n, K
@@ -362,6 +363,14 @@ class CompiledProgram(object):
                     rec[L.S_PLAW_AMP + k] = rec[L.S_PLAW_IDX + k] = zero_row
             templ.append(ltab.ravel()); toff += ltab.size
             ltabs.append(ltab)
+            if getattr(blk, "aberration", None):
+                # G[l] = kappa / (ln ell_l - ln ell_{l-1}), G[0] = 0 and 0 on the padding (SPTSZ_lowl.py:78-79, 84-89)
+                gt = np.zeros(nlp)
+                lnx = np.log(np.arange(blk.ell0, blk.ell0 + nl, dtype=float))
+                gt[1:nl] = float(blk.aberration) / (lnx[1:] - lnx[:-1])
+                rec[L.S_ABERR], rec[L.S_ABTAB] = 1, toff
+                templ.append(gt); toff += gt.size
+                P['has_aberr'] = 1
             cal = blk.cal
             if isinstance(cal, Expr) and not (isinstance(cal, Const) and cal.v == 1.0):
                 rec[L.S_CAL] = code.coef(cal)
@@ -376,6 +385,8 @@ class CompiledProgram(object):
             # rows whose supports barely overlap (top-hat bins): every cl[l] is needed by ~one row, so a
             # per-row segmented sum does the minimum work; dense windows go to the DMMA tile product
             seg = self.binning == "segsum" or (self.binning == "auto" and covered <= 2 * nl)
+            if getattr(blk, "aberration", None):
+                seg = False          # the aberration factor is built in the DMMA kernel's Cl stage only
             per_elem = len(terms) + 20 * len(m.plaws)
             NTr = len(terms) if len(terms) + NP > 0 else NT      # segmented-sum class: real term count
             if seg:

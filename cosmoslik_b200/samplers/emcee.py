@@ -256,6 +256,9 @@ class emcee(SlikSampler):
             pending[0] = ticket
             return out
 
+        hooks = getattr(self, "hooks", None) or {}      # bench.py: callables run right before the first / after the last launch
+        if "start" in hooks:
+            hooks["start"]()
         # Fast path: whole steps are enqueued from C (csl_stretch_run) -- no Python between the kernel
         # launches of a step.  Needs device streams and either one GPU or the symmetric-memory replica.
         native = self.streams is None and timers is None and (size == 1 or replica is not None) \
@@ -342,6 +345,8 @@ class emcee(SlikSampler):
                     out = end_of_block()
                     if emit and out is not None:
                         yield out
+            if "end" in hooks:
+                hooks["end"]()
             if pending[0] is not None:
                 out = hand_over(pending[0])
                 pending[0] = None

@@ -265,10 +265,13 @@ class LnlSum(LnlTerm):
 class SpectrumBlock(object):
     """One binned spectrum of a bandpower likelihood: windows [nbins, nl] applied
     to model columns [lmin, lmin+nl), data [nbins], calibration multiplying the data."""
-    def __init__(self, model, windows, data, cal=1.0, cal_on_model=False):
+    def __init__(self, model, windows, data, cal=1.0, cal_on_model=False, aberration=None, ell0=0):
         self.model, self.windows, self.data, self.cal = model, np.asarray(windows, dtype=float), \
             np.asarray(data, dtype=float), cal
         self.cal_on_model = cal_on_model      # False: r = cal*d - b (spt_lowl, mspec); True: r = d - cal*b (SPTSZ)
+        # aberration = kappa: the model is multiplied by 1 + kappa * dln(cl)/dln(l) (forward differences over the
+        # columns, 0 at the first) before it is binned (SPTSZ_lowl.py:78-79, 84-89); ell0 = ell of column 0
+        self.aberration, self.ell0 = aberration, int(ell0)
 
 
 class BandpowerTerm(LnlTerm):
@@ -282,7 +285,8 @@ class LowRankCovBandpowerTerm(LnlTerm):
     """1/2 r^T (Sigma + V V^T)^-1 r  with  r = d - cal * W.cl  and  V_k = (W diag(b_k)).cl:
     a bandpower likelihood whose covariance depends on the model through rank-one beam modes
     (SPTSZ_lowl.py:62-81, beam_cov = W (B o dl dl^T) W^T with B = sum_k b_k b_k^T)."""
-    def __init__(self, model, windows, data, cal, sigma, modes):
+    def __init__(self, model, windows, data, cal, sigma, modes, aberration=None, ell0=0):
+        self.aberration, self.ell0 = aberration, int(ell0)
         self.model, self.cal = model, cal
         self.windows, self.data = np.asarray(windows, dtype=float), np.asarray(data, dtype=float)
         self.sigma, self.modes = np.asarray(sigma, dtype=float), np.asarray(modes, dtype=float)

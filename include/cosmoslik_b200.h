@@ -63,6 +63,9 @@ enum {
   CSL_S_NPLAW = 2,   /* NP: power-law terms, padded to the class size {0,1,2,4}    */
   CSL_S_CAL   = 3,   /* coef row multiplying the data of this spectrum, -1 = 1.0 */
   CSL_S_CALMODE = 5, /* 0: r = cal*d - b (spt_lowl.py:132, mspec);  1: r = d - cal*b (SPTSZ_lowl.py:68) */
+  CSL_S_ABERR = 6,   /* 1: aberration -- cl[l] *= 1 + G[l] (ln cl[l] - ln cl[l-1]) before binning (SPTSZ_lowl.py:78-79,
+                        84-89), G[l] = 0.26 * 1.23e-3 / (ln ell_l - ln ell_{l-1}), G[0] = 0 (DMMA-binned spectra only) */
+  CSL_S_ABTAB = 7,   /* offset (doubles) of G [nl_pad] in `templates`                                  */
   CSL_S_LTAB  = 4,   /* offset (doubles) of the ell-table in `templates`: nl_pad rows of
                         [T_0..T_{NT-1}, (logB_q, M_q, D_q, 0) q<NP], D_q[l] = logB_q[l+1] - logB_q[l];
                         cl[l] = sum_t coef[TERM_COEF[t]] T_t[l]
@@ -175,7 +178,7 @@ typedef struct csl_program {
                                sums are added in rank order).  Fixed per PROGRAM by the host from the chunks per
                                tile -- never from the launch size -- so that a walker's result does not depend on
                                the batch it is evaluated in.                                            */
-  int32_t reserved0;
+  int32_t has_aberr;        /* some spectrum carries CSL_S_ABERR                                          */
 } csl_program_t;
 
 int csl_abi_version(void);

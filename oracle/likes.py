@@ -104,25 +104,34 @@ class SptLowl(Plugin):
 
 
 class SptszLowl(Plugin):
-    """likelihoods/SPTSZ_lowl_2017/SPTSZ_lowl.py:62-81 from arrays (the loader :25-57 and the beam-grid
-    reader :95-145 cannot run: py2 bytes/str at :31, cwd-relative path :35-36, SPTSZ_beam_errors.tar
-    missing).  PARITY UNPINNED against the reference itself; the arithmetic below is the reference's,
-    line for line:  dl (:74-77), db = W dl and beam_cov = W (beam_corr o dl dl^T) W^T (:81),
-    cho_factor(beam_cov + sigma) on every call (:67), deldb = spec - db*cal (:68), no log-det (:69)."""
+    """likelihoods/SPTSZ_lowl_2017/SPTSZ_lowl.py:62-89 from arrays (the loader :25-57 and the beam-grid reader
+    :95-145 cannot run: py2 bytes/str at :31, cwd-relative path :35-36, SPTSZ_beam_errors.tar missing).
+    PINNED by tests/golden/sptsz.npz: the reference's own ``__call__`` / ``get_cl_model_and_beam_cov`` /
+    ``DlnClDlnl`` executed on an instance that was handed these arrays (oracle/make_golden_sptsz.py).
+      dl (:74-77); aberration dl *= 1 + .26 * 1.23e-3 * dlnCl/dlnl (:78-79, 84-89: forward differences of ln dl
+      over ln l, 0 for the first ell); db = W dl and beam_cov = W (beam_corr o dl dl^T) W^T (:81);
+      cho_factor(beam_cov + sigma) on every call (:67); deldb = spec - db*cal (:68); no log-det (:69)."""
 
-    def __init__(self, spec, sigma, windows, lmin_window, beam_corr, egfs, cal=1):
+    def __init__(self, spec, sigma, windows, lmin_window, beam_corr, egfs, cal=1, ab_on=False):
         super().__init__()
         self.spec, self.sigma = np.asarray(spec), np.asarray(sigma)
         self.windows = np.asarray(windows)
         self.windowrange = slice(int(lmin_window), int(lmin_window) + self.windows.shape[1])
         self.lmax = self.windowrange.stop
         self.beam_corr = np.asarray(beam_corr)
-        self.egfs, self.cal = egfs, cal
+        self.egfs, self.cal, self.ab_on = egfs, cal, ab_on
+
+    def dlncl_dlnl(self, y):
+        lnx = np.log(np.arange(self.lmax)[self.windowrange])
+        lny = np.log(y)
+        return np.concatenate([[0.0], (lny[1:] - lny[:-1]) / (lnx[1:] - lnx[:-1])])
 
     def __call__(self, cmb):
         eg = self.egfs(lmax=self.lmax)[:self.lmax]
         tt = cmb["TT"][:self.lmax]
         dl = tt[self.windowrange] + eg[self.windowrange]
+        if self.ab_on:
+            dl = dl * (1 + .26 * 1.23e-3 * self.dlncl_dlnl(dl))
         db = np.dot(self.windows, dl)
         beam_cov = np.dot(self.windows, np.dot(self.beam_corr * np.outer(dl, dl), self.windows.T))
         cho = cho_factor(beam_cov + self.sigma)

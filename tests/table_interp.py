@@ -89,13 +89,21 @@ def residual(cp, coef):
         l0, l1 = tile[L.T_LBEGIN], tile[L.T_LEND]
         NT, NP = spec[L.S_NTERM], spec[L.S_NPLAW]
         stride = NT + 4 * NP
-        ltab = t["templates"][spec[L.S_LTAB]: spec[L.S_LTAB] + spec[L.S_NLPAD] * stride].reshape(-1, stride)[l0:l1]
-        cl = np.zeros(l1 - l0)
+        full = t["templates"][spec[L.S_LTAB]: spec[L.S_LTAB] + spec[L.S_NLPAD] * stride].reshape(-1, stride)
+        lo_eval = 0 if spec[L.S_ABERR] else l0           # the aberration factor needs the previous column
+        ltab = full[lo_eval:l1]
+        cl = np.zeros(l1 - lo_eval)
         for k in range(NT):
             cl += coef[spec[L.S_TERM_COEF + k]] * ltab[:, k]
         for k in range(NP):
             with np.errstate(over="ignore"):
                 cl += coef[spec[L.S_PLAW_AMP + k]] * ltab[:, NT + 4 * k + 1] * np.exp(coef[spec[L.S_PLAW_IDX + k]] * ltab[:, NT + 4 * k])
+        if spec[L.S_ABERR]:
+            G = t["templates"][spec[L.S_ABTAB]: spec[L.S_ABTAB] + spec[L.S_NLPAD]][:l1]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                lncl = np.log(cl)
+                d = np.concatenate([[0.0], lncl[1:] - lncl[:-1]])
+            cl = np.where(G != 0, cl * (1 + G * d), cl)[l0:]
         woff = (int(tile[L.T_WINOFF_HI]) << 32) | (int(tile[L.T_WINOFF_LO]) & 0xFFFFFFFF)
         ld = tile[L.T_WINLD]
         cal = 1.0 if spec[L.S_CAL] < 0 else coef[spec[L.S_CAL]]

@@ -187,6 +187,20 @@ def test_model_dependent_covariance_tables(by_modes):
         assert abs(TI.lnl(cp, x0 * f) - ref) <= 1e-11 * abs(ref)
 
 
+@pytest.mark.parametrize("tag", ["m6_ab0", "m6_ab1", "m8_ab1"])
+def test_sptsz_tables_against_the_reference_golden(tag):
+    """the compiled tables (aberration table included) interpreted in numpy against what the reference's own
+    SPTSZ_lowl.__call__ returned for the same arrays (tests/golden/sptsz.npz)"""
+    import sptsz_problem as SP
+    script, X, want = SP.reference_golden_script(tag)
+    slik = Slik(script())
+    assert list(slik.get_sampled()) == ["cal", "egfs.Acl", "egfs.Aps", "egfs.Asz"]
+    cp = CompiledProgram(list(slik.get_sampled()), slik.params.priors, slik.trace())
+    assert cp.meta["has_aberr"] == int(tag.endswith("ab1")) and cp.meta["nsegclass"] == 0
+    for x, ref in list(zip(X, want))[::6]:
+        assert abs(TI.lnl(cp, x) - ref) <= 1e-10 * abs(ref)
+
+
 def test_bench_reference_arm_prints_one_json_line():
     """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm): exactly one JSON line on
     stdout with the contract's keys; the oracle port on all host cores, no GPU needed."""
@@ -241,13 +255,16 @@ def test_output_extra_params_compile_to_bytecode():
 
 
 def test_sampler_extra_params_bookkeeping():
-    """constructor side of output_extra_params: name -> dtype map like the reference (:103); non-float
-    columns are refused"""
+    """constructor side of output_extra_params: name -> dtype map like the reference (:103); scalar numeric
+    dtypes are cast, array / object columns are refused"""
     from cosmoslik_b200 import samplers
     s = B.derived_script(lambda p: samplers.metropolis_hastings(p, num_samples=10, output_extra_params=["r2", ("ratio", "float64")]))()
     assert list(s.sampler.output_extra_params.items()) == [("r2", "float64"), ("ratio", "float64")]
-    with pytest.raises(NotImplementedError):
-        B.derived_script(lambda p: samplers.metropolis_hastings(p, num_samples=10, output_extra_params=[("n", "int64")]))()
+    s = B.derived_script(lambda p: samplers.metropolis_hastings(p, num_samples=10, output_extra_params=[("n", "int64")]))()
+    assert list(s.sampler.output_extra_params.items()) == [("n", "int64")]
+    for bad in ("object", "(3,)f8", "U8"):
+        with pytest.raises(NotImplementedError):
+            B.derived_script(lambda p: samplers.metropolis_hastings(p, num_samples=10, output_extra_params=[("n", bad)]))()
 
 
 def test_mspec_cleaning_and_resgal():
