@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 METRIC = "posterior evals/sec (whole box) for batched bandpower lnL"
 UNIT = "evals/s"
 LITERAL_WALKERS = 65536
-PREROLL = 40        # untimed steps run right before every timed region (>= the --warmup asked for)
+PREROLL = int(os.environ.get("CSL_BENCH_PREROLL", "40"))   # untimed steps run right before every timed region (>= --warmup)
 
 
 def parse():

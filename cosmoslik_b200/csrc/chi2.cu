@@ -418,10 +418,12 @@ int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi
     return csl_check_launch("k_trigemm_chi2");
   }
   CSL_REQUIRE(p->Lmat && p->Linv_diag, "csl_chi2: program has no factor");
-  // shape: 0 = the round-1 kernel (one CTA per SM, T tile in shared memory): best while every walker tile has an
-  // SM to itself; 1 / 2 = two CTAs per SM with a 2- / 3-stage cp.async ring: best from there on
+  // shape: 0 = the round-1 kernel (one CTA per SM, T tile in shared memory); 1 / 2 = two CTAs per SM with a 2- / 3-stage
+  // cp.async ring and device-scope fences; 3 (default) = 3 stages and CTA-scope fences.  Measured at n = 613 on
+  // 4096 / 32 768 / 65 536 walkers: shape 0 0.332 / 0.668 / 1.331 ms, shape 2 0.338 / 0.600 / 1.164, shape 3
+  // 0.323 / 0.596 / 1.151 (58 % / 60 % of the FP64 peak at the two large sizes); all bitwise equal
   int shape = csl_option_value("trsm_shape");
-  if (shape < 0) shape = (W / CSL_BN > csl_sm_count()) ? 2 : 0;
+  if (shape < 0) shape = 3;
   if (shape != 0) {
     const int nst = shape == 1 ? 2 : 3;
     const size_t smem2 = (size_t)(nst * (CSL_ASZ + CSL_BSZ) + 2 * CSL_BN) * sizeof(double);
