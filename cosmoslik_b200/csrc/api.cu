@@ -1,6 +1,6 @@
 // C-ABI glue: error reporting, device info and the composed posterior evaluation.
 #include <string.h>
-#include "common.cuh"
+#include "eval_device.cuh"
 #include <stdlib.h>
 
 thread_local char csl_err_buf[256] = "";
@@ -55,6 +55,14 @@ int csl_sm_count() {
 int csl_env_int(const char* name, int fallback) {
   const char* e = getenv(name);
   return (e && *e) ? atoi(e) : fallback;
+}
+
+// bytecode + prior tables are interpreted from shared memory when they fit the staging area (eval_device.cuh);
+// CSL_NO_STAGE_TABLES=1 keeps them in global memory (A/B measurements)
+int csl_small_stage_bytes(const csl_program_t* p) {
+  static const int off = csl_env_int("CSL_NO_STAGE_TABLES", 0);
+  const int tb = csl_small_tables_bytes(p->ncode, p->nbox, p->ngauss);
+  return (off || tb > CSL_SMALL_STAGE_MAX) ? 0 : tb;
 }
 
 // ---- tuning options (sweeps, A/B tests): process-wide integers, initialised from the environment variable

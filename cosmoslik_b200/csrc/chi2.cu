@@ -189,6 +189,213 @@ k_trsm_chi2_v2(csl_program_t p, double* R, int ldr, double* __restrict__ chi2) {
   if (tid < CSL_BN) chi2[c0 + tid] = red[tid] + red[CSL_BN + tid];
 }
 
+// ---- the blocked solve as independent 16-walker column slabs (no CTA barrier, no T round trip) ---------------
+// Forward substitution never mixes walkers: column w of Y depends on column w of R only.  A WARP therefore owns a
+// slab of 16 walkers through ALL row blocks (warp tile 64 x 16, 32 accumulators per thread), and everything that
+// made k_trsm_chi2 wait disappears:
+//   * the B operand of the off-diagonal update, Y_j, was written by this same warp: it comes back through a
+//     warp-PRIVATE cp.async ring of [16 x 16] tiles (4 stages, ordered by __syncwarp, no CTA barrier);
+//   * T_i = R_i - sum_j L_ij Y_j goes from the accumulators into the warp's private shared-memory tile (which aliases
+//     the idle ring) and is the B operand of the diagonal solve at once: no global round trip, no fence;
+//   * the A operands -- the L_ij tiles and then the four inv(L_ii) tiles of every block, one continuous sequence --
+//     are fed to all warps of the CTA by ONE producer warp with bulk copies (cp.async.bulk of the tile-major
+//     tables LmatT / LinvT) through a ring of mbarrier-guarded stages; warps drift apart by up to 4 tiles.
+// Zero 8-row groups of the triangular inv(L_ii) tiles are skipped at compile time (slab_mma_chunk<LO>).
+// Because a slab is 16 walkers wide, the CTA size is chosen per launch (1..14 slabs per CTA) so that the slabs
+// spread evenly over the SMs: 32 768 walkers = 2048 slabs = 147 CTAs of 14 (98.8 % of 148 x 14), where 128-walker
+// tiles left 40 of 148 SMs with half the work of the others.
+// Per output element the DMMA sequence, T = R - acc and the order of the sums of squares (two partial sums per
+// column: rows 0..31 and 32..63 of every block, exactly the two warp rows of k_trsm_chi2) are those of the
+// kernels above: chi^2 is bitwise the same.
+#define SLAB_LD 20                                   // row stride of a warp's private tiles (conflict-free B fragments)
+#define SLAB_STAGES 4
+#define SLAB_WARP_DOUBLES (CSL_BM * SLAB_LD)         // T tile [64][20]  ==  4 ring stages of [16][20]
+#define SLAB_MAX_WARPS 14
+
+// 8-row groups LO .. HI-1 of the A tile are multiplied; the others are zero (above the diagonal of an inv(L_ii)
+// tile, or padding rows past n in the last block) and are dropped at compile time
+template <int LO, int HI>
+__device__ __forceinline__ void slab_mma_chunk(double (&acc)[8][2][2], const double* __restrict__ As,
+                                               const double* __restrict__ Bs, int lane) {
+  if (LO >= HI) return;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < CSL_KC / 4; ++ks) {
+    double a[8], b[2];
+#pragma unroll
+    for (int mi = LO; mi < HI; ++mi) a[mi] = As[(mi * 8 + g) * CSL_LDA + ks * 4 + t];
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) b[ni] = Bs[(ks * 4 + t) * SLAB_LD + ni * 8 + g];
+#pragma unroll
+    for (int mi = LO; mi < HI; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+  }
+}
+// runtime (lo, hi) of the LAST block -> the compile-time variants (warp-uniform switch)
+template <int LO>
+__device__ __forceinline__ void slab_mma_chunk_hi(double (&acc)[8][2][2], const double* __restrict__ As,
+                                                  const double* __restrict__ Bs, int lane, int hi) {
+  switch (hi) {
+    case 1: slab_mma_chunk<LO, 1>(acc, As, Bs, lane); break;
+    case 2: slab_mma_chunk<LO, 2>(acc, As, Bs, lane); break;
+    case 3: slab_mma_chunk<LO, 3>(acc, As, Bs, lane); break;
+    case 4: slab_mma_chunk<LO, 4>(acc, As, Bs, lane); break;
+    case 5: slab_mma_chunk<LO, 5>(acc, As, Bs, lane); break;
+    case 6: slab_mma_chunk<LO, 6>(acc, As, Bs, lane); break;
+    case 7: slab_mma_chunk<LO, 7>(acc, As, Bs, lane); break;
+    default: slab_mma_chunk<LO, 8>(acc, As, Bs, lane); break;
+  }
+}
+
+__global__ void __launch_bounds__((SLAB_MAX_WARPS + 1) * 32, 1)
+k_trsm_chi2_slab(csl_program_t p, double* R, int ldr, double* __restrict__ chi2, int nslab, int nw) {
+  extern __shared__ __align__(128) double smem[];
+  double* Aring = smem;                                          // [SLAB_STAGES][CSL_ASZ]
+  double* Wreg = Aring + SLAB_STAGES * CSL_ASZ;                  // [nw][SLAB_WARP_DOUBLES]
+  uint64_t* full = reinterpret_cast<uint64_t*>(Wreg + nw * SLAB_WARP_DOUBLES);
+  uint64_t* empty = full + SLAB_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int npad = p.n_pad, nblk = npad / CSL_BM, nct = npad / CSL_KC;
+  const int nact = min(nw, nslab - (int)blockIdx.x * nw);        // consumer warps with a slab
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < SLAB_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, nact); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (warp == nw) {
+    // ---------------- producer: the A tiles of every block, in the order every consumer uses them
+    if (lane == 0) {
+      int q = 0;
+      for (int i = 0; i < nblk; ++i) {
+        for (int c = 0; c < 4 * i + 4; ++c, ++q) {
+          const int s = q % SLAB_STAGES;
+          if (q >= SLAB_STAGES) mbar_wait(empty + s, ((q / SLAB_STAGES) - 1) & 1);
+          const double* src = c < 4 * i ? p.LmatT + ((long long)i * nct + c) * CSL_ATILE
+                                        : p.LinvT + ((long long)i * 4 + (c - 4 * i)) * CSL_ATILE;
+          mbar_arrive_expect_tx(full + s, CSL_ATILE * sizeof(double));
+          bulk_g2s(Aring + s * CSL_ASZ, src, CSL_ATILE * sizeof(double), full + s);
+        }
+      }
+    }
+    return;
+  }
+  if (warp >= nact) return;
+  // ---------------- consumers
+  const int g = lane >> 2, t = lane & 3;
+  const int c0 = ((int)blockIdx.x * nw + warp) * 16;
+  double* my = Wreg + warp * SLAB_WARP_DOUBLES;
+  double acc[8][2][2], colsq[2][2][2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) colsq[h][ni][0] = colsq[h][ni][1] = 0.0;
+  // rows 16 c .. of this slab -> ring stage c % 4 (4 pieces of 16 bytes per lane)
+  auto issue = [&](int c) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int piece = lane + 32 * it, row = piece >> 3, q8 = piece & 7;
+      cp_async16(my + (c % SLAB_STAGES) * (CSL_KC * SLAB_LD) + row * SLAB_LD + 2 * q8,
+                 R + (long long)(c * CSL_KC + row) * ldr + c0 + 2 * q8);
+    }
+  };
+  int q = 0;
+  for (int i = 0; i < nblk; ++i) {
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    // rows >= n (last block only) are identity rows of L acting on zero rows of R: their 8-row groups are skipped,
+    // Y stays zero there
+    const int hi = min(8, (p.n - i * CSL_BM + 7) / 8);
+    // acc = sum_{j<i} L_ij Y_j.  The B stream is the nup = 4 i chunks of Y rows followed by the FOUR chunks of R_i
+    // itself: nup is a multiple of the ring depth, so R_i chunk c lands in stage c -- rows 16 c .. of the T tile --
+    // and the residual block is in place when the update ends, its load latency hidden behind the last products
+    const int nup = 4 * i, nall = nup + 4;
+#pragma unroll
+    for (int c = 0; c < SLAB_STAGES - 1; ++c) {
+      issue(c);                                       // c < nall always
+      cp_async_commit();
+    }
+    for (int c = 0; c < nup; ++c, ++q) {
+      if (c + SLAB_STAGES - 1 < nall) issue(c + SLAB_STAGES - 1);    // into the stage chunk c-1 has left
+      cp_async_commit();                              // always a group: wait_group counts groups
+      cp_async_wait<SLAB_STAGES - 1>();               // chunk c has landed (this lane's pieces)
+      __syncwarp();                                   // ... and every other lane's
+      const int s = q % SLAB_STAGES;
+      mbar_wait(full + s, (q / SLAB_STAGES) & 1);
+      if (hi == 8) slab_mma_chunk<0, 8>(acc, Aring + s * CSL_ASZ, my + (c % SLAB_STAGES) * (CSL_KC * SLAB_LD), lane);
+      else slab_mma_chunk_hi<0>(acc, Aring + s * CSL_ASZ, my + (c % SLAB_STAGES) * (CSL_KC * SLAB_LD), lane, hi);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+    issue(nall - 1);                                  // the last chunk of R_i, into the stage the last product has left
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    // T_i = R_i - acc, in place in the warp's private tile (every thread rewrites exactly what it read)
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        double2* cell = reinterpret_cast<double2*>(my + (mi * 8 + g) * SLAB_LD + ni * 8 + 2 * t);
+        double2 v = *cell;
+        v.x = v.x - acc[mi][ni][0];
+        v.y = v.y - acc[mi][ni][1];
+        *cell = v;
+        acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      }
+    __syncwarp();
+    // Y_i = inv(L_ii) T_i : chunk c of the inverse has zero rows above 16 c
+#pragma unroll
+    for (int c = 0; c < 4; ++c, ++q) {
+      const int s = q % SLAB_STAGES;
+      mbar_wait(full + s, (q / SLAB_STAGES) & 1);
+      const double* As = Aring + s * CSL_ASZ;
+      const double* Bs = my + c * (CSL_KC * SLAB_LD);
+      if (hi == 8) {
+        if (c == 0) slab_mma_chunk<0, 8>(acc, As, Bs, lane);
+        else if (c == 1) slab_mma_chunk<2, 8>(acc, As, Bs, lane);
+        else if (c == 2) slab_mma_chunk<4, 8>(acc, As, Bs, lane);
+        else slab_mma_chunk<6, 8>(acc, As, Bs, lane);
+      } else {                                     // last block: T rows >= 8 hi are zero, so are the chunks past them
+        if (c == 0) slab_mma_chunk_hi<0>(acc, As, Bs, lane, hi);
+        else if (c == 1) slab_mma_chunk_hi<2>(acc, As, Bs, lane, hi);
+        else if (c == 2) slab_mma_chunk_hi<4>(acc, As, Bs, lane, hi);
+        else slab_mma_chunk_hi<6>(acc, As, Bs, lane, hi);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        double2 y;
+        y.x = acc[mi][ni][0];
+        y.y = acc[mi][ni][1];
+        *reinterpret_cast<double2*>(R + (long long)(i * CSL_BM + mi * 8 + g) * ldr + c0 + ni * 8 + 2 * t) = y;
+        colsq[mi >> 2][ni][0] = fma(y.x, y.x, colsq[mi >> 2][ni][0]);
+        colsq[mi >> 2][ni][1] = fma(y.y, y.y, colsq[mi >> 2][ni][1]);
+      }
+    // Y_i is read back by this warp's own cp.async.cg (other lanes) from the next block on.  cp.async.cg reads L2
+    // past the L1: a CTA-scope fence is NOT enough (measured: about one launch in five returned a few stale rows);
+    // the device-scope fence waits for L2 to hold the rows
+    __threadfence();
+    __syncwarp();
+  }
+#pragma unroll
+  for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double v0 = colsq[0][ni][e], v1 = colsq[1][ni][e];
+      v0 += shfl_xor_d(v0, 4); v0 += shfl_xor_d(v0, 8); v0 += shfl_xor_d(v0, 16);
+      v1 += shfl_xor_d(v1, 4); v1 += shfl_xor_d(v1, 8); v1 += shfl_xor_d(v1, 16);
+      if (g == 0) chi2[c0 + ni * 8 + 2 * t + e] = v0 + v1;
+    }
+}
+
 // ---- explicit-inverse mode ---------------------------------------------------------------------------
 // Y = M R with M = L^-1 (lower triangular, inverted once on the host in extended precision and verified
 // against the substitution result before it is used).  Every row block of Y is an independent tile
@@ -380,11 +587,19 @@ int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi
   cudaStream_t s = (cudaStream_t)stream;
   if (p->chi2_mode == 1) {
     CSL_REQUIRE(p->Minv && ws_part, "csl_chi2: explicit-inverse mode needs Minv and the partial-sum workspace");
-    // super-group: as many column tiles as keep their R panels (n_pad x 128 doubles each) within ~96 MB
-    // (measured at n_pad = 640, 256 tiles: tile-major 0.445 ms, 16: 0.45, 64: 0.409, 256: 0.408)
+    // super-group: as many column tiles as keep their R panels (n_pad x 128 doubles each) within 48 MB of the
+    // 126 MB L2.  Measured at n_pad = 640, 256 tiles (profiles/r2_trigemm_group_sweep.json): DRAM read per launch /
+    // time = 166 MB / 0.402 ms at 32 tiles, 167 / 0.386 at 64, 181 / 0.388 at 96, 248 / 0.383 at 146 (the round-1
+    // choice: 96 MB of panels), 675 / 0.382 at 256 -- algorithmic 164 MB.  73 tiles keep the traffic at the
+    // algorithmic figure for ~1 % of the time (DRAM is never the bound here: 0.7 TB/s at worst)
     long long panel = (long long)p->n_pad * CSL_BN * sizeof(double);
-    int grp = (int)((96ll << 20) / panel);
+    int grp = (int)((48ll << 20) / panel);
     grp = grp < 1 ? 1 : (grp > 256 ? 256 : grp);
+    {   // equal super-groups: a short last group ends the launch on a thin ladder (73, 73, 73, 37 tiles: 0.403 ms
+        // against 0.386 ms for 4 x 64 at 256 tiles)
+      const int nt = W / CSL_BN, ng = (nt + grp - 1) / grp;
+      grp = (nt + ng - 1) / ng;
+    }
     if (csl_option_value("trigemm_group") > 0) grp = csl_option_value("trigemm_group");
     // tile shape: 64-row CTAs (2 per SM) unless the launch would leave SMs idle -- then 32-row CTAs: twice as
     // many, half as long, so the last wave is shorter.  Work of a launch in 64-row-block units: every column
@@ -423,7 +638,21 @@ int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi
   // 4096 / 32 768 / 65 536 walkers: shape 0 0.332 / 0.668 / 1.331 ms, shape 2 0.338 / 0.600 / 1.164, shape 3
   // 0.323 / 0.596 / 1.151 (58 % / 60 % of the FP64 peak at the two large sizes); all bitwise equal
   int shape = csl_option_value("trsm_shape");
-  if (shape < 0) shape = 3;
+  if (shape < 0) shape = (p->LmatT && p->LinvT) ? 4 : 2;
+  if (shape == 4) {
+    CSL_REQUIRE(p->LmatT && p->LinvT, "csl_chi2: the slab kernel needs the tile-major factor tables");
+    // slabs per CTA: as few rounds of (SMs x 14 slabs) as the launch needs, the slabs spread evenly over them
+    const int nslab = W / 16, sms = csl_sm_count();
+    const int rounds = (nslab + sms * SLAB_MAX_WARPS - 1) / (sms * SLAB_MAX_WARPS);
+    int nw = (nslab + sms * rounds - 1) / (sms * rounds);
+    nw = nw < 1 ? 1 : (nw > SLAB_MAX_WARPS ? SLAB_MAX_WARPS : nw);
+    const int grid = (nslab + nw - 1) / nw;
+    const size_t smem4 = (size_t)(SLAB_STAGES * CSL_ASZ + nw * SLAB_WARP_DOUBLES) * sizeof(double) + 2 * SLAB_STAGES * sizeof(uint64_t);
+    cudaError_t e = cudaFuncSetAttribute(k_trsm_chi2_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+    if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
+    k_trsm_chi2_slab<<<grid, (nw + 1) * 32, smem4, s>>>(*p, R, ldr, chi2, nslab, nw);
+    return csl_check_launch("k_trsm_chi2_slab");
+  }
   if (shape != 0) {
     const int nst = shape == 1 ? 2 : 3;
     const size_t smem2 = (size_t)(nst * (CSL_ASZ + CSL_BSZ) + 2 * CSL_BN) * sizeof(double);
@@ -434,7 +663,7 @@ int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi
       return csl_check_launch("k_trsm_chi2_v2");
     };
     if (shape == 1) return go(k_trsm_chi2_v2<2, false>);
-    if (shape == 3) return go(k_trsm_chi2_v2<3, true>);
+    if (shape == 3) return go(k_trsm_chi2_v2<3, true>);      // CTA-scope fences: sweeps only (see k_trsm_chi2_slab: unsafe with cp.async.cg)
     return go(k_trsm_chi2_v2<3, false>);
   }
   const size_t smem = (size_t)CHI2_SMEM_DOUBLES * sizeof(double);

@@ -45,6 +45,7 @@ int csl_direct_residual_ld(const csl_program_t* p, int W, int Wp, const double* 
 int csl_sm_count();
 int csl_env_int(const char* name, int fallback);
 int csl_option_value(const char* name);     // tuning option (csl_set_option / environment), -1 = unset
+int csl_small_stage_bytes(const csl_program_t* p);   // shared-memory bytes of the staged bytecode / prior tables, 0 = not staged
 
 #define CSL_REQUIRE(cond, msg) do { if (!(cond)) return csl_fail(CSL_E_BADARG, msg); } while (0)
 

@@ -28,23 +28,42 @@ __global__ void __launch_bounds__(MHP_THREADS)
 k_mh_propose_prepare(csl_program_t p, int W, int Wp, const double* __restrict__ cur_x, double* __restrict__ test_x,
                      const double* __restrict__ F, int mode, const double* __restrict__ inj, uint64_t seed,
                      const uint32_t* __restrict__ step_ptr, uint32_t step_off, uint32_t chain0,
-                     double* __restrict__ coef, int ldc, double* __restrict__ prior) {
-  extern __shared__ double sm[];
+                     double* __restrict__ coef, int ldc, double* __restrict__ prior, int stage_tables) {
+  extern __shared__ __align__(16) double sm[];
   const int nd = p.ndim, lds = mh_row_stride(nd);
   double* sF = sm;                               // [nd*nd]
   double* zt = sF + nd * nd;                     // [MHP_THREADS][lds]  normals (or offsets)
   double* xt = zt + MHP_THREADS * lds;           // [MHP_THREADS][lds]  cur_x, then test_x
+  // bytecode + prior tables: staged with the same round of loads as the proposal factor and the chain states
+  const csl_small_tables tabs = stage_tables ? stage_small_tables(p, xt + MHP_THREADS * lds, threadIdx.x, MHP_THREADS)
+                                             : small_tables_global(p);
   const int w0 = blockIdx.x * MHP_THREADS;
   const int nw = min(MHP_THREADS, Wp - w0);
   const uint32_t step = *step_ptr + step_off;
   if (mode != 0)
     for (int i = threadIdx.x; i < nd * nd; i += MHP_THREADS) sF[i] = F[i];
   // coalesced staging; columns W..Wp-1 (tile padding) replay chain W-1
-  for (int i = threadIdx.x; i < nw * nd; i += MHP_THREADS) {
-    const int r = i / nd, c = i - r * nd;
-    const long long g = (long long)min(w0 + r, W - 1) * nd + c;
-    xt[r * lds + c] = cur_x[g];
-    if (mode != 2) zt[r * lds + c] = inj[(long long)step_off * W * nd + g];
+  const int tot = nw * nd;
+  for (int i0 = threadIdx.x; i0 < tot; i0 += 4 * MHP_THREADS) {      // four independent loads in flight per trip
+    double vx[4], vz[4];
+    int dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * MHP_THREADS;
+      if (i < tot) {
+        const int r = i / nd, c = i - r * nd;
+        const long long g = (long long)min(w0 + r, W - 1) * nd + c;
+        dst[u] = r * lds + c;
+        vx[u] = cur_x[g];
+        if (mode != 2) vz[u] = inj[(long long)step_off * W * nd + g];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * MHP_THREADS < tot) {
+        xt[dst[u]] = vx[u];
+        if (mode != 2) zt[dst[u]] = vz[u];
+      }
   }
   __syncthreads();
   const int tl = threadIdx.x, w = w0 + tl;
@@ -70,7 +89,7 @@ k_mh_propose_prepare(csl_program_t p, int W, int Wp, const double* __restrict__ 
         x[i] = __dadd_rn(x[i], d);
       }
     }
-    prepare_walker(p, x, w, W, coef, ldc, prior);
+    prepare_walker(p, tabs, x, w, W, coef, ldc, prior);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nw * nd; i += MHP_THREADS) {
@@ -301,7 +320,9 @@ static int mh_step(const csl_program_t* p, const csl_mh_t* m, int off, void* str
   const int mode = m->inj_z ? (m->inj_is_delta ? 0 : 1) : 2;
   cudaStream_t s = (cudaStream_t)stream;
   const int lds = mh_row_stride(nd);
-  const size_t smem = (size_t)(nd * nd + 2 * MHP_THREADS * lds) * sizeof(double);
+  size_t smem = (size_t)(nd * nd + 2 * MHP_THREADS * lds) * sizeof(double);
+  const int stage_tables = csl_small_stage_bytes(p) > 0 ? 1 : 0;
+  smem += csl_small_stage_bytes(p);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_mh_propose_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
@@ -309,7 +330,7 @@ static int mh_step(const csl_program_t* p, const csl_mh_t* m, int off, void* str
   const int ldc = Wp;
   k_mh_propose_prepare<<<(Wp + MHP_THREADS - 1) / MHP_THREADS, MHP_THREADS, smem, s>>>(
       *p, W, p->ncoef > 0 ? Wp : W, m->cur_x, m->test_x, m->F, mode, m->inj_z, m->seed, m->step, (uint32_t)off,
-      m->chain0, m->ws_coef, ldc, m->ws_prior);
+      m->chain0, m->ws_coef, ldc, m->ws_prior, stage_tables);
   int rc = csl_check_launch("k_mh_propose_prepare");
   if (rc) return rc;
   const double* chi2 = nullptr;

@@ -9,22 +9,40 @@
 // bytecode on its own row.  HBM traffic: 8*ndim B read + 8*(ncoef+1) B written per walker.
 __global__ void __launch_bounds__(PREP_THREADS)
 k_prepare(csl_program_t p, int W, int Wp, const double* __restrict__ x, double* __restrict__ coef, int ldc,
-          double* __restrict__ prior) {
-  extern __shared__ double sx[];
+          double* __restrict__ prior, int stage_tables) {
+  extern __shared__ __align__(16) double sx[];
   const int nd = p.ndim, lds = nd + 1;
   const int w0 = blockIdx.x * PREP_THREADS;
   const int nw = min(PREP_THREADS, Wp - w0);
+  // the bytecode and prior tables ride in with the x tile: one round of loads, one barrier
+  const csl_small_tables tabs = stage_tables ? stage_small_tables(p, sx + PREP_THREADS * lds, threadIdx.x, PREP_THREADS)
+                                             : small_tables_global(p);
   // columns W..Wp-1 (padding up to the 128-walker tile) replay walker W-1 so they stay finite
-  for (int i = threadIdx.x; i < nw * nd; i += PREP_THREADS) {
-    int r = i / nd, c = i - r * nd;
-    sx[r * lds + c] = x[(long long)min(w0 + r, W - 1) * nd + c];
+  // four elements per thread and trip: the loads of a trip are independent and leave together (one element per
+  // trip made every thread wait out nd / 128 * 128 global-memory latencies in series)
+  const int tot = nw * nd;
+  for (int i0 = threadIdx.x; i0 < tot; i0 += 4 * PREP_THREADS) {
+    double v[4];
+    int dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * PREP_THREADS;
+      if (i < tot) {
+        const int r = i / nd, c = i - r * nd;
+        dst[u] = r * lds + c;
+        v[u] = x[(long long)min(w0 + r, W - 1) * nd + c];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * PREP_THREADS < tot) sx[dst[u]] = v[u];
   }
   __syncthreads();
   if (threadIdx.x >= nw) return;
   const double* xr = sx + threadIdx.x * lds;
   const int w = w0 + threadIdx.x;
 
-  prepare_walker(p, xr, w, W, coef, ldc, prior);
+  prepare_walker(p, tabs, xr, w, W, coef, ldc, prior);
 }
 
 // lnl = like + prior with like = sum scalar coefs (+ chi2/2), cosmoslik.py:141; +inf on a hard prior (:135-137)
@@ -55,13 +73,15 @@ int csl_eval_prepare_ld(const csl_program_t* p, int W, int Wp, const double* x, 
   CSL_REQUIRE(p->ncoef == 0 || (coef && ldc >= Wp && Wp >= W), "csl_eval_prepare: coef buffer / ldc");
   int grid = (Wp + PREP_THREADS - 1) / PREP_THREADS;
   size_t smem = (size_t)PREP_THREADS * (p->ndim + 1) * sizeof(double);
+  const int stage_tables = csl_small_stage_bytes(p) > 0 ? 1 : 0;
+  smem += csl_small_stage_bytes(p);
   // the x tile of 128 walkers passes the 48 KB default limit of dynamic shared memory from ndim = 48 on
   // (66.5 KB at CSL_MAX_DIM = 64): opt in to what this program needs (per device; cheap, so every time)
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
   }
-  k_prepare<<<grid, PREP_THREADS, smem, (cudaStream_t)stream>>>(*p, W, Wp, x, coef, ldc, prior);
+  k_prepare<<<grid, PREP_THREADS, smem, (cudaStream_t)stream>>>(*p, W, Wp, x, coef, ldc, prior, stage_tables);
   return csl_check_launch("k_prepare");
 }
 

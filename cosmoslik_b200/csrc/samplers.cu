@@ -330,10 +330,11 @@ __device__ __forceinline__ bool peer_wait_flag(const unsigned long long* mine, u
 
 // all CTAs call this after their last peer store; the last one to arrive signals every peer
 __device__ __forceinline__ void peer_signal_last_cta(const unsigned long long* __restrict__ flag_ptrs, int rank, int world,
-                                                     unsigned long long epoch, unsigned int* sync) {
+                                                     unsigned long long epoch, unsigned int* sync, int debug = 0) {
   __shared__ unsigned int s_last;
   __syncthreads();                                  // this CTA's stores are all issued
   if (threadIdx.x == 0) {
+    if (debug & 2) __threadfence(); else
     __threadfence_system();                         // ... and ordered before the ticket
     const unsigned int t = atomicAdd(sync + 1, 1u);
     s_last = (t == gridDim.x - 1) ? 1u : 0u;
@@ -355,23 +356,23 @@ struct csl_peer_sync {
   unsigned long long epoch;              // wait: the epoch every peer must have reached; signal: the epoch announced
   long long timeout_cycles;
   int rank, world;
+  int debug;                             // CSL_XCHG_DEBUG (timing experiments only; results are WRONG when set):
+                                         // 1 no remote stores, 2 device-scope instead of system-scope CTA fence, 4 no wait
 };
 
 __global__ void __launch_bounds__(SPP_THREADS)
 k_stretch_propose_prepare(csl_program_t p, int Ns, int Wp, int Nc, const double* __restrict__ s,
                           const double* comp, double a, uint64_t seed, uint32_t step, uint32_t half,
                           uint32_t walker0, double* __restrict__ q, double* __restrict__ zz,
-                          double* __restrict__ coef, int ldc, double* __restrict__ prior, csl_peer_sync ps) {
-  extern __shared__ double sq[];
-  if (ps.flag_ptrs) {                    // sharded: the peers' stores of the previous half-step must have landed
-    if ((int)threadIdx.x < ps.world)
-      peer_wait_flag(reinterpret_cast<const unsigned long long*>(ps.flag_ptrs[ps.rank]) + threadIdx.x, ps.epoch,
-                     ps.sync, ps.timeout_cycles);
-    __syncthreads();
-  }
+                          double* __restrict__ coef, int ldc, double* __restrict__ prior, csl_peer_sync ps,
+                          int stage_tables) {
+  extern __shared__ __align__(16) double sq[];
   const int nd = p.ndim, lds = nd + 1;
+  // everything that does not depend on the other ranks first: the bytecode / prior tables into shared memory and
+  // the walker's Philox draws, all in flight while thread r polls peer r's flag
+  const csl_small_tables tabs = stage_tables ? stage_small_tables(p, sq + SPP_THREADS * lds, threadIdx.x, SPP_THREADS)
+                                             : small_tables_global(p);
   const int w = blockIdx.x * SPP_THREADS + threadIdx.x;
-  if (w >= Wp) return;
   const int k = min(w, Ns - 1);
   double uz, ua;
   int64_t j;
@@ -379,16 +380,34 @@ k_stretch_propose_prepare(csl_program_t p, int Ns, int Wp, int Nc, const double*
   // zz = ((a - 1.) * u + 1) ** 2. / a
   const double tq = __dadd_rn(__dmul_rn(a - 1.0, uz), 1.0);
   const double z = __ddiv_rn(__dmul_rn(tq, tq), a);
+  if (ps.flag_ptrs && !(ps.debug & 4)) { // sharded: the peers' stores of the previous half-step must have landed
+    if ((int)threadIdx.x < ps.world)
+      peer_wait_flag(reinterpret_cast<const unsigned long long*>(ps.flag_ptrs[ps.rank]) + threadIdx.x, ps.epoch,
+                     ps.sync, ps.timeout_cycles);
+  }
+  __syncthreads();
+  if (w >= Wp) return;
   const long long sb = (long long)k * nd, cb = (long long)j * nd;
   double* qr = sq + threadIdx.x * lds;
-  for (int i = 0; i < nd; ++i) {
-    const double c = __ldcg(comp + cb + i);            // L2 is the point of coherence for the peers' stores
-    const double v = __dsub_rn(c, __dmul_rn(z, __dsub_rn(c, s[sb + i])));     // q = c - zz * (c - s)
-    qr[i] = v;
-    if (w < Ns) q[sb + i] = v;
+  // four components at a time: the partner-row loads of a group are independent and leave together
+  for (int i0 = 0; i0 < nd; i0 += 4) {
+    double c[4], sv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u < nd) {
+        c[u] = __ldcg(comp + cb + i0 + u);             // L2 is the point of coherence for the peers' stores
+        sv[u] = s[sb + i0 + u];
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u < nd) {
+        const double v = __dsub_rn(c[u], __dmul_rn(z, __dsub_rn(c[u], sv[u])));     // q = c - zz * (c - s)
+        qr[i0 + u] = v;
+        if (w < Ns) q[sb + i0 + u] = v;
+      }
   }
   if (w < Ns) zz[w] = z;
-  prepare_walker(p, qr, w, Ns, coef, ldc, prior);
+  prepare_walker(p, tabs, qr, w, Ns, coef, ldc, prior);
 }
 
 // Accept + publish.  With walkers sharded over several GPUs every rank keeps a replica of ALL walkers'
@@ -540,11 +559,12 @@ k_stretch_combine_accept(int Ns, int nd, double* __restrict__ s, double* __restr
       double* dst = reinterpret_cast<double*>(mc_ptr) + dbase + idx;
       asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" :: "l"(dst), "d"(v) : "memory");
     } else {
-      for (int r = 0; r < npeers; ++r) reinterpret_cast<double*>(peers[r])[dbase + idx] = v;
+      for (int r = 0; r < npeers; ++r)
+        if (!(ps.debug & 1) || r == ps.rank) reinterpret_cast<double*>(peers[r])[dbase + idx] = v;
     }
   }
   // sharded: announce this half-step to every peer once ALL CTAs of this launch have stored
-  if (ps.flag_ptrs) peer_signal_last_cta(ps.flag_ptrs, ps.rank, ps.world, ps.epoch, ps.sync);
+  if (ps.flag_ptrs) peer_signal_last_cta(ps.flag_ptrs, ps.rank, ps.world, ps.epoch, ps.sync, ps.debug);
 }
 
 // Chain.add_gauss_prior on the device (chains.py:206-233): every stored row of every chain gets
@@ -804,6 +824,8 @@ static csl_peer_sync make_peer_sync(const csl_peer_args* a) {
   ps.timeout_cycles = csl_barrier_timeout_cycles();
   ps.rank = a ? a->rank : 0;
   ps.world = a ? a->world : 0;
+  static const int dbg = csl_env_int("CSL_XCHG_DEBUG", 0);
+  ps.debug = dbg;
   return ps;
 }
 
@@ -811,13 +833,15 @@ int csl_fused_propose_prepare(const csl_program_t* p, int Ns, int Wp, int Nc, co
                               double a, uint64_t seed, uint32_t step, uint32_t half, uint32_t walker0, double* q,
                               double* zz, double* coef, int ldc, double* prior, const csl_peer_args* wait,
                               void* stream) {
-  const size_t smem = (size_t)SPP_THREADS * (p->ndim + 1) * sizeof(double);
+  size_t smem = (size_t)SPP_THREADS * (p->ndim + 1) * sizeof(double);
+  const int stage_tables = csl_small_stage_bytes(p) > 0 ? 1 : 0;
+  smem += csl_small_stage_bytes(p);
   if (smem > 48 * 1024) {                      // above the default from ndim = 48 on; per device, cheap: set every time
     cudaError_t e = cudaFuncSetAttribute(k_stretch_propose_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
   }
   k_stretch_propose_prepare<<<(Wp + SPP_THREADS - 1) / SPP_THREADS, SPP_THREADS, smem, (cudaStream_t)stream>>>(
-      *p, Ns, Wp, Nc, s, comp, a, seed, step, half, walker0, q, zz, coef, ldc, prior, make_peer_sync(wait));
+      *p, Ns, Wp, Nc, s, comp, a, seed, step, half, walker0, q, zz, coef, ldc, prior, make_peer_sync(wait), stage_tables);
   return csl_check_launch("k_stretch_propose_prepare");
 }
 

@@ -7,6 +7,7 @@
 #include "../../include/cosmoslik_b200.h"
 #define CSL_HOST_TWIN
 #define __device__
+#define __host__
 #define __forceinline__ inline
 #define CUDART_INF ((double)INFINITY)
 static inline double __dadd_rn(double a, double b) { return a + b; }
@@ -20,7 +21,7 @@ extern "C" {
 void twin_prepare(const csl_program_t* p, int W, int Wp, const double* x, double* coef, int ldc, double* prior) {
   for (int w = 0; w < Wp; ++w) {
     const double* xr = x + (long long)(w < W ? w : W - 1) * p->ndim;
-    prepare_walker(*p, xr, w, W, coef, ldc, prior);
+    prepare_walker(*p, small_tables_global(*p), xr, w, W, coef, ldc, prior);
   }
 }
 void twin_combine(const csl_program_t* p, int W, const double* coef, int ldc, const double* prior, const double* chi2,

@@ -77,7 +77,7 @@ def main():
                              dict(pipe=1, trigemm_rows=64, trigemm_stages=4),
                              dict(pipe=1, trigemm_rows=32, trigemm_stages=3), dict(pipe=1, trigemm_rows=32, trigemm_stages=4)]
             else:
-                variants += [dict(trsm_shape=0), dict(trsm_shape=2)] + [dict(trsm_shape=3)] * 12
+                variants = [dict(trsm_shape=0), dict(trsm_shape=2)] + [dict(trsm_shape=4)] * int(os.environ.get('SLAB_REPEATS', '2'))
             for v in variants:
                 try:
                     ms, chi2 = time_chi2(prog, W, **v)
