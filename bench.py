@@ -366,17 +366,33 @@ def measure_stretch(args, prob, k_total, instrument=True, e2e=True):
     replica = smp["_replica"][1] if "_replica" in smp and smp["_replica"] is not None else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier(); torch.cuda.synchronize()
+    # Short regions (K steps x 10 launches that fit the launch queue) are PRE-QUEUED: a host-released gate kernel
+    # holds the stream while the host enqueues the barrier, the first event, all K steps and the last event, and
+    # is opened by the host afterwards.  A sampler run of thousands of steps looks like that to the device anyway
+    # (the host enqueues a step ~8x faster than the device runs it); without the gate a 20-step region of 6-26 ms
+    # starts with an empty queue, and one host stall in its first steps (8 processes + their NVML samplers on 16
+    # cores) put ~1 ms into it: 0.329 ms per step at 20 steps against 0.281 at 200 (8 GPUs, 8192 walkers each).
+    from cosmoslik_b200 import _lib as L
+    nlaunch = args.steps * (2 * (2 + int(prog.meta.get("nclass", 0)) + int(prog.meta.get("nsegclass", 0)) + 1) + 2)
+    use_gate = (not os.environ.get("CSL_BENCH_NO_GATE")) and nlaunch <= 600
+    gate = torch.zeros(1, dtype=torch.int32).pin_memory()
     def open_region():
         # every rank's timed region opens at the same point of the device timeline: a device-side barrier on the
         # stream right before the first event (a host barrier alone leaves the ranks' launch skew in the step time)
+        if use_gate:
+            L.check(L.lib().csl_host_gate(gate.data_ptr(), 10.0, L.stream_ptr()), "csl_host_gate")
         if replica is not None:
             replica.barrier()
         e0.record()
+    def close_region():
+        e1.record()
+        if use_gate:
+            gate[0] = 1          # everything is queued: let the device go
 
     # the events sit on the stream immediately before the first and after the last launch of the K steps: the
     # sampler's host-side set-up before its first launch and its closing device->host read of the acceptance counter
     # are host work around the steps, not part of them (at 20 steps of 0.28 ms they were a sixth of the region)
-    smp.hooks = dict(start=open_region, end=e1.record)
+    smp.hooks = dict(start=open_region, end=close_region)
     with clk:
         smp.run(prog, nsteps=args.steps, resume=True)     # exactly K steps, continuing the warmed-up ensemble
         torch.cuda.synchronize()
@@ -388,6 +404,7 @@ def measure_stretch(args, prob, k_total, instrument=True, e2e=True):
     rec = {"walkers_total": k_total, "walkers_per_gpu": k_total // size, "value": k_total * args.steps / (ms * 1e-3),
            "ms_per_step": ms / args.steps, "ms_per_rank": [m / args.steps for m in per_rank],
            "untimed_preroll_steps": max(args.warmup, 3, PREROLL),
+           "launches": "pre-queued behind a host-released gate (csl_host_gate)" if use_gate else "enqueued while the region runs",
            "acceptance": smp.stats["accepted"] / float(smp.stats["evals"]),
            "host_enqueue_ms_per_step": smp.stats.get("host_ms_per_step"), "exchange": smp.stats.get("exchange"),
            "clocks": clk.summary()}
@@ -524,7 +541,7 @@ def run_b200(args):
             "config": config_of(args, prob), "e2e": literal.get("e2e"), "gpu_launches": literal["gpu_launches"],
             "roofline": literal.get("roofline"), "cpu_baseline": cpu, "clocks": literal["clocks"],
             "ms_per_rank": literal["ms_per_rank"], "exchange": literal["exchange"], "exchange_parity": parity,
-            "untimed_preroll_steps": literal["untimed_preroll_steps"],
+            "untimed_preroll_steps": literal["untimed_preroll_steps"], "launches": literal["launches"],
             "acceptance": literal["acceptance"], "host_enqueue_ms_per_step": literal["host_enqueue_ms_per_step"],
             "ms_per_step_instrumented_pass": literal.get("ms_per_step_instrumented_pass"),
             "flops_per_eval": literal["flops_per_eval"],

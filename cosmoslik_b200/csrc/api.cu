@@ -74,6 +74,7 @@ static csl_option g_options[] = {
     {"trigemm_group", "CSL_TRIGEMM_GROUP", -1, false},  // column tiles per super-group of k_trigemm_chi2
     {"trigemm_stages", "CSL_TRIGEMM_STAGES", -1, false},
     {"trsm_shape", "CSL_TRSM_SHAPE", -1, false},        // k_trsm_chi2 variant
+    {"slab_warps", "CSL_SLAB_WARPS", -1, false},        // k_trsm_chi2_slab: all-wide CTAs of this many consumer warps
     {"bin_split", "CSL_BIN_SPLIT", -1, false},          // ell splits of k_bin_residual (0 = by launch size)
     {"bin_variant", "CSL_BIN_VARIANT", -1, false},      // k_bin_residual variant
     {"sab_threads", "CSL_SAB_THREADS", -1, false},      // CTA size of k_stretch_combine_accept
@@ -182,6 +183,22 @@ extern "C" int csl_lnl_host(const csl_program_t* p, int W, const double* x_host,
   CSL_CUDA(cudaStreamSynchronize(s));
 #undef CSL_CUDA
   return 0;
+}
+
+// ---- host-released gate (bench.py: short timed regions start with their launches already queued) -------------
+__global__ void k_host_gate(const volatile int32_t* flag, long long timeout_ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (*flag == 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if ((long long)(t - t0) > timeout_ns) break;
+    __nanosleep(500);
+  }
+}
+extern "C" int csl_host_gate(const int32_t* host_flag, double timeout_s, void* stream) {
+  CSL_REQUIRE(host_flag && timeout_s > 0 && timeout_s <= 30.0, "csl_host_gate: null flag or timeout outside (0, 30] s");
+  k_host_gate<<<1, 1, 0, (cudaStream_t)stream>>>(host_flag, (long long)(timeout_s * 1e9));
+  return csl_check_launch("k_host_gate");
 }
 
 // ---- whole stretch-move steps enqueued from C -------------------------------------------------------------

@@ -189,115 +189,120 @@ k_trsm_chi2_v2(csl_program_t p, double* R, int ldr, double* __restrict__ chi2) {
   if (tid < CSL_BN) chi2[c0 + tid] = red[tid] + red[CSL_BN + tid];
 }
 
-// ---- the blocked solve as independent 16-walker column slabs (no CTA barrier, no T round trip) ---------------
+// ---- the blocked solve as independent warp-owned column slabs (no CTA barrier, no T round trip) --------------
 // Forward substitution never mixes walkers: column w of Y depends on column w of R only.  A WARP therefore owns a
-// slab of 16 walkers through ALL row blocks (warp tile 64 x 16, 32 accumulators per thread), and everything that
-// made k_trsm_chi2 wait disappears:
+// slab of 16 (or 8) walkers through ALL row blocks (warp tile 64 x 16: 32 accumulators per thread), and everything
+// that made k_trsm_chi2 wait disappears:
 //   * the B operand of the off-diagonal update, Y_j, was written by this same warp: it comes back through a
 //     warp-PRIVATE cp.async ring of [16 x 16] tiles (4 stages, ordered by __syncwarp, no CTA barrier);
-//   * T_i = R_i - sum_j L_ij Y_j goes from the accumulators into the warp's private shared-memory tile (which aliases
-//     the idle ring) and is the B operand of the diagonal solve at once: no global round trip, no fence;
+//   * the ring carries on into the four chunks of R_i itself, which land exactly on the warp's private T tile (the
+//     ring's four stages ARE that tile); T_i = R_i - sum_j L_ij Y_j is formed in place and is the B operand of the
+//     diagonal solve at once: no global round trip, no fence, the load of R_i hidden behind the last products;
 //   * the A operands -- the L_ij tiles and then the four inv(L_ii) tiles of every block, one continuous sequence --
-//     are fed to all warps of the CTA by ONE producer warp with bulk copies (cp.async.bulk of the tile-major
-//     tables LmatT / LinvT) through a ring of mbarrier-guarded stages; warps drift apart by up to 4 tiles.
-// Zero 8-row groups of the triangular inv(L_ii) tiles are skipped at compile time (slab_mma_chunk<LO>).
-// Because a slab is 16 walkers wide, the CTA size is chosen per launch (1..14 slabs per CTA) so that the slabs
-// spread evenly over the SMs: 32 768 walkers = 2048 slabs = 147 CTAs of 14 (98.8 % of 148 x 14), where 128-walker
-// tiles left 40 of 148 SMs with half the work of the others.
+//     reach all warps of the CTA as bulk copies (cp.async.bulk of the tile-major tables LmatT / LinvT) through a
+//     ring of mbarrier-guarded stages, kept full by lane 0 of warp 0 between its own products; warps drift apart
+//     by up to 4 tiles.
+// Zero 8-row groups -- above the diagonal of the inv(L_ii) tiles, padding rows past n in the last block -- are
+// skipped at compile time (slab_mma_chunk<LO, HI, NI>).
+// Balance.  The unit of work is 8 walkers.  A launch is cut into as few rounds of (SMs x 28 units) as it needs and
+// the units are spread evenly over the CTAs; a CTA of 16 consumer warps gives its first (units - 16) warps 16
+// walkers and the others 8, so that at 28 units every SM sub-partition (warps w, w+4, w+8, w+12) carries 3 wide
+// and 1 narrow slab = 7 units: 32 768 walkers = 4096 units = 147 CTAs x 28.  (14 wide warps per CTA left two
+// sub-partitions with 4 slabs and two with 3 -- 0.461 ms against 0.xxx; 128-walker tiles, k_trsm_chi2_v2, left 40 of
+// 148 SMs with half the work of the others -- 0.598 ms.)
 // Per output element the DMMA sequence, T = R - acc and the order of the sums of squares (two partial sums per
 // column: rows 0..31 and 32..63 of every block, exactly the two warp rows of k_trsm_chi2) are those of the
 // kernels above: chi^2 is bitwise the same.
-#define SLAB_LD 20                                   // row stride of a warp's private tiles (conflict-free B fragments)
 #define SLAB_STAGES 4
-#define SLAB_WARP_DOUBLES (CSL_BM * SLAB_LD)         // T tile [64][20]  ==  4 ring stages of [16][20]
-#define SLAB_MAX_WARPS 14
+#define SLAB_MAX_WARPS 16
+#define SLAB_MAX_UNITS 28
+__host__ __device__ constexpr int slab_ld(int ni) { return ni == 2 ? 20 : 12; }   // row strides with conflict-free B-fragment loads
+__host__ __device__ constexpr int slab_region(int ni) { return CSL_BM * slab_ld(ni) + ni * 4 * 32; }   // T tile + sums of squares
 
-// 8-row groups LO .. HI-1 of the A tile are multiplied; the others are zero (above the diagonal of an inv(L_ii)
-// tile, or padding rows past n in the last block) and are dropped at compile time
-template <int LO, int HI>
-__device__ __forceinline__ void slab_mma_chunk(double (&acc)[8][2][2], const double* __restrict__ As,
+// 8-row groups LO .. HI-1 of the A tile are multiplied; the others are zero and are dropped at compile time
+template <int LO, int HI, int NI>
+__device__ __forceinline__ void slab_mma_chunk(double (&acc)[8][NI][2], const double* __restrict__ As,
                                                const double* __restrict__ Bs, int lane) {
   if (LO >= HI) return;
+  constexpr int LD = slab_ld(NI);
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int ks = 0; ks < CSL_KC / 4; ++ks) {
-    double a[8], b[2];
+    double a[8], b[NI];
 #pragma unroll
     for (int mi = LO; mi < HI; ++mi) a[mi] = As[(mi * 8 + g) * CSL_LDA + ks * 4 + t];
 #pragma unroll
-    for (int ni = 0; ni < 2; ++ni) b[ni] = Bs[(ks * 4 + t) * SLAB_LD + ni * 8 + g];
+    for (int ni = 0; ni < NI; ++ni) b[ni] = Bs[(ks * 4 + t) * LD + ni * 8 + g];
 #pragma unroll
     for (int mi = LO; mi < HI; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
   }
 }
-// runtime (lo, hi) of the LAST block -> the compile-time variants (warp-uniform switch)
-template <int LO>
-__device__ __forceinline__ void slab_mma_chunk_hi(double (&acc)[8][2][2], const double* __restrict__ As,
+// runtime hi of the LAST block -> the compile-time variants (warp-uniform switch)
+template <int LO, int NI>
+__device__ __forceinline__ void slab_mma_chunk_hi(double (&acc)[8][NI][2], const double* __restrict__ As,
                                                   const double* __restrict__ Bs, int lane, int hi) {
   switch (hi) {
-    case 1: slab_mma_chunk<LO, 1>(acc, As, Bs, lane); break;
-    case 2: slab_mma_chunk<LO, 2>(acc, As, Bs, lane); break;
-    case 3: slab_mma_chunk<LO, 3>(acc, As, Bs, lane); break;
-    case 4: slab_mma_chunk<LO, 4>(acc, As, Bs, lane); break;
-    case 5: slab_mma_chunk<LO, 5>(acc, As, Bs, lane); break;
-    case 6: slab_mma_chunk<LO, 6>(acc, As, Bs, lane); break;
-    case 7: slab_mma_chunk<LO, 7>(acc, As, Bs, lane); break;
-    default: slab_mma_chunk<LO, 8>(acc, As, Bs, lane); break;
+    case 1: slab_mma_chunk<LO, 1, NI>(acc, As, Bs, lane); break;
+    case 2: slab_mma_chunk<LO, 2, NI>(acc, As, Bs, lane); break;
+    case 3: slab_mma_chunk<LO, 3, NI>(acc, As, Bs, lane); break;
+    case 4: slab_mma_chunk<LO, 4, NI>(acc, As, Bs, lane); break;
+    case 5: slab_mma_chunk<LO, 5, NI>(acc, As, Bs, lane); break;
+    case 6: slab_mma_chunk<LO, 6, NI>(acc, As, Bs, lane); break;
+    case 7: slab_mma_chunk<LO, 7, NI>(acc, As, Bs, lane); break;
+    default: slab_mma_chunk<LO, 8, NI>(acc, As, Bs, lane); break;
   }
 }
 
-__global__ void __launch_bounds__((SLAB_MAX_WARPS + 1) * 32, 1)
-k_trsm_chi2_slab(csl_program_t p, double* R, int ldr, double* __restrict__ chi2, int nslab, int nw) {
-  extern __shared__ __align__(128) double smem[];
-  double* Aring = smem;                                          // [SLAB_STAGES][CSL_ASZ]
-  double* Wreg = Aring + SLAB_STAGES * CSL_ASZ;                  // [nw][SLAB_WARP_DOUBLES]
-  uint64_t* full = reinterpret_cast<uint64_t*>(Wreg + nw * SLAB_WARP_DOUBLES);
-  uint64_t* empty = full + SLAB_STAGES;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int npad = p.n_pad, nblk = npad / CSL_BM, nct = npad / CSL_KC;
-  const int nact = min(nw, nslab - (int)blockIdx.x * nw);        // consumer warps with a slab
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < SLAB_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, nact); }
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (warp == nw) {
-    // ---------------- producer: the A tiles of every block, in the order every consumer uses them
-    if (lane == 0) {
-      int q = 0;
-      for (int i = 0; i < nblk; ++i) {
-        for (int c = 0; c < 4 * i + 4; ++c, ++q) {
-          const int s = q % SLAB_STAGES;
-          if (q >= SLAB_STAGES) mbar_wait(empty + s, ((q / SLAB_STAGES) - 1) & 1);
-          const double* src = c < 4 * i ? p.LmatT + ((long long)i * nct + c) * CSL_ATILE
-                                        : p.LinvT + ((long long)i * 4 + (c - 4 * i)) * CSL_ATILE;
-          mbar_arrive_expect_tx(full + s, CSL_ATILE * sizeof(double));
-          bulk_g2s(Aring + s * CSL_ASZ, src, CSL_ATILE * sizeof(double), full + s);
-        }
-      }
+// The A-tile sequence of a CTA: block i contributes its 4 i off-diagonal tiles L(i, c) and then the four tiles of
+// inv(L_ii).  Lane 0 of warp 0 keeps the ring filled on the side of its own products (a 17th, producer-only warp
+// would put five warps on one SM sub-partition: 5 x 32 x 112 registers no longer fit its 16 K, and 16 x 128 do).
+struct slab_filler {
+  int next, fi, fc;         // tile index of the next fill and its (block, chunk)
+};
+__device__ __forceinline__ void slab_fill_ahead(slab_filler& f, int q, const csl_program_t& p, double* Aring, uint64_t* full,
+                                                uint64_t* empty) {
+  const int nblk = p.n_pad / CSL_BM, nct = p.n_pad / CSL_KC;
+  // tile q must be on its way before this warp waits for it; tiles up to q + STAGES - 1 are filled when their
+  // stage happens to be free already (probe, no wait)
+  while (f.fi < nblk && f.next <= q + SLAB_STAGES - 1) {
+    const int s = f.next % SLAB_STAGES;
+    if (f.next >= SLAB_STAGES) {
+      const uint32_t par = ((f.next / SLAB_STAGES) - 1) & 1;
+      if (f.next <= q) mbar_wait(empty + s, par);
+      else if (!mbar_test(empty + s, par)) break;
     }
-    return;
+    const double* src = f.fc < 4 * f.fi ? p.LmatT + ((long long)f.fi * nct + f.fc) * CSL_ATILE
+                                        : p.LinvT + ((long long)f.fi * 4 + (f.fc - 4 * f.fi)) * CSL_ATILE;
+    mbar_arrive_expect_tx(full + s, CSL_ATILE * sizeof(double));
+    bulk_g2s(Aring + s * CSL_ASZ, src, CSL_ATILE * sizeof(double), full + s);
+    ++f.next;
+    if (++f.fc == 4 * f.fi + 4) { f.fc = 0; ++f.fi; }
   }
-  if (warp >= nact) return;
-  // ---------------- consumers
+}
+
+// one warp, one slab of 8 NI walkers starting at column c0, all row blocks
+template <int NI, bool FILL>
+__device__ __forceinline__ void slab_consumer(const csl_program_t& p, double* R, int ldr, double* __restrict__ chi2, int c0,
+                                              double* my, double* Aring, uint64_t* full, uint64_t* empty, int lane) {
+  constexpr int LD = slab_ld(NI), STG = CSL_KC * LD;            // doubles of one ring stage = 16 rows of the T tile
   const int g = lane >> 2, t = lane & 3;
-  const int c0 = ((int)blockIdx.x * nw + warp) * 16;
-  double* my = Wreg + warp * SLAB_WARP_DOUBLES;
-  double acc[8][2][2], colsq[2][2][2];
+  const int nblk = p.n_pad / CSL_BM;
+  slab_filler fill;
+  fill.next = 0; fill.fi = 0; fill.fc = 0;
+  // the running sums of squares of a thread are touched once per block: they live in shared memory (element e
+  // of lane l at csq[32 e + l]) so that the accumulators and fragments of the products keep the registers
+  double* csq = my + CSL_BM * LD + lane;
+  double acc[8][NI][2];
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int ni = 0; ni < 2; ++ni) colsq[h][ni][0] = colsq[h][ni][1] = 0.0;
-  // rows 16 c .. of this slab -> ring stage c % 4 (4 pieces of 16 bytes per lane)
+  for (int e = 0; e < 4 * NI; ++e) csq[32 * e] = 0.0;
+  // rows 16 c .. of this slab -> ring stage c % 4 (pieces of 16 bytes: 8 NI per row)
   auto issue = [&](int c) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int piece = lane + 32 * it, row = piece >> 3, q8 = piece & 7;
-      cp_async16(my + (c % SLAB_STAGES) * (CSL_KC * SLAB_LD) + row * SLAB_LD + 2 * q8,
-                 R + (long long)(c * CSL_KC + row) * ldr + c0 + 2 * q8);
+    for (int it = 0; it < 2 * NI; ++it) {
+      const int piece = lane + 32 * it, row = piece / (4 * NI), q8 = piece % (4 * NI);
+      cp_async16(my + (c % SLAB_STAGES) * STG + row * LD + 2 * q8, R + (long long)(c * CSL_KC + row) * ldr + c0 + 2 * q8);
     }
   };
   int q = 0;
@@ -305,13 +310,12 @@ k_trsm_chi2_slab(csl_program_t p, double* R, int ldr, double* __restrict__ chi2,
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     // rows >= n (last block only) are identity rows of L acting on zero rows of R: their 8-row groups are skipped,
     // Y stays zero there
     const int hi = min(8, (p.n - i * CSL_BM + 7) / 8);
     // acc = sum_{j<i} L_ij Y_j.  The B stream is the nup = 4 i chunks of Y rows followed by the FOUR chunks of R_i
-    // itself: nup is a multiple of the ring depth, so R_i chunk c lands in stage c -- rows 16 c .. of the T tile --
-    // and the residual block is in place when the update ends, its load latency hidden behind the last products
+    // itself: nup is a multiple of the ring depth, so R_i chunk c lands in stage c -- rows 16 c .. of the T tile
     const int nup = 4 * i, nall = nup + 4;
 #pragma unroll
     for (int c = 0; c < SLAB_STAGES - 1; ++c) {
@@ -319,14 +323,15 @@ k_trsm_chi2_slab(csl_program_t p, double* R, int ldr, double* __restrict__ chi2,
       cp_async_commit();
     }
     for (int c = 0; c < nup; ++c, ++q) {
-      if (c + SLAB_STAGES - 1 < nall) issue(c + SLAB_STAGES - 1);    // into the stage chunk c-1 has left
-      cp_async_commit();                              // always a group: wait_group counts groups
+      issue(c + SLAB_STAGES - 1);                     // < nall; into the stage chunk c-1 has left
+      cp_async_commit();
       cp_async_wait<SLAB_STAGES - 1>();               // chunk c has landed (this lane's pieces)
       __syncwarp();                                   // ... and every other lane's
       const int s = q % SLAB_STAGES;
+      if (FILL && lane == 0) slab_fill_ahead(fill, q, p, Aring, full, empty);
       mbar_wait(full + s, (q / SLAB_STAGES) & 1);
-      if (hi == 8) slab_mma_chunk<0, 8>(acc, Aring + s * CSL_ASZ, my + (c % SLAB_STAGES) * (CSL_KC * SLAB_LD), lane);
-      else slab_mma_chunk_hi<0>(acc, Aring + s * CSL_ASZ, my + (c % SLAB_STAGES) * (CSL_KC * SLAB_LD), lane, hi);
+      if (hi == 8) slab_mma_chunk<0, 8, NI>(acc, Aring + s * CSL_ASZ, my + (c % SLAB_STAGES) * STG, lane);
+      else slab_mma_chunk_hi<0, NI>(acc, Aring + s * CSL_ASZ, my + (c % SLAB_STAGES) * STG, lane, hi);
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
     }
@@ -338,8 +343,8 @@ k_trsm_chi2_slab(csl_program_t p, double* R, int ldr, double* __restrict__ chi2,
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni) {
-        double2* cell = reinterpret_cast<double2*>(my + (mi * 8 + g) * SLAB_LD + ni * 8 + 2 * t);
+      for (int ni = 0; ni < NI; ++ni) {
+        double2* cell = reinterpret_cast<double2*>(my + (mi * 8 + g) * LD + ni * 8 + 2 * t);
         double2 v = *cell;
         v.x = v.x - acc[mi][ni][0];
         v.y = v.y - acc[mi][ni][1];
@@ -351,33 +356,40 @@ k_trsm_chi2_slab(csl_program_t p, double* R, int ldr, double* __restrict__ chi2,
 #pragma unroll
     for (int c = 0; c < 4; ++c, ++q) {
       const int s = q % SLAB_STAGES;
+      if (FILL && lane == 0) slab_fill_ahead(fill, q, p, Aring, full, empty);
       mbar_wait(full + s, (q / SLAB_STAGES) & 1);
       const double* As = Aring + s * CSL_ASZ;
-      const double* Bs = my + c * (CSL_KC * SLAB_LD);
+      const double* Bs = my + c * STG;
       if (hi == 8) {
-        if (c == 0) slab_mma_chunk<0, 8>(acc, As, Bs, lane);
-        else if (c == 1) slab_mma_chunk<2, 8>(acc, As, Bs, lane);
-        else if (c == 2) slab_mma_chunk<4, 8>(acc, As, Bs, lane);
-        else slab_mma_chunk<6, 8>(acc, As, Bs, lane);
+        if (c == 0) slab_mma_chunk<0, 8, NI>(acc, As, Bs, lane);
+        else if (c == 1) slab_mma_chunk<2, 8, NI>(acc, As, Bs, lane);
+        else if (c == 2) slab_mma_chunk<4, 8, NI>(acc, As, Bs, lane);
+        else slab_mma_chunk<6, 8, NI>(acc, As, Bs, lane);
       } else {                                     // last block: T rows >= 8 hi are zero, so are the chunks past them
-        if (c == 0) slab_mma_chunk_hi<0>(acc, As, Bs, lane, hi);
-        else if (c == 1) slab_mma_chunk_hi<2>(acc, As, Bs, lane, hi);
-        else if (c == 2) slab_mma_chunk_hi<4>(acc, As, Bs, lane, hi);
-        else slab_mma_chunk_hi<6>(acc, As, Bs, lane, hi);
+        if (c == 0) slab_mma_chunk_hi<0, NI>(acc, As, Bs, lane, hi);
+        else if (c == 1) slab_mma_chunk_hi<2, NI>(acc, As, Bs, lane, hi);
+        else if (c == 2) slab_mma_chunk_hi<4, NI>(acc, As, Bs, lane, hi);
+        else slab_mma_chunk_hi<6, NI>(acc, As, Bs, lane, hi);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
     }
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni) {
-        double2 y;
-        y.x = acc[mi][ni][0];
-        y.y = acc[mi][ni][1];
-        *reinterpret_cast<double2*>(R + (long long)(i * CSL_BM + mi * 8 + g) * ldr + c0 + ni * 8 + 2 * t) = y;
-        colsq[mi >> 2][ni][0] = fma(y.x, y.x, colsq[mi >> 2][ni][0]);
-        colsq[mi >> 2][ni][1] = fma(y.y, y.y, colsq[mi >> 2][ni][1]);
+      for (int ni = 0; ni < NI; ++ni) {
+        double s0 = csq[32 * (2 * NI * h + 2 * ni)], s1 = csq[32 * (2 * NI * h + 2 * ni + 1)];
+#pragma unroll
+        for (int mi = 4 * h; mi < 4 * h + 4; ++mi) {
+          double2 y;
+          y.x = acc[mi][ni][0];
+          y.y = acc[mi][ni][1];
+          *reinterpret_cast<double2*>(R + (long long)(i * CSL_BM + mi * 8 + g) * ldr + c0 + ni * 8 + 2 * t) = y;
+          s0 = fma(y.x, y.x, s0);
+          s1 = fma(y.y, y.y, s1);
+        }
+        csq[32 * (2 * NI * h + 2 * ni)] = s0;
+        csq[32 * (2 * NI * h + 2 * ni + 1)] = s1;
       }
     // Y_i is read back by this warp's own cp.async.cg (other lanes) from the next block on.  cp.async.cg reads L2
     // past the L1: a CTA-scope fence is NOT enough (measured: about one launch in five returned a few stale rows);
@@ -386,14 +398,54 @@ k_trsm_chi2_slab(csl_program_t p, double* R, int ldr, double* __restrict__ chi2,
     __syncwarp();
   }
 #pragma unroll
-  for (int ni = 0; ni < 2; ++ni)
+  for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      double v0 = colsq[0][ni][e], v1 = colsq[1][ni][e];
+      double v0 = csq[32 * (2 * ni + e)], v1 = csq[32 * (2 * NI + 2 * ni + e)];
       v0 += shfl_xor_d(v0, 4); v0 += shfl_xor_d(v0, 8); v0 += shfl_xor_d(v0, 16);
       v1 += shfl_xor_d(v1, 4); v1 += shfl_xor_d(v1, 8); v1 += shfl_xor_d(v1, 16);
       if (g == 0) chi2[c0 + ni * 8 + 2 * t + e] = v0 + v1;
     }
+}
+
+// nunit = 8-walker units of the launch, upc = units per CTA (<= 28), k = consumer warps per CTA (<= 16);
+// sep = 1: warp k is a dedicated producer of the A ring (CTAs of fewer than 16 warps), 0: lane 0 of warp 0 feeds it
+__global__ void __launch_bounds__(SLAB_MAX_WARPS * 32, 1)
+k_trsm_chi2_slab(csl_program_t p, double* R, int ldr, double* __restrict__ chi2, int nunit, int upc, int k, int sep) {
+  extern __shared__ __align__(128) double smem[];
+  double* Aring = smem;                                          // [SLAB_STAGES][CSL_ASZ]
+  uint64_t* full = reinterpret_cast<uint64_t*>(Aring + SLAB_STAGES * CSL_ASZ);
+  uint64_t* empty = full + SLAB_STAGES;
+  double* Wreg = reinterpret_cast<double*>(empty + SLAB_STAGES);   // the warps' private regions, wide ones first
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int u0 = (int)blockIdx.x * upc, uh = min(upc, nunit - u0);       // this CTA's units
+  const int nwide = max(0, min(uh - k, k)), nact = min(k, uh - nwide);   // warps 0..nwide-1: 16 walkers; ..nact-1: 8
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < SLAB_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, nact); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (sep && warp == k) {
+    if (lane == 0) {
+      slab_filler fill;
+      fill.next = 0; fill.fi = 0; fill.fc = 0;
+      const int nblk = p.n_pad / CSL_BM;
+      while (fill.fi < nblk) slab_fill_ahead(fill, fill.next, p, Aring, full, empty);   // always blocking: next <= q
+    }
+    return;
+  }
+  if (warp >= nact) return;
+  const int c0 = warp < nwide ? (u0 + 2 * warp) * 8 : (u0 + 2 * nwide + (warp - nwide)) * 8;
+  double* my = warp < nwide ? Wreg + warp * slab_region(2) : Wreg + nwide * slab_region(2) + (warp - nwide) * slab_region(1);
+  if (warp == 0 && !sep) {                                       // warp 0 also feeds the A ring
+    if (nwide > 0) slab_consumer<2, true>(p, R, ldr, chi2, c0, my, Aring, full, empty, lane);
+    else slab_consumer<1, true>(p, R, ldr, chi2, c0, my, Aring, full, empty, lane);
+  } else if (warp < nwide) {
+    slab_consumer<2, false>(p, R, ldr, chi2, c0, my, Aring, full, empty, lane);
+  } else {
+    slab_consumer<1, false>(p, R, ldr, chi2, c0, my, Aring, full, empty, lane);
+  }
 }
 
 // ---- explicit-inverse mode ---------------------------------------------------------------------------
@@ -641,16 +693,28 @@ int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi
   if (shape < 0) shape = (p->LmatT && p->LinvT) ? 4 : 2;
   if (shape == 4) {
     CSL_REQUIRE(p->LmatT && p->LinvT, "csl_chi2: the slab kernel needs the tile-major factor tables");
-    // slabs per CTA: as few rounds of (SMs x 14 slabs) as the launch needs, the slabs spread evenly over them
-    const int nslab = W / 16, sms = csl_sm_count();
-    const int rounds = (nslab + sms * SLAB_MAX_WARPS - 1) / (sms * SLAB_MAX_WARPS);
-    int nw = (nslab + sms * rounds - 1) / (sms * rounds);
-    nw = nw < 1 ? 1 : (nw > SLAB_MAX_WARPS ? SLAB_MAX_WARPS : nw);
-    const int grid = (nslab + nw - 1) / nw;
-    const size_t smem4 = (size_t)(SLAB_STAGES * CSL_ASZ + nw * SLAB_WARP_DOUBLES) * sizeof(double) + 2 * SLAB_STAGES * sizeof(uint64_t);
+    // units of 8 walkers: as few rounds of (SMs x 28 units) as the launch needs, the units spread evenly over the
+    // CTAs; k consumer warps: 16 when a CTA carries 16 units or more (wide + narrow slabs), else the multiple of 4
+    // that holds them as wide slabs
+    const int nunit = W / 8, sms = csl_sm_count();
+    const int rounds = (nunit + sms * SLAB_MAX_UNITS - 1) / (sms * SLAB_MAX_UNITS);
+    int upc = (nunit + sms * rounds - 1) / (sms * rounds);
+    upc = upc < 1 ? 1 : (upc > SLAB_MAX_UNITS ? SLAB_MAX_UNITS : upc);
+    // narrow (8-walker) slabs while a warp per unit fits: twice the warps of the wide cut hide each other's latency
+    int k = upc >= SLAB_MAX_WARPS ? SLAB_MAX_WARPS : upc;      // below 16 units: one narrow warp per unit + the producer warp
+    if (csl_option_value("slab_warps") > 0) {            // sweeps: all-wide CTAs of this many warps
+      k = csl_option_value("slab_warps");
+      k = k > SLAB_MAX_WARPS ? SLAB_MAX_WARPS : k;
+      upc = 2 * k > SLAB_MAX_UNITS ? SLAB_MAX_UNITS : 2 * k;
+    }
+    const int sep = k < SLAB_MAX_WARPS ? 1 : 0;          // a 17th warp does not fit the register file: fold the producer
+    const int grid = (nunit + upc - 1) / upc;
+    const int nwide = upc - k > 0 ? (upc - k < k ? upc - k : k) : 0, nnarrow = (upc - nwide < k ? upc - nwide : k) - nwide;
+    const size_t smem4 = (size_t)(SLAB_STAGES * CSL_ASZ + nwide * slab_region(2) + nnarrow * slab_region(1)) * sizeof(double) +
+                         2 * SLAB_STAGES * sizeof(uint64_t);
     cudaError_t e = cudaFuncSetAttribute(k_trsm_chi2_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
     if (e != cudaSuccess) return csl_fail((int)e, cudaGetErrorString(e));
-    k_trsm_chi2_slab<<<grid, (nw + 1) * 32, smem4, s>>>(*p, R, ldr, chi2, nslab, nw);
+    k_trsm_chi2_slab<<<grid, (k + sep) * 32, smem4, s>>>(*p, R, ldr, chi2, nunit, upc, k, sep);
     return csl_check_launch("k_trsm_chi2_slab");
   }
   if (shape != 0) {

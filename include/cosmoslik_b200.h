@@ -388,6 +388,14 @@ int csl_peer_barrier(const uint64_t* flag_ptrs, int rank, int world, uint64_t ep
 /* wait only: returns (stream ordered) once every peer has announced `epoch` */
 int csl_peer_wait(const uint64_t* flag_ptrs, int rank, int world, uint64_t epoch, uint32_t* sync, void* stream);
 
+/* Host-released gate on `stream`: a one-thread kernel that spins until *host_flag (an int32 in PINNED host memory,
+ * read through its unified address) becomes non-zero, or timeout_s seconds have passed.  Work enqueued behind it
+ * starts the moment the host writes the flag, with all of its launches already queued -- what a sampler run of
+ * thousands of steps looks like to the device anyway (the host enqueues a step several times faster than the
+ * device runs it).  bench.py opens short timed regions this way so that a host hiccup at the start of a 20-step
+ * region is not booked as step time; nothing in the samplers uses it.  (No reference counterpart.) */
+int csl_host_gate(const int32_t* host_flag, double timeout_s, void* stream);
+
 /* wrapper bookkeeping of samplers/emcee.py:70-88 after a full step: a walker that did not move
  * gains weight; one that moved (or any walker on the last step) emits (lnl_next, weight, x_old) and its
  * pos_old row is refreshed to pos_new (ready for the next step). */

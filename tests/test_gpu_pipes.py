@@ -21,7 +21,7 @@ def torch():
 
 def set_opts(**kw):
     lib = L.lib()
-    for k in ("pipe", "trigemm_rows", "trigemm_stages", "trsm_shape", "bin_variant", "bin_split"):
+    for k in ("pipe", "trigemm_rows", "trigemm_stages", "trsm_shape", "bin_variant", "bin_split", "slab_warps"):
         L.check(lib.csl_set_option(k.encode(), int(kw.get(k, -1))))
 
 
@@ -59,7 +59,8 @@ def test_chi2_bulk_pipeline_is_bitwise_the_cp_async_one(torch, kind, mode):
         # against LAPACK: chi2 = r^T C^-1 r
         want = np.einsum("iw,iw->w", R0[:prog.n], np.linalg.solve(prob["cov"], R0[:prog.n]))
         np.testing.assert_allclose(ref, want, rtol=1e-10)
-        variants = [dict(pipe=1), dict(trsm_shape=1), dict(trsm_shape=2), dict(trsm_shape=3)]
+        variants = [dict(pipe=1), dict(trsm_shape=1), dict(trsm_shape=2), dict(trsm_shape=3), dict(trsm_shape=4),
+                    dict(trsm_shape=4, slab_warps=1), dict(trsm_shape=4, slab_warps=5), dict(trsm_shape=4, slab_warps=14)]
         if mode == "inverse":
             variants += [dict(pipe=p, trigemm_rows=r, trigemm_stages=s) for p in (0, 1) for r in (32, 64) for s in (3, 4)]
         for v in variants:
@@ -115,3 +116,21 @@ def test_binning_warp_specialised_cluster_kernel(torch, spt_data, kind):
     a = prog.lnl(Xd).cpu().numpy()
     b = np.concatenate([prog.lnl(Xd[:130].contiguous()).cpu().numpy(), prog.lnl(Xd[130:].contiguous()).cpu().numpy()])
     np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("W", [128, 384, 2048, 4224, 33152 + 128])
+def test_slab_substitution_kernel_over_launch_widths(torch, W):
+    """k_trsm_chi2_slab (one warp per 16- / 8-walker slab, the default substitution kernel): CTAs of wide slabs only,
+    of wide + narrow slabs (16 consumer warps), a ragged last CTA and a second round of CTAs -- chi^2 and the
+    Y = L^-1 R it leaves in place are bit for bit those of the round-1 kernel; run twice (the kernel reads rows it
+    wrote itself: a stale read would differ between runs)"""
+    prob = synthetic.planck_lite_problem(0)
+    prog = Slik(synthetic.build_script(PRODUCT, prob)()).program(chi2_mode="trsm")
+    g = torch.Generator(device="cuda"); g.manual_seed(W)
+    d = torch.zeros((prog.n_pad, W), dtype=torch.float64, device="cuda")
+    d[:prog.n] = torch.randn((prog.n, W), dtype=torch.float64, device="cuda", generator=g)
+    ref, Rref = chi2_of(torch, prog, d, trsm_shape=0)
+    for rep in range(2):
+        got, Rgot = chi2_of(torch, prog, d)                  # the default shape
+        np.testing.assert_array_equal(got, ref)
+        np.testing.assert_array_equal(Rgot, Rref)

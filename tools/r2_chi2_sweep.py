@@ -27,7 +27,7 @@ def program(kind, chi2_mode="auto"):
 
 
 def set_opts(**kw):
-    for k in ("pipe", "trigemm_rows", "trigemm_stages", "trigemm_group", "trsm_shape"):
+    for k in ("pipe", "trigemm_rows", "trigemm_stages", "trigemm_group", "trsm_shape", "slab_warps"):
         L.check(lib.csl_set_option(k.encode(), int(kw.get(k, -1))))
 
 
@@ -77,7 +77,7 @@ def main():
                              dict(pipe=1, trigemm_rows=64, trigemm_stages=4),
                              dict(pipe=1, trigemm_rows=32, trigemm_stages=3), dict(pipe=1, trigemm_rows=32, trigemm_stages=4)]
             else:
-                variants = [dict(trsm_shape=0), dict(trsm_shape=2)] + [dict(trsm_shape=4)] * int(os.environ.get('SLAB_REPEATS', '2'))
+                variants = [dict(trsm_shape=0), dict(trsm_shape=2), dict(trsm_shape=4, slab_warps=14)] + [dict(trsm_shape=4)] * int(os.environ.get('SLAB_REPEATS', '2'))
             for v in variants:
                 try:
                     ms, chi2 = time_chi2(prog, W, **v)

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-export SLAB_REPEATS=12
+export SLAB_REPEATS=6
 timeout 900 python tools/r2_chi2_sweep.py planck trsm > gpurun_out/chi2_sweep_slab.jsonl 2> gpurun_out/chi2_sweep_slab.err
 timeout 600 python tools/r2_chi2_sweep.py spt trsm >> gpurun_out/chi2_sweep_slab.jsonl 2>> gpurun_out/chi2_sweep_slab.err
 tail -3 gpurun_out/chi2_sweep_slab.err
