@@ -373,7 +373,7 @@ def measure_stretch(args, prob, k_total, instrument=True, e2e=True):
     # starts with an empty queue, and one host stall in its first steps (8 processes + their NVML samplers on 16
     # cores) put ~1 ms into it: 0.329 ms per step at 20 steps against 0.281 at 200 (8 GPUs, 8192 walkers each).
     from cosmoslik_b200 import _lib as L
-    nlaunch = args.steps * (2 * (2 + int(prog.meta.get("nclass", 0)) + int(prog.meta.get("nsegclass", 0)) + 1) + 2)
+    nlaunch = args.steps * (2 * (2 + int(L.lib().csl_bin_residual_launches(prog.struct)) + 1) + 2)
     use_gate = (not os.environ.get("CSL_BENCH_NO_GATE")) and nlaunch <= 600
     gate = torch.zeros(1, dtype=torch.int32).pin_memory()
     def open_region():
@@ -408,7 +408,7 @@ def measure_stretch(args, prob, k_total, instrument=True, e2e=True):
            "acceptance": smp.stats["accepted"] / float(smp.stats["evals"]),
            "host_enqueue_ms_per_step": smp.stats.get("host_ms_per_step"), "exchange": smp.stats.get("exchange"),
            "clocks": clk.summary()}
-    nbin = int(prog.meta.get("nclass", 0)) + int(prog.meta.get("nsegclass", 0))
+    nbin = int(L.lib().csl_bin_residual_launches(prog.struct))       # launches of the binning stage
     fused = os.environ.get("CSL_NO_FUSE") is None and prog.meta["resid_mode"] == 1
     # my kernels per stretch step in the native loop: per half-update the fused propose+prepare(+wait), one
     # binning launch per spectrum class, chi2, the fused combine+accept(+rows+publish+signal)

@@ -102,6 +102,7 @@ SIGNATURES = {
     "csl_peer_barrier": (_int, [_vp, _int, _int, _u64, _vp, _vp]),
     "csl_peer_wait": (_int, [_vp, _int, _int, _u64, _vp, _vp]),
     "csl_host_gate": (_int, [_vp, _dbl, _vp]),
+    "csl_bin_residual_launches": (_int, [_P]),
     "csl_sizeof_mh": (_int, []),
     "csl_mh_run": (_int, [_P, C.POINTER(MHState), _int, _vp]),
     "csl_mh_graph_create": (_int, [_P, C.POINTER(MHState), _int, C.POINTER(C.c_void_p)]),

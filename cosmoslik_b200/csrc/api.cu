@@ -78,6 +78,7 @@ static csl_option g_options[] = {
     {"bin_split", "CSL_BIN_SPLIT", -1, false},          // ell splits of k_bin_residual (0 = by launch size)
     {"bin_variant", "CSL_BIN_VARIANT", -1, false},      // k_bin_residual variant
     {"sab_threads", "CSL_SAB_THREADS", -1, false},      // CTA size of k_stretch_combine_accept
+    {"seg_pair", "CSL_SEG_PAIR", -1, false},            // k_bin_segsum_pair: 0 = one launch per class
     {"seg_small", "CSL_SEG_SMALL", -1, false},          // k_bin_segsum: 1 walker per thread below this many walkers
 };
 static csl_option* find_option(const char* name) {

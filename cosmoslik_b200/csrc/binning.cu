@@ -624,15 +624,14 @@ __device__ __forceinline__ void seg_cols(const double* __restrict__ row, int nco
   for (; c < ncol; ++c, row += RS) column(row, l + c);
 }
 
+// one CTA's work: group `gy` of the class that starts at bin `bin0`, SEG_WPT * SEG_TPB walkers from blockIdx.x on;
+// srow / sg are the CTA's staging area and group record (shared memory, owned by the kernel)
 template <int NT, int NP, int SEG_WPT>
-__global__ void __launch_bounds__(SEG_TPB, SEG_MINB)
-k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restrict__ coef, int ldc,
-             double* __restrict__ R, int ldr) {
+__device__ __forceinline__ void seg_group(const csl_program_t& p, int bin0, int gy, int W, const double* __restrict__ coef,
+                                          int ldc, double* __restrict__ R, int ldr, double* srow, int32_t* sg) {
   constexpr int RS = seg_row_stride(NT, NP);         // > 0: the host never emits an empty class
   constexpr int CAP = SEG_SMEM_DOUBLES / (RS > 0 ? RS : 1);
   constexpr int NPX = NP > 0 ? NP : 1, NTX = NT > 0 ? NT : 1;
-  __shared__ __align__(16) double srow[SEG_SMEM_DOUBLES];
-  __shared__ __align__(16) int32_t sg[CSL_GRP_STRIDE];          // the group record (host-built, CSL_G_*)
   const int tid = threadIdx.x;
   int w[SEG_WPT];
   bool live_w[SEG_WPT];
@@ -643,7 +642,7 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
     if (!live_w[j]) w[j] = W - 1;             // replay a valid walker, never stored
   }
   // bin records come in whole groups and classes start on a group boundary: group = bin0 / 8 + blockIdx.y
-  const int32_t* __restrict__ grec = p.grp_tab + (long long)(bin0 / CSL_SEG_GROUP + blockIdx.y) * CSL_GRP_STRIDE;
+  const int32_t* __restrict__ grec = p.grp_tab + (long long)(bin0 / CSL_SEG_GROUP + gy) * CSL_GRP_STRIDE;
   if (tid < CSL_GRP_STRIDE / 4)
     reinterpret_cast<int4*>(sg)[tid] = __ldg(reinterpret_cast<const int4*>(grec) + tid);
   const int32_t* spec = p.spec_tab + (long long)__ldg(grec + CSL_G_SPEC) * CSL_SPEC_STRIDE;   // one spectrum per group
@@ -775,6 +774,67 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
   }
 }
 
+template <int NT, int NP, int SEG_WPT>
+__global__ void __launch_bounds__(SEG_TPB, SEG_MINB)
+k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restrict__ coef, int ldc,
+             double* __restrict__ R, int ldr) {
+  __shared__ __align__(16) double srow[SEG_SMEM_DOUBLES];
+  __shared__ __align__(16) int32_t sg[CSL_GRP_STRIDE];          // the group record (host-built, CSL_G_*)
+  seg_group<NT, NP, SEG_WPT>(p, bin0, (int)blockIdx.y, W, coef, ldc, R, ldr, srow, sg);
+}
+
+// TWO spectrum classes in one launch (grid.y = groups of class A, then groups of class B): the classes write
+// different rows of R and read the same coefficients, so nothing orders them; as two launches the second waited
+// for the first one's last CTAs (a few us per half-step, which is several per cent of a 4096-walker launch).
+// Instantiated for the class pairs that occur (launch_seg_pair); any other pair takes the two launches.
+template <int NTA, int NPA, int NTB, int NPB, int SEG_WPT>
+__global__ void __launch_bounds__(SEG_TPB, SEG_MINB)
+k_bin_segsum_pair(csl_program_t p, int bin0a, int ngrpa, int bin0b, int W, const double* __restrict__ coef, int ldc,
+                  double* __restrict__ R, int ldr) {
+  __shared__ __align__(16) double srow[SEG_SMEM_DOUBLES];
+  __shared__ __align__(16) int32_t sg[CSL_GRP_STRIDE];
+  if ((int)blockIdx.y < ngrpa) seg_group<NTA, NPA, SEG_WPT>(p, bin0a, (int)blockIdx.y, W, coef, ldc, R, ldr, srow, sg);
+  else seg_group<NTB, NPB, SEG_WPT>(p, bin0b, (int)blockIdx.y - ngrpa, W, coef, ldc, R, ldr, srow, sg);
+}
+
+static int seg_small_limit() {
+  int small = csl_option_value("seg_small");
+  return small < 0 ? 8192 : small;
+}
+
+template <int NTA, int NPA, int NTB, int NPB>
+static int launch_seg_pair(const csl_program_t* p, const int32_t* ka, const int32_t* kb, int W, const double* coef,
+                           int ldc, double* R, int ldr, cudaStream_t s) {
+  const int nga = (ka[3] + CSL_SEG_GROUP - 1) / CSL_SEG_GROUP, ngb = (kb[3] + CSL_SEG_GROUP - 1) / CSL_SEG_GROUP;
+  if (W <= seg_small_limit()) {
+    dim3 grid((W + SEG_TPB - 1) / SEG_TPB, nga + ngb);
+    k_bin_segsum_pair<NTA, NPA, NTB, NPB, 1><<<grid, SEG_TPB, 0, s>>>(*p, ka[2], nga, kb[2], W, coef, ldc, R, ldr);
+  } else {
+    dim3 grid((W + 2 * SEG_TPB - 1) / (2 * SEG_TPB), nga + ngb);
+    k_bin_segsum_pair<NTA, NPA, NTB, NPB, 2><<<grid, SEG_TPB, 0, s>>>(*p, ka[2], nga, kb[2], W, coef, ldc, R, ldr);
+  }
+  return 0;
+}
+
+// the class pairs with a fused launch: (template terms, power laws) of the first and the second class
+static bool dispatch_seg_pair(const csl_program_t* p, const int32_t* ka, const int32_t* kb, int W, const double* coef,
+                              int ldc, double* R, int ldr, cudaStream_t s) {
+  if (csl_option_value("seg_pair") == 0) return false;      // option / CSL_SEG_PAIR=0: one launch per class
+#define CSL_SEG_PAIR(A, B, C, D)                                                                  \
+  if (ka[0] == A && ka[1] == B && kb[0] == C && kb[1] == D) {                                     \
+    launch_seg_pair<A, B, C, D>(p, ka, kb, W, coef, ldc, R, ldr, s);                              \
+    return true;                                                                                  \
+  }
+  CSL_SEG_PAIR(3, 2, 1, 1)      // TT with two power laws + TE / EE with one (plik-lite-like TT/TE/EE)
+  CSL_SEG_PAIR(1, 1, 3, 2)
+  CSL_SEG_PAIR(2, 1, 1, 1)
+  CSL_SEG_PAIR(1, 1, 2, 1)
+  CSL_SEG_PAIR(4, 2, 2, 1)
+  CSL_SEG_PAIR(2, 1, 4, 2)
+#undef CSL_SEG_PAIR
+  return false;
+}
+
 template <int NT, int NP>
 static int launch_seg(const csl_program_t* p, int bin0, int nbins, int W, const double* coef, int ldc,
                       double* R, int ldr, cudaStream_t s) {
@@ -869,6 +929,25 @@ static int dispatch_class(int nt, int np, const csl_program_t* p, int tile0, int
   }
 }
 
+// kernel launches one csl_bin_residual call makes for this program (bench.py counts its launches with it)
+extern "C" int csl_bin_residual_launches(const csl_program_t* p) {
+  if (!p) return 0;
+  int n = p->nclass;
+  const bool off = csl_option_value("seg_pair") == 0;
+  for (int c = 0; c < p->nsegclass; ++c) {
+    ++n;
+    if (!off && c + 1 < p->nsegclass) {
+      const int32_t* a = p->segcls[c];
+      const int32_t* b = p->segcls[c + 1];
+      const int key[4] = {a[0], a[1], b[0], b[1]};
+      static const int pairs[6][4] = {{3, 2, 1, 1}, {1, 1, 3, 2}, {2, 1, 1, 1}, {1, 1, 2, 1}, {4, 2, 2, 1}, {2, 1, 4, 2}};
+      for (const auto& q : pairs)
+        if (q[0] == key[0] && q[1] == key[1] && q[2] == key[2] && q[3] == key[3]) { ++c; break; }
+    }
+  }
+  return n;
+}
+
 extern "C" int csl_bin_residual(const csl_program_t* p, int W, const double* coef, int ldc, double* R, int ldr,
                                 void* stream) {
   CSL_REQUIRE(p && coef && R, "csl_bin_residual: null argument");
@@ -900,6 +979,10 @@ extern "C" int csl_bin_residual(const csl_program_t* p, int W, const double* coe
   for (int c = 0; c < p->nsegclass; ++c) {
     const int32_t* k = p->segcls[c];
     CSL_REQUIRE(k[0] + 2 * k[1] > 0 && p->bin_tab && p->grp_tab, "csl_bin_residual: empty segmented class");
+    if (c + 1 < p->nsegclass && dispatch_seg_pair(p, k, p->segcls[c + 1], W, coef, ldc, R, ldr, s)) {
+      ++c;                       // both classes went out in one launch
+      continue;
+    }
     int rc = dispatch_seg(k[0], k[1], p, k[2], k[3], W, coef, ldc, R, ldr, s);
     if (rc) return rc;
   }

@@ -527,9 +527,18 @@ k_stretch_combine_accept(int Ns, int nd, double* __restrict__ s, double* __restr
       // step once its half is updated: unmoved -> weight + 1; moved (or last step) -> emit (lnl_next, weight, x_old).
       // k_emcee_rows compares the walker's previous position with the new one; here the previous position is s
       // itself (not yet overwritten: phase 2 below comes after a CTA barrier) and the new one is q if accepted.
+      // (all components are loaded, four at a time: a short-circuit `&&` chained nd dependent L2 round trips)
       bool same = true;
       if (acc)
-        for (int d = 0; d < nd; ++d) same = same && (q[(long long)k * nd + d] == s[(long long)k * nd + d]);
+        for (int d0 = 0; d0 < nd; d0 += 4) {
+          double a[4], b[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (d0 + u < nd) { a[u] = q[(long long)k * nd + d0 + u]; b[u] = s[(long long)k * nd + d0 + u]; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (d0 + u < nd) same &= (a[u] == b[u]);
+        }
       const double wt = fr.weight[k];
       if (same && !fr.last_step) {
         fr.weight[k] = wt + 1.0;
@@ -539,7 +548,15 @@ k_stretch_combine_accept(int Ns, int nd, double* __restrict__ s, double* __restr
           double* r = fr.rows + ((long long)k * fr.cap + slot) * (2 + nd);
           r[0] = acc ? lq : -lnp0;
           r[1] = wt;
-          for (int d = 0; d < nd; ++d) r[2 + d] = s[(long long)k * nd + d];
+          for (int d0 = 0; d0 < nd; d0 += 4) {
+            double a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (d0 + u < nd) a[u] = s[(long long)k * nd + d0 + u];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (d0 + u < nd) r[2 + d0 + u] = a[u];
+          }
         }
         fr.nrows[k] = slot + 1;                 // counts past cap signal overflow to the host
         fr.weight[k] = 1.0;

@@ -203,6 +203,9 @@ int csl_eval_prepare(const csl_program_t* p, int W, const double* x, double* coe
  * builds every cl[l] exactly once.  W must be a multiple of CSL_BN (pad with copies of a valid walker). */
 int csl_bin_residual(const csl_program_t* p, int W, const double* coef, int ldc, double* R, int ldr,
                      void* stream);
+/* number of kernel launches one csl_bin_residual call makes for this program (one per spectrum class; two
+ * segmented-sum classes whose pair has a fused kernel go out as one launch).  No reference counterpart. */
+int csl_bin_residual_launches(const csl_program_t* p);
 
 /* resid_mode 2: R[i, w] = coef[direct_coef[i], w] - data[i] (zero rows up to n_pad). */
 int csl_direct_residual(const csl_program_t* p, int W, const double* coef, int ldc, double* R, int ldr,

@@ -21,7 +21,7 @@ def torch():
 
 def set_opts(**kw):
     lib = L.lib()
-    for k in ("pipe", "trigemm_rows", "trigemm_stages", "trsm_shape", "bin_variant", "bin_split", "slab_warps"):
+    for k in ("pipe", "trigemm_rows", "trigemm_stages", "trsm_shape", "bin_variant", "bin_split", "slab_warps", "seg_pair", "seg_small"):
         L.check(lib.csl_set_option(k.encode(), int(kw.get(k, -1))))
 
 
@@ -134,3 +134,24 @@ def test_slab_substitution_kernel_over_launch_widths(torch, W):
         got, Rgot = chi2_of(torch, prog, d)                  # the default shape
         np.testing.assert_array_equal(got, ref)
         np.testing.assert_array_equal(Rgot, Rref)
+
+
+def test_two_segmented_sum_classes_in_one_launch(torch):
+    """k_bin_segsum_pair (TT and TE / EE classes of the plik-lite-like problem in one grid) against one launch per class:
+    the same bits, with one and with two walkers per thread, ragged walker counts"""
+    prob = synthetic.planck_lite_problem(0)
+    slik = Slik(synthetic.build_script(PRODUCT, prob)())
+    prog = slik.program()
+    assert prog.meta["nsegclass"] == 2 and prog.meta["nclass"] == 0
+    lib = L.lib()
+    names = sorted(prob["truth"])
+    rs = np.random.RandomState(5)
+    for W, small in ((300, -1), (1000, 0), (9000, -1)):
+        X = np.array([prob["truth"][k] for k in names]) + np.array([prob["scales"][k] for k in names]) * rs.standard_normal((W, len(names)))
+        Xd = torch.from_numpy(np.ascontiguousarray(X)).cuda()
+        set_opts(seg_pair=0, seg_small=small)
+        assert lib.csl_bin_residual_launches(prog.struct) == 2
+        ref = prog.lnl(Xd).cpu().numpy()
+        set_opts(seg_small=small)
+        assert lib.csl_bin_residual_launches(prog.struct) == 1
+        np.testing.assert_array_equal(prog.lnl(Xd).cpu().numpy(), ref)

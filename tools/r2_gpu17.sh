@@ -1,0 +1,21 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_multi.py > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+for w in 8192 65536; do
+  for pair in 0 1; do
+    CSL_SEG_PAIR=$pair timeout 300 python bench.py --steps 50 --warmup 5 --walkers $w --secondary none --no-cpu-baseline > gpurun_out/bench_pair${pair}_w$w.json 2> gpurun_out/bench_pair${pair}_w$w.err
+    python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_pair${pair}_w$w.json'))
+print('walkers $w SEG_PAIR=$pair', d['ms_per_step'], d['value'], d['acceptance'], d['gpu_launches'], {k:round(v['ms_per_launch'],4) for k,v in d['roofline']['kernels'].items()})
+PY
+  done
+done
+timeout 600 python tools/r2_chi2_sweep.py planck trsm > gpurun_out/chi2_sweep_slab.jsonl 2> gpurun_out/chi2_sweep_slab.err
+timeout 600 python tools/r2_chi2_sweep.py spt trsm >> gpurun_out/chi2_sweep_slab.jsonl 2>> gpurun_out/chi2_sweep_slab.err
+python - <<'PY'
+import json
+for ln in open('gpurun_out/chi2_sweep_slab.jsonl'):
+    d=json.loads(ln)
+    if d.get('variant')=={'trsm_shape':4}: print(d.get('kind'), d.get('W'), d.get('ms'), d.get('frac'), d.get('bitwise'))
+PY

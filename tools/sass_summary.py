@@ -19,13 +19,13 @@ for ln in out.splitlines():
         if pat in cur:
             funcs[cur] = []
         continue
-    if cur in funcs and re.search(r"/\*[0-9a-f]{4}\*/", ln):
+    if cur in funcs and re.search(r"/\*[0-9a-f]{4,6}\*/", ln):
         funcs[cur].append(ln)
 for name, lines in funcs.items():
     dem = subprocess.run(["cu++filt", name], capture_output=True, text=True).stdout.strip() or name
     ops = collections.Counter()
     for ln in lines:
-        m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", ln)
+        m = re.search(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", ln)
         if m:
             ops[m.group(1)] += 1
     print("# %s" % dem)
