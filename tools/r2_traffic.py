@@ -38,8 +38,9 @@ def main():
                "walkers_per_launch": walkers,
                "dram_bytes_per_launch": dram_bytes(os.path.join(ROOT, "profiles", "r2_ncu_full_k_bin_segsum.txt")),
                "algorithmic_bytes_per_launch": npad * walkers * 8,
-               "source": "profiles/r2_ncu_full_k_bin_segsum.txt (ONE of the two class launches of a half-step; "
-                         "algorithmic = R written once over both, 640 x 32768 x 8 B)"}}
+               "source": "profiles/r2_ncu_full_k_bin_segsum.txt (k_bin_segsum_pair: both classes of a half-step in one "
+                         "launch; algorithmic = R written once, 640 x 32768 x 8 B -- part of it is still in L2 when "
+                         "the launch ends, so the capture counts fewer DRAM bytes than that)"}}
     with open(os.path.join(ROOT, "profiles", "r2_traffic.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out, indent=1))
