@@ -208,7 +208,7 @@ k_trsm_chi2_v2(csl_program_t p, double* R, int ldr, double* __restrict__ chi2) {
 // the units are spread evenly over the CTAs; a CTA of 16 consumer warps gives its first (units - 16) warps 16
 // walkers and the others 8, so that at 28 units every SM sub-partition (warps w, w+4, w+8, w+12) carries 3 wide
 // and 1 narrow slab = 7 units: 32 768 walkers = 4096 units = 147 CTAs x 28.  (14 wide warps per CTA left two
-// sub-partitions with 4 slabs and two with 3 -- 0.461 ms against 0.xxx; 128-walker tiles, k_trsm_chi2_v2, left 40 of
+// sub-partitions with 4 slabs and two with 3 -- 0.461 ms against 0.438; 128-walker tiles, k_trsm_chi2_v2, left 40 of
 // 148 SMs with half the work of the others -- 0.598 ms.)
 // Per output element the DMMA sequence, T = R - acc and the order of the sums of squares (two partial sums per
 // column: rows 0..31 and 32..63 of every block, exactly the two warp rows of k_trsm_chi2) are those of the

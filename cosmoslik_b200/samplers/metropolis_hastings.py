@@ -242,7 +242,10 @@ class metropolis_hastings(SlikSampler):
                 self._print_block(lo, mine)
             return mine
 
+        hooks = getattr(self, "hooks", None) or {}      # bench.py: callables run right before the first / after the last block
         try:
+            if "start" in hooks:
+                hooks["start"]()
             while done < steps:
                 nb = min(S, steps - done)
                 t0 = time.perf_counter()
@@ -305,6 +308,8 @@ class metropolis_hastings(SlikSampler):
                         if emit and out is not None:
                             yield out
                     pending = ticket
+            if "end" in hooks:
+                hooks["end"]()
             if pending is not None:
                 out = hand_over(pending)
                 pending = None
