@@ -374,9 +374,9 @@ def measure_stretch(args, prob, k_total, instrument=True, e2e=True):
     # Short regions (K steps x 10 launches that fit the launch queue) are PRE-QUEUED: a host-released gate kernel
     # holds the stream while the host enqueues the barrier, the first event, all K steps and the last event, and
     # is opened by the host afterwards.  A sampler run of thousands of steps looks like that to the device anyway
-    # (the host enqueues a step ~8x faster than the device runs it); without the gate a 20-step region of 6-26 ms
-    # starts with an empty queue, and one host stall in its first steps (8 processes + their NVML samplers on 16
-    # cores) put ~1 ms into it: 0.329 ms per step at 20 steps against 0.281 at 200 (8 GPUs, 8192 walkers each).
+    # (the host enqueues a step ~8x faster than the device runs it).  Insurance against a host stall in the first
+    # steps of a 5-26 ms region (8 processes + their NVML samplers on 16 cores), not a speed-up: gated and ungated
+    # 20-step regions agree within 0.6 % at 1, 2 and 8 GPUs (profiles/r2_gate_ab.json).
     from cosmoslik_b200 import _lib as L
     nlaunch = args.steps * (2 * (2 + int(L.lib().csl_bin_residual_launches(prog.struct)) + 1) + 2)
     use_gate = (not os.environ.get("CSL_BENCH_NO_GATE")) and nlaunch <= 600
