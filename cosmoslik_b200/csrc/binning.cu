@@ -788,7 +788,7 @@ k_bin_segsum(csl_program_t p, int bin0, int nbins, int W, const double* __restri
 // for the first one's last CTAs (a few us per half-step, which is several per cent of a 4096-walker launch).
 // Instantiated for the class pairs that occur (launch_seg_pair); any other pair takes the two launches.
 template <int NTA, int NPA, int NTB, int NPB, int SEG_WPT>
-__global__ void __launch_bounds__(SEG_TPB, SEG_MINB)
+__global__ void __launch_bounds__(SEG_TPB, 5)          // <= 96 registers: five CTAs per SM like the single-class kernels (98 gave four)
 k_bin_segsum_pair(csl_program_t p, int bin0a, int ngrpa, int bin0b, int W, const double* __restrict__ coef, int ldc,
                   double* __restrict__ R, int ldr) {
   __shared__ __align__(16) double srow[SEG_SMEM_DOUBLES];
