@@ -27,8 +27,6 @@ def main():
     walkers = 32768
     n, npad = 613, 640
     out = {"source_digest": bench.kernel_source_digest(),
-           "note": "captures taken by tools/r2_final_n1.sh at commit 31668fd; the kernel sources stamped here differ "
-                   "from that commit by one comment line in chi2.cu",
            "k_trigemm_chi2": {
                "walkers_per_launch": walkers,
                "dram_bytes_per_launch": dram_bytes(os.path.join(ROOT, "profiles", "r2_ncu_full_k_trigemm_chi2.txt")),
