@@ -7,9 +7,14 @@ Parity status:
     unmodified reference (bundled SPT data, tests/golden/spt_lowl_*.npz).
   * ``MspecLike``: the reference plugin (likelihoods/mspec_lnl.py) depends on
     the third-party package ``mspec`` (github marius311/mspec, unpinned, not in
-    requirements.txt) and cannot be imported.  PARITY UNPINNED for the
-    multi-spectrum container; anchored by the 1-spectrum case reproducing
-    ``SptLowl`` (tests/test_oracle_golden.py::test_mspec_one_spectrum_is_spt).
+    requirements.txt), which is absent.  The plugin's OWN code is pinned: it runs
+    here over a stand-in of that container (oracle/mspec_standin.py) and its
+    outputs are tests/golden/mspec.npz (oracle/make_golden_mspec.py; live in
+    tests/test_oracle_vs_reference.py).  PARITY UNPINNED only for the container's
+    semantics (stacking order, ``lincombo``, ``binned``), which the stand-in
+    states from the way mspec_lnl.py uses them; further anchored by the
+    1-spectrum case reproducing ``SptLowl``
+    (tests/test_oracle_golden.py::test_mspec_one_spectrum_is_spt).
   * ``GaussLike``: the reference has no Gaussian plugin; this is the quickstart
     script body (doc/quickstart.md:41-43) generalised to x^T C^-1 x / 2.
 """

@@ -112,6 +112,21 @@ def test_multispectrum_lnl_matches_the_oracle(torch, kind):
     assert relerr(got, ref) < RTOL
 
 
+@pytest.mark.parametrize("name", ["spt", "subset", "clean", "planck"])
+def test_multispectrum_lnl_matches_the_reference_golden(torch, name):
+    """the CUDA path against what the UNMODIFIED reference's mspec_lnl.py returns for the same scripts
+    (tests/golden/mspec.npz: oracle/make_golden_mspec.py ran them through the reference's Slik.evaluate over the
+    stand-in of its absent container package): lnL within 1e-10, the same hard-prior rejections"""
+    import mspec_cases
+    prob, ns, X, want = mspec_cases.case(name, PRODUCT)
+    slik = Slik(synthetic.build_script(ns, prob)())
+    got = slik.evaluate_batch(X)
+    fin = np.isfinite(want)
+    assert not fin.all()
+    np.testing.assert_array_equal(np.isfinite(got), fin)
+    np.testing.assert_allclose(got[fin], want[fin], rtol=RTOL)
+
+
 @pytest.mark.parametrize("mode", ["trsm", "inverse"])
 def test_both_chi2_kernels_match_the_oracle(torch, spt_data, mode):
     """blocked forward substitution (k_trsm_chi2) and the explicit-inverse tile product (k_trigemm_chi2)"""

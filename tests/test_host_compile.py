@@ -321,3 +321,21 @@ def test_mspec_cleaning_and_resgal():
     scaled, _ = lincombo(base["signal"], None, {m: {m: cal[m]} for m in base["maps"]}, normalize=False)
     for (a, b) in base["keys"]:
         np.testing.assert_allclose(scaled[(a, b)], base["signal"][(a, b)] * cal[a] * cal[b], rtol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["spt", "subset", "clean", "planck"])
+def test_mspec_tables_against_the_reference_golden(name):
+    """the product's traced + compiled multi-spectrum programs (device tables interpreted in numpy) against what
+    the UNMODIFIED reference's mspec_lnl.py returns for the same scripts (tests/golden/mspec.npz, generated over the
+    container stand-in: oracle/make_golden_mspec.py): per-map calibration, a `use` subset, cleaning + resgal,
+    TT / TE / EE with calibration on the data"""
+    import mspec_cases
+    from namespaces import PRODUCT
+    from cosmoslik_b200 import synthetic
+    prob, ns, X, want = mspec_cases.case(name, PRODUCT)
+    slik, cp = compiled(synthetic.build_script(ns, prob))
+    n = 10 if name != "planck" else len(X)
+    got = np.array([TI.lnl(cp, x) for x in X[:n]])
+    fin = np.isfinite(want[:n])
+    np.testing.assert_array_equal(np.isfinite(got), fin)
+    np.testing.assert_allclose(got[fin], want[:n][fin], rtol=1e-10)

@@ -267,3 +267,30 @@ def test_spt_lowl_loader_and_trimming_match_the_live_reference():
     for t in ("template_sz", "template_cl", "template_ps"):
         n = min(len(getattr(mine.egfs, t)), len(getattr(ref.egfs, t)))
         np.testing.assert_array_equal(getattr(mine.egfs, t)[:n], getattr(ref.egfs, t)[:n])
+
+
+def test_mspec_lnl_live_over_the_container_stand_in(R):
+    """the reference's own mspec_lnl.py (over oracle/mspec_standin.py) against the oracle restatement AND the
+    product's compiled tables on a FRESH problem and fresh points -- the live version of tests/golden/mspec.npz"""
+    import table_interp as TI
+    from namespaces import ORACLE, PRODUCT
+    from cosmoslik_b200 import Slik, synthetic
+    from cosmoslik_b200.program import CompiledProgram
+    from oracle.make_golden_mspec import points, reference_namespace
+    prob = synthetic.spt_multifreq_problem(17, nbins=7, lmax=451)
+    R2, ns = reference_namespace()
+    rslik = R2.core.Slik(synthetic.build_script(ns, prob)())
+    names, X = points(prob, 6, 5)
+    assert list(rslik.get_sampled()) == names
+    want = np.array([rslik.evaluate(*x)[0] for x in X])
+    oslik = runtime.Slik(synthetic.build_script(ORACLE, prob)())
+    got = np.array([oslik.evaluate(*x)[0] for x in X])
+    fin = np.isfinite(want)
+    assert fin.sum() >= 4 and not fin.all()
+    np.testing.assert_array_equal(np.isfinite(got), fin)
+    np.testing.assert_allclose(got[fin], want[fin], rtol=1e-12)
+    pslik = Slik(synthetic.build_script(PRODUCT, prob)())
+    cp = CompiledProgram(list(pslik.get_sampled()), pslik.params.priors, pslik.trace())
+    tab = np.array([TI.lnl(cp, x) for x in X])
+    np.testing.assert_array_equal(np.isfinite(tab), fin)
+    np.testing.assert_allclose(tab[fin], want[fin], rtol=1e-10)
