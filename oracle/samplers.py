@@ -13,7 +13,10 @@ Parity status:
     this image and from the reference tree.  PARITY UNPINNED: restated from
     the published algorithm (Goodman & Weare 2010, eq. 7-10; emcee 2.x
     ``EnsembleSampler.sample`` / ``_propose_stretch``).  The wrapper logic
-    around it (``emcee_wrapper_rows``) follows samplers/emcee.py:34-88.
+    around it (``emcee_wrapper_rows``) follows samplers/emcee.py:34-88 and IS
+    pinned: the reference's own wrapper file runs over a stand-in of the
+    package (oracle/emcee_standin.py) whose move is ``ensemble_step``, and its
+    yields and chain file are tests/golden/emcee_wrapper.npz / ref_emcee.chain.
   * ``mh_lockstep``: the reference's adaptive mode is an asynchronous MPI
     master/worker protocol whose timing is not deterministic
     (metropolis_hastings.py:188-241).  The lock-step analogue used by the

@@ -91,6 +91,35 @@ def test_emcee_file_extras_are_those_of_the_next_position(tmp_path):
             np.testing.assert_allclose(chains[w][n], [r[3][i] for r in rows[w]], rtol=1e-13, atol=0)
 
 
+def test_emcee_chain_file_matches_the_reference_wrapper(tmp_path):
+    """the chain file of samplers.emcee against the file the UNMODIFIED reference wrapper wrote for the same script,
+    initial positions and injected streams (tests/golden/ref_emcee.chain: oracle/make_golden_emcee_wrapper.py ran
+    cosmoslik_plugins/samplers/emcee.py over a stand-in of the absent ``emcee`` package): header, walkers, records,
+    weights and positions exact, lnl and the derived columns (those of the NEXT position) to 1e-13; both files are
+    read by this package's loader"""
+    import os
+    from conftest import GOLDEN, golden
+    g = golden("emcee_wrapper.npz")
+    k, nsteps, freq = int(g["nwalkers"]), int(g["nsteps"]), int(g["output_freq"])
+    out = str(tmp_path / "emcee_ref.chain")
+    slik = Slik(B.derived_script(lambda s: samplers.emcee(
+        s, num_samples=k * nsteps, nwalkers=k, streams=lambda i: (g["u_z"][i], g["j"][i], g["u_acc"][i]), seed=3,
+        output_file=out, output_freq=freq, output_extra_params=["r2", "ratio"]))())
+    assert list(slik.get_sampled()) == list(g["names"])
+    np.testing.assert_allclose(slik.sampler.cov_est, g["cov_est"], rtol=0, atol=0)
+    slik.sampler.init_pos = np.array(g["pos0"])
+    yielded = list(slik.sample())
+    assert len(yielded) == len(g["field_weight"])
+    mine, ref = load_chain(out), load_chain(os.path.join(GOLDEN, "ref_emcee.chain"))
+    assert len(mine) == len(ref) == k
+    for w in range(k):
+        assert list(mine[w].keys()) == list(ref[w].keys()) == ["lnl", "weight", "a", "b", "r2", "ratio"]
+        for col in ("weight", "a", "b"):
+            np.testing.assert_array_equal(mine[w][col], ref[w][col])
+        for col in ("lnl", "r2", "ratio"):
+            np.testing.assert_allclose(mine[w][col], ref[w][col], rtol=1e-13, atol=0)
+
+
 def test_evaluate_returns_the_evaluated_tree():
     """cosmoslik.py:141: the second element of Slik.evaluate carries what the script stored on itself"""
     slik = Slik(B.derived_script(lambda s: samplers.metropolis_hastings(s, num_samples=10))())

@@ -294,3 +294,33 @@ def test_mspec_lnl_live_over_the_container_stand_in(R):
     tab = np.array([TI.lnl(cp, x) for x in X])
     np.testing.assert_array_equal(np.isfinite(tab), fin)
     np.testing.assert_allclose(tab[fin], want[fin], rtol=1e-10)
+
+
+def test_emcee_wrapper_live_over_the_move_stand_in(R, tmp_path):
+    """the reference's own samplers/emcee.py (over oracle/emcee_standin.py) with FRESH streams, walker count, step
+    count and output_freq, against the oracle's restatement of the wrapper -- the live version of
+    tests/golden/emcee_wrapper.npz"""
+    import pickle
+    import oracle_scripts as S
+    from oracle.make_golden_emcee_wrapper import run
+    out = str(tmp_path / "live_emcee.chain")
+    g = run(out, k=10, nsteps=7, freq=2, stream_seed=5, scatter_seed=6)
+    slik = runtime.Slik(S.derived_script()())
+    lnprob = lambda q: np.array([-slik.evaluate(*x)[0] for x in np.atleast_2d(q)])
+    blob = lambda x: [slik.evaluate(*x)[1][n] for n in ("r2", "ratio")]
+    rows, _, _ = samplers.emcee_wrapper_rows(g["pos0"], lnprob, 7, lambda i: (g["u_z"][i], g["j"][i], g["u_acc"][i]),
+                                             blob_fn=blob)
+    per = {}
+    with open(out, "rb") as f:
+        pickle.load(f)
+        while True:
+            try:
+                w, rec = pickle.load(f)
+            except EOFError:
+                break
+            assert len(rec) <= 2
+            per.setdefault(int(w), []).extend(list(r) for r in rec)
+    for w in range(10):
+        mine = np.array([[r[0], r[1]] + list(r[2]) + list(r[3]) for r in rows[w]])
+        np.testing.assert_allclose(mine, np.array(per[w], dtype=float), rtol=1e-13)
+    assert int(g["evals"]) == 2 * 10 * 7
