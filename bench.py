@@ -420,7 +420,7 @@ def measure_stretch(args, prob, k_total, instrument=True, e2e=True):
     if fused:           # the row bookkeeping rides in the accept kernels (CSL_NO_FOLD_ROWS=1: its own launch per step)
         per_step = 2 * (1 + nbin + 1 + 1) + (1 if os.environ.get("CSL_NO_FOLD_ROWS") else 0)
     else:
-        per_step = 2 * (2 + nbin + (2 if prog.meta.get("chi2_mode") else 1) + 1 + 1 + (1 if size > 1 else 0)) + 1
+        per_step = 2 * (2 + nbin + 1 + 1 + 1 + (1 if size > 1 else 0)) + 1
     rec["gpu_launches"] = per_step * args.steps + (1 if (fused and size > 1) else 0)
     half = (k_total // size) // 2
     fl = prog.flops

@@ -82,6 +82,8 @@ SIGNATURES = {
     "csl_chi2": (_int, [_P, _int, _vp, _int, _vp, _vp, _vp]),
     "csl_cov_chi2": (_int, [_P, _int, _vp, _int, _vp, _vp]),
     "csl_combine": (_int, [_P, _int, _vp, _int, _vp, _vp, _vp, _vp]),
+    "csl_combine_parts": (_int, [_P, _int, _vp, _int, _vp, _vp, _int, _vp, _vp]),
+    "csl_chi2_parts": (_int, [_P, _int, _vp, _int, _vp, _vp]),
     "csl_lnl": (_int, [_P, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "csl_lnl_host": (_int, [_P, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "csl_mh_propose": (_int, [_int, _int, _vp, _vp, _int, _vp, _vp, _u64, _u32, _u32, _vp]),

@@ -114,7 +114,11 @@ static int lnl_ld(const csl_program_t* p, int W, const double* x, double* lnl, d
     else rc = csl_direct_residual_ld(p, W, Wp, ws_coef, ld, ws_R, ld, stream);
     if (rc) return rc;
     if (p->resid_mode == 3) rc = csl_cov_chi2(p, W, ws_R, ld, ws_chi2, stream);
-    else rc = csl_chi2(p, Wp, ws_R, ld, ws_chi2, ws_part, stream);
+    else if (p->chi2_mode == 1) {                     // the partial sums are added by the combine kernel
+      rc = csl_chi2_parts(p, Wp, ws_R, ld, ws_part, stream);
+      if (rc) return rc;
+      return csl_combine_parts(p, W, ws_coef, ld, ws_prior, ws_part, ld, lnl, stream);
+    } else rc = csl_chi2(p, Wp, ws_R, ld, ws_chi2, ws_part, stream);
     if (rc) return rc;
     chi2 = ws_chi2;
   }

@@ -629,6 +629,13 @@ extern "C" int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, doubl
   return csl_chi2_impl(p, W, R, ldr, chi2, ws_part, true, stream);
 }
 
+// chi^2 left as per-32-row partial sums in ws_part[i, :] (explicit-inverse mode; csl_combine_parts adds them): returns
+// CSL_E_BADARG for a program in substitution mode, whose kernel writes chi2 directly
+extern "C" int csl_chi2_parts(const csl_program_t* p, int W, double* R, int ldr, double* ws_part, void* stream) {
+  CSL_REQUIRE(p && p->chi2_mode == 1 && ws_part, "csl_chi2_parts: explicit-inverse programs only");
+  return csl_chi2_impl(p, W, R, ldr, ws_part, ws_part, false, stream);
+}
+
 // sum_partials = false (explicit-inverse mode only): leave the per-row-block column sums in ws_part[i, :]
 // for a consumer that adds them itself (the fused accept kernel of csl_stretch_run)
 int csl_chi2_impl(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part, bool sum_partials,

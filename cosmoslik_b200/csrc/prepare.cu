@@ -54,6 +54,18 @@ __global__ void k_combine(csl_program_t p, int W, const double* __restrict__ coe
   lnl[w] = combine_walker(p, w, coef, ldc, prior[w], chi2 != nullptr, chi2 != nullptr ? chi2[w] : 0.0);
 }
 
+// the same with chi^2 still in its per-32-row partial sums (explicit-inverse mode): they are added here, in the order
+// k_sum_partials adds them, so the separate 5 us reduction launch of the staged / end-to-end path disappears
+__global__ void k_combine_parts(csl_program_t p, int W, const double* __restrict__ coef, int ldc,
+                                const double* __restrict__ prior, const double* __restrict__ part, int nblk, int ldp,
+                                double* __restrict__ lnl) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  double s = 0.0;
+  for (int i = 0; i < nblk; ++i) s += part[(long long)i * ldp + w];
+  lnl[w] = combine_walker(p, w, coef, ldc, prior[w], true, s);
+}
+
 // resid_mode 2: R[i, w] = coef[direct_coef[i], w] - data[i]; rows n..n_pad and columns W..Wp are zero
 __global__ void k_direct_residual(csl_program_t p, int W, int Wp, const double* __restrict__ coef, int ldc,
                                   double* __restrict__ R, int ldr) {
@@ -96,6 +108,13 @@ extern "C" int csl_combine(const csl_program_t* p, int W, const double* coef, in
   CSL_REQUIRE(p && prior && lnl && W > 0, "csl_combine: null argument");
   k_combine<<<(W + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p, W, coef, ldc, prior, chi2, lnl);
   return csl_check_launch("k_combine");
+}
+
+extern "C" int csl_combine_parts(const csl_program_t* p, int W, const double* coef, int ldc, const double* prior,
+                                 const double* part, int ldp, double* lnl, void* stream) {
+  CSL_REQUIRE(p && prior && lnl && part && W > 0 && ldp >= W && p->n_pad > 0, "csl_combine_parts: bad argument");
+  k_combine_parts<<<(W + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p, W, coef, ldc, prior, part, p->n_pad / 32, ldp, lnl);
+  return csl_check_launch("k_combine_parts");
 }
 
 int csl_direct_residual_ld(const csl_program_t* p, int W, int Wp, const double* coef, int ldc, double* R, int ldr,

@@ -663,6 +663,12 @@ class DeviceProgram(CompiledProgram):
         if self.meta["resid_mode"] == 3:
             stage("cov_chi2", lambda: self.lib.csl_cov_chi2(P, W, ws["R"].data_ptr(), Wp, ws["chi2"].data_ptr(), st))
             chi2 = ws["chi2"].data_ptr()
+        elif self.meta["resid_mode"] and self.meta.get("chi2_mode"):
+            # explicit inverse: the tile product leaves partial sums, the combine kernel adds them (as csl_lnl does)
+            stage("chi2", lambda: self.lib.csl_chi2_parts(P, Wp, ws["R"].data_ptr(), Wp, ws["part"].data_ptr(), st))
+            stage("combine", lambda: self.lib.csl_combine_parts(P, W, ws["coef"].data_ptr(), Wp, ws["prior"].data_ptr(),
+                                                                ws["part"].data_ptr(), Wp, out.data_ptr(), st))
+            return out
         elif self.meta["resid_mode"]:
             stage("chi2", lambda: self.lib.csl_chi2(P, Wp, ws["R"].data_ptr(), Wp, ws["chi2"].data_ptr(),
                                                     ws["part"].data_ptr(), st))

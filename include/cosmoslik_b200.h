@@ -216,6 +216,9 @@ int csl_direct_residual(const csl_program_t* p, int W, const double* coef, int l
  *   chi2_mode 1: tile products with the host-inverted factor Minv (chosen by the host only when the
  *                inverse reproduces the substitution result to 1e-13); needs ws_part [n_pad/32, ldr] (one partial sum per 32 rows). */
 int csl_chi2(const csl_program_t* p, int W, double* R, int ldr, double* chi2, double* ws_part, void* stream);
+/* Explicit-inverse programs only: the tile product alone, the column sums of squares of every 32 rows of Y = L^-1 R
+ * left in ws_part[n_pad/32, ldr] for csl_combine_parts (one reduction launch fewer than csl_chi2 + csl_combine). */
+int csl_chi2_parts(const csl_program_t* p, int W, double* R, int ldr, double* ws_part, void* stream);
 
 /* resid_mode 3 (replaces cho_factor(beam_cov + sigma) + cho_solve per call, SPTSZ_lowl.py:66-69):
  * R [(1 + nmode) * n_base (padded), ldr] holds r and the columns of V for every walker; one warp per
@@ -226,6 +229,10 @@ int csl_cov_chi2(const csl_program_t* p, int W, const double* R, int ldr, double
  * chi2 may be NULL when the program has no quadratic form. */
 int csl_combine(const csl_program_t* p, int W, const double* coef, int ldc, const double* prior,
                 const double* chi2, double* lnl, void* stream);
+/* The same for a program in explicit-inverse mode whose chi^2 is still in the per-32-row partial sums csl_chi2_parts
+ * left in part[n_pad/32, ldp]: they are added here in row order (the order csl_chi2 adds them), then combined. */
+int csl_combine_parts(const csl_program_t* p, int W, const double* coef, int ldc, const double* prior,
+                      const double* part, int ldp, double* lnl, void* stream);
 
 /* The four calls above in sequence.  Workspace (device, caller owned):
  *   coef [ncoef, Wp], prior [Wp], R [n_pad, Wp], chi2 [Wp], part [n_pad/32, Wp]
