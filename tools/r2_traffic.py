@@ -27,8 +27,6 @@ def main():
     walkers = 32768
     n, npad = 613, 640
     out = {"source_digest": bench.kernel_source_digest(),
-           "note": "captures taken by tools/r2_final_n1.sh at commit 3dac958; since then only the HOST-side wait of "
-                   "csl_lnl_host in api.cu changed (no kernel changed)",
            "k_trigemm_chi2": {
                "walkers_per_launch": walkers,
                "dram_bytes_per_launch": dram_bytes(os.path.join(ROOT, "profiles", "r2_ncu_full_k_trigemm_chi2.txt")),
